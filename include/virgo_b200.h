@@ -1,0 +1,167 @@
+/* virgo_b200.h -- C ABI of the B200-native Virgo++ GKR sumcheck prover.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. The C++ class
+ * `prover` shipped in virgo-plus_b200/host/prover.{h,cpp} (same public API as the reference's
+ * src/prover.h:12-42) forwards 1:1 to these entry points; INTEGRATION.md shows the binding.
+ * Citations are into /root/reference.
+ *
+ * Conventions: every function returns 0 on success or a negative vp_status; vp_last_error()
+ * returns a description of the last failure on the calling thread. There is NO CPU fallback: all
+ * prover entry points fail with VP_ERR_CUDA when no sm_100 device / driver is usable.
+ * A context is single-threaded (like the reference prover: one prover per process).
+ */
+#ifndef VIRGO_B200_H
+#define VIRGO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bit-identical to virgo::fieldElement {real, img} (lib/virgo/src/fieldElement.hpp:96-97) */
+typedef struct { uint64_t re, im; } vp_F;
+
+typedef struct vp_circuit vp_circuit; /* host-side layered circuit (+ instance count) */
+typedef struct vp_ctx vp_ctx;         /* prover context: owns all device memory */
+
+typedef enum {
+    VP_OK = 0,
+    VP_ERR_ARG = -1,      /* bad argument / call out of protocol order */
+    VP_ERR_CIRCUIT = -2,  /* malformed circuit or .pws */
+    VP_ERR_CUDA = -3,     /* CUDA / NCCL failure, or no usable device */
+    VP_ERR_ASSERT = -4,   /* an is_assert gate evaluates to non-zero (prover.cpp:18-21, :211) */
+    VP_ERR_NOMEM = -5
+} vp_status;
+
+const char* vp_last_error(void);
+const char* vp_version(void);
+
+/* ------------------------------------------------------------------ circuit (host side)
+ * Replaces parse()+DAG_to_layered() (src/main.cpp:15-137,176-231) and layeredCircuit::subsetInit()
+ * (src/circuit.cpp:43-80), including their observable quirks. */
+int vp_circuit_load_pws(const char* path, vp_circuit** out);
+int vp_circuit_load_pws_text(const char* text, size_t len, vp_circuit** out);
+/* Synthetic random add/mul circuit, semantics of layeredCircuit::randomize (circuit.cpp:17-41). */
+int vp_circuit_random(int n_layers, int log_size, uint64_t seed, vp_circuit** out);
+/* Build from flat arrays (concatenated over layers 0..n-1, gate_off-style: layer i occupies
+ * [sum_{j<i} layer_size[j], ...)). Layer-0 entries carry the input VALUE in u (like gate.u of an
+ * Input gate, main.cpp:108-110). If dad_size == NULL the subsets and lv are derived with the
+ * subsetInit rule; otherwise lv / dad_size[i*n+l] / dad_id (concatenated in (i,l) order) are taken
+ * as given (what the reference's `layeredCircuit` holds after c.subsetInit()). c / is_assert may be
+ * NULL. */
+int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, const uint8_t* ty, const int32_t* l,
+                           const uint64_t* u, const uint64_t* v, const uint64_t* lv, const vp_F* c,
+                           const uint8_t* is_assert, const uint64_t* dad_size, const uint64_t* dad_id,
+                           vp_circuit** out);
+/* K data-parallel instances of the same template (instance-major replication);
+ * inputs are drawn like the reference draws them at parse time (main.cpp:188). */
+int vp_circuit_replicate(const vp_circuit* c, uint64_t instances, vp_circuit** out);
+/* Materialise the instances into one flat circuit (instances == 1), subsets re-derived. */
+int vp_circuit_expand(const vp_circuit* c, vp_circuit** out);
+void vp_circuit_free(vp_circuit* c);
+
+int vp_circuit_num_layers(const vp_circuit* c);
+uint64_t vp_circuit_instances(const vp_circuit* c);
+uint64_t vp_circuit_layer_size(const vp_circuit* c, int layer);      /* of ONE instance */
+int vp_circuit_bit_length(const vp_circuit* c, int layer);          /* of the replicated layer */
+uint64_t vp_circuit_dad_size(const vp_circuit* c, int layer, int src); /* of ONE instance */
+int vp_circuit_max_dad_bit_length(const vp_circuit* c, int layer);  /* -1: phase 2 skipped */
+uint64_t vp_circuit_total_gates(const vp_circuit* c);               /* non-input gates, all instances */
+uint64_t vp_circuit_num_inputs(const vp_circuit* c);                /* instances * layer_size(0) */
+/* Export the gates of one template layer (arrays of layer_size entries; any pointer may be NULL). */
+int vp_circuit_export_layer(const vp_circuit* c, int layer, uint8_t* ty, int32_t* l, uint32_t* u, uint32_t* v,
+                            uint32_t* lv, vp_F* cst, uint8_t* is_assert);
+int vp_circuit_export_dad(const vp_circuit* c, int layer, int src, uint32_t* dad_id /* dad_size entries */);
+int vp_circuit_get_inputs(const vp_circuit* c, uint64_t* out /* num_inputs */);
+int vp_circuit_set_inputs(vp_circuit* c, const uint64_t* in /* num_inputs, each < p */);
+
+/* Challenges in the verifier's draw order (src/verifier.cpp:144-145,196,202,236,278-279) from glibc
+ * random() after srand(seed) (fieldElement.cpp:106-124); seed 3396 reproduces F::init(). */
+size_t vp_challenge_count(const vp_circuit* c);
+int vp_draw_challenges(const vp_circuit* c, unsigned seed, vp_F* out /* vp_challenge_count */);
+/* Prover messages: Vres; per layer top..1: bl(i-1) x (a,b,c), claim_u, [maxDad(i) x (a,b,c), claims_v[0..i)],
+ * bl(i-1) x (a,b,c), claim_liu; finally the input-layer MLE. */
+size_t vp_transcript_len(const vp_circuit* c);
+
+/* ------------------------------------------------------------------ prover
+ * One context = one `prover` object (src/prover.h:12-67) on one GPU. */
+int vp_create(const vp_circuit* c, int device, vp_ctx** out);
+/* Sharded context: this process is `rank` of `world` GPUs of one box; nccl_id is the 128-byte
+ * ncclUniqueId shared by all ranks (vp_nccl_unique_id on rank 0, broadcast by the caller). */
+int vp_nccl_unique_id(uint8_t out[128]);
+int vp_create_sharded(const vp_circuit* c, int device, int rank, int world, const uint8_t nccl_id[128],
+                      vp_ctx** out);
+void vp_destroy(vp_ctx* ctx);
+
+/* Upload the witness inputs (instances * layer_size(0) values < p); default: the circuit's own. */
+int vp_set_inputs(vp_ctx* ctx, const uint64_t* inputs, size_t n);
+/* prover::evaluate (prover.cpp:27-91) + the assert check of the constructor (:16-24). */
+int vp_evaluate(vp_ctx* ctx);
+/* Copy circuitValue[layer] to the host (layer 0 is what commit_private hands to the PC, :524-530). */
+int vp_get_values(vp_ctx* ctx, int layer, vp_F* out, size_t n);
+
+/* prover::Vres (prover.cpp:99-129): MLE of the output layer at r[0..n). */
+int vp_vres(vp_ctx* ctx, const vp_F* r, int n, vp_F* out);
+/* prover::sumcheckInitAll (:162-170) */
+int vp_sumcheck_init_all(vp_ctx* ctx, const vp_F* r_last, int n);
+/* prover::sumcheckInit (:177-184): step to the next layer (top -> 1). */
+int vp_sumcheck_init(vp_ctx* ctx);
+/* prover::sumcheckInitPhase1 (:189-280) / Phase2 (:282-367) / Liu (:369-420; sig has n entries,
+ * n >= n_layers - layer + 1). */
+int vp_init_phase1(vp_ctx* ctx, const vp_F* assert_random);
+int vp_init_phase2(vp_ctx* ctx);
+int vp_init_liu(vp_ctx* ctx, const vp_F* sig, int n);
+/* prover::sumcheckUpdatePhase1 / Phase2 / LiuUpdate (:422-455): phase = 1, 2, 3. out_abc = the
+ * round's quadratic_poly {a,b,c}. */
+int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_F out_abc[3]);
+/* prover::sumcheckFinalize1 (:494-501), Finalize2 (:504-516; claims has `layer` entries),
+ * LiuFinalize (:518-521). */
+int vp_finalize1(vp_ctx* ctx, const vp_F* previous_random, vp_F* claim);
+int vp_finalize2(vp_ctx* ctx, const vp_F* previous_random, vp_F* claims, int n);
+int vp_finalize_liu(vp_ctx* ctx, const vp_F* previous_random, vp_F* claim);
+/* prover::inner_prod(circuitValue[0], pub, n) as used by commit_public (:532-546). */
+int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out);
+/* Input-layer MLE at r[0..n): <circuitValue[0], eq(r,.)> without materialising eq on the host. */
+int vp_input_mle(vp_ctx* ctx, const vp_F* r, int n, vp_F* out);
+/* prover::proofSize() in bytes (:451,:500,:512) and the accumulated device time inside prover
+ * entry points in seconds (the analogue of proveTime(), :549-551). */
+uint64_t vp_proof_size_bytes(const vp_ctx* ctx);
+double vp_prove_seconds(const vp_ctx* ctx);
+
+/* ------------------------------------------------------------------ whole proof, no per-round host sync
+ * The reference verifier's challenges do not depend on prover messages, so the whole
+ * stream can be handed over up front. vp_prove runs evaluate + every phase of every layer on the
+ * device and returns the transcript (vp_transcript_len entries).
+ * host_io != 0: `inputs`/`challenges`/`transcript` are HOST buffers (copied inside the call).
+ * host_io == 0: inputs already uploaded with vp_set_inputs and challenges with vp_set_challenges;
+ *               the transcript stays on the device until vp_get_transcript. */
+int vp_set_challenges(vp_ctx* ctx, const vp_F* challenges, size_t n);
+int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
+             size_t n_challenges, vp_F* transcript, size_t transcript_cap);
+int vp_get_transcript(vp_ctx* ctx, vp_F* transcript, size_t cap);
+/* Device-side time of the last vp_prove (CUDA events on the context's stream), milliseconds. */
+float vp_last_prove_ms(const vp_ctx* ctx);
+/* Number of kernel launches issued by the last vp_prove. */
+uint64_t vp_last_prove_launches(const vp_ctx* ctx);
+/* The context's CUDA stream (cudaStream_t) so callers can bracket it with their own events. */
+void* vp_stream(vp_ctx* ctx);
+
+/* ------------------------------------------------------------------ stand-alone sumcheck (config C2)
+ * Three tables V, add, mult of 2^log_n entries (device-resident copies are made once); runs the
+ * log_n rounds of sumcheckUpdateEach with challenges r[0..log_n) and returns 3*log_n + 3 values:
+ * per round (a,b,c), then the three fully-folded table values. */
+typedef struct vp_sumcheck vp_sumcheck;
+int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out);
+int vp_sumcheck_load(vp_sumcheck* s, const vp_F* V, const vp_F* add, const vp_F* mult); /* host -> device */
+int vp_sumcheck_fill_random(vp_sumcheck* s, uint64_t seed);  /* SplitMix64 per entry, on device */
+int vp_sumcheck_export(vp_sumcheck* s, vp_F* V, vp_F* add, vp_F* mult);  /* device -> host (pristine copy) */
+int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out /* 3*log_n+3 */, float* device_ms);
+/* per-round device time of the last run (log_n floats, ms) */
+int vp_sumcheck_round_ms(vp_sumcheck* s, float* out);
+void vp_sumcheck_destroy(vp_sumcheck* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

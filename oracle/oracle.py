@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrapper of oracle/libgkr_oracle.so (the CPU restatement in
+gkr_oracle.c). Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs; never by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgkr_oracle.so")
+F_DTYPE = np.dtype([("re", "<u8"), ("im", "<u8")])
+
+
+class _Circuit(C.Structure):
+    _fields_ = [("n_layers", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "layer_size", "gate_off", "ty", "l", "u", "v", "lv", "c", "is_assert", "dad_size", "dad_off", "dad_id", "inputs")]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.ogkr_transcript_len.restype = C.c_size_t
+        L.ogkr_transcript_len.argtypes = [C.c_void_p]
+        L.ogkr_challenge_count.restype = C.c_size_t
+        L.ogkr_challenge_count.argtypes = [C.c_void_p]
+        L.ogkr_prove.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.ogkr_verify.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ogkr_evaluate.argtypes = [C.c_void_p, C.c_void_p]
+        L.ogkr_evaluate.restype = None
+        L.ogkr_sumcheck_tables.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p]
+        L.ogkr_sumcheck_tables.restype = None
+        L.ogkr_beta_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.ogkr_beta_table.restype = None
+        for fn in (L.ofe_add, L.ofe_sub, L.ofe_mul):
+            fn.argtypes = [C.c_uint64] * 4
+            fn.restype = _Fe
+        L.ogkr_seed.argtypes = [C.c_uint]
+        L.ogkr_seed.restype = None
+        L.ogkr_random_field.restype = _Fe
+        _lib = L
+    return _lib
+
+
+class _Fe(C.Structure):
+    _fields_ = [("re", C.c_uint64), ("im", C.c_uint64)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleCircuit:
+    """Wraps the dict produced by binding.Circuit.flat() as an ogkr_circuit."""
+
+    def __init__(self, flat):
+        self.flat = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in flat.items()}
+        f = self.flat
+        any_c = bool(np.any(f["c"]["re"] | f["c"]["im"]))
+        any_a = bool(np.any(f["is_assert"]))
+        self.s = _Circuit(
+            f["n_layers"], _p(f["layer_size"]), _p(f["gate_off"]), _p(f["ty"]), _p(f["l"]), _p(f["u"]), _p(f["v"]),
+            _p(f["lv"]), _p(f["c"]) if any_c else None, _p(f["is_assert"]) if any_a else None, _p(f["dad_size"]),
+            _p(f["dad_off"]), _p(f["dad_id"]), _p(f["inputs"]))
+
+    @property
+    def ref(self):
+        return C.byref(self.s)
+
+    @property
+    def transcript_len(self):
+        return lib().ogkr_transcript_len(self.ref)
+
+    @property
+    def challenge_count(self):
+        return lib().ogkr_challenge_count(self.ref)
+
+    def prove(self, seed=3396):
+        """-> (transcript, challenges, prove_seconds); raises if an assert gate is violated."""
+        tr = np.zeros(self.transcript_len, F_DTYPE)
+        ch = np.zeros(self.challenge_count, F_DTYPE)
+        sec = C.c_double()
+        rc = lib().ogkr_prove(self.ref, seed, _p(tr), _p(ch), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError("oracle: assert gate violated")
+        return tr, ch, sec.value
+
+    def verify(self, transcript, seed=3396):
+        """-> (accept: bool, fail_code, fail_layer)"""
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        assert len(tr) == self.transcript_len
+        code, layer = C.c_int(), C.c_int()
+        ok = lib().ogkr_verify(self.ref, seed, _p(tr), C.byref(code), C.byref(layer))
+        return bool(ok), code.value, layer.value
+
+    def evaluate(self):
+        n = int(self.flat["layer_size"].sum())
+        out = np.zeros(n, F_DTYPE)
+        lib().ogkr_evaluate(self.ref, _p(out))
+        return out
+
+
+def sumcheck_tables(V, add, mult, r):
+    V, add, mult, r = [np.ascontiguousarray(x, dtype=F_DTYPE) for x in (V, add, mult, r)]
+    log_n = len(r)
+    assert len(V) == 1 << log_n
+    out = np.zeros(3 * log_n + 3, F_DTYPE)
+    lib().ogkr_sumcheck_tables(_p(V), _p(add), _p(mult), log_n, _p(r), _p(out))
+    return out
+
+
+def beta_table(r, init=(1, 0)):
+    r = np.ascontiguousarray(r, dtype=F_DTYPE)
+    out = np.zeros(1 << len(r), F_DTYPE)
+    lib().ogkr_beta_table(_p(out), len(r), _p(r), init[0], init[1])
+    return out
+
+
+def _fe(x):
+    return (int(x["re"]), int(x["im"])) if not isinstance(x, tuple) else x
+
+
+def f_add(a, b):
+    a, b = _fe(a), _fe(b)
+    r = lib().ofe_add(a[0], a[1], b[0], b[1])
+    return (r.re, r.im)
+
+
+def f_sub(a, b):
+    a, b = _fe(a), _fe(b)
+    r = lib().ofe_sub(a[0], a[1], b[0], b[1])
+    return (r.re, r.im)
+
+
+def f_mul(a, b):
+    a, b = _fe(a), _fe(b)
+    r = lib().ofe_mul(a[0], a[1], b[0], b[1])
+    return (r.re, r.im)
+
+
+def draw_challenges(n, seed=3396):
+    """n field elements from srandom(seed) + fieldElement::random() (global glibc state)."""
+    L = lib()
+    L.ogkr_seed(seed)
+    out = np.zeros(n, F_DTYPE)
+    for i in range(n):
+        r = L.ogkr_random_field()
+        out[i] = (r.re, r.im)
+    return out

@@ -1,0 +1,603 @@
+// sm_100a kernels of the GKR sumcheck prover. One kernel per reference loop.
+// All tables hold one F (16 B) per entry: the reference's linear_poly {a,b} (src/polynomial.h:35-46)
+// is re-derived as a = T[2i+1]-T[2i], b = T[2i], so a table costs 16 B/entry instead of 32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "field.cuh"
+
+namespace vp {
+
+// gate type codes: /root/reference/src/inputCircuit.hpp:14-16
+enum : uint32_t { T_MUL = 0, T_ADD, T_SUB, T_ANTISUB, T_NAAB, T_ANTINAAB, T_INPUT, T_MULC, T_ADDC, T_XOR, T_NOT, T_COPY };
+static constexpr uint32_t TY_ASSERT_BIT = 0x80;
+
+// ------------------------------------------------------------------ loads / stores
+VP_D F ld_f(const F* p) {
+    ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    return F{t.x, t.y};
+}
+VP_D F ld_f_cg(const F* p) {  // bypass L1 (data written by other blocks of the same launch)
+    ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+    return F{t.x, t.y};
+}
+VP_D void st_f(F* p, const F& v) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v.re, v.im); }
+
+// eq(r, idx) = half_f[idx & mask] * half_s[idx >> fh]   (utils.cpp:41-42)
+struct EqTab {
+    const F* f;
+    const F* s;
+    uint32_t fh;
+    uint32_t mask;
+};
+VP_D F eq_at(const EqTab& t, uint32_t idx) { return f_mul(ld_f(t.f + (idx & t.mask)), ld_f(t.s + (idx >> t.fh))); }
+
+// ------------------------------------------------------------------ reductions
+VP_D F warp_sum(F x) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        F y;
+        y.re = __shfl_down_sync(0xffffffffu, x.re, off);
+        y.im = __shfl_down_sync(0xffffffffu, x.im, off);
+        x = f_add(x, y);
+    }
+    return x;
+}
+
+// Block-wide sum of NV field elements per thread; result valid in thread 0. smem: NV * 32 F.
+template <int NV>
+VP_D void block_sum(F (&v)[NV], F* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            F x = lane < nwarp ? smem[i * 32 + lane] : f_zero();
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
+// Grid-wide: every block deposits NV partials; the last block to arrive sums them.
+// Returns true in ALL threads of the last block; the total is valid in its thread 0.
+template <int NV>
+VP_D bool grid_sum(F (&v)[NV], F* smem, F* partials, unsigned int* counter) {
+    __shared__ bool s_last;
+    block_sum<NV>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) st_f(partials + (size_t)blockIdx.x * NV + i, v[i]);
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = f_zero();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = f_add(v[i], ld_f_cg(partials + (size_t)b * NV + i));
+    }
+    block_sum<NV>(v, smem);
+    if (threadIdx.x == 0) *counter = 0;
+    return true;
+}
+
+// ------------------------------------------------------------------ K2: eq half tables
+// utils.cpp:8-27 initHalfTable. One block per half table.
+struct EqBuild {
+    uint32_t r_idx;      // index of the first challenge of this half in the challenge array
+    uint32_t nbits;      // bits of this half
+    int32_t scale_idx;   // challenge index of the `init` scalar, or -1 for F_ONE
+    uint32_t out_off;    // offset (entries) into the eq scratch buffer
+};
+
+__global__ void __launch_bounds__(1024) k_eq_build(const EqBuild* __restrict__ descs, const F* __restrict__ chal,
+                                                    F* __restrict__ eqbuf) {
+    const EqBuild d = descs[blockIdx.x];
+    F* T = eqbuf + d.out_off;
+    if (threadIdx.x == 0) T[0] = d.scale_idx >= 0 ? chal[d.scale_idx] : f_one();
+    __syncthreads();
+    for (uint32_t i = 0; i < d.nbits; ++i) {
+        const F r = chal[d.r_idx + i];
+        const uint32_t n = 1u << i;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            F t0 = T[j];
+            F tmp = f_mul(t0, r);
+            T[j | n] = tmp;
+            T[j] = f_sub(t0, tmp);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ K1: evaluate
+// prover.cpp:30-36: layer 0 = F((long long) gate.u)
+__global__ void k_load_inputs(const uint64_t* __restrict__ in, F* __restrict__ val, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_f(val + i, F{in[i], 0});
+}
+
+struct GateArrays {          // one template layer (one instance)
+    const uint8_t* ty;       // low 7 bits gate type, bit 7 = is_assert
+    const int16_t* l;
+    const uint32_t* u;
+    const uint32_t* v;
+    const F* c;              // may be null
+};
+
+// prover.cpp:38-90. Thread per gate of the replicated layer: g = k*S + g0.
+// vals[l] = device pointer of circuitValue[l]; sizes[l] = template size S_l.
+__global__ void __launch_bounds__(256) k_eval_layer(GateArrays G, uint32_t S, uint32_t K, int layer,
+                                                     F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
+                                                     F* __restrict__ out, unsigned int* __restrict__ assert_fail) {
+    const uint32_t n = S * K;
+    const uint32_t S_pre = sizes[layer - 1];
+    const F* __restrict__ pre = vals[layer - 1];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t k = g / S, g0 = g - k * S;
+        const uint32_t tyb = G.ty[g0], ty = tyb & 0x7f;
+        const int l = G.l[g0];
+        const F x = ld_f(pre + (size_t)k * S_pre + G.u[g0]);
+        F y = f_zero();
+        if (l >= 0) y = ld_f(vals[l] + (size_t)k * sizes[l] + G.v[g0]);
+        F r;
+        switch (ty) {
+            case T_ADD: r = f_add(x, y); break;
+            case T_SUB: r = f_sub(x, y); break;
+            case T_ANTISUB: r = f_sub(y, x); break;
+            case T_MUL: r = f_mul(x, y); break;
+            case T_NAAB: r = f_sub(y, f_mul(x, y)); break;
+            case T_ANTINAAB: r = f_sub(x, f_mul(x, y)); break;
+            case T_ADDC: r = f_add(x, G.c[g0]); break;
+            case T_MULC: r = f_mul(x, G.c[g0]); break;
+            case T_COPY: r = x; break;
+            case T_NOT: r = f_sub(f_one(), x); break;
+            case T_XOR: r = f_sub(f_add(x, y), f_dbl(f_mul(x, y))); break;
+            default: r = f_zero(); break;
+        }
+        st_f(out + g, r);
+        if ((tyb & TY_ASSERT_BIT) && !f_is_zero(r)) atomicExch(assert_fail, 1u + (unsigned)layer);
+    }
+}
+
+// ------------------------------------------------------------------ K3: phase-1 table init
+// prover.cpp:214-273. Owner-computes by output index u = k*S_pre + u0; the gates of layer i that
+// read u0 are a CSR row (sorted by u0 on the host), so no atomics are needed.
+struct CsrP1 {
+    const uint32_t* off;   // [S_pre + 1]
+    const uint32_t* g0;    // template gate id (for the eq lookup and the constant)
+    const uint32_t* v0;    // template v
+    const uint32_t* tyl;   // ty | assert<<7 | (l+1)<<8
+};
+
+__global__ void __launch_bounds__(256)
+k_init_phase1(CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, const F* __restrict__ assert_r,
+              F* const* __restrict__ vals, const uint32_t* __restrict__ sizes, const F* __restrict__ cst,
+              const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
+    const uint32_t n = S_pre * K;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        const uint32_t k = u / S_pre, u0 = u - k * S_pre;
+        F M = f_zero(), A = f_zero();
+        const uint32_t e0 = csr.off[u0], e1 = csr.off[u0 + 1];
+        for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e], ty = tyl & 0x7f;
+            const int l = (int)(tyl >> 8) - 1;
+            F beta = eq_at(eqg, k * S_cur + g0);
+            if (tyl & TY_ASSERT_BIT) beta = f_mul(beta, *assert_r);
+            F Vv = f_zero();
+            if (l >= 0) Vv = ld_f(vals[l] + (size_t)k * sizes[l] + csr.v0[e]);
+            switch (ty) {
+                case T_ADD:
+                    A = f_add(A, f_mul(Vv, beta));
+                    M = f_add(M, beta);
+                    break;
+                case T_SUB:
+                    A = f_sub(A, f_mul(Vv, beta));
+                    M = f_add(M, beta);
+                    break;
+                case T_ANTISUB:
+                    A = f_add(A, f_mul(Vv, beta));
+                    M = f_sub(M, beta);
+                    break;
+                case T_MUL:
+                    M = f_add(M, f_mul(Vv, beta));
+                    break;
+                case T_NAAB: {
+                    F t = f_mul(Vv, beta);
+                    A = f_add(A, t);
+                    M = f_sub(M, t);
+                    break;
+                }
+                case T_ANTINAAB:
+                    M = f_add(M, f_sub(beta, f_mul(Vv, beta)));
+                    break;
+                case T_ADDC:
+                    A = f_add(A, f_mul(cst[g0], beta));
+                    M = f_add(M, beta);
+                    break;
+                case T_MULC:
+                    M = f_add(M, f_mul(cst[g0], beta));
+                    break;
+                case T_COPY:
+                    M = f_add(M, beta);
+                    break;
+                case T_NOT:
+                    A = f_add(A, beta);
+                    M = f_sub(M, beta);
+                    break;
+                case T_XOR: {
+                    F t = f_mul(Vv, beta);
+                    A = f_add(A, t);
+                    M = f_add(M, f_sub(beta, f_dbl(t)));
+                    break;
+                }
+                default: break;
+            }
+        }
+        st_f(tV + u, ld_f(Vpre + u));
+        st_f(tM + u, M);
+        st_f(tA + u, A);
+    }
+}
+
+// ------------------------------------------------------------------ K4: phase-2 table init
+// prover.cpp:291-361. Output index = (table slot, lv); lv = (K-1-k)*D + lv0.
+// Per gate t = beta_g[g]*beta_u[u]; contributions are linear in t:  mult += cM[ty]*t, add += cA[ty]*t
+// with cM/cA built from V_u (see make_p2_coef).
+struct P2Table {
+    const uint32_t* off;     // CSR row offsets over lv0 [D + 1]
+    const uint32_t* dadId;   // [D] template v of each subset slot
+    uint32_t D;              // subset size of one instance
+    uint32_t src_S;          // template size of the source layer
+    uint32_t tab_off;        // offset of this table in the output buffers (entries)
+    uint32_t pad;
+    const F* src_val;        // circuitValue[l]
+};
+struct CsrP2 {
+    const uint32_t* g0;
+    const uint32_t* u0;
+    const uint8_t* ty;
+};
+
+VP_D void make_p2_coef(const F& Vu, F* cM, F* cA) {
+    // prover.cpp:319-357, mult / add coefficient of tmp for each binary gate type
+    const F one = f_one(), z = f_zero();
+    for (int t = 0; t < 12; ++t) { cM[t] = z; cA[t] = z; }
+    cM[T_ADD] = one;                          cA[T_ADD] = Vu;
+    cM[T_SUB] = f_neg(one);                   cA[T_SUB] = Vu;
+    cM[T_ANTISUB] = one;                      cA[T_ANTISUB] = f_neg(Vu);
+    cM[T_MUL] = Vu;
+    cM[T_NAAB] = f_sub(one, Vu);
+    cM[T_ANTINAAB] = f_neg(Vu);               cA[T_ANTINAAB] = Vu;
+    cM[T_XOR] = f_sub(one, f_dbl(Vu));        cA[T_XOR] = Vu;
+}
+
+__global__ void __launch_bounds__(256)
+k_init_phase2(const P2Table* __restrict__ tabs, int n_tabs, const uint32_t* __restrict__ work_end, CsrP2 csr,
+              uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, const F* __restrict__ assert_r,
+              const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
+    __shared__ F s_cM[12], s_cA[12];
+    __shared__ uint32_t s_wend[128];
+    if (threadIdx.x == 0) make_p2_coef(*Vu_ptr, s_cM, s_cA);
+    for (int i = threadIdx.x; i < n_tabs; i += blockDim.x) s_wend[i] = work_end[i];
+    __syncthreads();
+    const uint32_t total = s_wend[n_tabs - 1];
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        int t = 0;
+        while (w >= s_wend[t]) ++t;
+        const P2Table T = tabs[t];
+        const uint32_t idx = w - (t ? s_wend[t - 1] : 0);   // lv of the replicated subset
+        const uint32_t kk = idx / T.D, lv0 = idx - kk * T.D, k = K - 1 - kk;
+        F M = f_zero(), A = f_zero();
+        const uint32_t e0 = T.off[lv0], e1 = T.off[lv0 + 1];
+        for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t g0 = csr.g0[e], tyb = csr.ty[e], ty = tyb & 0x7f;
+            F bg = eq_at(eqg, k * S_cur + g0);
+            if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
+            const F tmp = f_mul(bg, eq_at(equ, k * S_pre + csr.u0[e]));
+            M = f_add(M, f_mul(tmp, s_cM[ty]));
+            if (ty != T_MUL && ty != T_NAAB) A = f_add(A, f_mul(tmp, s_cA[ty]));
+        }
+        const uint32_t o = T.tab_off + idx;
+        st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[lv0]));
+        st_f(tM + o, M);
+        st_f(tA + o, A);
+    }
+}
+
+// Unary gates of phase 2 (prover.cpp:342-353): all of them add into addVArray[i-1][0].
+// U = sum_g beta_g[g]*beta_u[u] * coef(ty), coef = c+Vu | c*Vu | Vu | 1-Vu. Grid reduction; the last
+// block ADDS U into *dst (entry 0 of the A table of source layer i-1).
+struct CsrUnary {
+    const uint32_t* g0;
+    const uint32_t* u0;
+    const uint8_t* ty;
+    uint32_t n;   // unary gates in one instance
+};
+__global__ void __launch_bounds__(256)
+k_phase2_unary(CsrUnary un, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ,
+               const F* __restrict__ assert_r, const F* __restrict__ Vu_ptr, const F* __restrict__ cst,
+               F* __restrict__ dst, F* partials, unsigned int* counter) {
+    __shared__ F smem[32];
+    const F Vu = *Vu_ptr;
+    const uint64_t total = (uint64_t)un.n * K;
+    F acc[1] = {f_zero()};
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(w / un.n), j = (uint32_t)(w - (uint64_t)k * un.n);
+        const uint32_t g0 = un.g0[j], tyb = un.ty[j], ty = tyb & 0x7f;
+        F bg = eq_at(eqg, k * S_cur + g0);
+        if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
+        const F tmp = f_mul(bg, eq_at(equ, k * S_pre + un.u0[j]));
+        F coef;
+        switch (ty) {
+            case T_ADDC: coef = f_add(cst[g0], Vu); break;
+            case T_MULC: coef = f_mul(cst[g0], Vu); break;
+            case T_COPY: coef = Vu; break;
+            default: coef = f_sub(f_one(), Vu); break;  // T_NOT
+        }
+        acc[0] = f_add(acc[0], f_mul(tmp, coef));
+    }
+    if (grid_sum<1>(acc, smem, partials, counter) && threadIdx.x == 0) st_f(dst, f_add(*dst, acc[0]));
+}
+
+// ------------------------------------------------------------------ K5: Liu table init
+// prover.cpp:389-414. mult[u] = s0*eq(r_u,u) + sum_{(j,slot): dadId_j[pre][slot]==u} eq_j(slot)
+// where eq_j already carries the scale s[j-i+1] in its first half table.
+struct LiuEntry {       // one (j, slot0) pair pointing at template u0
+    uint32_t eq_id;     // index into the per-init EqTab array
+    uint32_t slot0;
+    uint32_t D;         // subset size of one instance (for the reversed instance order)
+};
+__global__ void __launch_bounds__(256)
+k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
+           uint32_t S_pre, uint32_t K, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
+           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
+    const uint32_t n = S_pre * K;
+    const F s0 = *s0_ptr;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        const uint32_t k = u / S_pre, u0 = u - k * S_pre;
+        F M = f_mul(s0, eq_at(equ, u));
+        for (uint32_t e = off[u0]; e < off[u0 + 1]; ++e) {
+            const LiuEntry E = ent[e];
+            M = f_add(M, eq_at(eqs[E.eq_id], (K - 1 - k) * E.D + E.slot0));
+        }
+        st_f(tV + u, ld_f(Vpre + u));
+        st_f(tM + u, M);
+        st_f(tA + u, f_zero());
+    }
+}
+
+// ------------------------------------------------------------------ K6: fused fold + round polynomial
+// prover.cpp:436-492 (sumcheckUpdate / sumcheckUpdateEach).
+struct TabDesc {        // a table that is still >= one pair in this round
+    uint32_t in_off;    // entries into the input buffers (multiple of 4)
+    uint32_t in_live;   // live (possibly non-zero) stored entries; entries beyond are zero and never read
+    uint32_t out_off;   // entries into the output buffers (FOLD rounds)
+    uint32_t work_end;  // inclusive prefix of work items (pairs when !FOLD, quads when FOLD)
+};
+struct ColDesc {        // a table that collapses to a scalar in this round (total == 1, prover.cpp:462-467)
+    uint32_t in_off;
+    uint32_t n_vals;    // stored live values: 0, 1 or 2 (2 => fold with the previous challenge)
+    int32_t claim_slot; // where to keep V for Finalize2, or -1
+    uint32_t pad;
+};
+struct RoundArgs {
+    const F *inV, *inM, *inA;
+    F *outV, *outM, *outA;
+    const TabDesc* tabs;
+    const ColDesc* cols;
+    uint32_t n_tabs, n_cols;
+    const F* prev_r;          // previous challenge (ignored when !FOLD and no 2-value collapse)
+    F* add_term;              // device scalar (prover.h:62)
+    F* claims;                // V of collapsed tables
+    F* out_poly;              // 3 F: a, b, c
+    F* partials;
+    unsigned int* counter;
+    uint32_t first_round;     // 1: add_term is not scaled by (1 - prev) (prev == 0)
+    uint32_t reset_add_term;  // 1: start from add_term = 0
+};
+
+VP_D F ld_bound(const F* base, uint32_t idx, uint32_t live) { return idx < live ? ld_f(base + idx) : f_zero(); }
+
+struct RoundAcc {
+    Acc a, b, c;       // sum dm*dv, sum m1*v1, sum m0*v0 (lazy)
+    F sa0, sa1;        // sum add0, sum add1
+    F ra, rb, rc;      // compressed running totals
+    int pending;
+};
+VP_D void racc_init(RoundAcc& s) {
+    s.a = acc_zero(); s.b = acc_zero(); s.c = acc_zero();
+    s.sa0 = f_zero(); s.sa1 = f_zero();
+    s.ra = f_zero(); s.rb = f_zero(); s.rc = f_zero();
+    s.pending = 0;
+}
+VP_D void racc_compress(RoundAcc& s) {
+    s.ra = f_add(s.ra, acc_reduce(s.a));
+    s.rb = f_add(s.rb, acc_reduce(s.b));
+    s.rc = f_add(s.rc, acc_reduce(s.c));
+    s.a = acc_zero(); s.b = acc_zero(); s.c = acc_zero();
+    s.pending = 0;
+}
+VP_D void racc_pair(RoundAcc& s, const F& v0, const F& v1, const F& m0, const F& m1, const F& a0, const F& a1) {
+    acc_mad(s.a, f_sub(m1, m0), f_sub(v1, v0));
+    acc_mad(s.b, m1, v1);
+    acc_mad(s.c, m0, v0);
+    s.sa0 = f_add(s.sa0, a0);
+    s.sa1 = f_add(s.sa1, a1);
+    if (++s.pending == 8) racc_compress(s);
+}
+
+template <bool FOLD>
+__global__ void __launch_bounds__(256) k_round(RoundArgs p) {
+    __shared__ F smem[3 * 32];
+    __shared__ uint32_t s_wend[128];
+    for (uint32_t i = threadIdx.x; i < p.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[i].work_end;
+    __syncthreads();
+    const uint32_t total = p.n_tabs ? s_wend[p.n_tabs - 1] : 0;
+    F r = f_zero();
+    if (FOLD) r = *p.prev_r;
+    RoundAcc acc;
+    racc_init(acc);
+    int t = 0;
+    TabDesc T = p.n_tabs ? p.tabs[0] : TabDesc{0, 0, 0, 0};
+    uint32_t wbeg = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        if (w >= s_wend[t]) {
+            do { ++t; } while (w >= s_wend[t]);
+            T = p.tabs[t];
+            wbeg = s_wend[t - 1];
+        }
+        const uint32_t q = w - wbeg;
+        const F* V = p.inV + T.in_off;
+        const F* M = p.inM + T.in_off;
+        const F* A = p.inA + T.in_off;
+        if (!FOLD) {
+            const uint32_t i0 = 2 * q;
+            F v0 = ld_bound(V, i0, T.in_live), v1 = ld_bound(V, i0 + 1, T.in_live);
+            F m0 = ld_bound(M, i0, T.in_live), m1 = ld_bound(M, i0 + 1, T.in_live);
+            F a0 = ld_bound(A, i0, T.in_live), a1 = ld_bound(A, i0 + 1, T.in_live);
+            racc_pair(acc, v0, v1, m0, m1, a0, a1);
+        } else {
+            const uint32_t i0 = 4 * q;
+            F xv[4], xm[4], xa[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                xv[j] = ld_bound(V, i0 + j, T.in_live);
+                xm[j] = ld_bound(M, i0 + j, T.in_live);
+                xa[j] = ld_bound(A, i0 + j, T.in_live);
+            }
+            const F v0 = f_fold(xv[0], xv[1], r), v1 = f_fold(xv[2], xv[3], r);
+            const F m0 = f_fold(xm[0], xm[1], r), m1 = f_fold(xm[2], xm[3], r);
+            const F a0 = f_fold(xa[0], xa[1], r), a1 = f_fold(xa[2], xa[3], r);
+            const uint32_t o = T.out_off + 2 * q;
+            st_f(p.outV + o, v0); st_f(p.outM + o, m0); st_f(p.outA + o, a0);
+            if (i0 + 2 < T.in_live) {
+                st_f(p.outV + o + 1, v1); st_f(p.outM + o + 1, m1); st_f(p.outA + o + 1, a1);
+            }
+            racc_pair(acc, v0, v1, m0, m1, a0, a1);
+        }
+    }
+    racc_compress(acc);
+    // a = sum dm*dv ; c = sum m0*v0 + sum a0 ; b = sum m1*v1 - sum m0*v0 - sum dm*dv + sum a1 - sum a0
+    F v[3];
+    v[0] = acc.ra;
+    v[1] = f_add(f_sub(f_sub(acc.rb, acc.rc), acc.ra), f_sub(acc.sa1, acc.sa0));
+    v[2] = f_add(acc.rc, acc.sa0);
+    if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
+    if (threadIdx.x != 0) return;
+    // ---- epilogue (one thread): add_term bookkeeping, prover.cpp:445-448,462-467
+    F at = p.reset_add_term ? f_zero() : *p.add_term;
+    if (!p.first_round) at = f_mul(at, f_sub(f_one(), *p.prev_r));
+    for (uint32_t i = 0; i < p.n_cols; ++i) {
+        const ColDesc c = p.cols[i];
+        F cv = f_zero(), cm = f_zero(), ca = f_zero();
+        if (c.n_vals >= 1) {
+            cv = ld_f_cg(p.inV + c.in_off); cm = ld_f_cg(p.inM + c.in_off); ca = ld_f_cg(p.inA + c.in_off);
+            if (!p.first_round) {
+                F v1 = f_zero(), m1 = f_zero(), a1 = f_zero();
+                if (c.n_vals >= 2) {
+                    v1 = ld_f_cg(p.inV + c.in_off + 1); m1 = ld_f_cg(p.inM + c.in_off + 1); a1 = ld_f_cg(p.inA + c.in_off + 1);
+                }
+                const F rr = *p.prev_r;
+                cv = f_fold(cv, v1, rr); cm = f_fold(cm, m1, rr); ca = f_fold(ca, a1, rr);
+            }
+        }
+        at = f_add(at, f_add(f_mul(cv, cm), ca));
+        if (c.claim_slot >= 0) st_f(p.claims + c.claim_slot, cv);
+    }
+    st_f(p.add_term, at);
+    st_f(p.out_poly + 0, v[0]);
+    st_f(p.out_poly + 1, f_sub(v[1], at));
+    st_f(p.out_poly + 2, f_add(v[2], at));
+}
+
+// ------------------------------------------------------------------ K7: finalize
+// prover.cpp:494-521: claim = Vmult[.][0].eval(last challenge) for tables still alive, the kept
+// collapse value otherwise.
+struct FinDesc {
+    uint32_t in_off;
+    uint32_t n_vals;     // 0,1,2 stored live values of V; 2 => fold with last challenge
+    int32_t from_claim;  // >= 0: table collapsed earlier, value is claims[from_claim]
+    uint32_t out_idx;    // transcript index
+};
+__global__ void k_finalize(const FinDesc* __restrict__ d, int n, const F* __restrict__ V, const F* __restrict__ last_r,
+                           int have_r, const F* __restrict__ claims, F* __restrict__ transcript, F* __restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FinDesc f = d[i];
+    F c;
+    if (f.from_claim >= 0) c = claims[f.from_claim];
+    else {
+        F v0 = f.n_vals >= 1 ? V[f.in_off] : f_zero();
+        if (have_r) {
+            F v1 = f.n_vals >= 2 ? V[f.in_off + 1] : f_zero();
+            c = f_fold(v0, v1, *last_r);
+        } else c = v0;
+    }
+    st_f(transcript + f.out_idx, c);
+    if (keep && i == 0) st_f(keep, c);   // V_u for phase 2 (prover.cpp:497)
+}
+
+// ------------------------------------------------------------------ K8 / K9: MLE evaluation = dot with eq
+// prover.cpp:99-129 (Vres) and :532-540 (inner_prod against eq(r_liu,.), verifier.cpp:368-369).
+__global__ void __launch_bounds__(256)
+k_dot_eq(const F* __restrict__ X, uint32_t n, EqTab eq, F* __restrict__ out, F* partials, unsigned int* counter) {
+    __shared__ F smem[32];
+    Acc acc = acc_zero();
+    F run = f_zero();
+    int pending = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        acc_mad(acc, ld_f(X + i), eq_at(eq, i));
+        if (++pending == 8) { run = f_add(run, acc_reduce(acc)); acc = acc_zero(); pending = 0; }
+    }
+    F v[1] = {f_add(run, acc_reduce(acc))};
+    if (grid_sum<1>(v, smem, partials, counter) && threadIdx.x == 0) st_f(out, v[0]);
+}
+__global__ void __launch_bounds__(256)
+k_dot(const F* __restrict__ X, const F* __restrict__ Y, uint32_t n, F* __restrict__ out, F* partials,
+      unsigned int* counter) {
+    __shared__ F smem[32];
+    Acc acc = acc_zero();
+    F run = f_zero();
+    int pending = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        acc_mad(acc, ld_f(X + i), ld_f(Y + i));
+        if (++pending == 8) { run = f_add(run, acc_reduce(acc)); acc = acc_zero(); pending = 0; }
+    }
+    F v[1] = {f_add(run, acc_reduce(acc))};
+    if (grid_sum<1>(v, smem, partials, counter) && threadIdx.x == 0) st_f(out, v[0]);
+}
+
+// ------------------------------------------------------------------ misc
+// SplitMix64-filled random table entries (limbs uniform in [0,p) by rejection), config C2.
+__global__ void k_fill_random(F* __restrict__ T, uint32_t n, uint64_t seed) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = seed + 0x9E3779B97F4A7C15ULL * (2ULL * i + 1);
+    uint64_t out[2];
+    for (int k = 0; k < 2; ++k) {
+        uint64_t z;
+        do {
+            s += 0x9E3779B97F4A7C15ULL;
+            z = s;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+            z = (z ^ (z >> 31)) >> 3;
+        } while (z >= P);
+        out[k] = z;
+    }
+    st_f(T + i, F{out[0], out[1]});
+}
+
+}  // namespace vp

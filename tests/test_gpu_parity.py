@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA prover (through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_fe(B, rng, n):
+    a = np.zeros(n, B.F_DTYPE)
+    a["re"] = rng.integers(0, B.P, n, dtype=np.uint64)
+    a["im"] = rng.integers(0, B.P, n, dtype=np.uint64)
+    return a
+
+
+def _assert_same(got, want, what):
+    bad = np.nonzero((got["re"] != want["re"]) | (got["im"] != want["im"]))[0]
+    assert len(bad) == 0, f"{what}: {len(bad)} of {len(want)} field elements differ, first at {bad[:5]}: " \
+                          f"got {got[bad[:3]]} want {want[bad[:3]]}"
+
+
+# ------------------------------------------------------------------ stand-alone sumcheck (config C2 shape)
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 11, 14])
+def test_sumcheck_tables_vs_oracle(B, O, log_n):
+    rng = np.random.default_rng(100 + log_n)
+    n = 1 << log_n
+    V, A, M = (_rand_fe(B, rng, n) for _ in range(3))
+    r = _rand_fe(B, rng, log_n)
+    s = B.Sumcheck(log_n)
+    s.load(V, A, M)
+    got, _ = s.run(r)
+    want = O.sumcheck_tables(V, A, M, r)
+    _assert_same(got, want, f"sumcheck 2^{log_n}")
+    got2, _ = s.run(r)  # tables are restored between runs
+    _assert_same(got2, want, "second run")
+    s.close()
+
+
+def test_sumcheck_edge_values(B, O):
+    """all-zero, all p-1, and base-field tables"""
+    log_n = 6
+    n = 1 << log_n
+    rng = np.random.default_rng(5)
+    r = _rand_fe(B, rng, log_n)
+    r[0] = (0, 0)
+    r[1] = (B.P - 1, B.P - 1)
+    for fill in [(0, 0), (B.P - 1, B.P - 1), (B.P - 1, 0), (1, 0)]:
+        T = np.zeros(n, B.F_DTYPE)
+        T["re"], T["im"] = fill
+        s = B.Sumcheck(log_n)
+        s.load(T, T, T)
+        got, _ = s.run(r)
+        _assert_same(got, O.sumcheck_tables(T, T, T, r), f"fill {fill}")
+        s.close()
+
+
+def test_sumcheck_device_random_fill(B, O):
+    log_n = 10
+    s = B.Sumcheck(log_n)
+    s.fill_random(1)
+    V, A, M = s.export()
+    assert (V["re"] < B.P).all() and (M["im"] < B.P).all()
+    r = O.draw_challenges(log_n)
+    got, _ = s.run(r)
+    _assert_same(got, O.sumcheck_tables(V, A, M, r), "device-filled tables")
+    s.close()
+
+
+# ------------------------------------------------------------------ full GKR proofs
+def _prove_both_ways(B, O, circ, flat_circ=None):
+    """batched + interactive GPU transcripts must equal the oracle's, and the oracle verifier accepts."""
+    oc = O.OracleCircuit((flat_circ or circ).flat())
+    want, ch_o, _ = oc.prove()
+    ch = circ.draw_challenges()
+    _assert_same(ch, ch_o, "challenge stream")
+    p = B.Prover(circ)
+    got = p.prove(inputs=circ.inputs(), challenges=ch)
+    _assert_same(got, want, "batched transcript")
+    ok, code, layer = oc.verify(got)
+    assert ok, f"oracle verifier rejected the GPU transcript (code {code}, layer {layer})"
+    p.close()
+    p = B.Prover(circ)
+    got_i = B.prove_interactive(p, circ)
+    _assert_same(got_i, want, "interactive transcript")
+    p.close()
+    return want
+
+
+@pytest.mark.parametrize("n_layers,log_size,seed", [(2, 0, 1), (2, 1, 2), (3, 2, 3), (4, 3, 4), (5, 5, 5), (9, 7, 6), (3, 10, 7)])
+def test_random_circuits(B, O, n_layers, log_size, seed):
+    circ = B.Circuit.random(n_layers, log_size, seed)
+    _prove_both_ways(B, O, circ)
+
+
+def test_evaluate_matches_oracle(B, O, sha_circuit):
+    p = B.Prover(sha_circuit)
+    p.evaluate()
+    want = O.OracleCircuit(sha_circuit.flat()).evaluate()
+    off = 0
+    for i in range(sha_circuit.n_layers):
+        n = sha_circuit.layer_size(i)
+        _assert_same(p.values(i), want[off:off + n], f"layer {i} values")
+        off += n
+    p.close()
+
+
+def test_sha256_64_transcript(B, O, sha_circuit):
+    tr = _prove_both_ways(B, O, sha_circuit)
+    # known-answer values recorded from the unmodified reference
+    assert (int(tr[0]["re"]), int(tr[0]["im"])) == (724662900143931110, 476060367020167324)
+    assert (int(tr[1]["re"]), int(tr[1]["im"])) == (2211877472072237705, 669034324121346583)
+    assert (int(tr[-2]["re"]), int(tr[-2]["im"])) == (2060928321185694165, 125737238808708621)
+
+
+@pytest.mark.parametrize("K", [2, 3, 5])
+def test_sha256_replicated_matches_expanded(B, O, sha_circuit, K):
+    """K data-parallel instances through the template path == the oracle on the materialised circuit."""
+    rep = sha_circuit.replicate(K)
+    flat = rep.expand()
+    assert flat.instances == 1 and flat.total_gates == rep.total_gates
+    _prove_both_ways(B, O, rep, flat_circ=flat)
+
+
+def test_replicated_random_circuit(B, O):
+    circ = B.Circuit.random(4, 3, 11).replicate(7)
+    _prove_both_ways(B, O, circ, flat_circ=circ.expand())
+
+
+def test_negative_tampered_table_rejected(B, O, sha_circuit):
+    """flip one input after the proof: the transcript no longer verifies against the circuit"""
+    p = B.Prover(sha_circuit)
+    ch = sha_circuit.draw_challenges()
+    inp = sha_circuit.inputs()
+    tr = p.prove(inputs=inp, challenges=ch)
+    oc = O.OracleCircuit(sha_circuit.flat())
+    assert oc.verify(tr)[0]
+    bad = tr.copy()
+    bad[7]["re"] = (int(bad[7]["re"]) + 1) % B.P
+    assert not oc.verify(bad)[0]
+    inp2 = inp.copy()
+    inp2[0] ^= 1
+    tr2 = p.prove(inputs=inp2, challenges=ch)
+    assert not oc.verify(tr2)[0]  # oracle circuit still holds the original inputs
+    p.close()
+
+
+def test_inner_prod_and_proof_size(B, O, sha_circuit):
+    p = B.Prover(sha_circuit)
+    tr = B.prove_interactive(p, sha_circuit)
+    assert abs(p.proofSize() - 22.4375) < 1e-9  # `proof size = 22.437500 kb` of the reference run
+    n0 = sha_circuit.layer_size(0)
+    rng = np.random.default_rng(3)
+    pub = _rand_fe(B, rng, n0)
+    got = p.inner_prod(pub)
+    vals = p.values(0)
+    acc = (0, 0)
+    for i in range(n0):
+        acc = O.f_add(acc, O.f_mul(vals[i], pub[i]))
+    assert (int(got["re"]), int(got["im"])) == acc
+    p.close()

@@ -23,7 +23,7 @@ public:
     void evaluate() { ref.evaluate(); }
     void init() { ref.init(); }
     void sumcheckInitAll(const vector<F>::const_iterator &r_last) { ref.sumcheckInitAll(r_last); }
-    void sumcheckInit() { ref.sumcheckInit(); }
+    void sumcheckInit() { ref.sumcheckInit(); --cur_layer; }
     void sumcheckInitPhase1(const F &assert_random) { ref.sumcheckInitPhase1(assert_random); }
     void sumcheckInitPhase2() { ref.sumcheckInitPhase2(); }
     void sumcheckInitLiu(vector<F>::const_iterator s) { ref.sumcheckInitLiu(s); }
@@ -74,6 +74,6 @@ public:
 
     ref_prover ref;
     virgo::poly_commit::poly_commit_prover &poly_prover;
-    int cur_layer = 0;  // set by the harness hooks below
+    int cur_layer = 0;  // harness sets it to C.size; sumcheckInit counts it down like sumcheckLayerId
     int n_fin2 = 0;
 };

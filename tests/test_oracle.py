@@ -1,0 +1,199 @@
+"""CPU tests (no GPU): the oracle and the host loader against golden fixtures recorded from the
+UNMODIFIED reference (tests/golden/make_golden.py), plus the C-ABI surface of the product library."""
+import hashlib
+import importlib.util
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = ["small_allops", "small_chain", "small_notquirk", "small_random_a", "small_random_b", "small_random_c"]
+
+
+def _make_golden():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(H.GOLDEN, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _case_circuit(B, name, sha_pws_text):
+    if name == "sha256_64":
+        return B.Circuit.from_pws_text(sha_pws_text)
+    if name.startswith("sha256_64_x"):
+        return B.Circuit.from_pws_text(_make_golden().replicate_pws(sha_pws_text, int(name[-1])))
+    return B.Circuit.from_pws_text(H.golden_bytes(name + ".pws.xz"))
+
+
+# ------------------------------------------------------------------ loader == reference loader
+@pytest.mark.parametrize("name", ["sha256_64", "sha256_64_x2", "sha256_64_x3"] + SMALL)
+def test_loader_matches_reference_circuit(B, sha_pws_text, name):
+    circ = _case_circuit(B, name, sha_pws_text)
+    assert H.circuit_digest(circ) == H.golden_text(name + ".circuit.sha256").strip()
+    if name in SMALL:
+        assert H.circuit_dump(circ) == H.golden_bytes(name + ".circuit.bin.xz")
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_template_replication_equals_reference_layering(B, sha_circuit, K):
+    """template x K, materialised by the index rules, == the reference's layering of the K-fold .pws"""
+    ex = sha_circuit.replicate(K).expand()
+    assert H.circuit_digest(ex) == H.golden_text(f"sha256_64_x{K}.circuit.sha256").strip()
+
+
+# ------------------------------------------------------------------ oracle == reference prover
+@pytest.mark.parametrize("name", ["sha256_64", "sha256_64_x2", "sha256_64_x3"] + SMALL)
+def test_oracle_transcript_matches_reference(B, O, sha_pws_text, name):
+    circ = _case_circuit(B, name, sha_pws_text)
+    oc = O.OracleCircuit(circ.flat())
+    tr, ch, _ = oc.prove()
+    want = H.golden_bytes(name + ".transcript.txt.xz").decode()
+    got = H.transcript_text(circ, tr, ch)
+    assert got == want
+    ok, code, layer = oc.verify(tr)
+    assert ok, (code, layer)
+    # the host challenge stream (private random_r state) equals the oracle's (global srandom state)
+    ch2 = circ.draw_challenges()
+    assert (ch2["re"] == ch["re"]).all() and (ch2["im"] == ch["im"]).all()
+
+
+def test_sha256_64_known_answers(B, O, sha_circuit):
+    """values recorded independently by the surveyor from the unmodified reference."""
+    want = H.golden_bytes("sha256_64.transcript.txt.xz").decode()
+    first_1918 = "".join(l + "\n" for l in want.split("\n")[:1918])
+    assert hashlib.sha256(first_1918.encode()).hexdigest() == \
+        "6754c5ba1182b4f9914e2ea79ae7367c164e1d3fcc3db0b5d227bb5acaa2d622"
+    ch = sha_circuit.draw_challenges()
+    assert len(ch) == 813
+    assert (int(ch[0]["re"]), int(ch[0]["im"])) == (69318801402563806, 1662776802730791352)
+    assert (int(ch[1]["re"]), int(ch[1]["im"])) == (1980605035210677997, 152700460719136691)
+    assert sha_circuit.inputs()[:3].tolist() == [1804289383, 846930886, 1681692777]
+    assert [sha_circuit.layer_size(i) for i in range(15)] == \
+        [7226, 37116, 24713, 14216, 8148, 4106, 2053, 1164, 487, 176, 176, 176, 64, 64, 64]
+    assert [sha_circuit.max_dad_bit_length(i) for i in range(1, 15)] == [13, 14, 12, 13, 12, 12, 10, 9, 8, 7, 7, 6, 6, 6]
+    assert sha_circuit.total_gates == 92723
+
+
+def test_oracle_rejects_tampering(B, O):
+    circ = B.Circuit.from_pws_text(H.golden_bytes("small_allops.pws.xz"))
+    oc = O.OracleCircuit(circ.flat())
+    tr, _, _ = oc.prove()
+    for idx in [0, 1, 5, len(tr) // 2, len(tr) - 2, len(tr) - 1]:
+        bad = tr.copy()
+        bad[idx]["im"] = (int(bad[idx]["im"]) + 1) % B.P
+        assert not oc.verify(bad)[0], idx
+
+
+# ------------------------------------------------------------------ field
+def test_field_against_python_ints(B, O):
+    P = B.P
+    rng = np.random.default_rng(1)
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 60), (1 << 60) + 1, (1 << 32) - 1, 1 << 32]
+    vals = [(a, b) for a in edge for b in edge[:4]] + \
+        [tuple(int(x) for x in rng.integers(0, P, 2, dtype=np.uint64)) for _ in range(300)]
+    for x in vals[:60]:
+        for y in vals[::7]:
+            assert O.f_add(x, y) == ((x[0] + y[0]) % P, (x[1] + y[1]) % P)
+            assert O.f_sub(x, y) == ((x[0] - y[0]) % P, (x[1] - y[1]) % P)
+            assert O.f_mul(x, y) == ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+
+def test_beta_table_is_eq(B, O):
+    P = B.P
+    rng = np.random.default_rng(2)
+    for nb in [0, 1, 2, 5]:
+        r = np.zeros(nb, B.F_DTYPE)
+        r["re"] = rng.integers(0, P, nb, dtype=np.uint64)
+        r["im"] = rng.integers(0, P, nb, dtype=np.uint64)
+        init = (int(rng.integers(0, P)), int(rng.integers(0, P)))
+        tab = O.beta_table(r, init)
+        for i in range(1 << nb):
+            acc = init
+            for k in range(nb):
+                rk = (int(r[k]["re"]), int(r[k]["im"]))
+                acc = O.f_mul(acc, rk if (i >> k) & 1 else O.f_sub((1, 0), rk))
+            assert (int(tab[i]["re"]), int(tab[i]["im"])) == acc
+
+
+# ------------------------------------------------------------------ loader edge cases
+def test_loader_rejects_bad_input(B):
+    with pytest.raises(B.VpError):
+        B.Circuit.from_pws_text(b"")                                  # nothing parsed
+    with pytest.raises(B.VpError):
+        B.Circuit.from_pws_text(b"P V0 = I0 E\nP V2 = V0 + V0 E\n")   # hole: V1 never defined
+    with pytest.raises(B.VpError):
+        B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = V0 + V5 E\n")   # undefined operand
+    with pytest.raises(B.VpError):
+        # NOT of a non-input whose raw id is out of range of the previous layer (reference: OOB read)
+        B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 + V1 E\nP V3 = V2 NOT V2 E\n")
+    with pytest.raises(B.VpError):
+        B.Circuit.load_pws("/nonexistent/file.pws")
+
+
+def test_loader_ignores_unknown_lines(B):
+    """Release build of the reference skips lines no regex matches (assert(false) compiled out)."""
+    a = B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 * V1 E\nP V3 = V2 + V0 E\nP O4 = V3 E\n")
+    b = B.Circuit.from_pws_text(b"# comment\nP V0 = I0 E\nP V1 = I1 E\n\nP V2 = V0 * V1 E\r\nP V2 = V0 * V1 E\n"
+                                b"P V3 = V2 + V0 E\nP V9 = V2 / V0 E\nP O4 = V3 E\n")
+    assert H.circuit_dump(a) == H.circuit_dump(b)
+
+
+def test_random_circuit_is_valid_and_deterministic(B, O):
+    a, b = B.Circuit.random(5, 4, 9), B.Circuit.random(5, 4, 9)
+    assert H.circuit_dump(a) == H.circuit_dump(b)
+    assert H.circuit_dump(a) != H.circuit_dump(B.Circuit.random(5, 4, 10))
+    oc = O.OracleCircuit(a.flat())
+    tr, _, _ = oc.prove()
+    assert oc.verify(tr)[0]
+
+
+def test_oracle_handles_one_gate_layers(B, O):
+    """bitLength-0 layers: the reference corrupts its heap here (r_u[-1], prover.cpp:496); the oracle
+    and the product define the natural behaviour (zero rounds, claim = the single value)."""
+    circ = B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 * V1 E\nP V3 = V2 + V2 E\nP V4 = V3 * V2 E\n")
+    oc = O.OracleCircuit(circ.flat())
+    tr, _, _ = oc.prove()
+    assert oc.verify(tr)[0]
+
+
+# ------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol(B):
+    hdr = open(os.path.join(ROOT, "include", "virgo_b200.h")).read()
+    declared = set(re.findall(r"\b(vp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 50
+    out = subprocess.check_output(["nm", "-D", "--defined-only", B.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = sorted(declared - exported)
+    assert not missing, f"declared in include/virgo_b200.h but not exported: {missing}"
+    lib = B.lib()
+    for name in declared:
+        getattr(lib, name)
+    assert b"sm_100a" in lib.vp_version()
+
+
+def test_no_cpu_fallback(B, sha_circuit):
+    """Without a GPU every prover entry point must fail loudly (never compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(B.VpError) as e:
+        B.Prover(sha_circuit)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(B.VpError):
+        B.Sumcheck(4)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "virgo-plus_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "gkr_oracle" not in txt and "oracle/" not in txt, fn

@@ -263,7 +263,7 @@ class Circuit:
         return out
 
     def flat(self):
-        """Flat arrays of this circuit (instances must be 1): the layout oracle/gkr_oracle.h takes."""
+        """Flat arrays of this circuit (instances must be 1), concatenated over layers (used by tests)."""
         assert self.instances == 1
         n = self.n_layers
         layers = [self.export_layer(i) for i in range(n)]

@@ -122,6 +122,8 @@ int vp_finalize2(vp_ctx* ctx, const vp_F* previous_random, vp_F* claims, int n);
 int vp_finalize_liu(vp_ctx* ctx, const vp_F* previous_random, vp_F* claim);
 /* prover::inner_prod(circuitValue[0], pub, n) as used by commit_public (:532-546). */
 int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out);
+/* prover::inner_prod(a, b, n) for two HOST vectors (the public method, prover.h:40). */
+int vp_dot_host(vp_ctx* ctx, const vp_F* a, const vp_F* b, size_t n, vp_F* out);
 /* Input-layer MLE at r[0..n): <circuitValue[0], eq(r,.)> without materialising eq on the host. */
 int vp_input_mle(vp_ctx* ctx, const vp_F* r, int n, vp_F* out);
 /* prover::proofSize() in bytes (:451,:500,:512) and the accumulated device time inside prover
@@ -144,6 +146,13 @@ int vp_get_transcript(vp_ctx* ctx, vp_F* transcript, size_t cap);
 float vp_last_prove_ms(const vp_ctx* ctx);
 /* Number of kernel launches issued by the last vp_prove. */
 uint64_t vp_last_prove_launches(const vp_ctx* ctx);
+/* Run every kernel of the context on the caller's stream (cudaStream_t; NULL: back to an own stream). */
+int vp_set_stream(vp_ctx* ctx, void* cuda_stream);
+/* Per-kernel-class device timing (CUDA events around every launch while on). Classes, in order:
+ * 0 round(fold) [K6], 1 round(first), 2 phase-1 init [K3], 3 phase-2 init [K4], 4 Liu init [K5],
+ * 5 evaluate [K1], 6 other. bytes = algorithmic bytes of the launches. */
+int vp_set_profiling(vp_ctx* ctx, int on);
+int vp_get_profile(vp_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int n_classes);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket it with their own events. */
 void* vp_stream(vp_ctx* ctx);
 

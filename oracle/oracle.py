@@ -157,3 +157,30 @@ def draw_challenges(n, seed=3396):
         r = L.ogkr_random_field()
         out[i] = (r.re, r.im)
     return out
+
+
+# ---------------------------------------------------------------- the compiled reference (oracle/_ref)
+REF_DIR = os.path.join(HERE, "_ref")
+REF_LIB = os.path.join(REF_DIR, "libref_gkr.so")
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_LIB)
+
+
+def ref_prove(flat):
+    """Run the UNMODIFIED reference prover (libref_gkr.so) on a flat circuit dict.
+    -> (transcript, prove_seconds (the reference's `Prove Time`), evaluate_seconds)"""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(REF_LIB)
+        _ref.ref_gkr_prove.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_uint, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in flat.items()}
+    oc = OracleCircuit(flat)
+    tr = np.zeros(oc.transcript_len, F_DTYPE)
+    ps, es = C.c_double(), C.c_double()
+    n = _ref.ref_gkr_prove(f["n_layers"], _p(f["layer_size"]), _p(f["ty"]), _p(f["l"]), _p(f["u"]), _p(f["v"]),
+                           _p(f["inputs"]), 3396, _p(tr), C.byref(ps), C.byref(es))
+    assert n == len(tr), (n, len(tr))
+    return tr, ps.value, es.value

@@ -157,3 +157,20 @@ def test_inner_prod_and_proof_size(B, O, sha_circuit):
         acc = O.f_add(acc, O.f_mul(vals[i], pub[i]))
     assert (int(got["re"]), int(got["im"])) == acc
     p.close()
+
+
+def test_dropin_reference_verifier_accepts(tmp_path, sha_pws_text):
+    """The UNMODIFIED reference main.cpp + verifier.cpp (+ its polynomial commitment), compiled against
+    virgo-plus_b200/host/prover.h and linked with the B200 prover (oracle/_ref/virgo_plus_run_b200,
+    built by `make -C oracle ref`), must print `Verification pass` and the reference's proof size."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "virgo_plus_run_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/virgo_plus_run_b200 not built (needs /root/reference at build time)")
+    pws = tmp_path / "SHA256_64.pws"
+    pws.write_bytes(sha_pws_text)
+    r = subprocess.run([exe, str(pws)], capture_output=True, text=True, timeout=300)
+    assert "Verification pass" in r.stderr, r.stderr[-2000:]
+    assert "proof size = 22.437500 kb" in r.stdout, r.stdout
+    assert "Input size 7226" in r.stdout

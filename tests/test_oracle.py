@@ -197,3 +197,17 @@ def test_product_does_not_reference_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "gkr_oracle" not in txt and "oracle/" not in txt, fn
+
+
+# ------------------------------------------------------------------ oracle == compiled reference (in-memory circuits)
+@pytest.mark.parametrize("n_layers,log_size,seed", [(3, 3, 1), (6, 6, 2), (4, 9, 3)])
+def test_oracle_matches_compiled_reference_on_random_circuits(B, O, n_layers, log_size, seed):
+    """Random add/mul circuits have no .pws form; compare against libref_gkr.so (the unmodified
+    reference prover driven in verifier order). Runs wherever oracle/_ref was built."""
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libref_gkr.so not built (needs /root/reference)")
+    circ = B.Circuit.random(n_layers, log_size, seed)
+    flat = circ.flat()
+    want, _, _ = O.ref_prove(flat)
+    got, _, _ = O.OracleCircuit(flat).prove()
+    assert (got["re"] == want["re"]).all() and (got["im"] == want["im"]).all()

@@ -90,6 +90,7 @@ def _declare(L):
     L.vp_finalize_liu.argtypes = [vp, vp, vp]
     L.vp_inner_prod.argtypes = [vp, vp, C.c_size_t, vp]
     L.vp_input_mle.argtypes = [vp, vp, C.c_int, vp]
+    L.vp_dot_host.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.vp_proof_size_bytes.argtypes = [vp]
     L.vp_proof_size_bytes.restype = C.c_uint64
     L.vp_prove_seconds.argtypes = [vp]
@@ -102,6 +103,9 @@ def _declare(L):
     L.vp_last_prove_launches.argtypes = [vp]
     L.vp_last_prove_launches.restype = C.c_uint64
     L.vp_stream.argtypes = [vp]
+    L.vp_set_stream.argtypes = [vp, vp]
+    L.vp_set_profiling.argtypes = [vp, C.c_int]
+    L.vp_get_profile.argtypes = [vp, vp, vp, vp, C.c_int]
     L.vp_stream.restype = C.c_void_p
     L.vp_sumcheck_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.vp_sumcheck_load.argtypes = [vp, vp, vp, vp]
@@ -434,6 +438,20 @@ class Prover:
     @property
     def stream(self):
         return lib().vp_stream(self.h)
+
+    def set_stream(self, cuda_stream):
+        _ck(lib().vp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    KERNEL_CLASSES = ("round_fold", "round_first", "init_phase1", "init_phase2", "init_liu", "evaluate", "other")
+
+    def set_profiling(self, on):
+        _ck(lib().vp_set_profiling(self.h, 1 if on else 0))
+
+    def profile(self):
+        n = len(self.KERNEL_CLASSES)
+        ms, by, la = np.zeros(n), np.zeros(n), np.zeros(n, np.uint64)
+        _ck(lib().vp_get_profile(self.h, _ptr(ms), _ptr(by), _ptr(la), n))
+        return {k: dict(ms=float(ms[i]), bytes=float(by[i]), launches=int(la[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
 
 def prove_interactive(prover, circuit, seed=3396):

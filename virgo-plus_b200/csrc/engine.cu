@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "../../include/virgo_b200.h"
-#include "../host/circuit.h"
+#include "../host/circuit_model.h"
 #include "kernels.cuh"
 
 using namespace vp;
@@ -95,6 +95,7 @@ struct RoundPlan {
     uint32_t work;     // total work items
     int in_buf;        // 0 / 1
     bool fold;
+    double bytes;      // algorithmic bytes of this round: 48 B read per live entry (+ 48 B written per live output entry)
 };
 struct SumcheckPlan {
     int rounds = 0;
@@ -135,12 +136,14 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
         R.tab_begin = (uint32_t)A.tabs.size();
         R.col_begin = (uint32_t)A.cols.size();
         uint32_t work = 0, oo = 0;
+        R.bytes = 0;
         for (size_t t = 0; t < nt; ++t) {
             const int b = tabs[t].bits;
             if (b >= j) {
                 TabDesc d;
                 d.in_off = off[t];
                 d.in_live = live[t];
+                R.bytes += 48.0 * live[t] + (R.fold ? 48.0 * cdiv(live[t], 2) : 0.0);
                 d.out_off = oo;
                 work += R.fold ? cdiv(live[t], 4) : cdiv(live[t], 2);
                 d.work_end = work;
@@ -271,11 +274,52 @@ struct Engine {
     float last_ms = 0;
     uint64_t launches = 0, last_launches = 0;
     bool evaluated = false, inputs_loaded = false;
+    bool own_stream = true;
+
+    // optional per-kernel-class profiling (CUDA events around every launch of a class)
+    enum { KC_ROUND_FOLD = 0, KC_ROUND_FIRST, KC_INIT1, KC_INIT2, KC_INIT_LIU, KC_EVAL, KC_OTHER, KC_N };
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct ProfRec { int kc; size_t e0, e1; double bytes; };
+    std::vector<ProfRec> prof;
+    size_t ev_used = 0;
+    double prof_ms[KC_N] = {0}, prof_bytes[KC_N] = {0};
+    uint64_t prof_launches[KC_N] = {0};
+
+    size_t prof_begin(int kc) {
+        if (!profiling) return (size_t)-1;
+        while (ev_pool.size() < ev_used + 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        CK(cudaEventRecord(ev_pool[ev_used], stream));
+        prof.push_back(ProfRec{kc, ev_used, ev_used + 1, 0.0});
+        ev_used += 2;
+        return prof.size() - 1;
+    }
+    void prof_end(size_t h, double bytes) {
+        if (h == (size_t)-1) return;
+        CK(cudaEventRecord(ev_pool[prof[h].e1], stream));
+        prof[h].bytes = bytes;
+    }
+    void prof_collect() {  // stream must be idle
+        for (const ProfRec& r : prof) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ev_pool[r.e0], ev_pool[r.e1]));
+            prof_ms[r.kc] += ms;
+            prof_bytes[r.kc] += r.bytes;
+            ++prof_launches[r.kc];
+        }
+        prof.clear();
+        ev_used = 0;
+    }
 
     ~Engine() {
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        if (stream && own_stream) cudaStreamDestroy(stream);
     }
 
     // ---------------------------------------------------------------- helpers
@@ -634,8 +678,10 @@ void Engine::evaluate() {
     ++launches;
     for (int i = 1; i < n; ++i) {
         const uint32_t tot = L[i].S * K;
+        size_t h = prof_begin(KC_EVAL);
         k_eval_layer<<<grid_for(tot), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p, val[i].p,
                                                          d_counter.p + 1);
+        prof_end(h, (double)tot * (16.0 + 32.0 + 11.0 / K));  // out + two operand gathers (+ amortised wiring)
         ++launches;
     }
     CK(cudaGetLastError());
@@ -669,9 +715,12 @@ void Engine::do_init_phase1(int i) {
     const uint32_t S_pre = L[i - 1].S ? L[i - 1].S : (uint32_t)C.layers[i - 1].size;
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     CsrP1 csr{D.p1_off.p, D.p1_g0.p, D.p1_v0.p, D.p1_tyl.p};
+    size_t h = prof_begin(KC_INIT1);
     k_init_phase1<<<grid_for(tot), 256, 0, stream>>>(csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)),
                                                       d_chal.p + D.ci_assert, d_valptr.p, d_sizes.p, D.c.p,
                                                       val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p);
+    // per output: V read + 3 table writes; per gate: one gathered operand
+    prof_end(h, (double)tot * 64.0 + (double)D.S * K * 16.0);
     ++launches;
     have_equ = false;
 }
@@ -689,9 +738,11 @@ void Engine::do_init_phase2(int i) {
     }
     if (D.p2_ntabs > 0) {
         CsrP2 csr{D.p2_g0.p, D.p2_u0.p, D.p2_ty.p};
+        size_t h = prof_begin(KC_INIT2);
         k_init_phase2<<<grid_for(D.p2_work), 256, 0, stream>>>(D.p2_tabs.p, D.p2_ntabs, D.p2_wend.p, csr, S_pre, D.S, K,
                                                                 eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU),
                                                                 bufV[0].p, bufM[0].p, bufA[0].p);
+        prof_end(h, (double)D.p2_work * 64.0);
         ++launches;
     }
     if (D.n_unary > 0) {
@@ -711,9 +762,11 @@ void Engine::do_init_liu(int i) {
     have_equ = false;
     run_eq(D.eqb_liu, D.n_eqb_liu);
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
+    size_t h = prof_begin(KC_INIT_LIU);
     k_init_liu<<<grid_for(tot), 256, 0, stream>>>(D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K,
                                                    eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
                                                    bufV[0].p, bufM[0].p, bufA[0].p);
+    prof_end(h, (double)tot * 64.0);
     ++launches;
 }
 
@@ -737,8 +790,10 @@ void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t t
     a.first_round = j == 1;
     a.reset_add_term = j == 1;
     const int grid = grid_for(R.work);
+    size_t h = prof_begin(R.fold ? KC_ROUND_FOLD : KC_ROUND_FIRST);
     if (R.fold) k_round<true><<<grid, 256, 0, stream>>>(a);
     else k_round<false><<<grid, 256, 0, stream>>>(a);
+    prof_end(h, R.bytes);
     ++launches;
 }
 
@@ -1186,6 +1241,24 @@ extern "C" int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out) 
     return VP_OK;
     API_END
 }
+extern "C" int vp_dot_host(vp_ctx* ctx, const vp_F* a, const vp_F* b, size_t n, vp_F* out) {
+    if (!ctx || !a || !b || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    ScopedTimer t(e);
+    if (n > 0xffffffffULL) return fail(VP_ERR_ARG, "vp_dot_host: n too large");
+    DBuf<F> da, db;
+    da.alloc(std::max<size_t>(n, 1));
+    db.alloc(std::max<size_t>(n, 1));
+    CK(cudaMemcpyAsync(da.p, a, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
+    CK(cudaMemcpyAsync(db.p, b, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
+    k_dot<<<e.grid_for((uint32_t)n), 256, 0, e.stream>>>(da.p, db.p, (uint32_t)n, e.d_tr.p + e.tr_input, e.d_partials.p,
+                                                           e.d_counter.p);
+    ++e.launches;
+    e.get_tr(e.tr_input, out);
+    return VP_OK;
+    API_END
+}
 extern "C" int vp_input_mle(vp_ctx* ctx, const vp_F* r, int n, vp_F* out) {
     if (!ctx || !out || (!r && n)) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN
@@ -1252,6 +1325,48 @@ extern "C" int vp_get_transcript(vp_ctx* ctx, vp_F* transcript, size_t cap) {
     cudaSetDevice(e.device);
     if (cap < e.n_tr) return fail(VP_ERR_ARG, "transcript buffer too small");
     e.get_tr(0, transcript, e.n_tr);
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_set_stream(vp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    CK(cudaStreamSynchronize(e.stream));
+    if (e.own_stream && e.stream) cudaStreamDestroy(e.stream);
+    if (cuda_stream) {
+        e.stream = (cudaStream_t)cuda_stream;
+        e.own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+        e.own_stream = true;
+    }
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_set_profiling(vp_ctx* ctx, int on) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    CK(cudaStreamSynchronize(e.stream));
+    e.prof_collect();
+    e.profiling = on != 0;
+    if (on) {
+        for (int k = 0; k < Engine::KC_N; ++k) { e.prof_ms[k] = 0; e.prof_bytes[k] = 0; e.prof_launches[k] = 0; }
+    }
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_get_profile(vp_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int n) {
+    if (!ctx || !ms || !bytes || !launches) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    CK(cudaStreamSynchronize(e.stream));
+    e.prof_collect();
+    for (int k = 0; k < n && k < Engine::KC_N; ++k) { ms[k] = e.prof_ms[k]; bytes[k] = e.prof_bytes[k]; launches[k] = e.prof_launches[k]; }
     return VP_OK;
     API_END
 }

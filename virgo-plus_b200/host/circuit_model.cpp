@@ -1,6 +1,6 @@
 // Host circuit model: .pws loader, layering, dad subsets, replication, challenge stream.
-// See circuit.h for the reference files each piece mirrors.
-#include "circuit.h"
+// See circuit_model.h for the reference files each piece mirrors.
+#include "circuit_model.h"
 
 #include <stdlib.h>
 #include <string.h>

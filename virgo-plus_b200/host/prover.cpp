@@ -1,0 +1,164 @@
+// Drop-in `prover` over the B200 engine; see prover.h. Method-by-method counterpart of
+// /root/reference/src/prover.cpp (line ranges cited per method).
+#include "prover.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "virgo_b200.h"
+
+static_assert(sizeof(F) == sizeof(vp_F), "fieldElement must be {u64 real; u64 img;}");
+
+namespace {
+[[noreturn]] void die(const char *what) {
+    fprintf(stderr, "virgo_b200 prover: %s failed: %s\n", what, vp_last_error());
+    exit(EXIT_FAILURE);
+}
+inline void ck(int rc, const char *what) {
+    if (rc != 0) die(what);
+}
+inline const vp_F *cf(const F *p) { return reinterpret_cast<const vp_F *>(p); }
+inline vp_F *mf(F *p) { return reinterpret_cast<vp_F *>(p); }
+}  // namespace
+
+// prover.cpp:14-25: evaluate, then fail if an assert gate is non-zero.
+prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr), sumcheckLayerId(0) {
+    const int n = C.size;
+    std::vector<uint64_t> layer_size(n), u, v, lv, dad_size((size_t)n * n, 0), dad_id;
+    std::vector<uint8_t> ty, is_assert;
+    std::vector<int32_t> l;
+    std::vector<vp_F> cst;
+    for (int i = 0; i < n; ++i) {
+        const layer &L = C.circuit[i];
+        layer_size[i] = L.size;
+        for (u64 g = 0; g < L.size; ++g) {
+            const gate &G = L.gates[g];
+            ty.push_back((uint8_t)G.ty);
+            l.push_back(G.l);
+            u.push_back(G.u);
+            v.push_back(G.v);
+            lv.push_back(G.lv);
+            cst.push_back(vp_F{G.c.real, G.c.img});
+            is_assert.push_back(G.is_assert ? 1 : 0);
+        }
+        for (int s = 0; s < i; ++s) {
+            dad_size[(size_t)i * n + s] = L.dadSize[s];
+            for (u64 x = 0; x < L.dadSize[s]; ++x) dad_id.push_back(L.dadId[s][x]);
+        }
+    }
+    if (dad_id.empty()) dad_id.push_back(0);
+    ck(vp_circuit_from_arrays(n, layer_size.data(), ty.data(), l.data(), u.data(), v.data(), lv.data(), cst.data(),
+                              is_assert.data(), dad_size.data(), dad_id.data(), &circ),
+       "vp_circuit_from_arrays");
+    const char *dev = getenv("VP_DEVICE");
+    ck(vp_create(circ, dev ? atoi(dev) : 0, &ctx), "vp_create");
+    evaluate();
+}
+
+prover::~prover() {
+    vp_destroy(ctx);
+    vp_circuit_free(circ);
+}
+
+// prover.cpp:27-91
+void prover::evaluate() {
+    int rc = vp_evaluate(ctx);
+    if (rc == VP_ERR_ASSERT) {
+        fprintf(stderr, "FAIL ON: %s\n", vp_last_error());
+        exit(EXIT_FAILURE);
+    }
+    ck(rc, "vp_evaluate");
+}
+
+// prover.cpp:131-155: only sizes host-side state in the reference; the engine sized everything at create.
+void prover::init() {}
+
+// prover.cpp:99-129
+F prover::Vres(const vector<F>::const_iterator &r_0, int r_0_size) {
+    F out;
+    ck(vp_vres(ctx, cf(&*r_0), r_0_size, mf(&out)), "vp_vres");
+    return out;
+}
+
+// prover.cpp:162-170
+void prover::sumcheckInitAll(const vector<F>::const_iterator &r_last) {
+    sumcheckLayerId = C.size;
+    ck(vp_sumcheck_init_all(ctx, cf(&*r_last), C.circuit[C.size - 1].bitLength), "vp_sumcheck_init_all");
+}
+
+// prover.cpp:177-184
+void prover::sumcheckInit() {
+    --sumcheckLayerId;
+    ck(vp_sumcheck_init(ctx), "vp_sumcheck_init");
+}
+
+// prover.cpp:189-280 (incl. its progress lines on stderr)
+void prover::sumcheckInitPhase1(const F &assert_random) {
+    fprintf(stderr, "sumcheck level %d, phase1 init start\n", sumcheckLayerId);
+    ck(vp_init_phase1(ctx, cf(&assert_random)), "vp_init_phase1");
+    fprintf(stderr, "sumcheck level %d, phase1 init finished\n", sumcheckLayerId);
+}
+
+// prover.cpp:282-367
+void prover::sumcheckInitPhase2() {
+    fprintf(stderr, "sumcheck level %d, phase2 init start\n", sumcheckLayerId);
+    ck(vp_init_phase2(ctx), "vp_init_phase2");
+}
+
+// prover.cpp:369-420: reads s[0 .. C.size - layer + 1) of the verifier's sigma vector
+void prover::sumcheckInitLiu(vector<F>::const_iterator s) {
+    ck(vp_init_liu(ctx, cf(&*s), C.size - sumcheckLayerId + 1), "vp_init_liu");
+}
+
+quadratic_poly prover::round(int phase, const F &previousRandom) {
+    F abc[3];
+    ck(vp_round(ctx, phase, cf(&previousRandom), mf(abc)), "vp_round");
+    return quadratic_poly(abc[0], abc[1], abc[2]);
+}
+// prover.cpp:422-434
+quadratic_poly prover::sumcheckUpdatePhase1(const F &previousRandom) { return round(1, previousRandom); }
+quadratic_poly prover::sumcheckUpdatePhase2(const F &previousRandom) { return round(2, previousRandom); }
+quadratic_poly prover::sumcheckLiuUpdate(const F &previousRandom) { return round(3, previousRandom); }
+
+// prover.cpp:494-501
+void prover::sumcheckFinalize1(const F &previousRandom, F &claim) {
+    ck(vp_finalize1(ctx, cf(&previousRandom), mf(&claim)), "vp_finalize1");
+}
+// prover.cpp:504-516: writes claims[0 .. layer)
+void prover::sumcheckFinalize2(const F &previousRandom, vector<F>::iterator claims) {
+    ck(vp_finalize2(ctx, cf(&previousRandom), mf(&*claims), sumcheckLayerId), "vp_finalize2");
+}
+// prover.cpp:518-521
+void prover::sumcheckLiuFinalize(const F &previousRandom, F &claim) {
+    ck(vp_finalize_liu(ctx, cf(&previousRandom), mf(&claim)), "vp_finalize_liu");
+}
+
+// prover.cpp:549-555
+double prover::proveTime() const { return vp_prove_seconds(ctx); }
+double prover::proofSize() const { return (double)vp_proof_size_bytes(ctx) / 1024.0; }
+
+#ifdef USE_VIRGO
+// prover.cpp:524-530: the polynomial commitment stays the reference's CPU library (out of scope,
+// SURVEY 8f N1); it is handed the input layer copied back from the device.
+virgo::__hhash_digest prover::commit_private() {
+    std::vector<F> mask(1, F_ZERO);
+    const int bl = C.circuit[0].bitLength;
+    input_values.assign(1ULL << bl, F_ZERO);
+    ck(vp_get_values(ctx, 0, mf(input_values.data()), C.circuit[0].size), "vp_get_values");
+    return poly_prover.commit_private_array(input_values.data(), bl, mask);
+}
+
+// prover.cpp:532-540
+F prover::inner_prod(const vector<F> &a, const vector<F> &b, u64 l) {
+    F out;
+    ck(vp_dot_host(ctx, cf(a.data()), cf(b.data()), l, mf(&out)), "vp_dot_host");
+    return out;
+}
+
+// prover.cpp:542-546
+virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum, std::vector<F> &mask,
+                                            vector<F> &all_sum) {
+    ck(vp_inner_prod(ctx, cf(pub.data()), C.circuit[0].size, mf(&inner_product_sum)), "vp_inner_prod");
+    return poly_prover.commit_public_array(mask, pub.data(), C.circuit[0].bitLength, inner_product_sum, all_sum.data());
+}
+#endif

@@ -1,0 +1,140 @@
+"""CPU tests of the product's field arithmetic (virgo-plus_b200/csrc/field.cuh compiled for the host:
+the very same inline integer code nvcc compiles for sm_100a) against Python big integers."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = (1 << 61) - 1
+FD = np.dtype([("re", "<u8"), ("im", "<u8")])
+
+
+@pytest.fixture(scope="module")
+def H(tmp_path_factory):
+    so = tmp_path_factory.mktemp("fh") / "field_harness.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
+                           os.path.join(ROOT, "tests", "native", "field_harness.cpp"), "-o", str(so)])
+    return C.CDLL(str(so))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+EDGE = [0, 1, 2, 3, P - 1, P - 2, P - 3, (1 << 60), (1 << 60) - 1, (1 << 60) + 1, (1 << 31) - 1, 1 << 31, (1 << 31) + 1,
+        (1 << 32) - 1, 1 << 32, (1 << 30), (1 << 30) - 1, 0x7FFFFFFF7FFFFFFF % P, (1 << 61) - (1 << 31), (1 << 61) - (1 << 31) - 1]
+
+
+def _operands(rng, n_rand, hi=P):
+    vals = list(EDGE) + [int(x) for x in rng.integers(0, hi, n_rand, dtype=np.uint64)]
+    return [v % hi if hi == P else v for v in vals]
+
+
+def _fe_arrays(rng, n):
+    base = _operands(rng, 40)
+    re = rng.choice(base, n)
+    im = rng.choice(base, n)
+    a = np.zeros(n, FD)
+    a["re"] = re.astype(np.uint64)
+    a["im"] = im.astype(np.uint64)
+    return a
+
+
+def _cmul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def _t(x):
+    return (int(x["re"]), int(x["im"]))
+
+
+def test_mul_add_sub_fold(H):
+    rng = np.random.default_rng(7)
+    n = 20000
+    a, b, c = _fe_arrays(rng, n), _fe_arrays(rng, n), _fe_arrays(rng, n)
+    out = np.zeros(n, FD)
+    H.h_mul(_p(a), _p(b), _p(out), n)
+    for i in range(n):
+        assert _t(out[i]) == _cmul(_t(a[i]), _t(b[i])), (i, a[i], b[i])
+    H.h_mul_add(_p(a), _p(b), _p(c), _p(out), n)
+    for i in range(0, n, 3):
+        m = _cmul(_t(a[i]), _t(b[i]))
+        assert _t(out[i]) == ((m[0] + int(c[i]["re"])) % P, (m[1] + int(c[i]["im"])) % P)
+    H.h_fold(_p(a), _p(b), _p(c), _p(out), n)  # a + c*(b - a)
+    for i in range(0, n, 3):
+        d = ((int(b[i]["re"]) - int(a[i]["re"])) % P, (int(b[i]["im"]) - int(a[i]["im"])) % P)
+        m = _cmul(d, _t(c[i]))
+        assert _t(out[i]) == ((m[0] + int(a[i]["re"])) % P, (m[1] + int(a[i]["im"])) % P), i
+    H.h_add(_p(a), _p(b), _p(out), n)
+    assert all(_t(out[i]) == ((int(a[i]["re"]) + int(b[i]["re"])) % P, (int(a[i]["im"]) + int(b[i]["im"])) % P) for i in range(0, n, 5))
+    H.h_sub(_p(a), _p(b), _p(out), n)
+    assert all(_t(out[i]) == ((int(a[i]["re"]) - int(b[i]["re"])) % P, (int(a[i]["im"]) - int(b[i]["im"])) % P) for i in range(0, n, 5))
+    assert (out["re"] < P).all() and (out["im"] < P).all()
+
+
+def test_all_edge_pairs_exhaustive(H):
+    """every (re, im) x (re, im) combination of the edge values"""
+    e = np.array(EDGE, dtype=np.uint64)
+    g = np.array(np.meshgrid(e, e, e, e, indexing="ij")).reshape(4, -1)
+    n = g.shape[1]
+    a, b = np.zeros(n, FD), np.zeros(n, FD)
+    a["re"], a["im"], b["re"], b["im"] = g
+    out = np.zeros(n, FD)
+    H.h_mul(_p(a), _p(b), _p(out), n)
+    ar, ai, br, bi = (x.astype(object) for x in g)
+    want_re = (ar * br - ai * bi) % P
+    want_im = (ar * bi + ai * br) % P
+    assert (out["re"].astype(object) == want_re).all() and (out["im"].astype(object) == want_im).all()
+
+
+def test_loose_operands_up_to_2p(H):
+    rng = np.random.default_rng(8)
+    n = 20000
+    loose_edge = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P, (1 << 61), (1 << 62) - 3, (1 << 31) * ((1 << 31) - 1)]
+    def arr():
+        vals = loose_edge + [int(x) for x in rng.integers(0, 2 * P + 1, 50, dtype=np.uint64)]
+        a = np.zeros(n, FD)
+        a["re"] = rng.choice(vals, n).astype(np.uint64)
+        a["im"] = rng.choice(vals, n).astype(np.uint64)
+        return a
+    a, b, c = arr(), arr(), _fe_arrays(rng, n)
+    out = np.zeros(n, FD)
+    H.h_mul_add_loose(_p(a), _p(b), _p(c), _p(out), n)
+    for i in range(n):
+        m = _cmul(_t(a[i]), _t(b[i]))
+        assert _t(out[i]) == ((m[0] + int(c[i]["re"])) % P, (m[1] + int(c[i]["im"])) % P), (i, a[i], b[i])
+
+
+def test_fp_mul_and_reductions(H):
+    rng = np.random.default_rng(9)
+    n = 20000
+    big = [0, 1, (1 << 64) - 1, (1 << 63), (1 << 63) - 1, (1 << 61), (1 << 61) - 1, (1 << 62), 0xFFFFFFFF00000000, 0x3FFFFFFF, 0x40000000]
+    def u64s(hi):
+        v = [x for x in big if x < hi] + [int(x) for x in rng.integers(0, min(hi, (1 << 64) - 1), 60, dtype=np.uint64)]
+        return rng.choice(np.array(v, dtype=np.uint64), n)
+    a, b = u64s(1 << 62), u64s(1 << 62)
+    out = np.zeros(n, np.uint64)
+    H.h_fp_mul(_p(a), _p(b), _p(out), n)
+    assert all(int(out[i]) == int(a[i]) * int(b[i]) % P for i in range(n))
+    u, t, w, e = u64s(1 << 64), u64s(1 << 64), u64s(1 << 64), u64s(1 << 62)
+    H.h_reduce_ut(_p(u), _p(t), _p(e), _p(out), n)
+    assert all(int(out[i]) == (int(u[i]) + (int(t[i]) << 31) + int(e[i])) % P for i in range(n))
+    H.h_reduce_utw(_p(u), _p(t), _p(w), _p(e), _p(out), n)
+    assert all(int(out[i]) == (int(u[i]) + (int(t[i]) << 31) + (int(w[i]) << 62) + int(e[i])) % P for i in range(n))
+
+
+def test_lazy_accumulator_dot(H):
+    rng = np.random.default_rng(10)
+    for n in [1, 7, 8, 9, 100]:
+        a, b = _fe_arrays(rng, n), _fe_arrays(rng, n)
+        a["re"][0] = a["im"][0] = b["re"][0] = b["im"][0] = P - 1
+        out = np.zeros(1, FD)
+        H.h_acc_dot(_p(a), _p(b), _p(out), n)
+        acc = (0, 0)
+        for i in range(n):
+            m = _cmul(_t(a[i]), _t(b[i]))
+            acc = ((acc[0] + m[0]) % P, (acc[1] + m[1]) % P)
+        assert _t(out[0]) == acc

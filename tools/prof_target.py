@@ -1,0 +1,18 @@
+"""Short workloads for ncu captures: `c2` = one 2^24 sumcheck, `gkr K` = one proof of SHA256_64 x K."""
+import lzma, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "virgo-plus_b200"))
+import binding as B
+
+if sys.argv[1] == "c2":
+    log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+    s = B.Sumcheck(log_n); s.fill_random(1)
+    r = np.zeros(log_n, B.F_DTYPE); r["re"] = np.arange(1, log_n + 1) * 1234567891; r["im"] = 77
+    s.run(r); s.run(r)
+else:
+    K = int(sys.argv[2])
+    with lzma.open(os.path.join(ROOT, "tests/golden/SHA256_64.pws.xz")) as f:
+        c = B.Circuit.from_pws_text(f.read()).replicate(K)
+    p = B.Prover(c); p.set_challenges(c.draw_challenges()); p.prove(); p.prove()
+    print("ms", p.last_prove_ms)

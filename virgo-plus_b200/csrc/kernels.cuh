@@ -410,43 +410,49 @@ struct RoundArgs {
 
 VP_D F ld_bound(const F* base, uint32_t idx, uint32_t live) { return idx < live ? ld_f(base + idx) : f_zero(); }
 
+// Per-thread running sums of one round. With B = sum m1*v1, C = sum m0*v0, E = sum (m0+m1)*(v0+v1):
+//   a = sum (m1-m0)(v1-v0)               = 2B + 2C - E
+//   b = sum (m1-m0)v0 + (v1-v0)m0 + ...  = E - B - 3C + (sum a1 - sum a0)
+//   c = sum m0*v0 + sum a0               = C + sum a0
+// (three complex products per pair, no differences to canonicalise). B, C, E stay canonical: the
+// running value rides as the `extra` term of each product's single reduction.
 struct RoundAcc {
-    Acc a, b, c;       // sum dm*dv, sum m1*v1, sum m0*v0 (lazy)
-    F sa0, sa1;        // sum add0, sum add1
-    F ra, rb, rc;      // compressed running totals
+    F B, C, E;
+    u64 s0re, s0im, s1re, s1im;  // lazy sums of the add table (folded every 4 pairs)
     int pending;
 };
 VP_D void racc_init(RoundAcc& s) {
-    s.a = acc_zero(); s.b = acc_zero(); s.c = acc_zero();
-    s.sa0 = f_zero(); s.sa1 = f_zero();
-    s.ra = f_zero(); s.rb = f_zero(); s.rc = f_zero();
-    s.pending = 0;
-}
-VP_D void racc_compress(RoundAcc& s) {
-    s.ra = f_add(s.ra, acc_reduce(s.a));
-    s.rb = f_add(s.rb, acc_reduce(s.b));
-    s.rc = f_add(s.rc, acc_reduce(s.c));
-    s.a = acc_zero(); s.b = acc_zero(); s.c = acc_zero();
+    s.B = f_zero(); s.C = f_zero(); s.E = f_zero();
+    s.s0re = s.s0im = s.s1re = s.s1im = 0;
     s.pending = 0;
 }
 VP_D void racc_pair(RoundAcc& s, const F& v0, const F& v1, const F& m0, const F& m1, const F& a0, const F& a1) {
-    acc_mad(s.a, f_sub(m1, m0), f_sub(v1, v0));
-    acc_mad(s.b, m1, v1);
-    acc_mad(s.c, m0, v0);
-    s.sa0 = f_add(s.sa0, a0);
-    s.sa1 = f_add(s.sa1, a1);
-    if (++s.pending == 8) racc_compress(s);
+    s.C = f_mul_add_k(make_lop(m0.re, m0.im), make_ropd(v0), s.C);
+    s.B = f_mul_add_k(make_lop(m1.re, m1.im), make_ropd(v1), s.B);
+    s.E = f_mul_add_loose(make_lop(m0.re + m1.re, m0.im + m1.im), make_rop(v0.re + v1.re, v0.im + v1.im), s.E);
+    s.s0re += a0.re; s.s0im += a0.im; s.s1re += a1.re; s.s1im += a1.im;
+    if (++s.pending == 4) {
+        s.s0re = fp_fold(s.s0re); s.s0im = fp_fold(s.s0im); s.s1re = fp_fold(s.s1re); s.s1im = fp_fold(s.s1im);
+        s.pending = 0;
+    }
+}
+VP_D void racc_finish(const RoundAcc& s, F (&v)[3]) {
+    const F sa0 = F{fp_canon(s.s0re), fp_canon(s.s0im)}, sa1 = F{fp_canon(s.s1re), fp_canon(s.s1im)};
+    const F twoBC = f_dbl(f_add(s.B, s.C));
+    v[0] = f_sub(twoBC, s.E);
+    v[1] = f_add(f_sub(f_sub(s.E, s.B), f_add(f_dbl(s.C), s.C)), f_sub(sa1, sa0));
+    v[2] = f_add(s.C, sa0);
 }
 
 template <bool FOLD>
-__global__ void __launch_bounds__(256) k_round(RoundArgs p) {
+__global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
     __shared__ F smem[3 * 32];
     __shared__ uint32_t s_wend[128];
     for (uint32_t i = threadIdx.x; i < p.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[i].work_end;
     __syncthreads();
     const uint32_t total = p.n_tabs ? s_wend[p.n_tabs - 1] : 0;
-    F r = f_zero();
-    if (FOLD) r = *p.prev_r;
+    FoldK rk = make_foldk(f_zero());
+    if (FOLD) rk = make_foldk(*p.prev_r);
     RoundAcc acc;
     racc_init(acc);
     int t = 0;
@@ -464,22 +470,33 @@ __global__ void __launch_bounds__(256) k_round(RoundArgs p) {
         const F* A = p.inA + T.in_off;
         if (!FOLD) {
             const uint32_t i0 = 2 * q;
-            F v0 = ld_bound(V, i0, T.in_live), v1 = ld_bound(V, i0 + 1, T.in_live);
-            F m0 = ld_bound(M, i0, T.in_live), m1 = ld_bound(M, i0 + 1, T.in_live);
-            F a0 = ld_bound(A, i0, T.in_live), a1 = ld_bound(A, i0 + 1, T.in_live);
+            F v0, v1, m0, m1, a0, a1;
+            if (i0 + 1 < T.in_live) {
+                v0 = ld_f(V + i0); v1 = ld_f(V + i0 + 1);
+                m0 = ld_f(M + i0); m1 = ld_f(M + i0 + 1);
+                a0 = ld_f(A + i0); a1 = ld_f(A + i0 + 1);
+            } else {
+                v0 = ld_f(V + i0); m0 = ld_f(M + i0); a0 = ld_f(A + i0);
+                v1 = m1 = a1 = f_zero();
+            }
             racc_pair(acc, v0, v1, m0, m1, a0, a1);
         } else {
             const uint32_t i0 = 4 * q;
             F xv[4], xm[4], xa[4];
+            if (i0 + 3 < T.in_live) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                xv[j] = ld_bound(V, i0 + j, T.in_live);
-                xm[j] = ld_bound(M, i0 + j, T.in_live);
-                xa[j] = ld_bound(A, i0 + j, T.in_live);
+                for (int j = 0; j < 4; ++j) { xv[j] = ld_f(V + i0 + j); xm[j] = ld_f(M + i0 + j); xa[j] = ld_f(A + i0 + j); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    xv[j] = ld_bound(V, i0 + j, T.in_live);
+                    xm[j] = ld_bound(M, i0 + j, T.in_live);
+                    xa[j] = ld_bound(A, i0 + j, T.in_live);
+                }
             }
-            const F v0 = f_fold(xv[0], xv[1], r), v1 = f_fold(xv[2], xv[3], r);
-            const F m0 = f_fold(xm[0], xm[1], r), m1 = f_fold(xm[2], xm[3], r);
-            const F a0 = f_fold(xa[0], xa[1], r), a1 = f_fold(xa[2], xa[3], r);
+            const F v0 = f_fold_k(xv[0], xv[1], rk), v1 = f_fold_k(xv[2], xv[3], rk);
+            const F m0 = f_fold_k(xm[0], xm[1], rk), m1 = f_fold_k(xm[2], xm[3], rk);
+            const F a0 = f_fold_k(xa[0], xa[1], rk), a1 = f_fold_k(xa[2], xa[3], rk);
             const uint32_t o = T.out_off + 2 * q;
             st_f(p.outV + o, v0); st_f(p.outM + o, m0); st_f(p.outA + o, a0);
             if (i0 + 2 < T.in_live) {
@@ -488,12 +505,8 @@ __global__ void __launch_bounds__(256) k_round(RoundArgs p) {
             racc_pair(acc, v0, v1, m0, m1, a0, a1);
         }
     }
-    racc_compress(acc);
-    // a = sum dm*dv ; c = sum m0*v0 + sum a0 ; b = sum m1*v1 - sum m0*v0 - sum dm*dv + sum a1 - sum a0
     F v[3];
-    v[0] = acc.ra;
-    v[1] = f_add(f_sub(f_sub(acc.rb, acc.rc), acc.ra), f_sub(acc.sa1, acc.sa0));
-    v[2] = f_add(acc.rc, acc.sa0);
+    racc_finish(acc, v);
     if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
     if (threadIdx.x != 0) return;
     // ---- epilogue (one thread): add_term bookkeeping, prover.cpp:445-448,462-467
@@ -509,8 +522,7 @@ __global__ void __launch_bounds__(256) k_round(RoundArgs p) {
                 if (c.n_vals >= 2) {
                     v1 = ld_f_cg(p.inV + c.in_off + 1); m1 = ld_f_cg(p.inM + c.in_off + 1); a1 = ld_f_cg(p.inA + c.in_off + 1);
                 }
-                const F rr = *p.prev_r;
-                cv = f_fold(cv, v1, rr); cm = f_fold(cm, m1, rr); ca = f_fold(ca, a1, rr);
+                cv = f_fold_k(cv, v1, rk); cm = f_fold_k(cm, m1, rk); ca = f_fold_k(ca, a1, rk);
             }
         }
         at = f_add(at, f_add(f_mul(cv, cm), ca));

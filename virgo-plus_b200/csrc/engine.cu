@@ -191,6 +191,33 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
     return P;
 }
 
+// ------------------------------------------------------------------ CSR rows -> work items
+static constexpr uint32_t ROW_CHUNK = 8;
+struct ItemPlan {
+    std::vector<RowItem> items;
+    std::vector<LongRow> longs;
+    uint32_t n_slots = 0;
+};
+// off: R+1 absolute entry positions of the rows of one table
+static void add_rows(ItemPlan& P, const std::vector<uint32_t>& off, uint32_t tab) {
+    const uint32_t R = (uint32_t)off.size() - 1;
+    for (uint32_t r = 0; r < R; ++r) {
+        const uint32_t len = off[r + 1] - off[r];
+        if (len <= ROW_CHUNK) {
+            P.items.push_back(RowItem{r, off[r], len, tab});
+            continue;
+        }
+        LongRow lr{r, P.n_slots, 0, tab};
+        for (uint32_t e = off[r]; e < off[r + 1]; e += ROW_CHUNK) {
+            const uint32_t cnt = std::min(ROW_CHUNK, off[r + 1] - e);
+            P.items.push_back(RowItem{r, e, cnt | ((P.n_slots + 1) << 8), tab});
+            ++P.n_slots;
+        }
+        lr.slot_end = P.n_slots;
+        P.longs.push_back(lr);
+    }
+}
+
 // ------------------------------------------------------------------ per-layer device data
 struct LayerDev {
     uint32_t S = 0;
@@ -199,15 +226,20 @@ struct LayerDev {
     DBuf<uint32_t> u, v;
     DBuf<F> c;
     GateArrays G{};
-    // phase 1 CSR (keyed by u0 in layer i-1)
-    DBuf<uint32_t> p1_off, p1_g0, p1_v0, p1_tyl;
+    // phase 1 CSR (keyed by u0 in layer i-1), cut into work items of <= ROW_CHUNK entries
+    DBuf<uint32_t> p1_g0, p1_v0, p1_tyl;
+    DBuf<RowItem> p1_items;
+    DBuf<LongRow> p1_long;
+    uint32_t p1_nslots = 0;
     // phase 2
-    DBuf<uint32_t> p2_off_all, p2_dad_all, p2_g0, p2_u0;
+    DBuf<uint32_t> p2_dad_all, p2_g0, p2_u0;
     DBuf<uint8_t> p2_ty;
     DBuf<P2Table> p2_tabs;
-    DBuf<uint32_t> p2_wend;
-    int p2_ntabs = 0;            // tables with a non-empty subset (those get an init work range)
-    uint32_t p2_work = 0;
+    DBuf<RowItem> p2_items;
+    DBuf<LongRow> p2_long;
+    uint32_t p2_nslots = 0;
+    int p2_ntabs = 0;            // tables with a non-empty subset
+    double p2_out_entries = 0, p2_gates = 0;
     DBuf<uint32_t> un_g0, un_u0;
     DBuf<uint8_t> un_ty;
     uint32_t n_unary = 0;
@@ -248,7 +280,7 @@ struct Engine {
     DBuf<uint64_t> d_inputs;
     DBuf<F> bufV[2], bufM[2], bufA[2];
     DBuf<F> d_eq;
-    DBuf<F> d_chal, d_tr, d_scal, d_claims, d_partials, d_pub;
+    DBuf<F> d_chal, d_tr, d_scal, d_claims, d_partials, d_pub, d_rowpart;
     DBuf<unsigned int> d_counter;      // [0] grid-sum ticket, [1] assert flag
     DBuf<TabDesc> d_tabs;
     DBuf<ColDesc> d_cols;
@@ -340,7 +372,15 @@ struct Engine {
         eq_descs.push_back(a);
         eq_descs.push_back(b);
     }
-    int grid_for(uint32_t work) const { return (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(work, 256), (uint32_t)max_grid)); }
+    int n_sm = 148;
+    int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0;
+    template <class Kern>
+    int occ_cap(Kern k) {  // resident blocks of 256 threads on the whole chip
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, 0));
+        return n_sm * std::max(1, occ);
+    }
+    int grid_for(uint32_t work, int cap) const { return (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(work, 256), (uint32_t)cap)); }
     F* scal(int i) { return d_scal.p + i; }
 
     void build(const Circuit& circ, int dev);
@@ -390,9 +430,17 @@ void Engine::build(const Circuit& circ, int dev) {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_round<true>, 256, 0));
-    max_grid = prop.multiProcessorCount * std::max(1, occ);
+    n_sm = prop.multiProcessorCount;
+    cap_round = occ_cap(k_round<true>);
+    cap_round1 = occ_cap(k_round<false>);
+    cap_eval = occ_cap(k_eval_layer);
+    cap_p1 = occ_cap(k_init_phase1);
+    cap_p2 = occ_cap(k_init_phase2);
+    cap_un = occ_cap(k_phase2_unary);
+    cap_liu = occ_cap(k_init_liu);
+    cap_dot = occ_cap(k_dot_eq);
+    cap_comb = occ_cap(k_combine_phase2);
+    max_grid = std::max({cap_round, cap_round1, cap_un, cap_dot});  // sizes the block-partials buffer
 
     // challenge / transcript index maps (draw order of verifier.cpp, see circuit.cpp draw_challenges)
     L.resize(n);
@@ -440,6 +488,7 @@ void Engine::build(const Circuit& circ, int dev) {
     d_inputs.alloc(C.layer_size(0));
 
     uint32_t cap0 = 4, cap1 = 4;
+    size_t max_partial = 2;
     eqb_out = (uint32_t)eq_descs.size();
     add_eq_build(2, ci_out, C.bit_length(n - 1), -1);
     for (int i = 1; i < n; ++i) {
@@ -476,7 +525,12 @@ void Engine::build(const Circuit& circ, int dev) {
                 uint32_t as = (!T.is_assert.empty() && T.is_assert[g]) ? TY_ASSERT_BIT : 0;
                 tyl[p] = (uint32_t)T.ty[g] | as | ((uint32_t)(T.l[g] + 1) << 8);
             }
-            D.p1_off.upload(off, stream);
+            ItemPlan ip;
+            add_rows(ip, off, 0);
+            D.p1_items.upload(ip.items, stream);
+            D.p1_long.upload(ip.longs, stream);
+            D.p1_nslots = ip.n_slots;
+            max_partial = std::max<size_t>(max_partial, (size_t)ip.n_slots * K * 2);
             D.p1_g0.upload(g0, stream);
             D.p1_v0.upload(v0, stream);
             D.p1_tyl.upload(tyl, stream);
@@ -525,11 +579,10 @@ void Engine::build(const Circuit& circ, int dev) {
             cap0 = std::max(cap0, D.plan2.cap0);
             cap1 = std::max(cap1, D.plan2.cap1);
             // CSR per table over lv0
-            std::vector<uint32_t> off_all, dad_all, g0, u0, wend;
+            std::vector<uint32_t> dad_all, g0, u0;
             std::vector<uint8_t> tyv;
             std::vector<P2Table> ptabs;
-            uint32_t work = 0;
-            std::vector<std::vector<uint32_t>> rows;  // reused per table
+            ItemPlan ip;
             for (size_t t = 0; t < order.size(); ++t) {
                 const int l = order[t];
                 const uint32_t Dsz = (uint32_t)T.dadSize[l];
@@ -560,28 +613,28 @@ void Engine::build(const Circuit& circ, int dev) {
                 pt.src_S = (uint32_t)C.layers[l].size;
                 pt.tab_off = D.plan2.tabs[t].off0;
                 pt.src_val = val[l].p;
-                // stash offsets relative to the concatenated arrays; patched to pointers after upload
-                pt.off = (const uint32_t*)(uintptr_t)off_all.size();
+                // stash the offset into the concatenated array; patched to a pointer after upload
                 pt.dadId = (const uint32_t*)(uintptr_t)dad_all.size();
-                for (uint32_t x = 0; x <= Dsz; ++x) off_all.push_back(base + cnt[x]);
+                std::vector<uint32_t> off(Dsz + 1);
+                for (uint32_t x = 0; x <= Dsz; ++x) off[x] = base + cnt[x];
                 for (uint32_t x = 0; x < Dsz; ++x) dad_all.push_back(T.dadId[l][x]);
-                work += Dsz * K;
-                wend.push_back(work);
+                add_rows(ip, off, (uint32_t)ptabs.size());
                 ptabs.push_back(pt);
             }
-            D.p2_off_all.upload(off_all, stream);
+            D.p2_items.upload(ip.items, stream);
+            D.p2_long.upload(ip.longs, stream);
+            D.p2_nslots = ip.n_slots;
+            max_partial = std::max<size_t>(max_partial, (size_t)ip.n_slots * K * 2);
             D.p2_dad_all.upload(dad_all, stream);
             D.p2_g0.upload(g0, stream);
             D.p2_u0.upload(u0, stream);
             D.p2_ty.upload(tyv, stream);
-            for (auto& pt : ptabs) {
-                pt.off = D.p2_off_all.p + (uintptr_t)pt.off;
-                pt.dadId = D.p2_dad_all.p + (uintptr_t)pt.dadId;
-            }
+            for (auto& pt : ptabs) pt.dadId = D.p2_dad_all.p + (uintptr_t)pt.dadId;
             D.p2_tabs.upload(ptabs, stream);
-            D.p2_wend.upload(wend, stream);
             D.p2_ntabs = (int)ptabs.size();
-            D.p2_work = work;
+            D.p2_gates = (double)g0.size();
+            D.p2_out_entries = 0;
+            for (auto& pt : ptabs) D.p2_out_entries += (double)pt.D * K;
             // unary gates
             std::vector<uint32_t> ug, uu;
             std::vector<uint8_t> ut;
@@ -643,6 +696,7 @@ void Engine::build(const Circuit& circ, int dev) {
         bufM[b].alloc(cap);
         bufA[b].alloc(cap);
     }
+    d_rowpart.alloc(max_partial);
     d_chal.alloc(n_chal + 1);
     d_tr.alloc(n_tr);
     d_scal.alloc(SC_N);
@@ -679,7 +733,7 @@ void Engine::evaluate() {
     for (int i = 1; i < n; ++i) {
         const uint32_t tot = L[i].S * K;
         size_t h = prof_begin(KC_EVAL);
-        k_eval_layer<<<grid_for(tot), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p, val[i].p,
+        k_eval_layer<<<grid_for(tot, cap_eval), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p, val[i].p,
                                                          d_counter.p + 1);
         prof_end(h, (double)tot * (16.0 + 32.0 + 11.0 / K));  // out + two operand gathers (+ amortised wiring)
         ++launches;
@@ -695,7 +749,7 @@ void Engine::run_eq(uint32_t first, uint32_t count) {
 }
 
 void Engine::run_dot_eq(const F* X, uint32_t cnt, EqTab eq, F* out) {
-    k_dot_eq<<<grid_for(cnt), 256, 0, stream>>>(X, cnt, eq, out, d_partials.p, d_counter.p);
+    k_dot_eq<<<grid_for(cnt, cap_dot), 256, 0, stream>>>(X, cnt, eq, out, d_partials.p, d_counter.p);
     ++launches;
 }
 
@@ -714,11 +768,18 @@ void Engine::do_init_phase1(int i) {
     run_eq(D.eqb_g, 2);
     const uint32_t S_pre = L[i - 1].S ? L[i - 1].S : (uint32_t)C.layers[i - 1].size;
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
-    CsrP1 csr{D.p1_off.p, D.p1_g0.p, D.p1_v0.p, D.p1_tyl.p};
+    CsrP1 csr{D.p1_g0.p, D.p1_v0.p, D.p1_tyl.p};
+    const uint64_t work = (uint64_t)D.p1_items.n * K;
     size_t h = prof_begin(KC_INIT1);
-    k_init_phase1<<<grid_for(tot), 256, 0, stream>>>(csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)),
-                                                      d_chal.p + D.ci_assert, d_valptr.p, d_sizes.p, D.c.p,
-                                                      val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p);
+    k_init_phase1<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1), 256, 0, stream>>>(
+        D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
+        d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p1_nslots);
+    if (D.p1_long.n) {
+        k_combine_phase1<<<grid_for((uint32_t)(D.p1_long.n * K), cap_comb), 256, 0, stream>>>(
+            D.p1_long.p, (uint32_t)D.p1_long.n, S_pre, K, val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p,
+            D.p1_nslots);
+        ++launches;
+    }
     // per output: V read + 3 table writes; per gate: one gathered operand
     prof_end(h, (double)tot * 64.0 + (double)D.S * K * 16.0);
     ++launches;
@@ -738,17 +799,23 @@ void Engine::do_init_phase2(int i) {
     }
     if (D.p2_ntabs > 0) {
         CsrP2 csr{D.p2_g0.p, D.p2_u0.p, D.p2_ty.p};
+        const uint64_t work = (uint64_t)D.p2_items.n * K;
         size_t h = prof_begin(KC_INIT2);
-        k_init_phase2<<<grid_for(D.p2_work), 256, 0, stream>>>(D.p2_tabs.p, D.p2_ntabs, D.p2_wend.p, csr, S_pre, D.S, K,
-                                                                eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU),
-                                                                bufV[0].p, bufM[0].p, bufA[0].p);
-        prof_end(h, (double)D.p2_work * 64.0);
+        k_init_phase2<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p2), 256, 0, stream>>>(
+            D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
+            scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots);
+        if (D.p2_long.n) {
+            k_combine_phase2<<<grid_for((uint32_t)(D.p2_long.n * K), cap_comb), 256, 0, stream>>>(
+                D.p2_long.p, (uint32_t)D.p2_long.n, D.p2_tabs.p, K, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots);
+            ++launches;
+        }
+        prof_end(h, (double)D.p2_out_entries * 64.0 + (double)D.p2_gates * K * 16.0);
         ++launches;
     }
     if (D.n_unary > 0) {
         CsrUnary un{D.un_g0.p, D.un_u0.p, D.un_ty.p, D.n_unary};
         const uint64_t tot = (uint64_t)D.n_unary * K;
-        k_phase2_unary<<<grid_for((uint32_t)std::min<uint64_t>(tot, 0xffffffffu)), 256, 0, stream>>>(
+        k_phase2_unary<<<grid_for((uint32_t)std::min<uint64_t>(tot, 0xffffffffu), cap_un), 256, 0, stream>>>(
             un, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU), D.c.p, bufA[0].p + D.un_dst_off,
             d_partials.p, d_counter.p);
         ++launches;
@@ -763,7 +830,7 @@ void Engine::do_init_liu(int i) {
     run_eq(D.eqb_liu, D.n_eqb_liu);
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
-    k_init_liu<<<grid_for(tot), 256, 0, stream>>>(D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K,
+    k_init_liu<<<grid_for(tot, cap_liu), 256, 0, stream>>>(D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K,
                                                    eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
                                                    bufV[0].p, bufM[0].p, bufA[0].p);
     prof_end(h, (double)tot * 64.0);
@@ -789,7 +856,7 @@ void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t t
     a.counter = d_counter.p;
     a.first_round = j == 1;
     a.reset_add_term = j == 1;
-    const int grid = grid_for(R.work);
+    const int grid = grid_for(R.work, R.fold ? cap_round : cap_round1);
     size_t h = prof_begin(R.fold ? KC_ROUND_FOLD : KC_ROUND_FIRST);
     if (R.fold) k_round<true><<<grid, 256, 0, stream>>>(a);
     else k_round<false><<<grid, 256, 0, stream>>>(a);
@@ -1234,7 +1301,7 @@ extern "C" int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out) 
     if (n > e.C.layer_size(0)) return fail(VP_ERR_ARG, "inner_prod: n exceeds the input layer");
     if (e.d_pub.n < n) e.d_pub.alloc(n);
     CK(cudaMemcpyAsync(e.d_pub.p, pub, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
-    k_dot<<<e.grid_for((uint32_t)n), 256, 0, e.stream>>>(e.val[0].p, e.d_pub.p, (uint32_t)n, e.d_tr.p + e.tr_input,
+    k_dot<<<e.grid_for((uint32_t)n, e.cap_dot), 256, 0, e.stream>>>(e.val[0].p, e.d_pub.p, (uint32_t)n, e.d_tr.p + e.tr_input,
                                                            e.d_partials.p, e.d_counter.p);
     ++e.launches;
     e.get_tr(e.tr_input, out);
@@ -1252,7 +1319,7 @@ extern "C" int vp_dot_host(vp_ctx* ctx, const vp_F* a, const vp_F* b, size_t n, 
     db.alloc(std::max<size_t>(n, 1));
     CK(cudaMemcpyAsync(da.p, a, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
     CK(cudaMemcpyAsync(db.p, b, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
-    k_dot<<<e.grid_for((uint32_t)n), 256, 0, e.stream>>>(da.p, db.p, (uint32_t)n, e.d_tr.p + e.tr_input, e.d_partials.p,
+    k_dot<<<e.grid_for((uint32_t)n, e.cap_dot), 256, 0, e.stream>>>(da.p, db.p, (uint32_t)n, e.d_tr.p + e.tr_input, e.d_partials.p,
                                                            e.d_counter.p);
     ++e.launches;
     e.get_tr(e.tr_input, out);
@@ -1388,7 +1455,7 @@ struct vp_sumcheck {
     DBuf<FinDesc> d_fins;
     PlanArena arena;
     SumcheckPlan plan;
-    int max_grid = 148 * 4;
+    int max_grid = 148 * 4, cap_fold = 148, cap_first = 148;
     std::vector<cudaEvent_t> ev;
     std::vector<float> round_ms;
     ~vp_sumcheck() {
@@ -1411,9 +1478,12 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    int occ = 0;
+    int occ = 0, occ1 = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_round<true>, 256, 0));
-    s->max_grid = prop.multiProcessorCount * std::max(1, occ);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_round<false>, 256, 0));
+    s->cap_fold = prop.multiProcessorCount * std::max(1, occ);
+    s->cap_first = prop.multiProcessorCount * std::max(1, occ1);
+    s->max_grid = std::max(s->cap_fold, s->cap_first);
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     // out layout: per round (a,b,c) at 3*(j-1); finals: V, add, mult at 3*log_n + {0,1,2}. The plan
     // finalises one table (V); add/mult finals are folded by two more k_finalize launches.
@@ -1515,7 +1585,7 @@ extern "C" int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out, float* 
         a.counter = s->d_counter.p;
         a.first_round = j == 1;
         a.reset_add_term = j == 1;
-        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(R.work, 256), (uint32_t)s->max_grid));
+        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(R.work, 256), (uint32_t)(R.fold ? s->cap_fold : s->cap_first)));
         if (R.fold) k_round<true><<<grid, 256, 0, st>>>(a);
         else k_round<false><<<grid, 256, 0, st>>>(a);
         CK(cudaEventRecord(s->ev[j], st));

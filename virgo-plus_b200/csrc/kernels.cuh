@@ -171,92 +171,136 @@ __global__ void __launch_bounds__(256) k_eval_layer(GateArrays G, uint32_t S, ui
     }
 }
 
-// ------------------------------------------------------------------ K3: phase-1 table init
-// prover.cpp:214-273. Owner-computes by output index u = k*S_pre + u0; the gates of layer i that
-// read u0 are a CSR row (sorted by u0 on the host), so no atomics are needed.
+// ------------------------------------------------------------------ K3 / K4: table init from the wiring
+// Both inits are "owner computes by output index": the gates that add into one table entry form a CSR
+// row (sorted on the host), so no atomics are needed. Fan-in is heavily skewed (SHA256: mean 2-5, max
+// 624), so rows are cut into work items of at most C entries: a row that fits one item is written
+// directly, longer rows deposit per-item partial sums that a small second kernel combines.
+struct RowItem {
+    uint32_t row;        // row of the template (phase 1: u0; phase 2: lv0 within table `tab`)
+    uint32_t e_begin;    // first CSR entry
+    uint32_t cnt_slot;   // low 8 bits: number of entries; high 24 bits: partial slot + 1 (0 = direct write)
+    uint32_t tab;        // phase 2: table id
+};
+struct LongRow {
+    uint32_t row, slot_begin, slot_end, tab;
+};
+
+// prover.cpp:214-273
 struct CsrP1 {
-    const uint32_t* off;   // [S_pre + 1]
     const uint32_t* g0;    // template gate id (for the eq lookup and the constant)
     const uint32_t* v0;    // template v
     const uint32_t* tyl;   // ty | assert<<7 | (l+1)<<8
 };
 
+VP_D void p1_gate(uint32_t tyl, const F& beta, const F& Vv, const F* cst, uint32_t g0, F& M, F& A) {
+    switch (tyl & 0x7f) {
+        case T_ADD:
+            A = f_mul_add(Vv, beta, A);
+            M = f_add(M, beta);
+            break;
+        case T_SUB:
+            A = f_sub(A, f_mul(Vv, beta));
+            M = f_add(M, beta);
+            break;
+        case T_ANTISUB:
+            A = f_mul_add(Vv, beta, A);
+            M = f_sub(M, beta);
+            break;
+        case T_MUL:
+            M = f_mul_add(Vv, beta, M);
+            break;
+        case T_NAAB: {
+            const F t = f_mul(Vv, beta);
+            A = f_add(A, t);
+            M = f_sub(M, t);
+            break;
+        }
+        case T_ANTINAAB:
+            M = f_add(M, f_sub(beta, f_mul(Vv, beta)));
+            break;
+        case T_ADDC:
+            A = f_mul_add(cst[g0], beta, A);
+            M = f_add(M, beta);
+            break;
+        case T_MULC:
+            M = f_mul_add(cst[g0], beta, M);
+            break;
+        case T_COPY:
+            M = f_add(M, beta);
+            break;
+        case T_NOT:
+            A = f_add(A, beta);
+            M = f_sub(M, beta);
+            break;
+        case T_XOR: {
+            const F t = f_mul(Vv, beta);
+            A = f_add(A, t);
+            M = f_add(M, f_sub(beta, f_dbl(t)));
+            break;
+        }
+        default: break;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-k_init_phase1(CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, const F* __restrict__ assert_r,
-              F* const* __restrict__ vals, const uint32_t* __restrict__ sizes, const F* __restrict__ cst,
-              const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
-    const uint32_t n = S_pre * K;
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-        const uint32_t k = u / S_pre, u0 = u - k * S_pre;
+k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
+              EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
+              const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
+              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots) {
+    const uint64_t total = (uint64_t)n_items * K;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)k * n_items);
+        const RowItem I = items[it];
         F M = f_zero(), A = f_zero();
-        const uint32_t e0 = csr.off[u0], e1 = csr.off[u0 + 1];
-        for (uint32_t e = e0; e < e1; ++e) {
-            const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e], ty = tyl & 0x7f;
+        const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+        for (uint32_t e = I.e_begin; e < e1; ++e) {
+            const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e];
             const int l = (int)(tyl >> 8) - 1;
             F beta = eq_at(eqg, k * S_cur + g0);
             if (tyl & TY_ASSERT_BIT) beta = f_mul(beta, *assert_r);
             F Vv = f_zero();
             if (l >= 0) Vv = ld_f(vals[l] + (size_t)k * sizes[l] + csr.v0[e]);
-            switch (ty) {
-                case T_ADD:
-                    A = f_add(A, f_mul(Vv, beta));
-                    M = f_add(M, beta);
-                    break;
-                case T_SUB:
-                    A = f_sub(A, f_mul(Vv, beta));
-                    M = f_add(M, beta);
-                    break;
-                case T_ANTISUB:
-                    A = f_add(A, f_mul(Vv, beta));
-                    M = f_sub(M, beta);
-                    break;
-                case T_MUL:
-                    M = f_add(M, f_mul(Vv, beta));
-                    break;
-                case T_NAAB: {
-                    F t = f_mul(Vv, beta);
-                    A = f_add(A, t);
-                    M = f_sub(M, t);
-                    break;
-                }
-                case T_ANTINAAB:
-                    M = f_add(M, f_sub(beta, f_mul(Vv, beta)));
-                    break;
-                case T_ADDC:
-                    A = f_add(A, f_mul(cst[g0], beta));
-                    M = f_add(M, beta);
-                    break;
-                case T_MULC:
-                    M = f_add(M, f_mul(cst[g0], beta));
-                    break;
-                case T_COPY:
-                    M = f_add(M, beta);
-                    break;
-                case T_NOT:
-                    A = f_add(A, beta);
-                    M = f_sub(M, beta);
-                    break;
-                case T_XOR: {
-                    F t = f_mul(Vv, beta);
-                    A = f_add(A, t);
-                    M = f_add(M, f_sub(beta, f_dbl(t)));
-                    break;
-                }
-                default: break;
-            }
+            p1_gate(tyl, beta, Vv, cst, g0, M, A);
         }
+        const uint32_t slot = I.cnt_slot >> 8;
+        if (slot == 0) {
+            const uint32_t u = k * S_pre + I.row;
+            st_f(tV + u, ld_f(Vpre + u));
+            st_f(tM + u, M);
+            st_f(tA + u, A);
+        } else {
+            F* dst = partial + 2 * ((size_t)k * n_slots + (slot - 1));
+            st_f(dst, M);
+            st_f(dst + 1, A);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
+                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots) {
+    const uint64_t total = (uint64_t)n_rows * K;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)k * n_rows);
+        const LongRow R = rows[j];
+        F M = f_zero(), A = f_zero();
+        for (uint32_t s = R.slot_begin; s < R.slot_end; ++s) {
+            const F* src = partial + 2 * ((size_t)k * n_slots + s);
+            M = f_add(M, ld_f_cg(src));
+            A = f_add(A, ld_f_cg(src + 1));
+        }
+        const uint32_t u = k * S_pre + R.row;
         st_f(tV + u, ld_f(Vpre + u));
         st_f(tM + u, M);
         st_f(tA + u, A);
     }
 }
 
-// ------------------------------------------------------------------ K4: phase-2 table init
-// prover.cpp:291-361. Output index = (table slot, lv); lv = (K-1-k)*D + lv0.
+// prover.cpp:291-361. Output index = (table, lv); lv = (K-1-k)*D + lv0.
 // Per gate t = beta_g[g]*beta_u[u]; contributions are linear in t:  mult += cM[ty]*t, add += cA[ty]*t
 // with cM/cA built from V_u (see make_p2_coef).
 struct P2Table {
-    const uint32_t* off;     // CSR row offsets over lv0 [D + 1]
     const uint32_t* dadId;   // [D] template v of each subset slot
     uint32_t D;              // subset size of one instance
     uint32_t src_S;          // template size of the source layer
@@ -284,33 +328,58 @@ VP_D void make_p2_coef(const F& Vu, F* cM, F* cA) {
 }
 
 __global__ void __launch_bounds__(256)
-k_init_phase2(const P2Table* __restrict__ tabs, int n_tabs, const uint32_t* __restrict__ work_end, CsrP2 csr,
+k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table* __restrict__ tabs, CsrP2 csr,
               uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, const F* __restrict__ assert_r,
-              const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
+              const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA,
+              F* __restrict__ partial, uint32_t n_slots) {
     __shared__ F s_cM[12], s_cA[12];
-    __shared__ uint32_t s_wend[128];
     if (threadIdx.x == 0) make_p2_coef(*Vu_ptr, s_cM, s_cA);
-    for (int i = threadIdx.x; i < n_tabs; i += blockDim.x) s_wend[i] = work_end[i];
     __syncthreads();
-    const uint32_t total = s_wend[n_tabs - 1];
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-        int t = 0;
-        while (w >= s_wend[t]) ++t;
-        const P2Table T = tabs[t];
-        const uint32_t idx = w - (t ? s_wend[t - 1] : 0);   // lv of the replicated subset
-        const uint32_t kk = idx / T.D, lv0 = idx - kk * T.D, k = K - 1 - kk;
+    const uint64_t total = (uint64_t)n_items * K;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t kk = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)kk * n_items), k = K - 1 - kk;
+        const RowItem I = items[it];
         F M = f_zero(), A = f_zero();
-        const uint32_t e0 = T.off[lv0], e1 = T.off[lv0 + 1];
-        for (uint32_t e = e0; e < e1; ++e) {
+        const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+        for (uint32_t e = I.e_begin; e < e1; ++e) {
             const uint32_t g0 = csr.g0[e], tyb = csr.ty[e], ty = tyb & 0x7f;
             F bg = eq_at(eqg, k * S_cur + g0);
             if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
             const F tmp = f_mul(bg, eq_at(equ, k * S_pre + csr.u0[e]));
-            M = f_add(M, f_mul(tmp, s_cM[ty]));
-            if (ty != T_MUL && ty != T_NAAB) A = f_add(A, f_mul(tmp, s_cA[ty]));
+            M = f_mul_add(tmp, s_cM[ty], M);
+            if (ty != T_MUL && ty != T_NAAB) A = f_mul_add(tmp, s_cA[ty], A);
         }
-        const uint32_t o = T.tab_off + idx;
-        st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[lv0]));
+        const uint32_t slot = I.cnt_slot >> 8;
+        if (slot == 0) {
+            const P2Table T = tabs[I.tab];
+            const uint32_t o = T.tab_off + kk * T.D + I.row;
+            st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[I.row]));
+            st_f(tM + o, M);
+            st_f(tA + o, A);
+        } else {
+            F* dst = partial + 2 * ((size_t)kk * n_slots + (slot - 1));
+            st_f(dst, M);
+            st_f(dst + 1, A);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_combine_phase2(const LongRow* __restrict__ rows, uint32_t n_rows, const P2Table* __restrict__ tabs, uint32_t K,
+                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots) {
+    const uint64_t total = (uint64_t)n_rows * K;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t kk = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)kk * n_rows), k = K - 1 - kk;
+        const LongRow R = rows[j];
+        F M = f_zero(), A = f_zero();
+        for (uint32_t s = R.slot_begin; s < R.slot_end; ++s) {
+            const F* src = partial + 2 * ((size_t)kk * n_slots + s);
+            M = f_add(M, ld_f_cg(src));
+            A = f_add(A, ld_f_cg(src + 1));
+        }
+        const P2Table T = tabs[R.tab];
+        const uint32_t o = T.tab_off + kk * T.D + R.row;
+        st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[R.row]));
         st_f(tM + o, M);
         st_f(tA + o, A);
     }

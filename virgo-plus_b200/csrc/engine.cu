@@ -101,6 +101,9 @@ struct SumcheckPlan {
     int rounds = 0;
     std::vector<RoundPlan> r;
     uint32_t fin_begin = 0, n_fin = 0;
+    uint32_t rdev_begin = 0;
+    uint32_t max_work = 0;
+    double bytes = 0;   // algorithmic bytes of all rounds
     int fin_buf = 0;
     uint32_t cap0 = 0, cap1 = 0;   // entries needed in buffer 0 / 1
     std::vector<PlanTable> tabs;
@@ -110,6 +113,7 @@ struct PlanArena {  // descriptor pools shared by all plans of a context
     std::vector<TabDesc> tabs;
     std::vector<ColDesc> cols;
     std::vector<FinDesc> fins;
+    std::vector<RoundDev> rdev;
 };
 
 // tabs must be sorted by bits descending. fin_out[t] = transcript index of table t's final claim.
@@ -129,6 +133,7 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
     P.cap0 = o;
     P.tabs = tabs;
     int cur_buf = 0;
+    P.rdev_begin = (uint32_t)A.rdev.size();
     for (int j = 1; j <= rounds; ++j) {
         RoundPlan R;
         R.fold = j >= 2;
@@ -165,6 +170,9 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
         R.n_tabs = (uint32_t)A.tabs.size() - R.tab_begin;
         R.n_cols = (uint32_t)A.cols.size() - R.col_begin;
         R.work = work;
+        A.rdev.push_back(RoundDev{R.tab_begin, R.n_tabs, R.col_begin, R.n_cols, R.work, (uint32_t)R.in_buf});
+        P.max_work = std::max(P.max_work, R.work);
+        P.bytes += R.bytes;
         if (R.fold) {
             if (cur_buf == 0) P.cap1 = std::max(P.cap1, oo);
             else P.cap0 = std::max(P.cap0, oo);
@@ -285,6 +293,7 @@ struct Engine {
     DBuf<TabDesc> d_tabs;
     DBuf<ColDesc> d_cols;
     DBuf<FinDesc> d_fins;
+    DBuf<RoundDev> d_rdev;
     DBuf<EqBuild> d_eqb;
     std::vector<EqBuild> eq_descs;
     PlanArena arena;
@@ -373,7 +382,7 @@ struct Engine {
         eq_descs.push_back(b);
     }
     int n_sm = 148;
-    int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0;
+    int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
     template <class Kern>
     int occ_cap(Kern k) {  // resident blocks of 256 threads on the whole chip
         int occ = 0;
@@ -395,6 +404,9 @@ struct Engine {
     void do_init_liu(int i);
     void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
+    void do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F* keep);
+    uint32_t tail_work = 512;
+    bool use_phase_kernel = true;
     void prove_all();
     void set_chal(uint32_t idx, const vp_F* v, size_t cnt = 1) {
         CK(cudaMemcpyAsync(d_chal.p + idx, v, cnt * sizeof(F), cudaMemcpyHostToDevice, stream));
@@ -440,7 +452,13 @@ void Engine::build(const Circuit& circ, int dev) {
     cap_liu = occ_cap(k_init_liu);
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
-    max_grid = std::max({cap_round, cap_round1, cap_un, cap_dot});  // sizes the block-partials buffer
+    cap_phase = occ_cap(k_sumcheck_phase);
+    {
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (!coop) throw CudaError{"device does not support cooperative launches"};
+    }
+    max_grid = std::max({cap_round, cap_round1, cap_un, cap_dot, cap_phase});  // sizes the block-partials buffer
 
     // challenge / transcript index maps (draw order of verifier.cpp, see circuit.cpp draw_challenges)
     L.resize(n);
@@ -701,11 +719,12 @@ void Engine::build(const Circuit& circ, int dev) {
     d_tr.alloc(n_tr);
     d_scal.alloc(SC_N);
     d_claims.alloc((size_t)n + 1);
-    d_partials.alloc((size_t)3 * (size_t)max_grid);
+    d_partials.alloc((size_t)6 * (size_t)max_grid);
     d_counter.alloc(2);
     d_tabs.upload(arena.tabs, stream);
     d_cols.upload(arena.cols, stream);
     d_fins.upload(arena.fins, stream);
+    d_rdev.upload(arena.rdev, stream);
     d_eqb.upload(eq_descs, stream);
     CK(cudaMemsetAsync(d_chal.p, 0, (n_chal + 1) * sizeof(F), stream));
     CK(cudaMemsetAsync(d_tr.p, 0, n_tr * sizeof(F), stream));
@@ -872,6 +891,33 @@ void Engine::do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep) {
     ++launches;
 }
 
+// All rounds + the final claims of one sumcheck phase in one cooperative launch.
+void Engine::do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F* keep) {
+    PhaseArgs a;
+    for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
+    a.rounds = d_rdev.p + P.rdev_begin;
+    a.tabs = d_tabs.p;
+    a.cols = d_cols.p;
+    a.fins = d_fins.p + P.fin_begin;
+    a.n_rounds = (uint32_t)P.rounds;
+    a.n_fin = P.n_fin;
+    a.fin_buf = (uint32_t)P.fin_buf;
+    a.tail_work = tail_work;
+    a.chal = d_chal.p + ci;
+    a.add_term = scal(SC_ADD_TERM);
+    a.claims = d_claims.p;
+    a.out_poly = d_tr.p + tr_rounds;
+    a.transcript = d_tr.p;
+    a.keep = keep;
+    a.partials = d_partials.p;
+    const int grid = P.max_work > tail_work ? grid_for(P.max_work, cap_phase) : 1;
+    void* args[] = {&a};
+    size_t h = prof_begin(KC_ROUND_FOLD);
+    CK(cudaLaunchCooperativeKernel((const void*)k_sumcheck_phase, dim3(grid), dim3(256), args, 0, stream));
+    prof_end(h, P.bytes);
+    ++launches;
+}
+
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
     evaluate();
@@ -880,16 +926,25 @@ void Engine::prove_all() {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
         do_init_phase1(i);
-        for (int j = 1; j <= pb; ++j) do_round(D.plan1, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1));
-        do_finalize(D.plan1, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
+        if (use_phase_kernel) do_phase(D.plan1, D.ci_ru, D.tr_p1, scal(SC_VU));
+        else {
+            for (int j = 1; j <= pb; ++j) do_round(D.plan1, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1));
+            do_finalize(D.plan1, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
+        }
         if (m != -1) {
             do_init_phase2(i);
-            for (int j = 1; j <= m; ++j) do_round(D.plan2, j, D.ci_rv + (uint32_t)std::max(0, j - 2), D.tr_p2 + 3u * (uint32_t)(j - 1));
-            do_finalize(D.plan2, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
+            if (use_phase_kernel) do_phase(D.plan2, D.ci_rv, D.tr_p2, nullptr);
+            else {
+                for (int j = 1; j <= m; ++j) do_round(D.plan2, j, D.ci_rv + (uint32_t)std::max(0, j - 2), D.tr_p2 + 3u * (uint32_t)(j - 1));
+                do_finalize(D.plan2, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
+            }
         }
         do_init_liu(i);
-        for (int j = 1; j <= pb; ++j) do_round(D.plan3, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1));
-        do_finalize(D.plan3, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
+        if (use_phase_kernel) do_phase(D.plan3, D.ci_rliu, D.tr_liu, nullptr);
+        else {
+            for (int j = 1; j <= pb; ++j) do_round(D.plan3, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1));
+            do_finalize(D.plan3, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
+        }
     }
     do_input_mle();
     CK(cudaGetLastError());

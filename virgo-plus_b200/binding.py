@@ -74,6 +74,8 @@ def _declare(L):
     L.vp_nccl_unique_id.argtypes = [vp]
     L.vp_create_sharded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.vp_destroy.argtypes = [vp]
+    L.vp_shard_describe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.vp_shard_map_index.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
     L.vp_destroy.restype = None
     L.vp_set_inputs.argtypes = [vp, vp, C.c_size_t]
     L.vp_evaluate.argtypes = [vp]
@@ -296,13 +298,40 @@ class Circuit:
         )
 
 
-class Prover:
-    """vp_ctx: the GPU prover (mirrors the method names of the reference's `prover`, src/prover.h:12-42)."""
+def nccl_unique_id():
+    out = np.zeros(128, np.uint8)
+    _ck(lib().vp_nccl_unique_id(_ptr(out)))
+    return out
 
-    def __init__(self, circuit, device=0):
+
+def shard_describe(circuit, world, rank, layer, phase):
+    out = np.zeros(10 * 256, np.uint32)
+    n = C.c_size_t()
+    _ck(lib().vp_shard_describe(circuit.h, world, rank, layer, phase, _ptr(out), len(out), C.byref(n)))
+    keys = ("bits", "live", "sharded", "m", "first", "local_live", "local_len", "present", "n_blocks", "rot")
+    return [dict(zip(keys, (int(x) for x in out[10 * t:10 * t + 10]))) for t in range(n.value)]
+
+
+def shard_map_index(m, logG, first, idx):
+    loc = C.c_uint32()
+    rc = lib().vp_shard_map_index(m, logG, first, idx, C.byref(loc))
+    assert rc >= 0, "shard_global(shard_local(idx)) != idx"
+    return (rc == 1), loc.value
+
+
+class Prover:
+    """vp_ctx: the GPU prover (mirrors the method names of the reference's `prover`, src/prover.h:12-42).
+    world > 1: this process is `rank` of a sharded context (one process per GPU, whole-proof mode only)."""
+
+    def __init__(self, circuit, device=0, rank=0, world=1, nccl_id=None):
         self.circuit = circuit
         h = C.c_void_p()
-        _ck(lib().vp_create(circuit.h, device, C.byref(h)))
+        if world == 1:
+            _ck(lib().vp_create(circuit.h, device, C.byref(h)))
+        else:
+            nccl_id = np.ascontiguousarray(nccl_id, dtype=np.uint8)
+            assert len(nccl_id) == 128
+            _ck(lib().vp_create_sharded(circuit.h, device, rank, world, _ptr(nccl_id), C.byref(h)))
         self.h = h
 
     def close(self):

@@ -107,6 +107,7 @@ struct SumcheckPlan {
     int fin_buf = 0;
     uint32_t cap0 = 0, cap1 = 0;   // entries needed in buffer 0 / 1
     std::vector<PlanTable> tabs;
+    std::vector<uint32_t> end_off, end_live;  // where each table's stored values are after the last round (fin_buf)
 };
 
 struct PlanArena {  // descriptor pools shared by all plans of a context
@@ -114,7 +115,151 @@ struct PlanArena {  // descriptor pools shared by all plans of a context
     std::vector<ColDesc> cols;
     std::vector<FinDesc> fins;
     std::vector<RoundDev> rdev;
+    std::vector<FoldOnlyDesc> fo;
+    std::vector<MergeTab> mt;
 };
+
+// ------------------------------------------------------------------ a sumcheck phase, possibly sharded over G ranks
+// world == 1 (or a small phase): `planB` is the whole phase. Sharded: tables are block-cyclic over the ranks
+// (block = 2^m entries); `planA` = the m local rounds on this rank's blocks, then fold-only + all-gather +
+// merge, then `planB` = the remaining c rounds on the gathered tables (run identically by every rank).
+struct PhaseTabG {   // one table of the phase, global view
+    int bits;        // ceil_log2 of the padded size (empty tables do not appear)
+    uint32_t live;   // live entries
+    int claim_slot;  // claims[] slot, or -1
+    uint32_t fin_out;  // transcript index of its final claim
+};
+struct PhasePlan {
+    bool sharded = false;
+    int rounds = 0, m = 0;
+    SumcheckPlan planA, planB;
+    std::vector<ShardMap> maps;        // per global table
+    std::vector<uint32_t> tab_off;     // offset of the table's level-0 values in buffer 0 on this rank
+    std::vector<uint32_t> local_len;   // padded local length (multiple of the block size when sharded)
+    std::vector<uint8_t> present;
+    uint32_t fo_begin = 0, n_fo = 0, mt_begin = 0, n_mt = 0;
+    uint32_t rec_len = 0, sc_base = 0, n_poly = 0, n_claims = 0;
+    uint32_t cap0 = 0, cap1 = 0;
+    double bytes_total() const { return planA.bytes + planB.bytes; }
+};
+
+static constexpr int CYC_BITS = 10;   // a sharded table is dealt out in 2^CYC_BITS blocks (the largest table of the phase)
+
+static uint32_t local_live_of(uint32_t n, int m, uint32_t G, uint32_t first, uint32_t* n_local_blocks) {
+    const uint32_t bs = 1u << m, n_blocks = (n + bs - 1) >> m;
+    const uint32_t cnt = n_blocks > first ? (n_blocks - first + G - 1) / G : 0;
+    if (n_local_blocks) *n_local_blocks = cnt;
+    if (!cnt) return 0;
+    const uint32_t last = first + (cnt - 1) * G, partial = n & (bs - 1);
+    return (cnt - 1) * bs + ((last == n_blocks - 1 && partial) ? partial : bs);
+}
+
+static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const std::vector<uint32_t>& fin_out,
+                               PlanArena& A);
+
+// empty_fin_out: transcript slots of tables that never enter a plan (empty subsets): claim 0
+static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const std::vector<uint32_t>& empty_fin_out, int world,
+                            int rank, int n_claims, PlanArena& A) {
+    PhasePlan P;
+    P.rounds = rounds;
+    const size_t nt = T.size();
+    P.maps.assign(nt, ShardMap{31, 0, 0, 0});
+    P.tab_off.assign(nt, 0);
+    P.local_len.assign(nt, 0);
+    P.present.assign(nt, 1);
+    int logG = 0;
+    while ((1 << logG) < world) ++logG;
+    const int c = std::min(rounds, std::max(CYC_BITS, logG));
+    const int m = rounds - c;
+    P.sharded = world > 1 && m >= 2;
+    auto add_empty_fins = [&](SumcheckPlan& pl) {
+        for (uint32_t o : empty_fin_out) {
+            A.fins.push_back(FinDesc{0, 0, -1, o});
+            ++pl.n_fin;
+        }
+    };
+    if (!P.sharded) {
+        std::vector<PlanTable> tabs;
+        std::vector<uint32_t> fo;
+        for (const auto& t : T) {
+            tabs.push_back(PlanTable{t.bits, t.live, t.claim_slot, 0});
+            fo.push_back(t.fin_out);
+        }
+        if (tabs.empty()) {  // phase without any table (cannot happen for phase 1 / Liu)
+            P.planB.rounds = rounds;
+            P.planB.fin_begin = (uint32_t)A.fins.size();
+            P.planB.rdev_begin = (uint32_t)A.rdev.size();
+        } else P.planB = build_plan(tabs, rounds, fo, A);
+        add_empty_fins(P.planB);
+        for (size_t t = 0; t < nt; ++t) {
+            P.tab_off[t] = P.planB.tabs[t].off0;
+            P.local_len[t] = T[t].live;
+        }
+        P.cap0 = P.planB.cap0;
+        P.cap1 = P.planB.cap1;
+        return P;
+    }
+    P.m = m;
+    const uint32_t G = (uint32_t)world;
+    std::vector<PlanTable> tabsA, tabsB;
+    std::vector<uint32_t> finB, idxA(nt, ~0u);
+    std::vector<FinDesc> collapsed_fins;
+    struct Dist { size_t t; uint32_t n_blocks, local_blocks, cnt; };
+    std::vector<Dist> dist;
+    for (size_t t = 0; t < nt; ++t) {
+        const uint32_t rot = (uint32_t)(t % G), first = ((uint32_t)rank + G - rot) % G;
+        P.maps[t] = ShardMap{(uint32_t)m, (uint32_t)logG, first, 0};
+        if (T[t].bits >= m) {  // distributed: stays alive through the m local rounds
+            uint32_t lb = 0;
+            const uint32_t ll = local_live_of(T[t].live, m, G, first, &lb);
+            const uint32_t nb = (T[t].live + (1u << m) - 1) >> m;
+            idxA[t] = (uint32_t)tabsA.size();
+            tabsA.push_back(PlanTable{99, ll, -1, 0});
+            P.local_len[t] = lb << m;
+            dist.push_back(Dist{t, nb, lb, (nb + G - 1) / G});
+            tabsB.push_back(PlanTable{T[t].bits - m, nb, T[t].claim_slot, 0});
+            finB.push_back(T[t].fin_out);
+        } else {               // a single block: lives (and collapses) entirely on its owner
+            P.present[t] = first == 0;
+            if (P.present[t]) {
+                idxA[t] = (uint32_t)tabsA.size();
+                tabsA.push_back(PlanTable{T[t].bits, T[t].live, T[t].claim_slot, 0});
+                P.local_len[t] = T[t].live;
+            }
+            collapsed_fins.push_back(FinDesc{0, 0, T[t].claim_slot, T[t].fin_out});
+        }
+    }
+    if (tabsA.empty()) tabsA.push_back(PlanTable{99, 0, -1, 0});
+    P.planA = build_plan(tabsA, m, {}, A);
+    for (size_t t = 0; t < nt; ++t)
+        if (idxA[t] != ~0u) P.tab_off[t] = P.planA.tabs[idxA[t]].off0;
+    P.planB = build_plan(tabsB, rounds - m, finB, A);
+    for (const FinDesc& f : collapsed_fins) {
+        A.fins.push_back(f);
+        ++P.planB.n_fin;
+    }
+    add_empty_fins(P.planB);
+    // gather record: per distributed table three regions of cnt entries, then the scalars
+    P.fo_begin = (uint32_t)A.fo.size();
+    P.mt_begin = (uint32_t)A.mt.size();
+    uint32_t base = 0;
+    for (size_t q = 0; q < dist.size(); ++q) {
+        const Dist& d = dist[q];
+        const uint32_t ia = idxA[d.t];
+        A.fo.push_back(FoldOnlyDesc{P.planA.end_off[ia], P.planA.end_live[ia], d.local_blocks, base, d.cnt, 1});
+        A.mt.push_back(MergeTab{base, d.cnt, d.n_blocks, P.planB.tabs[q].off0, (uint32_t)(d.t % G), 0});
+        base += 3 * d.cnt;
+    }
+    P.n_fo = (uint32_t)dist.size();
+    P.n_mt = (uint32_t)dist.size();
+    P.sc_base = base;
+    P.n_poly = 3u * (uint32_t)m;
+    P.n_claims = (uint32_t)n_claims;
+    P.rec_len = base + P.n_poly + 1 + P.n_claims;
+    P.cap0 = std::max(P.planA.cap0, P.planB.cap0);
+    P.cap1 = std::max(P.planA.cap1, P.planB.cap1);
+    return P;
+}
 
 // tabs must be sorted by bits descending. fin_out[t] = transcript index of table t's final claim.
 static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const std::vector<uint32_t>& fin_out,
@@ -181,7 +326,10 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
         P.r.push_back(R);
     }
     P.fin_buf = cur_buf;
+    P.end_off = off;
+    P.end_live = live;
     P.fin_begin = (uint32_t)A.fins.size();
+    if (fin_out.empty()) return P;  // stage A of a sharded phase: no final claims
     for (size_t t = 0; t < nt; ++t) {
         FinDesc f;
         f.out_idx = fin_out[t];
@@ -251,14 +399,12 @@ struct LayerDev {
     DBuf<uint32_t> un_g0, un_u0;
     DBuf<uint8_t> un_ty;
     uint32_t n_unary = 0;
-    uint32_t un_dst_off = 0;     // buffer-0 offset of entry 0 of the (i-1) table
-    bool un_dst_needs_zero = false;
     // Liu (tables into layer pre = i-1 from all layers j >= i)
     DBuf<uint32_t> liu_off;
     DBuf<LiuEntry> liu_ent;
     std::vector<int> liu_j;      // source layers j of the eq tables, in eq_id order
     // plans
-    SumcheckPlan plan1, plan2, plan3;
+    PhasePlan ph1, ph2, ph3;
     int max_dad_bl = -1;
     // eq build descriptor slices (indices into Engine::eq_descs)
     uint32_t eqb_g = 0, eqb_u = 0, eqb_liu = 0, n_eqb_liu = 0;
@@ -269,11 +415,59 @@ struct LayerDev {
     uint32_t tr_p1 = 0, tr_claim_u = 0, tr_p2 = 0, tr_claims_v = 0, tr_liu = 0, tr_claim_liu = 0;
 };
 
-struct NcclApi;
+// ------------------------------------------------------------------ NCCL, loaded at run time (torch's bundled
+// libnccl.so.2 is already in the process when the caller imported torch; otherwise the system one)
+typedef void* vp_ncclComm_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(vp_ncclComm_t*, int, /* ncclUniqueId by value: 128 bytes */ struct NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, vp_ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(vp_ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId {
+    char internal[128];
+};
+static NcclApi g_nccl;
+static void nccl_load() {
+    if (g_nccl.h) return;
+    const char* cands[] = {getenv("VP_NCCL_LIB"), "libnccl.so.2", "/usr/lib/x86_64-linux-gnu/libnccl.so.2", "libnccl.so"};
+    for (const char* c : cands) {
+        if (!c) continue;
+        g_nccl.h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) throw CudaError{std::string("cannot load libnccl.so.2 (set VP_NCCL_LIB): ") + dlerror()};
+    auto sym = [&](const char* n) {
+        void* p = dlsym(g_nccl.h, n);
+        if (!p) throw CudaError{std::string("libnccl: missing symbol ") + n};
+        return p;
+    };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(vp_ncclComm_t*, int, NcclId, int))sym("ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, vp_ncclComm_t, cudaStream_t))sym("ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(vp_ncclComm_t))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+}
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0) {                                                                                   \
+            char b_[300];                                                                                \
+            snprintf(b_, sizeof b_, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+            throw CudaError{b_};                                                                         \
+        }                                                                                                \
+    } while (0)
 
 struct Engine {
     Circuit C;
     int device = 0;
+    int world = 1, rank = 0;
+    vp_ncclComm_t comm = nullptr;
+    DBuf<F> d_send, d_recv;
+    DBuf<FoldOnlyDesc> d_fo;
+    DBuf<MergeTab> d_mt;
     int n = 0;            // layers
     uint32_t K = 1;
     int max_bl = 0;
@@ -303,7 +497,7 @@ struct Engine {
     size_t n_chal = 0, n_tr = 0;
 
     // scalars in d_scal
-    enum { SC_ADD_TERM = 0, SC_VU = 1, SC_ZERO = 2, SC_N = 4 };
+    enum { SC_ADD_TERM = 0, SC_VU = 1, SC_UNARY = 2, SC_N = 4 };
 
     // protocol state (interactive API)
     int cur_layer = 0;     // sumcheckLayerId
@@ -361,6 +555,7 @@ struct Engine {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream && own_stream) cudaStreamDestroy(stream);
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     }
 
     // ---------------------------------------------------------------- helpers
@@ -392,7 +587,7 @@ struct Engine {
     int grid_for(uint32_t work, int cap) const { return (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(work, 256), (uint32_t)cap)); }
     F* scal(int i) { return d_scal.p + i; }
 
-    void build(const Circuit& circ, int dev);
+    void build(const Circuit& circ, int dev, int world_, int rank_, const uint8_t* nccl_id);
     void load_inputs(const uint64_t* host, size_t cnt, bool from_host);
     void evaluate();
     void run_eq(uint32_t first, uint32_t count);
@@ -402,9 +597,11 @@ struct Engine {
     void do_init_phase1(int i);
     void do_init_phase2(int i);
     void do_init_liu(int i);
-    void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out);
+    void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
-    void do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F* keep);
+    void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init);
+    void launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
+                             F* claims, F* out_poly, F* keep);
     uint32_t tail_work = 512;
     bool use_phase_kernel = true;
     void prove_all();
@@ -424,9 +621,13 @@ struct Engine {
 };
 
 // ------------------------------------------------------------------ build: upload wiring, CSRs, plans
-void Engine::build(const Circuit& circ, int dev) {
+void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const uint8_t* nccl_id) {
     C = circ;
     device = dev;
+    world = world_;
+    rank = rank_;
+    if (world < 1 || (world & (world - 1)) || world > 8 || rank < 0 || rank >= world)
+        throw CudaError{"sharded context: world must be 1, 2, 4 or 8 and 0 <= rank < world"};
     n = C.n_layers();
     K = (uint32_t)C.instances;
     max_bl = C.max_bit_length();
@@ -505,7 +706,7 @@ void Engine::build(const Circuit& circ, int dev) {
     d_sizes.upload(h_sizes, stream);
     d_inputs.alloc(C.layer_size(0));
 
-    uint32_t cap0 = 4, cap1 = 4;
+    uint32_t cap0 = 4, cap1 = 4, max_rec = 0;
     size_t max_partial = 2;
     eqb_out = (uint32_t)eq_descs.size();
     add_eq_build(2, ci_out, C.bit_length(n - 1), -1);
@@ -557,11 +758,11 @@ void Engine::build(const Circuit& circ, int dev) {
         const int pb = C.bit_length(i - 1);
         // plans for phase 1 and Liu: one table over layer i-1
         {
-            std::vector<PlanTable> t1{{pb, (uint32_t)C.layer_size(i - 1), -1, 0}};
-            D.plan1 = build_plan(t1, pb, {D.tr_claim_u}, arena);
-            D.plan3 = build_plan(t1, pb, {D.tr_claim_liu}, arena);
-            cap0 = std::max(cap0, std::max(D.plan1.cap0, D.plan3.cap0));
-            cap1 = std::max(cap1, std::max(D.plan1.cap1, D.plan3.cap1));
+            D.ph1 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_u}}, pb, {}, world, rank, n, arena);
+            D.ph3 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_liu}}, pb, {}, world, rank, n, arena);
+            cap0 = std::max(cap0, std::max(D.ph1.cap0, D.ph3.cap0));
+            cap1 = std::max(cap1, std::max(D.ph1.cap1, D.ph3.cap1));
+            max_rec = std::max(max_rec, std::max(D.ph1.rec_len, D.ph3.rec_len));
         }
         D.eqb_g = (uint32_t)eq_descs.size();
         add_eq_build(0, D.ci_g, C.bit_length(i), -1);
@@ -570,32 +771,21 @@ void Engine::build(const Circuit& circ, int dev) {
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
-            // table order: bits descending (stable by l)
+            // table order: bits descending (stable by l); empty subsets get no table (their claim is 0)
             std::vector<int> order;
             for (int l = 0; l < i; ++l)
-                if (T.dadSize[l] > 0 || l == i - 1) order.push_back(l);
-            auto bits_of = [&](int l) { return std::max(0, C.dad_bit_length(i, l)); };
+                if (T.dadSize[l] > 0) order.push_back(l);
+            auto bits_of = [&](int l) { return C.dad_bit_length(i, l); };
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bits_of(a) > bits_of(b); });
-            std::vector<PlanTable> tabs;
-            std::vector<uint32_t> fin_out;
-            for (int l : order) {
-                uint32_t live = (uint32_t)C.dad_size(i, l);
-                if (live == 0) live = 1;  // the (i-1) table always has entry 0 (unary gates land there)
-                tabs.push_back({bits_of(l), live, l, 0});
-                fin_out.push_back(D.tr_claims_v + (uint32_t)l);
-            }
-            // empty subsets other than i-1: claim is 0; give them a FinDesc with n_vals = 0
-            std::vector<int> empties;
+            std::vector<PhaseTabG> tabs;
+            for (int l : order) tabs.push_back(PhaseTabG{bits_of(l), (uint32_t)C.dad_size(i, l), l, D.tr_claims_v + (uint32_t)l});
+            std::vector<uint32_t> empties;
             for (int l = 0; l < i; ++l)
-                if (T.dadSize[l] == 0 && l != i - 1) empties.push_back(l);
-            D.plan2 = build_plan(tabs, m, fin_out, arena);
-            for (int l : empties) {
-                FinDesc f{0, 0, -1, D.tr_claims_v + (uint32_t)l};
-                arena.fins.push_back(f);
-                ++D.plan2.n_fin;
-            }
-            cap0 = std::max(cap0, D.plan2.cap0);
-            cap1 = std::max(cap1, D.plan2.cap1);
+                if (T.dadSize[l] == 0) empties.push_back(D.tr_claims_v + (uint32_t)l);
+            D.ph2 = make_phase(tabs, m, empties, world, rank, n, arena);
+            cap0 = std::max(cap0, D.ph2.cap0);
+            cap1 = std::max(cap1, D.ph2.cap1);
+            max_rec = std::max(max_rec, D.ph2.rec_len);
             // CSR per table over lv0
             std::vector<uint32_t> dad_all, g0, u0;
             std::vector<uint8_t> tyv;
@@ -604,11 +794,6 @@ void Engine::build(const Circuit& circ, int dev) {
             for (size_t t = 0; t < order.size(); ++t) {
                 const int l = order[t];
                 const uint32_t Dsz = (uint32_t)T.dadSize[l];
-                if (l == i - 1) {
-                    D.un_dst_off = D.plan2.tabs[t].off0;
-                    D.un_dst_needs_zero = (Dsz == 0);
-                }
-                if (Dsz == 0) continue;
                 std::vector<uint32_t> cnt(Dsz + 1, 0);
                 for (uint32_t g = 0; g < S; ++g)
                     if (T.l[g] == l && is_binary(T.ty[g])) ++cnt[T.lv[g] + 1];
@@ -629,7 +814,9 @@ void Engine::build(const Circuit& circ, int dev) {
                 memset(&pt, 0, sizeof pt);
                 pt.D = Dsz;
                 pt.src_S = (uint32_t)C.layers[l].size;
-                pt.tab_off = D.plan2.tabs[t].off0;
+                pt.tab_off = D.ph2.tab_off[t];
+                pt.owned = D.ph2.present[t];
+                pt.sm = D.ph2.maps[t];
                 pt.src_val = val[l].p;
                 // stash the offset into the concatenated array; patched to a pointer after upload
                 pt.dadId = (const uint32_t*)(uintptr_t)dad_all.size();
@@ -715,6 +902,16 @@ void Engine::build(const Circuit& circ, int dev) {
         bufA[b].alloc(cap);
     }
     d_rowpart.alloc(max_partial);
+    if (world > 1) {
+        d_send.alloc(std::max<uint32_t>(max_rec, 1));
+        d_recv.alloc((size_t)std::max<uint32_t>(max_rec, 1) * world);
+        d_fo.upload(arena.fo, stream);
+        d_mt.upload(arena.mt, stream);
+        nccl_load();
+        NcclId id;
+        memcpy(id.internal, nccl_id, 128);
+        NCK(g_nccl.CommInitRank(&comm, world, id, rank));
+    }
     d_chal.alloc(n_chal + 1);
     d_tr.alloc(n_tr);
     d_scal.alloc(SC_N);
@@ -792,11 +989,12 @@ void Engine::do_init_phase1(int i) {
     size_t h = prof_begin(KC_INIT1);
     k_init_phase1<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1), 256, 0, stream>>>(
         D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
-        d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p1_nslots);
+        d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
+        bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0]);
     if (D.p1_long.n) {
         k_combine_phase1<<<grid_for((uint32_t)(D.p1_long.n * K), cap_comb), 256, 0, stream>>>(
-            D.p1_long.p, (uint32_t)D.p1_long.n, S_pre, K, val[i - 1].p, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p,
-            D.p1_nslots);
+            D.p1_long.p, (uint32_t)D.p1_long.n, S_pre, K, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0],
+            bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0]);
         ++launches;
     }
     // per output: V read + 3 table writes; per gate: one gathered operand
@@ -811,11 +1009,6 @@ void Engine::do_init_phase2(int i) {
     run_eq(D.eqb_u, 2);
     have_equ = true;
     const EqTab eqg = eqtab(0, C.bit_length(i)), equ = eqtab(1, C.bit_length(i - 1));
-    if (D.un_dst_needs_zero) {
-        CK(cudaMemsetAsync(bufV[0].p + D.un_dst_off, 0, sizeof(F), stream));
-        CK(cudaMemsetAsync(bufM[0].p + D.un_dst_off, 0, sizeof(F), stream));
-        CK(cudaMemsetAsync(bufA[0].p + D.un_dst_off, 0, sizeof(F), stream));
-    }
     if (D.p2_ntabs > 0) {
         CsrP2 csr{D.p2_g0.p, D.p2_u0.p, D.p2_ty.p};
         const uint64_t work = (uint64_t)D.p2_items.n * K;
@@ -831,14 +1024,17 @@ void Engine::do_init_phase2(int i) {
         prof_end(h, (double)D.p2_out_entries * 64.0 + (double)D.p2_gates * K * 16.0);
         ++launches;
     }
-    if (D.n_unary > 0) {
+    // unary gates: their sum starts the phase's add_term (see k_phase2_unary); each rank sums its instance slice
+    const bool slice = D.ph2.sharded;  // a replicated phase needs the whole sum on every rank
+    const uint32_t k0 = slice ? (uint32_t)((uint64_t)K * rank / world) : 0, k1 = slice ? (uint32_t)((uint64_t)K * (rank + 1) / world) : K;
+    if (D.n_unary > 0 && k1 > k0) {
         CsrUnary un{D.un_g0.p, D.un_u0.p, D.un_ty.p, D.n_unary};
-        const uint64_t tot = (uint64_t)D.n_unary * K;
+        const uint64_t tot = (uint64_t)D.n_unary * (k1 - k0);
         k_phase2_unary<<<grid_for((uint32_t)std::min<uint64_t>(tot, 0xffffffffu), cap_un), 256, 0, stream>>>(
-            un, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU), D.c.p, bufA[0].p + D.un_dst_off,
-            d_partials.p, d_counter.p);
+            un, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU), D.c.p, scal(SC_UNARY), d_partials.p,
+            d_counter.p, k0, k1);
         ++launches;
-    }
+    } else CK(cudaMemsetAsync(scal(SC_UNARY), 0, sizeof(F), stream));
 }
 
 void Engine::do_init_liu(int i) {
@@ -849,15 +1045,16 @@ void Engine::do_init_liu(int i) {
     run_eq(D.eqb_liu, D.n_eqb_liu);
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
-    k_init_liu<<<grid_for(tot, cap_liu), 256, 0, stream>>>(D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K,
-                                                   eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
-                                                   bufV[0].p, bufM[0].p, bufA[0].p);
-    prof_end(h, (double)tot * 64.0);
+    const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
+    k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
+        D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
+        bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local);
+    prof_end(h, (double)n_local * 64.0);
     ++launches;
 }
 
 // round j (1-based) of plan P; ci_prev = challenge index of the previous round's challenge (j >= 2)
-void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out) {
+void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init) {
     const RoundPlan& R = P.r[j - 1];
     RoundArgs a;
     const int ib = R.in_buf, ob = ib ^ 1;
@@ -875,6 +1072,7 @@ void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t t
     a.counter = d_counter.p;
     a.first_round = j == 1;
     a.reset_add_term = j == 1;
+    a.at_init = at_init;
     const int grid = grid_for(R.work, R.fold ? cap_round : cap_round1);
     size_t h = prof_begin(R.fold ? KC_ROUND_FOLD : KC_ROUND_FIRST);
     if (R.fold) k_round<true><<<grid, 256, 0, stream>>>(a);
@@ -891,8 +1089,9 @@ void Engine::do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep) {
     ++launches;
 }
 
-// All rounds + the final claims of one sumcheck phase in one cooperative launch.
-void Engine::do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F* keep) {
+// One cooperative launch of k_sumcheck_phase over `P`.
+void Engine::launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
+                                 F* claims, F* out_poly, F* keep) {
     PhaseArgs a;
     for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
     a.rounds = d_rdev.p + P.rdev_begin;
@@ -903,10 +1102,12 @@ void Engine::do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F*
     a.n_fin = P.n_fin;
     a.fin_buf = (uint32_t)P.fin_buf;
     a.tail_work = tail_work;
+    a.round_base = round_base;
+    a.at_init = at_init;
     a.chal = d_chal.p + ci;
-    a.add_term = scal(SC_ADD_TERM);
-    a.claims = d_claims.p;
-    a.out_poly = d_tr.p + tr_rounds;
+    a.add_term = add_term_out;
+    a.claims = claims;
+    a.out_poly = out_poly;
     a.transcript = d_tr.p;
     a.keep = keep;
     a.partials = d_partials.p;
@@ -918,6 +1119,48 @@ void Engine::do_phase(const SumcheckPlan& P, uint32_t ci, uint32_t tr_rounds, F*
     ++launches;
 }
 
+// All rounds + the final claims of one sumcheck phase. Unsharded: one cooperative launch. Sharded: the m local
+// rounds on this rank's blocks, fold-only, ONE all-gather of the per-rank records (collapsed blocks + partial
+// round polynomials + partial add_term + claims), merge, then the remaining rounds replicated on every rank.
+void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init) {
+    if (!P.sharded) {
+        launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
+        return;
+    }
+    F* rec = d_send.p;
+    F* sc = rec + P.sc_base;
+    CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
+    // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
+    launch_phase_kernel(P.planA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr);
+    if (P.n_fo) {
+        const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
+        dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);
+        const int fb = P.planA.fin_buf;
+        k_fold_only<<<grid, 128, 0, stream>>>(d_fo.p + P.fo_begin, (int)P.n_fo, bufV[fb].p, bufM[fb].p, bufA[fb].p,
+                                             d_chal.p + ci + (uint32_t)(P.m - 1), rec);
+        ++launches;
+    }
+    NCK(g_nccl.AllGather(rec, d_recv.p, (size_t)P.rec_len * 2, /*ncclUint64*/ 5, comm, stream));
+    MergeArgs ma;
+    ma.recv = d_recv.p;
+    ma.rec_len = P.rec_len;
+    ma.G = (uint32_t)world;
+    ma.tabs = d_mt.p + P.mt_begin;
+    ma.n_tabs = P.n_mt;
+    ma.sc_base = P.sc_base;
+    ma.n_poly = P.n_poly;
+    ma.n_claims = P.n_claims;
+    ma.outV = bufV[0].p; ma.outM = bufM[0].p; ma.outA = bufA[0].p;
+    ma.out_poly = d_tr.p + tr_rounds;
+    ma.add_term = scal(SC_ADD_TERM);
+    ma.claims = d_claims.p;
+    k_shard_merge<<<8, 256, 0, stream>>>(ma);
+    ++launches;
+    // stage B: replicated; starts from the summed add_term
+    launch_phase_kernel(P.planB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
+                        d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep);
+}
+
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
     evaluate();
@@ -926,24 +1169,24 @@ void Engine::prove_all() {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
         do_init_phase1(i);
-        if (use_phase_kernel) do_phase(D.plan1, D.ci_ru, D.tr_p1, scal(SC_VU));
+        if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, scal(SC_VU), nullptr);
         else {
-            for (int j = 1; j <= pb; ++j) do_round(D.plan1, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1));
-            do_finalize(D.plan1, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
+            for (int j = 1; j <= pb; ++j) do_round(D.ph1.planB, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1), nullptr);
+            do_finalize(D.ph1.planB, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
         }
         if (m != -1) {
             do_init_phase2(i);
-            if (use_phase_kernel) do_phase(D.plan2, D.ci_rv, D.tr_p2, nullptr);
+            if (use_phase_kernel) do_phase(D.ph2, D.ci_rv, D.tr_p2, nullptr, scal(SC_UNARY));
             else {
-                for (int j = 1; j <= m; ++j) do_round(D.plan2, j, D.ci_rv + (uint32_t)std::max(0, j - 2), D.tr_p2 + 3u * (uint32_t)(j - 1));
-                do_finalize(D.plan2, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
+                for (int j = 1; j <= m; ++j) do_round(D.ph2.planB, j, D.ci_rv + (uint32_t)std::max(0, j - 2), D.tr_p2 + 3u * (uint32_t)(j - 1), scal(SC_UNARY));
+                do_finalize(D.ph2.planB, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
             }
         }
         do_init_liu(i);
-        if (use_phase_kernel) do_phase(D.plan3, D.ci_rliu, D.tr_liu, nullptr);
+        if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr);
         else {
-            for (int j = 1; j <= pb; ++j) do_round(D.plan3, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1));
-            do_finalize(D.plan3, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
+            for (int j = 1; j <= pb; ++j) do_round(D.ph3.planB, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1), nullptr);
+            do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
         }
     }
     do_input_mle();
@@ -1150,17 +1393,75 @@ extern "C" int vp_create(const vp_circuit* c, int device, vp_ctx** out) {
     if (!c || !out) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN
     std::unique_ptr<vp_ctx> ctx(new vp_ctx());
-    ctx->e.build(c->c, device);
+    ctx->e.build(c->c, device, 1, 0, nullptr);
     *out = ctx.release();
     return VP_OK;
     API_END
 }
 extern "C" int vp_nccl_unique_id(uint8_t out[128]) {
-    (void)out;
-    return fail(VP_ERR_ARG, "sharded contexts are not built yet");
+    if (!out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    nccl_load();
+    NcclId id;
+    memset(&id, 0, sizeof id);
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return VP_OK;
+    API_END
 }
-extern "C" int vp_create_sharded(const vp_circuit*, int, int, int, const uint8_t*, vp_ctx**) {
-    return fail(VP_ERR_ARG, "sharded contexts are not built yet");
+extern "C" int vp_create_sharded(const vp_circuit* c, int device, int rank, int world, const uint8_t nccl_id[128],
+                                 vp_ctx** out) {
+    if (!c || !out || (world > 1 && !nccl_id)) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    std::unique_ptr<vp_ctx> ctx(new vp_ctx());
+    ctx->e.build(c->c, device, world, rank, nccl_id);
+    *out = ctx.release();
+    return VP_OK;
+    API_END
+}
+// Host-only view of how one phase is dealt out to the ranks (tests of the partition logic).
+// out: per table 10 values {bits, live, sharded, m, first, local_live, local_len, present, n_blocks, rot}.
+extern "C" int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int phase, uint32_t* out, size_t cap,
+                                 size_t* n_tables) {
+    if (!c || !out || !n_tables) return fail(VP_ERR_ARG, "null argument");
+    const Circuit& C = c->c;
+    if (layer < 1 || layer >= C.n_layers() || phase < 1 || phase > 3) return fail(VP_ERR_ARG, "bad layer / phase");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(VP_ERR_ARG, "bad world / rank");
+    std::vector<PhaseTabG> T;
+    int rounds;
+    if (phase == 2) {
+        rounds = C.max_dad_bit_length(layer);
+        if (rounds == -1) { *n_tables = 0; return VP_OK; }
+        std::vector<int> order;
+        for (int l = 0; l < layer; ++l)
+            if (C.layers[layer].dadSize[l] > 0) order.push_back(l);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return C.dad_bit_length(layer, a) > C.dad_bit_length(layer, b); });
+        for (int l : order) T.push_back(PhaseTabG{C.dad_bit_length(layer, l), (uint32_t)C.dad_size(layer, l), l, 0});
+    } else {
+        rounds = C.bit_length(layer - 1);
+        T.push_back(PhaseTabG{rounds, (uint32_t)C.layer_size(layer - 1), -1, 0});
+    }
+    PlanArena A;
+    PhasePlan P = make_phase(T, rounds, {}, world, rank, C.n_layers(), A);
+    if (cap < T.size() * 10) return fail(VP_ERR_ARG, "output buffer too small");
+    for (size_t t = 0; t < T.size(); ++t) {
+        uint32_t lb = 0, ll = T[t].live;
+        if (P.sharded && T[t].bits >= P.m) ll = local_live_of(T[t].live, P.m, (uint32_t)world, P.maps[t].first, &lb);
+        else if (P.sharded && !P.present[t]) ll = 0;
+        uint32_t* o = out + t * 10;
+        o[0] = (uint32_t)T[t].bits; o[1] = T[t].live; o[2] = P.sharded; o[3] = (uint32_t)P.m; o[4] = P.maps[t].first;
+        o[5] = ll; o[6] = P.local_len[t]; o[7] = P.present[t];
+        o[8] = P.sharded ? (T[t].live + (1u << P.m) - 1) >> P.m : 1; o[9] = (uint32_t)(t % (size_t)world);
+    }
+    *n_tables = T.size();
+    return VP_OK;
+}
+extern "C" int vp_shard_map_index(uint32_t m, uint32_t logG, uint32_t first, uint32_t idx, uint32_t* local) {
+    uint32_t loc = 0;
+    const bool mine = shard_local(ShardMap{m, logG, first, 0}, idx, loc);
+    if (local) *local = loc;
+    if (mine && shard_global(ShardMap{m, logG, first, 0}, loc) != idx) return -100;
+    return mine ? 1 : 0;
 }
 extern "C" void vp_destroy(vp_ctx* ctx) {
     if (!ctx) return;
@@ -1243,6 +1544,7 @@ extern "C" int vp_init_phase1(vp_ctx* ctx, const vp_F* assert_random) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "a sharded context only supports vp_prove (whole proof); the method-by-method entry points need one GPU");
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_phase1 outside a layer");
     e.set_chal(e.L[e.cur_layer].ci_assert, assert_random);
     e.do_init_phase1(e.cur_layer);
@@ -1288,7 +1590,7 @@ static uint32_t phase_ci(Engine& e, int phase) {
 }
 static const SumcheckPlan& phase_plan(Engine& e, int phase) {
     LayerDev& D = e.L[e.cur_layer];
-    return phase == 1 ? D.plan1 : phase == 2 ? D.plan2 : D.plan3;
+    return phase == 1 ? D.ph1.planB : phase == 2 ? D.ph2.planB : D.ph3.planB;
 }
 extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_F out_abc[3]) {
     if (!ctx || !previous_random || !out_abc) return fail(VP_ERR_ARG, "null argument");
@@ -1303,7 +1605,7 @@ extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_
     if (e.round >= 1) e.set_chal(ci + (uint32_t)(e.round - 1), previous_random);  // r_arr.at(round-1) = prev (prover.cpp:441)
     ++e.round;
     const uint32_t tr = (phase == 1 ? D.tr_p1 : phase == 2 ? D.tr_p2 : D.tr_liu) + 3u * (uint32_t)(e.round - 1);
-    e.do_round(P, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr);
+    e.do_round(P, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, phase == 2 ? e.scal(Engine::SC_UNARY) : nullptr);
     e.get_tr(tr, out_abc, 3);
     e.proof_size += 3 * sizeof(F);
     return VP_OK;

@@ -52,6 +52,29 @@ struct EqTab {
 };
 VP_D F eq_at(const EqTab& t, uint32_t idx) { return f_mul(ld_f(t.f + (idx & t.mask)), ld_f(t.s + (idx >> t.fh))); }
 
+// ------------------------------------------------------------------ sharding of a table over G GPUs
+// Block-cyclic by the table index: block beta = idx >> m (2^m contiguous entries) belongs to the rank with
+// beta mod G == first; that rank stores its blocks back to back (local block q = beta / G). Rounds 1..m of a
+// sumcheck pair entries inside one block, so they need no communication. G == 1: identity.
+struct ShardMap {
+    uint32_t m;       // log2(block size)
+    uint32_t logG;    // log2(number of ranks)
+    uint32_t first;   // this rank's residue
+    uint32_t pad;
+};
+VP_HD bool shard_local(const ShardMap& s, uint32_t idx, uint32_t& local) {
+    if (s.logG == 0) { local = idx; return true; }
+    const uint32_t beta = idx >> s.m;
+    if ((beta & ((1u << s.logG) - 1u)) != s.first) return false;
+    local = ((beta >> s.logG) << s.m) | (idx & ((1u << s.m) - 1u));
+    return true;
+}
+VP_HD uint32_t shard_global(const ShardMap& s, uint32_t local) {
+    if (s.logG == 0) return local;
+    const uint32_t q = local >> s.m;
+    return (((q << s.logG) | s.first) << s.m) | (local & ((1u << s.m) - 1u));
+}
+
 // ------------------------------------------------------------------ reductions
 VP_D F warp_sum(F x) {
 #pragma unroll
@@ -266,11 +289,13 @@ __global__ void __launch_bounds__(256)
 k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
               EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
               const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
-              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots) {
+              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm) {
     const uint64_t total = (uint64_t)n_items * K;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)k * n_items);
         const RowItem I = items[it];
+        uint32_t loc;
+        if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // another rank owns this table entry
         F M = f_zero(), A = f_zero();
         const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
         for (uint32_t e = I.e_begin; e < e1; ++e) {
@@ -284,10 +309,9 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
         }
         const uint32_t slot = I.cnt_slot >> 8;
         if (slot == 0) {
-            const uint32_t u = k * S_pre + I.row;
-            st_f(tV + u, ld_f(Vpre + u));
-            st_f(tM + u, M);
-            st_f(tA + u, A);
+            st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));
+            st_f(tM + loc, M);
+            st_f(tA + loc, A);
         } else {
             F* dst = partial + 2 * ((size_t)k * n_slots + (slot - 1));
             st_f(dst, M);
@@ -298,21 +322,24 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 
 __global__ void __launch_bounds__(256)
 k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
-                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots) {
+                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,
+                 ShardMap sm) {
     const uint64_t total = (uint64_t)n_rows * K;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)k * n_rows);
         const LongRow R = rows[j];
+        const uint32_t u = k * S_pre + R.row;
+        uint32_t loc;
+        if (!shard_local(sm, u, loc)) continue;
         F M = f_zero(), A = f_zero();
         for (uint32_t s = R.slot_begin; s < R.slot_end; ++s) {
             const F* src = partial + 2 * ((size_t)k * n_slots + s);
             M = f_add(M, ld_f_cg(src));
             A = f_add(A, ld_f_cg(src + 1));
         }
-        const uint32_t u = k * S_pre + R.row;
-        st_f(tV + u, ld_f(Vpre + u));
-        st_f(tM + u, M);
-        st_f(tA + u, A);
+        st_f(tV + loc, ld_f(Vpre + u));
+        st_f(tM + loc, M);
+        st_f(tA + loc, A);
     }
 }
 
@@ -324,8 +351,9 @@ struct P2Table {
     uint32_t D;              // subset size of one instance
     uint32_t src_S;          // template size of the source layer
     uint32_t tab_off;        // offset of this table in the output buffers (entries)
-    uint32_t pad;
+    uint32_t owned;          // 0: this rank holds no part of the table
     const F* src_val;        // circuitValue[l]
+    ShardMap sm;             // which entries of the table this rank holds, and where
 };
 struct CsrP2 {
     const uint32_t* g0;
@@ -358,6 +386,9 @@ k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t kk = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)kk * n_items), k = K - 1 - kk;
         const RowItem I = items[it];
+        const P2Table T = tabs[I.tab];
+        uint32_t loc;
+        if (!T.owned || !shard_local(T.sm, kk * T.D + I.row, loc)) continue;
         F M = f_zero(), A = f_zero();
         const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
         for (uint32_t e = I.e_begin; e < e1; ++e) {
@@ -370,8 +401,7 @@ k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table
         }
         const uint32_t slot = I.cnt_slot >> 8;
         if (slot == 0) {
-            const P2Table T = tabs[I.tab];
-            const uint32_t o = T.tab_off + kk * T.D + I.row;
+            const uint32_t o = T.tab_off + loc;
             st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[I.row]));
             st_f(tM + o, M);
             st_f(tA + o, A);
@@ -390,14 +420,16 @@ k_combine_phase2(const LongRow* __restrict__ rows, uint32_t n_rows, const P2Tabl
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t kk = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)kk * n_rows), k = K - 1 - kk;
         const LongRow R = rows[j];
+        const P2Table T = tabs[R.tab];
+        uint32_t loc;
+        if (!T.owned || !shard_local(T.sm, kk * T.D + R.row, loc)) continue;
         F M = f_zero(), A = f_zero();
         for (uint32_t s = R.slot_begin; s < R.slot_end; ++s) {
             const F* src = partial + 2 * ((size_t)kk * n_slots + s);
             M = f_add(M, ld_f_cg(src));
             A = f_add(A, ld_f_cg(src + 1));
         }
-        const P2Table T = tabs[R.tab];
-        const uint32_t o = T.tab_off + kk * T.D + R.row;
+        const uint32_t o = T.tab_off + loc;
         st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[R.row]));
         st_f(tM + o, M);
         st_f(tA + o, A);
@@ -405,8 +437,11 @@ k_combine_phase2(const LongRow* __restrict__ rows, uint32_t n_rows, const P2Tabl
 }
 
 // Unary gates of phase 2 (prover.cpp:342-353): all of them add into addVArray[i-1][0].
-// U = sum_g beta_g[g]*beta_u[u] * coef(ty), coef = c+Vu | c*Vu | Vu | 1-Vu. Grid reduction; the last
-// block ADDS U into *dst (entry 0 of the A table of source layer i-1).
+// U = sum_g beta_g[g]*beta_u[u] * coef(ty), coef = c+Vu | c*Vu | Vu | 1-Vu. The add table enters the
+// round polynomials only linearly, and entry 0 is "low bit 0" in every round, so adding U to add[i-1][0]
+// is the same as starting the phase with add_term = U (it is scaled by (1 - r) every round exactly like
+// the folded table entry would be). The grid sums U over the instances [k_begin, k_end) into *dst; a
+// sharded context gives every rank its own instance slice and the partial add_terms add up.
 struct CsrUnary {
     const uint32_t* g0;
     const uint32_t* u0;
@@ -416,13 +451,13 @@ struct CsrUnary {
 __global__ void __launch_bounds__(256)
 k_phase2_unary(CsrUnary un, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ,
                const F* __restrict__ assert_r, const F* __restrict__ Vu_ptr, const F* __restrict__ cst,
-               F* __restrict__ dst, F* partials, unsigned int* counter) {
+               F* __restrict__ dst, F* partials, unsigned int* counter, uint32_t k_begin, uint32_t k_end) {
     __shared__ F smem[32];
     const F Vu = *Vu_ptr;
-    const uint64_t total = (uint64_t)un.n * K;
+    const uint64_t total = (uint64_t)un.n * (k_end - k_begin);
     F acc[1] = {f_zero()};
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(w / un.n), j = (uint32_t)(w - (uint64_t)k * un.n);
+        const uint32_t k = k_begin + (uint32_t)(w / un.n), j = (uint32_t)(w % un.n);
         const uint32_t g0 = un.g0[j], tyb = un.ty[j], ty = tyb & 0x7f;
         F bg = eq_at(eqg, k * S_cur + g0);
         if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
@@ -436,7 +471,7 @@ k_phase2_unary(CsrUnary un, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eq
         }
         acc[0] = f_add(acc[0], f_mul(tmp, coef));
     }
-    if (grid_sum<1>(acc, smem, partials, counter) && threadIdx.x == 0) st_f(dst, f_add(*dst, acc[0]));
+    if (grid_sum<1>(acc, smem, partials, counter) && threadIdx.x == 0) st_f(dst, acc[0]);
 }
 
 // ------------------------------------------------------------------ K5: Liu table init
@@ -450,19 +485,21 @@ struct LiuEntry {       // one (j, slot0) pair pointing at template u0
 __global__ void __launch_bounds__(256)
 k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
            uint32_t S_pre, uint32_t K, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
-           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA) {
+           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local) {
     const uint32_t n = S_pre * K;
     const F s0 = *s0_ptr;
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    for (uint32_t loc = blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += gridDim.x * blockDim.x) {
+        const uint32_t u = shard_global(sm, loc);
+        if (u >= n) continue;
         const uint32_t k = u / S_pre, u0 = u - k * S_pre;
         F M = f_mul(s0, eq_at(equ, u));
         for (uint32_t e = off[u0]; e < off[u0 + 1]; ++e) {
             const LiuEntry E = ent[e];
             M = f_add(M, eq_at(eqs[E.eq_id], (K - 1 - k) * E.D + E.slot0));
         }
-        st_f(tV + u, ld_f(Vpre + u));
-        st_f(tM + u, M);
-        st_f(tA + u, f_zero());
+        st_f(tV + loc, ld_f(Vpre + u));
+        st_f(tM + loc, M);
+        st_f(tA + loc, f_zero());
     }
 }
 
@@ -493,7 +530,8 @@ struct RoundArgs {
     F* partials;
     unsigned int* counter;
     uint32_t first_round;     // 1: add_term is not scaled by (1 - prev) (prev == 0)
-    uint32_t reset_add_term;  // 1: start from add_term = 0
+    uint32_t reset_add_term;  // 1: start from add_term = *at_init (or 0)
+    const F* at_init;         // initial add_term of the phase (phase 2: the unary-gate sum), may be null
 };
 
 VP_D F ld_bound(const F* base, uint32_t idx, uint32_t live) { return idx < live ? ld_f(base + idx) : f_zero(); }
@@ -595,10 +633,13 @@ VP_D void round_work(RoundAcc& acc, const TabDesc* __restrict__ tabs, uint32_t n
 
 // add_term bookkeeping of one round (prover.cpp:445,462-467): at' = at*(1 - prev) + sum over tables that
 // collapse in this round of V*mult + add (their two stored values folded with prev when !first).
+// fold_vals: the collapsing tables hold two stored values still to be folded with prev (false in the first
+// round of a kernel's plan); scale: a previous challenge exists (false only in round 1 of the phase).
 template <bool NC>
 VP_D F collapse_update(F at, const ColDesc* __restrict__ cols, uint32_t n_cols, const F* inV, const F* inM, const F* inA,
-                       bool first, const F& prev, const FoldK& rk, F* claims) {
-    if (!first) at = f_mul(at, f_sub(f_one(), prev));
+                       bool fold_vals, bool scale, const F& prev, const FoldK& rk, F* claims) {
+    const bool first = !fold_vals;
+    if (scale) at = f_mul(at, f_sub(f_one(), prev));
     for (uint32_t i = 0; i < n_cols; ++i) {
         const ColDesc c = cols[i];
         F cv = f_zero(), cm = f_zero(), ca = f_zero();
@@ -636,10 +677,9 @@ __global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
     racc_finish(acc, v);
     if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
     if (threadIdx.x != 0) return;
-    F at = p.reset_add_term ? f_zero() : *p.add_term;
+    F at = p.reset_add_term ? (p.at_init ? *p.at_init : f_zero()) : *p.add_term;
     const F prev = p.first_round ? f_zero() : *p.prev_r;
-    if (!FOLD && !p.first_round) rk = make_foldk(prev);
-    at = collapse_update<true>(at, p.cols, p.n_cols, p.inV, p.inM, p.inA, p.first_round != 0, prev, rk, p.claims);
+    at = collapse_update<true>(at, p.cols, p.n_cols, p.inV, p.inM, p.inA, FOLD, !p.first_round, prev, rk, p.claims);
     st_f(p.add_term, at);
     st_f(p.out_poly + 0, v[0]);
     st_f(p.out_poly + 1, f_sub(v[1], at));
@@ -695,7 +735,9 @@ struct PhaseArgs {
     const FinDesc* fins;
     uint32_t n_rounds, n_fin, fin_buf;
     uint32_t tail_work;        // rounds with work <= tail_work run on block 0 alone
-    const F* chal;             // challenge of round j (1-based) = chal[j-1]; prev of round j = chal[j-2]
+    uint32_t round_base;       // rounds already done before this kernel (sharded: the local rounds); global round = base + j
+    const F* at_init;          // initial add_term (phase 2: unary-gate sum; stage B: the summed partial add_terms), may be null
+    const F* chal;             // challenge bound after GLOBAL round g = chal[g-1]; prev of global round g = chal[g-2]
     F* add_term;
     F* claims;
     F* out_poly;               // round j -> out_poly[3*(j-1) ..]
@@ -710,7 +752,7 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
     __shared__ F smem[3 * 32];
     __shared__ uint32_t s_wend[128];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-    F at = f_zero();  // add_term: meaningful in block 0 / thread 0 only
+    F at = p.at_init ? *p.at_init : f_zero();  // add_term: meaningful in block 0 / thread 0 only
     uint32_t j = 1;
     // ---- grid rounds
     for (; j <= p.n_rounds; ++j) {
@@ -721,7 +763,8 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
         for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
         __syncthreads();
         const uint32_t ib = R.in_buf, ob = ib ^ 1;
-        const F prev = fold ? p.chal[j - 2] : f_zero();
+        const bool scale = p.round_base + j >= 2;
+        const F prev = scale ? p.chal[p.round_base + j - 2] : f_zero();
         const FoldK rk = make_foldk(prev);
         RoundAcc acc;
         racc_init(acc);
@@ -740,8 +783,8 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
             // tables collapsing in this round are inputs of this round: read them before the barrier, the next
             // round may overwrite that buffer
             if (blockIdx.x == 0)
-                at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], !fold,
-                                            prev, rk, p.claims);
+                at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], fold,
+                                            scale, prev, rk, p.claims);
         }
         grid.sync();
         if (blockIdx.x == 0) {
@@ -769,7 +812,8 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
         for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
         __syncthreads();
         const uint32_t ib = R.in_buf, ob = ib ^ 1;
-        const F prev = fold ? p.chal[j - 2] : f_zero();
+        const bool scale = p.round_base + j >= 2;
+        const F prev = scale ? p.chal[p.round_base + j - 2] : f_zero();
         const FoldK rk = make_foldk(prev);
         RoundAcc acc;
         racc_init(acc);
@@ -781,8 +825,8 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
         racc_finish(acc, v);
         block_sum<3>(v, smem);
         if (threadIdx.x == 0) {
-            at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], !fold, prev, rk,
-                                        p.claims);
+            at = collapse_update<false>(at, p.cols + R.col_begin, R.n_cols, p.bufV[ib], p.bufM[ib], p.bufA[ib], fold, scale, prev,
+                                        rk, p.claims);
             F* o = p.out_poly + 3 * (j - 1);
             st_f(o + 0, v[0]);
             st_f(o + 1, f_sub(v[1], at));
@@ -801,11 +845,93 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
             const F v0 = f.n_vals >= 1 ? ld_one<false>(V + f.in_off) : f_zero();
             if (p.n_rounds >= 1) {
                 const F v1 = f.n_vals >= 2 ? ld_one<false>(V + f.in_off + 1) : f_zero();
-                c = f_fold(v0, v1, p.chal[p.n_rounds - 1]);
+                c = f_fold(v0, v1, p.chal[p.round_base + p.n_rounds - 1]);
             } else c = v0;
         }
         st_f(p.transcript + f.out_idx, c);
         if (p.keep && i == 0) st_f(p.keep, c);
+    }
+}
+
+// ------------------------------------------------------------------ sharded phases: hand-over between the local
+// rounds (stage A, tables block-cyclic over the ranks) and the replicated tail rounds (stage B)
+// After the m local rounds every block of a distributed table is down to two stored values; fold them with
+// r_m (no pairing: the partner block lives on another rank) and put the block's value into this rank's
+// gather record at [base + {0,1,2}*cnt + local_block].
+struct FoldOnlyDesc {
+    uint32_t in_off;     // local table in the stage-A final buffer
+    uint32_t in_live;    // live stored values (<= 2 * n_blocks)
+    uint32_t n_blocks;   // local blocks (records written, zero-filled beyond the live ones)
+    uint32_t out_base;   // offset (F) of this table's V region in the gather record
+    uint32_t cnt;        // region length (max local blocks over ranks)
+    uint32_t fold;       // 1: two values per block, fold with r; 0: one value per block (m == 0 never happens; m >= 1)
+};
+__global__ void k_fold_only(const FoldOnlyDesc* __restrict__ descs, int n_desc, const F* __restrict__ V, const F* __restrict__ M,
+                            const F* __restrict__ A, const F* __restrict__ r_ptr, F* __restrict__ rec) {
+    const FoldK rk = make_foldk(*r_ptr);
+    for (int t = blockIdx.y; t < n_desc; t += gridDim.y) {
+        const FoldOnlyDesc d = descs[t];
+        for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < d.cnt; b += gridDim.x * blockDim.x) {
+            F v = f_zero(), m = f_zero(), a = f_zero();
+            if (b < d.n_blocks) {
+                const uint32_t i0 = d.in_off + 2 * b, l0 = 2 * b;
+                if (l0 < d.in_live) {
+                    const F v0 = V[i0], m0 = M[i0], a0 = A[i0];
+                    F v1 = f_zero(), m1 = f_zero(), a1 = f_zero();
+                    if (l0 + 1 < d.in_live) { v1 = V[i0 + 1]; m1 = M[i0 + 1]; a1 = A[i0 + 1]; }
+                    v = f_fold_k(v0, v1, rk); m = f_fold_k(m0, m1, rk); a = f_fold_k(a0, a1, rk);
+                }
+            }
+            st_f(rec + d.out_base + b, v);
+            st_f(rec + d.out_base + d.cnt + b, m);
+            st_f(rec + d.out_base + 2 * d.cnt + b, a);
+        }
+    }
+}
+
+// After the all-gather of the per-rank records: build the stage-B tables (block beta of a table came from rank
+// (beta mod G == first_r) as its local block beta / G) and add up the per-rank partial scalars (round
+// polynomials of the local rounds, add_term, claims of tables that collapsed locally).
+struct MergeTab {
+    uint32_t rec_base;   // offset of the table's V region inside one rank's record
+    uint32_t cnt;        // region length
+    uint32_t n_blocks;   // live blocks of the whole table (= live entries of the stage-B table)
+    uint32_t out_off;    // stage-B table offset in buffer 0
+    uint32_t rot;        // rank owning block beta: (beta + rot) mod G
+    uint32_t pad;
+};
+struct MergeArgs {
+    const F* recv;            // G records of rec_len F
+    uint32_t rec_len, G;
+    const MergeTab* tabs;
+    uint32_t n_tabs;
+    uint32_t sc_base;         // offset of the scalar region inside a record
+    uint32_t n_poly;          // 3 * local rounds
+    uint32_t n_claims;
+    F *outV, *outM, *outA;    // stage-B buffers
+    F* out_poly;              // transcript slots of rounds 1..m
+    F* add_term;              // summed add_term
+    F* claims;
+};
+__global__ void k_shard_merge(MergeArgs p) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t t = 0; t < p.n_tabs; ++t) {
+        const MergeTab T = p.tabs[t];
+        for (uint32_t beta = tid; beta < T.n_blocks; beta += stride) {
+            const uint32_t owner = (beta + T.rot) & (p.G - 1), q = beta / p.G;
+            const F* rec = p.recv + (size_t)owner * p.rec_len + T.rec_base;
+            st_f(p.outV + T.out_off + beta, rec[q]);
+            st_f(p.outM + T.out_off + beta, rec[T.cnt + q]);
+            st_f(p.outA + T.out_off + beta, rec[2 * T.cnt + q]);
+        }
+    }
+    const uint32_t n_sc = p.n_poly + 1 + p.n_claims;
+    for (uint32_t i = tid; i < n_sc; i += stride) {
+        F s = f_zero();
+        for (uint32_t g = 0; g < p.G; ++g) s = f_add(s, p.recv[(size_t)g * p.rec_len + p.sc_base + i]);
+        if (i < p.n_poly) st_f(p.out_poly + i, s);
+        else if (i == p.n_poly) st_f(p.add_term, s);
+        else st_f(p.claims + (i - p.n_poly - 1), s);
     }
 }
 

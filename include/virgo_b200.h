@@ -173,7 +173,9 @@ int vp_sumcheck_load(vp_sumcheck* s, const vp_F* V, const vp_F* add, const vp_F*
 int vp_sumcheck_fill_random(vp_sumcheck* s, uint64_t seed);  /* SplitMix64 per entry, on device */
 int vp_sumcheck_export(vp_sumcheck* s, vp_F* V, vp_F* add, vp_F* mult);  /* device -> host (pristine copy) */
 int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out /* 3*log_n+3 */, float* device_ms);
-/* per-round device time of the last run (log_n floats, ms) */
+/* Same outputs, all rounds in one cooperative launch, two rounds per pass (the challenges are all known). */
+int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, float* device_ms);
+/* per-round device time of the last vp_sumcheck_run (log_n floats, ms) */
 int vp_sumcheck_round_ms(vp_sumcheck* s, float* out);
 void vp_sumcheck_destroy(vp_sumcheck* s);
 

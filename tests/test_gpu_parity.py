@@ -19,7 +19,7 @@ def _assert_same(got, want, what):
 
 
 # ------------------------------------------------------------------ stand-alone sumcheck (config C2 shape)
-@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 11, 14])
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 11, 12, 14, 17])
 def test_sumcheck_tables_vs_oracle(B, O, log_n):
     rng = np.random.default_rng(100 + log_n)
     n = 1 << log_n
@@ -32,6 +32,8 @@ def test_sumcheck_tables_vs_oracle(B, O, log_n):
     _assert_same(got, want, f"sumcheck 2^{log_n}")
     got2, _ = s.run(r)  # tables are restored between runs
     _assert_same(got2, want, "second run")
+    got3, _ = s.run(r, fused=True)  # all rounds in one launch, two rounds per pass
+    _assert_same(got3, want, "fused run")
     s.close()
 
 
@@ -50,6 +52,8 @@ def test_sumcheck_edge_values(B, O):
         s.load(T, T, T)
         got, _ = s.run(r)
         _assert_same(got, O.sumcheck_tables(T, T, T, r), f"fill {fill}")
+        got, _ = s.run(r, fused=True)
+        _assert_same(got, O.sumcheck_tables(T, T, T, r), f"fill {fill} fused")
         s.close()
 
 

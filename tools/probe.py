@@ -18,6 +18,10 @@ def c2(log_n=24):
     for j in range(min(6, log_n)):
         nb = (48 * N if j == 0 else 72 * (N >> (j - 1)))
         print(f"  round {j+1}: {rm[j]*1e3:.1f} us  {nb/rm[j]/1e6:.0f} GB/s")
+    for it in range(4):
+        out2, ms2 = s.run(r, fused=True)
+    assert (out2 == out).all()
+    print(f"C2 2^{log_n} fused (two rounds per pass, one launch): {ms2:.3f} ms")
     s.close()
 
 def gkr(K, reps=3):

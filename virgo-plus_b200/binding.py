@@ -114,6 +114,7 @@ def _declare(L):
     L.vp_sumcheck_fill_random.argtypes = [vp, C.c_uint64]
     L.vp_sumcheck_export.argtypes = [vp, vp, vp, vp]
     L.vp_sumcheck_run.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
+    L.vp_sumcheck_run_fused.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_sumcheck_round_ms.argtypes = [vp, vp]
     L.vp_sumcheck_destroy.argtypes = [vp]
     L.vp_sumcheck_destroy.restype = None
@@ -564,12 +565,15 @@ class Sumcheck:
         _ck(lib().vp_sumcheck_export(self.h, *[_ptr(x) for x in a]))
         return a
 
-    def run(self, r):
+    def run(self, r, fused=False):
+        """fused=False: one round per launch (what the interactive prover does); fused=True: one cooperative
+        launch, two rounds per pass (what vp_prove does)."""
         r = np.ascontiguousarray(r, dtype=F_DTYPE)
         assert len(r) == self.log_n
         out = np.zeros(3 * self.log_n + 3, F_DTYPE)
         ms = C.c_float()
-        _ck(lib().vp_sumcheck_run(self.h, _ptr(r), _ptr(out), C.byref(ms)))
+        fn = lib().vp_sumcheck_run_fused if fused else lib().vp_sumcheck_run
+        _ck(fn(self.h, _ptr(r), _ptr(out), C.byref(ms)))
         return out, ms.value
 
     def round_ms(self):

@@ -117,7 +117,94 @@ struct PlanArena {  // descriptor pools shared by all plans of a context
     std::vector<RoundDev> rdev;
     std::vector<FoldOnlyDesc> fo;
     std::vector<MergeTab> mt;
+    std::vector<PassTab> ptabs;
+    std::vector<PassCol> pcols;
+    std::vector<PassDev> pdev;
 };
+
+// ------------------------------------------------------------------ pass plan: two rounds per pass (k_phase_dfs)
+struct PassPlan {
+    int rounds = 0;
+    uint32_t pass_begin = 0, n_passes = 0, fin_begin = 0, n_fin = 0;
+    int fin_buf = 0;
+    uint32_t cap0 = 0, cap1 = 0, max_work = 0;
+    double bytes = 0;                          // algorithmic bytes: 48 B per live entry read + 48 B per entry written
+    std::vector<uint32_t> off0, end_off, end_live;
+};
+static PassPlan build_pass_plan(const std::vector<PlanTable>& tabs, int rounds, const std::vector<uint32_t>& fin_out,
+                                PlanArena& A) {
+    PassPlan P;
+    P.rounds = rounds;
+    const size_t nt = tabs.size();
+    std::vector<uint32_t> off(nt), live(nt);
+    std::vector<uint8_t> gone(nt, 0);
+    uint32_t o = 0;
+    for (size_t t = 0; t < nt; ++t) {
+        off[t] = o;
+        live[t] = tabs[t].live;
+        o += align4(std::max<uint32_t>(tabs[t].live, 1));
+    }
+    P.off0 = off;
+    P.cap0 = o;
+    P.pass_begin = (uint32_t)A.pdev.size();
+    int cur = 0;
+    for (int j = 1; j <= rounds;) {
+        const int nr = (j + 1 <= rounds) ? 2 : 1;
+        PassDev R;
+        memset(&R, 0, sizeof R);
+        R.tab_begin = (uint32_t)A.ptabs.size();
+        R.col_begin = (uint32_t)A.pcols.size();
+        R.in_buf = (uint32_t)cur;
+        R.n_rounds = (uint32_t)nr;
+        uint32_t work = 0, oo = 0;
+        for (size_t t = 0; t < nt; ++t) {
+            if (gone[t]) continue;
+            const int rem = tabs[t].bits - (j - 1);   // rounds this table still has at the pass's input level
+            if (rem <= 0) {                           // already a single value: joins add_term in round j
+                A.pcols.push_back(PassCol{off[t], std::min<uint32_t>(live[t], 1u), tabs[t].claim_slot, 0});
+                gone[t] = 1;
+                continue;
+            }
+            const bool two = nr == 2 && rem >= 2;
+            const uint32_t nl = two ? cdiv(cdiv(live[t], 2), 2) : cdiv(live[t], 2);
+            work += two ? cdiv(live[t], 4) : cdiv(live[t], 2);
+            A.ptabs.push_back(PassTab{off[t], live[t], oo, work, two ? 1u : 0u, 0});
+            P.bytes += 48.0 * live[t] + 48.0 * nl;
+            off[t] = oo;
+            live[t] = nl;
+            oo += align4(std::max<uint32_t>(nl, 1));
+            if (!two && rem == 1 && nr == 2) {        // reached one value in round j: joins add_term in round j+1
+                A.pcols.push_back(PassCol{off[t], std::min<uint32_t>(live[t], 1u), tabs[t].claim_slot, 1});
+                gone[t] = 1;
+            }
+        }
+        R.n_tabs = (uint32_t)A.ptabs.size() - R.tab_begin;
+        R.n_cols = (uint32_t)A.pcols.size() - R.col_begin;
+        R.work = work;
+        P.max_work = std::max(P.max_work, work);
+        if (cur == 0) P.cap1 = std::max(P.cap1, oo);
+        else P.cap0 = std::max(P.cap0, oo);
+        A.pdev.push_back(R);
+        cur ^= 1;
+        j += nr;
+    }
+    P.n_passes = (uint32_t)A.pdev.size() - P.pass_begin;
+    P.fin_buf = cur;
+    P.end_off = off;
+    P.end_live = live;
+    P.fin_begin = (uint32_t)A.fins.size();
+    if (fin_out.empty()) return P;
+    for (size_t t = 0; t < nt; ++t) {
+        FinDesc f;
+        f.out_idx = fin_out[t];
+        f.in_off = off[t];
+        if (!gone[t]) { f.from_claim = -1; f.n_vals = std::min<uint32_t>(live[t], 1u); }
+        else { f.from_claim = tabs[t].claim_slot; f.n_vals = 0; }
+        A.fins.push_back(f);
+    }
+    P.n_fin = (uint32_t)nt;
+    return P;
+}
 
 // ------------------------------------------------------------------ a sumcheck phase, possibly sharded over G ranks
 // world == 1 (or a small phase): `planB` is the whole phase. Sharded: tables are block-cyclic over the ranks
@@ -132,7 +219,8 @@ struct PhaseTabG {   // one table of the phase, global view
 struct PhasePlan {
     bool sharded = false;
     int rounds = 0, m = 0;
-    SumcheckPlan planA, planB;
+    SumcheckPlan planA, planB;         // one round per launch/pass (interactive entry points use planB)
+    PassPlan ppA, ppB;                 // two rounds per pass (vp_prove)
     std::vector<ShardMap> maps;        // per global table
     std::vector<uint32_t> tab_off;     // offset of the table's level-0 values in buffer 0 on this rank
     std::vector<uint32_t> local_len;   // padded local length (multiple of the block size when sharded)
@@ -140,7 +228,7 @@ struct PhasePlan {
     uint32_t fo_begin = 0, n_fo = 0, mt_begin = 0, n_mt = 0;
     uint32_t rec_len = 0, sc_base = 0, n_poly = 0, n_claims = 0;
     uint32_t cap0 = 0, cap1 = 0;
-    double bytes_total() const { return planA.bytes + planB.bytes; }
+    double bytes_total() const { return ppA.bytes + ppB.bytes; }
 };
 
 static constexpr int CYC_BITS = 10;   // a sharded table is dealt out in 2^CYC_BITS blocks (the largest table of the phase)
@@ -191,12 +279,18 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
             P.planB.rdev_begin = (uint32_t)A.rdev.size();
         } else P.planB = build_plan(tabs, rounds, fo, A);
         add_empty_fins(P.planB);
+        // the same phase as a pass plan (level-0 offsets are identical: both pack the tables 4-aligned in order)
+        P.ppB = build_pass_plan(tabs, rounds, fo, A);
+        for (uint32_t o : empty_fin_out) {
+            A.fins.push_back(FinDesc{0, 0, -1, o});
+            ++P.ppB.n_fin;
+        }
         for (size_t t = 0; t < nt; ++t) {
             P.tab_off[t] = P.planB.tabs[t].off0;
             P.local_len[t] = T[t].live;
         }
-        P.cap0 = P.planB.cap0;
-        P.cap1 = P.planB.cap1;
+        P.cap0 = std::max(P.planB.cap0, P.ppB.cap0);
+        P.cap1 = std::max(P.planB.cap1, P.ppB.cap1);
         return P;
     }
     P.m = m;
@@ -230,15 +324,18 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
         }
     }
     if (tabsA.empty()) tabsA.push_back(PlanTable{99, 0, -1, 0});
-    P.planA = build_plan(tabsA, m, {}, A);
+    P.ppA = build_pass_plan(tabsA, m, {}, A);
     for (size_t t = 0; t < nt; ++t)
-        if (idxA[t] != ~0u) P.tab_off[t] = P.planA.tabs[idxA[t]].off0;
-    P.planB = build_plan(tabsB, rounds - m, finB, A);
+        if (idxA[t] != ~0u) P.tab_off[t] = P.ppA.off0[idxA[t]];
+    P.ppB = build_pass_plan(tabsB, rounds - m, finB, A);
     for (const FinDesc& f : collapsed_fins) {
         A.fins.push_back(f);
-        ++P.planB.n_fin;
+        ++P.ppB.n_fin;
     }
-    add_empty_fins(P.planB);
+    for (uint32_t o : empty_fin_out) {
+        A.fins.push_back(FinDesc{0, 0, -1, o});
+        ++P.ppB.n_fin;
+    }
     // gather record: per distributed table three regions of cnt entries, then the scalars
     P.fo_begin = (uint32_t)A.fo.size();
     P.mt_begin = (uint32_t)A.mt.size();
@@ -246,8 +343,9 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
     for (size_t q = 0; q < dist.size(); ++q) {
         const Dist& d = dist[q];
         const uint32_t ia = idxA[d.t];
-        A.fo.push_back(FoldOnlyDesc{P.planA.end_off[ia], P.planA.end_live[ia], d.local_blocks, base, d.cnt, 1});
-        A.mt.push_back(MergeTab{base, d.cnt, d.n_blocks, P.planB.tabs[q].off0, (uint32_t)(d.t % G), 0});
+        // after the m local rounds every local block is down to one value: copy them into the record (fold = 0)
+        A.fo.push_back(FoldOnlyDesc{P.ppA.end_off[ia], P.ppA.end_live[ia], d.local_blocks, base, d.cnt, 0});
+        A.mt.push_back(MergeTab{base, d.cnt, d.n_blocks, P.ppB.off0[q], (uint32_t)(d.t % G), 0});
         base += 3 * d.cnt;
     }
     P.n_fo = (uint32_t)dist.size();
@@ -256,8 +354,8 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
     P.n_poly = 3u * (uint32_t)m;
     P.n_claims = (uint32_t)n_claims;
     P.rec_len = base + P.n_poly + 1 + P.n_claims;
-    P.cap0 = std::max(P.planA.cap0, P.planB.cap0);
-    P.cap1 = std::max(P.planA.cap1, P.planB.cap1);
+    P.cap0 = std::max(P.ppA.cap0, P.ppB.cap0);
+    P.cap1 = std::max(P.ppA.cap1, P.ppB.cap1);
     return P;
 }
 
@@ -468,6 +566,11 @@ struct Engine {
     DBuf<F> d_send, d_recv;
     DBuf<FoldOnlyDesc> d_fo;
     DBuf<MergeTab> d_mt;
+    DBuf<PassTab> d_ptabs;
+    DBuf<PassCol> d_pcols;
+    DBuf<PassDev> d_pdev;
+    bool use_dfs = true;   // two rounds per pass in vp_prove (k_phase_dfs); false: one round per pass (k_sumcheck_phase)
+    int cap_dfs = 0;
     int n = 0;            // layers
     uint32_t K = 1;
     int max_bl = 0;
@@ -600,6 +703,8 @@ struct Engine {
     void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
     void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init);
+    void launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out, F* claims,
+                           F* out_poly, F* keep);
     void launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
                              F* claims, F* out_poly, F* keep);
     uint32_t tail_work = 512;
@@ -654,12 +759,14 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
     cap_phase = occ_cap(k_sumcheck_phase);
+    cap_dfs = occ_cap(k_phase_dfs);
+    if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         if (!coop) throw CudaError{"device does not support cooperative launches"};
     }
-    max_grid = std::max({cap_round, cap_round1, cap_un, cap_dot, cap_phase});  // sizes the block-partials buffer
+    max_grid = std::max({cap_round, cap_round1, cap_un, cap_dot, cap_phase, cap_dfs});  // sizes the block-partials buffer
 
     // challenge / transcript index maps (draw order of verifier.cpp, see circuit.cpp draw_challenges)
     L.resize(n);
@@ -916,12 +1023,15 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     d_tr.alloc(n_tr);
     d_scal.alloc(SC_N);
     d_claims.alloc((size_t)n + 1);
-    d_partials.alloc((size_t)6 * (size_t)max_grid);
+    d_partials.alloc((size_t)12 * (size_t)max_grid);
     d_counter.alloc(2);
     d_tabs.upload(arena.tabs, stream);
     d_cols.upload(arena.cols, stream);
     d_fins.upload(arena.fins, stream);
     d_rdev.upload(arena.rdev, stream);
+    d_ptabs.upload(arena.ptabs, stream);
+    d_pcols.upload(arena.pcols, stream);
+    d_pdev.upload(arena.pdev, stream);
     d_eqb.upload(eq_descs, stream);
     CK(cudaMemsetAsync(d_chal.p, 0, (n_chal + 1) * sizeof(F), stream));
     CK(cudaMemsetAsync(d_tr.p, 0, n_tr * sizeof(F), stream));
@@ -1119,23 +1229,54 @@ void Engine::launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t ro
     ++launches;
 }
 
+// One cooperative launch of k_phase_dfs (two rounds per pass) over `P`.
+void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
+                               F* claims, F* out_poly, F* keep) {
+    DfsArgs a;
+    for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
+    a.passes = d_pdev.p + P.pass_begin;
+    a.tabs = d_ptabs.p;
+    a.cols = d_pcols.p;
+    a.fins = d_fins.p + P.fin_begin;
+    a.n_passes = P.n_passes;
+    a.n_fin = P.n_fin;
+    a.fin_buf = (uint32_t)P.fin_buf;
+    a.tail_work = tail_work;
+    a.round_base = round_base;
+    a.at_init = at_init;
+    a.chal = d_chal.p + ci;
+    a.add_term = add_term_out;
+    a.claims = claims;
+    a.out_poly = out_poly;
+    a.transcript = d_tr.p;
+    a.keep = keep;
+    a.partials = d_partials.p;
+    const int grid = P.max_work > tail_work ? grid_for(P.max_work, cap_dfs) : 1;
+    void* args[] = {&a};
+    size_t h = prof_begin(KC_ROUND_FOLD);
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs, dim3(grid), dim3(256), args, 0, stream));
+    prof_end(h, P.bytes);
+    ++launches;
+}
+
 // All rounds + the final claims of one sumcheck phase. Unsharded: one cooperative launch. Sharded: the m local
 // rounds on this rank's blocks, fold-only, ONE all-gather of the per-rank records (collapsed blocks + partial
 // round polynomials + partial add_term + claims), merge, then the remaining rounds replicated on every rank.
 void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init) {
     if (!P.sharded) {
-        launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
+        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
+        else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
     F* rec = d_send.p;
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
     // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
-    launch_phase_kernel(P.planA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr);
+    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr);
     if (P.n_fo) {
         const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
         dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);
-        const int fb = P.planA.fin_buf;
+        const int fb = P.ppA.fin_buf;
         k_fold_only<<<grid, 128, 0, stream>>>(d_fo.p + P.fo_begin, (int)P.n_fo, bufV[fb].p, bufM[fb].p, bufA[fb].p,
                                              d_chal.p + ci + (uint32_t)(P.m - 1), rec);
         ++launches;
@@ -1157,8 +1298,8 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     k_shard_merge<<<8, 256, 0, stream>>>(ma);
     ++launches;
     // stage B: replicated; starts from the summed add_term
-    launch_phase_kernel(P.planB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
-                        d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep);
+    launch_dfs_kernel(P.ppB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
+                      d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep);
 }
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
@@ -1812,7 +1953,11 @@ struct vp_sumcheck {
     DBuf<FinDesc> d_fins;
     PlanArena arena;
     SumcheckPlan plan;
-    int max_grid = 148 * 4, cap_fold = 148, cap_first = 148;
+    PassPlan pp;
+    DBuf<PassTab> d_ptabs;
+    DBuf<PassCol> d_pcols;
+    DBuf<PassDev> d_pdev;
+    int max_grid = 148 * 4, cap_fold = 148, cap_first = 148, cap_dfs = 148;
     std::vector<cudaEvent_t> ev;
     std::vector<float> round_ms;
     ~vp_sumcheck() {
@@ -1846,9 +1991,16 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     // finalises one table (V); add/mult finals are folded by two more k_finalize launches.
     std::vector<PlanTable> t{{log_n, s->N, -1, 0}};
     s->plan = build_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
+    s->pp = build_pass_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
+    {
+        int occd = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs, 256, 0));
+        s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
+        s->max_grid = std::max(s->max_grid, s->cap_dfs);
+    }
     for (int i = 0; i < 3; ++i) s->src[i].alloc(s->N);
     for (int b = 0; b < 2; ++b) {
-        const uint32_t cap = std::max<uint32_t>(4, b == 0 ? s->plan.cap0 : s->plan.cap1);
+        const uint32_t cap = std::max<uint32_t>(4, b == 0 ? std::max(s->plan.cap0, s->pp.cap0) : std::max(s->plan.cap1, s->pp.cap1));
         s->bufV[b].alloc(cap);
         s->bufM[b].alloc(cap);
         s->bufA[b].alloc(cap);
@@ -1857,8 +2009,11 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->d_out.alloc((size_t)3 * log_n + 3);
     s->d_scal.alloc(4);
     s->d_claims.alloc(4);
-    s->d_partials.alloc((size_t)3 * s->max_grid);
+    s->d_partials.alloc((size_t)12 * s->max_grid);
     s->d_counter.alloc(2);
+    s->d_ptabs.upload(s->arena.ptabs, s->stream);
+    s->d_pcols.upload(s->arena.pcols, s->stream);
+    s->d_pdev.upload(s->arena.pdev, s->stream);
     // FinDesc for add and mult finals (same offsets as V's)
     FinDesc fv = s->arena.fins[s->plan.fin_begin];
     FinDesc fa = fv, fm = fv;
@@ -1960,6 +2115,55 @@ extern "C" int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out, float* 
     float tot = 0;
     CK(cudaEventElapsedTime(&tot, s->ev[0], s->ev[n + 1]));
     for (int j = 1; j <= n; ++j) CK(cudaEventElapsedTime(&s->round_ms[j - 1], s->ev[j - 1], s->ev[j]));
+    if (device_ms) *device_ms = tot;
+    return VP_OK;
+    API_END
+}
+// Same result as vp_sumcheck_run, all rounds in ONE cooperative launch with two rounds per pass (k_phase_dfs):
+// possible because all challenges r[] are known up front.
+extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, float* device_ms) {
+    if (!s || !r || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    cudaSetDevice(s->device);
+    cudaStream_t st = s->stream;
+    const int n = s->log_n;
+    CK(cudaMemcpyAsync(s->d_r.p, r, (size_t)n * sizeof(F), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->bufV[0].p, s->src[0].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->bufA[0].p, s->src[1].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->bufM[0].p, s->src[2].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(s->ev[0], st));
+    DfsArgs a;
+    for (int b = 0; b < 2; ++b) { a.bufV[b] = s->bufV[b].p; a.bufM[b] = s->bufM[b].p; a.bufA[b] = s->bufA[b].p; }
+    a.passes = s->d_pdev.p + s->pp.pass_begin;
+    a.tabs = s->d_ptabs.p;
+    a.cols = s->d_pcols.p;
+    a.fins = s->d_fins.p + s->pp.fin_begin;   // arena.fins is uploaded as a whole: indices are global
+    a.n_passes = s->pp.n_passes;
+    a.n_fin = s->pp.n_fin;
+    a.fin_buf = (uint32_t)s->pp.fin_buf;
+    a.tail_work = 512;
+    a.round_base = 0;
+    a.at_init = nullptr;
+    a.chal = s->d_r.p;
+    a.add_term = s->d_scal.p;
+    a.claims = s->d_claims.p;
+    a.out_poly = s->d_out.p;
+    a.transcript = s->d_out.p;
+    a.keep = nullptr;
+    a.partials = s->d_partials.p;
+    const int grid = s->pp.max_work > 512 ? (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, 256), (uint32_t)s->cap_dfs)) : 1;
+    void* args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs, dim3(grid), dim3(256), args, 0, st));
+    // the fully folded add / mult values sit where V's does
+    const FinDesc fv = s->arena.fins[s->pp.fin_begin];
+    const F* fin_tabs[2] = {s->bufA[s->pp.fin_buf].p, s->bufM[s->pp.fin_buf].p};
+    for (int k = 0; k < 2; ++k)
+        CK(cudaMemcpyAsync(s->d_out.p + 3 * n + 1 + k, fin_tabs[k] + fv.in_off, sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(s->ev[1], st));
+    CK(cudaMemcpyAsync(out, s->d_out.p, ((size_t)3 * n + 3) * sizeof(F), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float tot = 0;
+    CK(cudaEventElapsedTime(&tot, s->ev[0], s->ev[1]));
     if (device_ms) *device_ms = tot;
     return VP_OK;
     API_END

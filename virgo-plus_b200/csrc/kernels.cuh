@@ -853,6 +853,220 @@ __global__ void __launch_bounds__(256, 2) k_sumcheck_phase(PhaseArgs p) {
     }
 }
 
+// ------------------------------------------------------------------ K6d: two rounds per pass (whole-proof mode)
+// With the challenges on the device a pass can run TWO rounds on data it holds in registers: a thread reads a
+// quad x[4q..4q+3] of level-L values, accumulates round L+1's polynomial from the pairs (x0,x1),(x2,x3), folds them
+// with r_{L+1}, accumulates round L+2's polynomial from the folded pair, folds with r_{L+2} and writes ONE value.
+// HBM traffic per table triple drops from 192*N (one round per pass: 144*N, plus the challenge-less first read)
+// to 48*N*(1 + 1/4 + ...) + 12*N*(...) = 80*N, which makes the kernel INT-pipe bound instead of HBM bound.
+// Stored tables hold level-L values with nothing pending (the one-round kernel keeps a fold pending).
+struct PassTab {
+    uint32_t in_off, in_live, out_off;
+    uint32_t work_end;   // inclusive prefix of work items: quads (two == 1) or pairs
+    uint32_t two;        // 1: the table runs both rounds of the pass; 0: one round (pair -> one value)
+    uint32_t pad;
+};
+struct PassCol {         // a table that is down to one value and joins add_term (prover.cpp:462-467)
+    uint32_t off;        // where its single value sits
+    uint32_t n_vals;     // 0: empty table
+    int32_t claim_slot;
+    uint32_t which;      // 0: collapses in the pass's first round (value in the IN buffer); 1: second round (OUT buffer)
+};
+struct PassDev {
+    uint32_t tab_begin, n_tabs, col_begin, n_cols;
+    uint32_t work, in_buf, n_rounds, pad;   // n_rounds: 1 or 2 rounds in this pass
+};
+struct DfsArgs {
+    F* bufV[2];
+    F* bufM[2];
+    F* bufA[2];
+    const PassDev* passes;
+    const PassTab* tabs;
+    const PassCol* cols;
+    const FinDesc* fins;
+    uint32_t n_passes, n_fin, fin_buf;
+    uint32_t tail_work;
+    uint32_t round_base;       // global rounds done before this kernel
+    const F* at_init;
+    const F* chal;             // chal[g-1] = challenge bound after global round g
+    F* add_term;
+    F* claims;
+    F* out_poly;               // local round j (1-based) -> out_poly[3*(j-1)]
+    F* transcript;
+    F* keep;
+    F* partials;               // 2 * gridDim.x * 6
+};
+
+template <bool NC>
+VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ tabs, uint32_t n_tabs, const uint32_t* s_wend,
+                   const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA, const FoldK& rk1, const FoldK& rk2,
+                   uint32_t first, uint32_t stride) {
+    const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;
+    uint32_t t = 0;
+    PassTab T = n_tabs ? tabs[0] : PassTab{0, 0, 0, 0, 0, 0};
+    uint32_t wbeg = 0;
+    for (uint32_t w = first; w < total; w += stride) {
+        if (w >= s_wend[t]) {
+            do { ++t; } while (w >= s_wend[t]);
+            T = tabs[t];
+            wbeg = s_wend[t - 1];
+        }
+        const uint32_t q = w - wbeg;
+        const F* V = inV + T.in_off;
+        const F* M = inM + T.in_off;
+        const F* A = inA + T.in_off;
+        if (T.two) {
+            const uint32_t i0 = 4 * q;
+            F xv[4], xm[4], xa[4];
+            if (i0 + 3 < T.in_live) {
+                ld_pair<NC>(V + i0, xv[0], xv[1]); ld_pair<NC>(V + i0 + 2, xv[2], xv[3]);
+                ld_pair<NC>(M + i0, xm[0], xm[1]); ld_pair<NC>(M + i0 + 2, xm[2], xm[3]);
+                ld_pair<NC>(A + i0, xa[0], xa[1]); ld_pair<NC>(A + i0 + 2, xa[2], xa[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool in = i0 + j < T.in_live;
+                    xv[j] = in ? ld_one<NC>(V + i0 + j) : f_zero();
+                    xm[j] = in ? ld_one<NC>(M + i0 + j) : f_zero();
+                    xa[j] = in ? ld_one<NC>(A + i0 + j) : f_zero();
+                }
+            }
+            racc_pair(acc1, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1]);
+            racc_pair(acc1, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3]);
+            const F v0 = f_fold_k(xv[0], xv[1], rk1), v1 = f_fold_k(xv[2], xv[3], rk1);
+            const F m0 = f_fold_k(xm[0], xm[1], rk1), m1 = f_fold_k(xm[2], xm[3], rk1);
+            const F a0 = f_fold_k(xa[0], xa[1], rk1), a1 = f_fold_k(xa[2], xa[3], rk1);
+            racc_pair(acc2, v0, v1, m0, m1, a0, a1);
+            const uint32_t o = T.out_off + q;
+            st_f(outV + o, f_fold_k(v0, v1, rk2));
+            st_f(outM + o, f_fold_k(m0, m1, rk2));
+            st_f(outA + o, f_fold_k(a0, a1, rk2));
+        } else {
+            const uint32_t i0 = 2 * q;
+            F v0, v1, m0, m1, a0, a1;
+            if (i0 + 1 < T.in_live) {
+                ld_pair<NC>(V + i0, v0, v1);
+                ld_pair<NC>(M + i0, m0, m1);
+                ld_pair<NC>(A + i0, a0, a1);
+            } else {
+                v0 = ld_one<NC>(V + i0); m0 = ld_one<NC>(M + i0); a0 = ld_one<NC>(A + i0);
+                v1 = m1 = a1 = f_zero();
+            }
+            racc_pair(acc1, v0, v1, m0, m1, a0, a1);
+            const uint32_t o = T.out_off + q;
+            st_f(outV + o, f_fold_k(v0, v1, rk1));
+            st_f(outM + o, f_fold_k(m0, m1, rk1));
+            st_f(outA + o, f_fold_k(a0, a1, rk1));
+        }
+    }
+}
+
+// add_term after one more round: at*(1 - prev) (if a previous challenge exists) + tables collapsing now
+VP_D F dfs_collapse(F at, const PassCol* __restrict__ cols, uint32_t n_cols, uint32_t which, const F* V, const F* M, const F* A,
+                    bool scale, const F& prev, F* claims) {
+    if (scale) at = f_mul(at, f_sub(f_one(), prev));
+    for (uint32_t i = 0; i < n_cols; ++i) {
+        const PassCol c = cols[i];
+        if (c.which != which) continue;
+        F cv = f_zero(), cm = f_zero(), ca = f_zero();
+        if (c.n_vals) { cv = ld_one<false>(V + c.off); cm = ld_one<false>(M + c.off); ca = ld_one<false>(A + c.off); }
+        at = f_add(at, f_mul_add(cv, cm, ca));
+        if (c.claim_slot >= 0) st_f(claims + c.claim_slot, cv);
+    }
+    return at;
+}
+
+__global__ void __launch_bounds__(256, 2) k_phase_dfs(DfsArgs p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ F smem[6 * 32];
+    __shared__ uint32_t s_wend[128];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    F at = p.at_init ? *p.at_init : f_zero();
+    uint32_t j = 1;       // local round of the pass's first round
+    uint32_t ps = 0;
+    bool tail = false;
+    for (; ps < p.n_passes; ++ps) {
+        const PassDev R = p.passes[ps];
+        if (!tail && R.work <= p.tail_work) {
+            tail = true;
+            if (blockIdx.x != 0) return;   // block 0 finishes alone; everything it needs was written before the last barrier
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
+        __syncthreads();
+        const uint32_t ib = R.in_buf, ob = ib ^ 1;
+        const uint32_t g1 = p.round_base + j;                    // global round of the pass's first round
+        const bool scale1 = g1 >= 2;
+        const F prev1 = scale1 ? p.chal[g1 - 2] : f_zero();
+        const F r1 = p.chal[g1 - 1];
+        const F r2 = R.n_rounds == 2 ? p.chal[g1] : f_zero();
+        const FoldK rk1 = make_foldk(r1), rk2 = make_foldk(r2);
+        RoundAcc acc1, acc2;
+        racc_init(acc1);
+        racc_init(acc2);
+        dfs_work<false>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib], p.bufV[ob],
+                        p.bufM[ob], p.bufA[ob], rk1, rk2, tail ? threadIdx.x : gtid, tail ? blockDim.x : gstride);
+        F v[6];
+        {
+            F a[3], b[3];
+            racc_finish(acc1, a);
+            racc_finish(acc2, b);
+            v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = b[0]; v[4] = b[1]; v[5] = b[2];
+        }
+        block_sum<6>(v, smem);
+        F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
+        const PassCol* cols = p.cols + R.col_begin;
+        // tables that were already down to one value join add_term in the pass's first round; their value sits in the
+        // IN buffer, which the next pass overwrites: read it before the barrier
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, prev1, p.claims);
+        if (!tail) {
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
+            }
+            grid.sync();
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) v[k] = f_zero();
+                for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v[k] = f_add(v[k], ld_one<false>(part + (size_t)b * 6 + k));
+                }
+                block_sum<6>(v, smem);
+            }
+        } else __syncthreads();   // this pass's outputs (a table reaching one value) are visible to thread 0
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            F* o = p.out_poly + 3 * (j - 1);
+            st_f(o + 0, v[0]);
+            st_f(o + 1, f_sub(v[1], at));
+            st_f(o + 2, f_add(v[2], at));
+            if (R.n_rounds == 2) {
+                // tables that reached one value in this pass's first round join in its second round (OUT buffer)
+                at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, r1, p.claims);
+                st_f(o + 3, v[3]);
+                st_f(o + 4, f_sub(v[4], at));
+                st_f(o + 5, f_add(v[5], at));
+            }
+        }
+        j += R.n_rounds;
+    }
+    if (blockIdx.x != 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) st_f(p.add_term, at);
+    // final claims: a table alive to the end is down to its level-R value (prover.cpp:494-521)
+    const F* V = p.bufV[p.fin_buf];
+    for (uint32_t i = threadIdx.x; i < p.n_fin; i += blockDim.x) {
+        const FinDesc f = p.fins[i];
+        F c;
+        if (f.from_claim >= 0) c = ld_one<false>(p.claims + f.from_claim);
+        else c = f.n_vals >= 1 ? ld_one<false>(V + f.in_off) : f_zero();
+        st_f(p.transcript + f.out_idx, c);
+        if (p.keep && i == 0) st_f(p.keep, c);
+    }
+}
+
 // ------------------------------------------------------------------ sharded phases: hand-over between the local
 // rounds (stage A, tables block-cyclic over the ranks) and the replicated tail rounds (stage B)
 // After the m local rounds every block of a distributed table is down to two stored values; fold them with
@@ -873,7 +1087,9 @@ __global__ void k_fold_only(const FoldOnlyDesc* __restrict__ descs, int n_desc, 
         const FoldOnlyDesc d = descs[t];
         for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < d.cnt; b += gridDim.x * blockDim.x) {
             F v = f_zero(), m = f_zero(), a = f_zero();
-            if (b < d.n_blocks) {
+            if (b < d.n_blocks && !d.fold) {          // the two-rounds-per-pass kernel leaves one value per block
+                if (b < d.in_live) { v = V[d.in_off + b]; m = M[d.in_off + b]; a = A[d.in_off + b]; }
+            } else if (b < d.n_blocks) {
                 const uint32_t i0 = d.in_off + 2 * b, l0 = 2 * b;
                 if (l0 < d.in_live) {
                     const F v0 = V[i0], m0 = M[i0], a0 = A[i0];

@@ -23,3 +23,12 @@ void h_acc_dot(const F* a, const F* b, F* out, int n) {  // lazy Acc with a redu
     *out = f_add(run, acc_reduce(acc));
 }
 }
+extern "C" {
+// loose running-sum variants: result must be in the right residue class and <= p + 5
+void h_mul_add_k_loose(const F* a, const F* b, const F* c, F* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = f_mul_add_k_loose(make_lop(a[i].re, a[i].im), make_ropd(b[i]), c[i]);
+}
+void h_mul_add_loose2(const F* a, const F* b, const F* c, F* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = f_mul_add_loose2(make_lop(a[i].re, a[i].im), make_rop(b[i].re, b[i].im), c[i]);
+}
+}

@@ -138,3 +138,23 @@ def test_lazy_accumulator_dot(H):
             m = _cmul(_t(a[i]), _t(b[i]))
             acc = ((acc[0] + m[0]) % P, (acc[1] + m[1]) % P)
         assert _t(out[0]) == acc
+
+
+def test_loose_running_sums(H):
+    """f_mul_add_k_loose / f_mul_add_loose2: right residue class, bounded by p + 5, and stable when fed back"""
+    rng = np.random.default_rng(11)
+    n = 5000
+    a, b = _fe_arrays(rng, n), _fe_arrays(rng, n)
+    acc = np.zeros(n, FD)
+    want = [(0, 0)] * n
+    for it in range(6):   # feed the loose result back as the addend, like the round kernel does
+        out = np.zeros(n, FD)
+        fn = H.h_mul_add_k_loose if it % 2 == 0 else H.h_mul_add_loose2
+        fn(_p(a), _p(b), _p(acc), _p(out), n)
+        for i in range(0, n, 7):
+            m = _cmul(_t(a[i]), _t(b[i]))
+            want[i] = ((want[i][0] + m[0]) % P, (want[i][1] + m[1]) % P)
+            assert int(out[i]["re"]) % P == want[i][0] and int(out[i]["im"]) % P == want[i][1]
+        assert int(out["re"].max()) <= P + 5 and int(out["im"].max()) <= P + 5
+        acc = out
+        a = np.roll(a, 1)

@@ -57,12 +57,36 @@ VP_HD Limbs split31(u64 x) {  // x < 2^63
     r.hi = (u32)(x >> 31);
     return r;
 }
-VP_HD u64 mul32(u32 a, u32 b) { return (u64)a * (u64)b; }  // IMAD.WIDE.U32
+// 32x32 -> 64 multiply and multiply-accumulate. On the device these are spelled as PTX mul.wide / mad.wide:
+// the C expression (u64)a * b + c makes nvcc 12.9 emit one junk "add 0 to the high word" (VIADD) per product.
+VP_HD u64 mul32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    u64 d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+#else
+    return (u64)a * (u64)b;
+#endif
+}
+VP_HD u64 mad32(u32 a, u32 b, u64 c) {  // a*b + c  (IMAD.WIDE.U32 with a 64-bit addend)
+#if defined(__CUDA_ARCH__)
+    u64 d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+#else
+    return (u64)a * (u64)b + c;
+#endif
+}
 
 // value = u + 2^31*t + extra (mod p), canonical.  u, t < 2^64; extra < 2^62.
 VP_HD u64 fp_reduce_ut(u64 u, u64 t, u64 extra) {
     u64 s = (u & P) + (u >> 61) + (t >> 30) + ((t & 0x3FFFFFFFULL) << 31) + extra;  // < 2^63 + 2^35
     return fp_canon(s);
+}
+// Same value, folded once only: result <= p + 4 (same residue class, not canonical). extra < 2^62.
+VP_HD u64 fp_reduce_ut_loose(u64 u, u64 t, u64 extra) {
+    u64 s = (u & P) + (u >> 61) + (t >> 30) + ((t & 0x3FFFFFFFULL) << 31) + extra;
+    return fp_fold(s);
 }
 // value = u + 2^31*t + 2^62*w + extra (mod p), canonical.  u, t, w < 2^64; extra < 2^62.
 VP_HD u64 fp_reduce_utw(u64 u, u64 t, u64 w, u64 extra) {
@@ -74,7 +98,7 @@ VP_HD u64 fp_reduce_utw(u64 u, u64 t, u64 w, u64 extra) {
 
 VP_HD u64 fp_mul(u64 a, u64 b) {  // a, b < 2^62
     const Limbs x = split31(a), y = split31(b);
-    const u64 u = mul32(x.lo, y.lo), t = mul32(x.lo, y.hi) + mul32(x.hi, y.lo), w = mul32(x.hi, y.hi);
+    const u64 u = mul32(x.lo, y.lo), t = mad32(x.hi, y.lo, mul32(x.lo, y.hi)), w = mul32(x.hi, y.hi);
     return fp_reduce_utw(u, t, w, 0);
 }
 
@@ -114,18 +138,28 @@ struct CPart {
 // Valid for m, v components <= 2p (hi limbs < 2^31): every chain is a sum of <= 4 products < 2^62.
 VP_HD CPart cprod_parts(const LOp& m, const ROp& v) {
     CPart c;
-    c.u_re = mul32(m.re0, v.re0) + mul32(m.nim0, v.im0);
-    c.t_re = mul32(m.re0, v.re1) + mul32(m.re1, v.re0) + mul32(m.nim0, v.im1) + mul32(m.nim1, v.im0);
-    c.w_re = mul32(m.re1, v.re1) + mul32(m.nim1, v.im1);
-    c.u_im = mul32(m.re0, v.im0) + mul32(m.im0, v.re0);
-    c.t_im = mul32(m.re0, v.im1) + mul32(m.re1, v.im0) + mul32(m.im0, v.re1) + mul32(m.im1, v.re0);
-    c.w_im = mul32(m.re1, v.im1) + mul32(m.im1, v.re1);
+    c.u_re = mad32(m.nim0, v.im0, mul32(m.re0, v.re0));
+    c.t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
+    c.w_re = mad32(m.nim1, v.im1, mul32(m.re1, v.re1));
+    c.u_im = mad32(m.im0, v.re0, mul32(m.re0, v.im0));
+    c.t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
+    c.w_im = mad32(m.im1, v.re1, mul32(m.re1, v.im1));
     return c;
 }
-// m*v + acc for operands with components <= 2p; acc canonical.
+// m*v + acc for operands with components <= 2p; acc < 2^62. Canonical result.
 VP_HD F f_mul_add_loose(const LOp& m, const ROp& v, const F& acc) {
     const CPart c = cprod_parts(m, v);
     return F{fp_reduce_utw(c.u_re, c.t_re, c.w_re, acc.re), fp_reduce_utw(c.u_im, c.t_im, c.w_im, acc.im)};
+}
+// Same with a result that is only folded once (<= p + 5, not canonical).
+VP_HD u64 fp_reduce_utw_loose(u64 u, u64 t, u64 w, u64 extra) {
+    u64 s = (u & P) + (u >> 61) + (t >> 30) + ((t & 0x3FFFFFFFULL) << 31) + extra;
+    u64 w2 = ((w << 1) & P) + ((w << 1) >> 61) + ((w >> 63) << 3);
+    return fp_fold(s + w2);
+}
+VP_HD F f_mul_add_loose2(const LOp& m, const ROp& v, const F& acc) {
+    const CPart c = cprod_parts(m, v);
+    return F{fp_reduce_utw_loose(c.u_re, c.t_re, c.w_re, acc.re), fp_reduce_utw_loose(c.u_im, c.t_im, c.w_im, acc.im)};
 }
 
 // Canonical operands (< 2^61: hi limbs < 2^30) let the 2^62-weight products ride in the u chain by
@@ -139,11 +173,19 @@ VP_HD ROpD make_ropd(const F& v) {  // v canonical
 }
 // m components <= 2p, v canonical: u chains hold 2 x (< 2^62) + 2 x (2^31 * 2^31) < 2^64.
 VP_HD F f_mul_add_k(const LOp& m, const ROpD& v, const F& acc) {
-    const u64 u_re = mul32(m.re0, v.re0) + mul32(m.nim0, v.im0) + mul32(m.re1, v.re1d) + mul32(m.nim1, v.im1d);
-    const u64 t_re = mul32(m.re0, v.re1) + mul32(m.re1, v.re0) + mul32(m.nim0, v.im1) + mul32(m.nim1, v.im0);
-    const u64 u_im = mul32(m.re0, v.im0) + mul32(m.im0, v.re0) + mul32(m.re1, v.im1d) + mul32(m.im1, v.re1d);
-    const u64 t_im = mul32(m.re0, v.im1) + mul32(m.re1, v.im0) + mul32(m.im0, v.re1) + mul32(m.im1, v.re0);
+    const u64 u_re = mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0))));
+    const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
+    const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
+    const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
     return F{fp_reduce_ut(u_re, t_re, acc.re), fp_reduce_ut(u_im, t_im, acc.im)};
+}
+// Same, but the result is only folded once (<= p + 4, NOT canonical): for running sums that are fed back as `acc`.
+VP_HD F f_mul_add_k_loose(const LOp& m, const ROpD& v, const F& acc) {
+    const u64 u_re = mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0))));
+    const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
+    const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
+    const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
+    return F{fp_reduce_ut_loose(u_re, t_re, acc.re), fp_reduce_ut_loose(u_im, t_im, acc.im)};
 }
 
 VP_HD F f_mul(const F& a, const F& b) {  // canonical operands

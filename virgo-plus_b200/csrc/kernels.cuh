@@ -553,9 +553,10 @@ VP_D void racc_init(RoundAcc& s) {
     s.pending = 0;
 }
 VP_D void racc_pair(RoundAcc& s, const F& v0, const F& v1, const F& m0, const F& m1, const F& a0, const F& a1) {
-    s.C = f_mul_add_k(make_lop(m0.re, m0.im), make_ropd(v0), s.C);
-    s.B = f_mul_add_k(make_lop(m1.re, m1.im), make_ropd(v1), s.B);
-    s.E = f_mul_add_loose(make_lop(m0.re + m1.re, m0.im + m1.im), make_rop(v0.re + v1.re, v0.im + v1.im), s.E);
+    // running sums stay "loose" (<= p + 5, folded once): they only ride as the next product's addend
+    s.C = f_mul_add_k_loose(make_lop(m0.re, m0.im), make_ropd(v0), s.C);
+    s.B = f_mul_add_k_loose(make_lop(m1.re, m1.im), make_ropd(v1), s.B);
+    s.E = f_mul_add_loose2(make_lop(m0.re + m1.re, m0.im + m1.im), make_rop(v0.re + v1.re, v0.im + v1.im), s.E);
     s.s0re += a0.re; s.s0im += a0.im; s.s1re += a1.re; s.s1im += a1.im;
     if (++s.pending == 4) {
         s.s0re = fp_fold(s.s0re); s.s0im = fp_fold(s.s0im); s.s1re = fp_fold(s.s1re); s.s1im = fp_fold(s.s1im);
@@ -564,10 +565,12 @@ VP_D void racc_pair(RoundAcc& s, const F& v0, const F& v1, const F& m0, const F&
 }
 VP_D void racc_finish(const RoundAcc& s, F (&v)[3]) {
     const F sa0 = F{fp_canon(s.s0re), fp_canon(s.s0im)}, sa1 = F{fp_canon(s.s1re), fp_canon(s.s1im)};
-    const F twoBC = f_dbl(f_add(s.B, s.C));
-    v[0] = f_sub(twoBC, s.E);
-    v[1] = f_add(f_sub(f_sub(s.E, s.B), f_add(f_dbl(s.C), s.C)), f_sub(sa1, sa0));
-    v[2] = f_add(s.C, sa0);
+    const F B = F{fp_red1(s.B.re), fp_red1(s.B.im)}, C = F{fp_red1(s.C.re), fp_red1(s.C.im)},
+            E = F{fp_red1(s.E.re), fp_red1(s.E.im)};   // loose (<= p + 5) -> canonical
+    const F twoBC = f_dbl(f_add(B, C));
+    v[0] = f_sub(twoBC, E);
+    v[1] = f_add(f_sub(f_sub(E, B), f_add(f_dbl(C), C)), f_sub(sa1, sa0));
+    v[2] = f_add(C, sa0);
 }
 
 // Work of one round over the tables [tabs, tabs + n_tabs): each thread strides over pairs (!FOLD) or

@@ -175,6 +175,8 @@ int vp_sumcheck_export(vp_sumcheck* s, vp_F* V, vp_F* add, vp_F* mult);  /* devi
 int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out /* 3*log_n+3 */, float* device_ms);
 /* Same outputs, all rounds in one cooperative launch, two rounds per pass (the challenges are all known). */
 int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, float* device_ms);
+/* profiling aid: ns time stamps of block 0 at {pass start, work done, barrier passed, pass end} per pass of the last fused run */
+int vp_sumcheck_pass_stamps(vp_sumcheck* s, unsigned long long* out, int n);
 /* per-round device time of the last vp_sumcheck_run (log_n floats, ms) */
 int vp_sumcheck_round_ms(vp_sumcheck* s, float* out);
 void vp_sumcheck_destroy(vp_sumcheck* s);

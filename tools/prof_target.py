@@ -10,6 +10,7 @@ if sys.argv[1] == "c2":
     s = B.Sumcheck(log_n); s.fill_random(1)
     r = np.zeros(log_n, B.F_DTYPE); r["re"] = np.arange(1, log_n + 1) * 1234567891; r["im"] = 77
     s.run(r); s.run(r)
+    if len(sys.argv) > 3: s.run(r, fused=True); s.run(r, fused=True)
 else:
     K = int(sys.argv[2])
     with lzma.open(os.path.join(ROOT, "tests/golden/SHA256_64.pws.xz")) as f:

@@ -116,6 +116,7 @@ def _declare(L):
     L.vp_sumcheck_run.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_sumcheck_run_fused.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_sumcheck_round_ms.argtypes = [vp, vp]
+    L.vp_sumcheck_pass_stamps.argtypes = [vp, vp, C.c_int]
     L.vp_sumcheck_destroy.argtypes = [vp]
     L.vp_sumcheck_destroy.restype = None
 
@@ -575,6 +576,13 @@ class Sumcheck:
         fn = lib().vp_sumcheck_run_fused if fused else lib().vp_sumcheck_run
         _ck(fn(self.h, _ptr(r), _ptr(out), C.byref(ms)))
         return out, ms.value
+
+    def pass_stamps(self):
+        out = np.zeros(256 + 2048, np.uint64)
+        _ck(lib().vp_sumcheck_pass_stamps(self.h, _ptr(out), len(out)))
+        n = (self.log_n + 1) // 2
+        self.block_stamps = out[256:].reshape(1024, 2)
+        return out[:4 * n].reshape(n, 4)
 
     def round_ms(self):
         out = np.zeros(self.log_n, np.float32)

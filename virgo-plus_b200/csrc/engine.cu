@@ -699,12 +699,12 @@ struct Engine {
     void do_input_mle();
     void do_init_phase1(int i);
     void do_init_phase2(int i);
-    void do_init_liu(int i);
     void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
-    void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init);
+    void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a = true);
+    void do_init_liu(int i, bool write_a);
     void launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out, F* claims,
-                           F* out_poly, F* keep);
+                           F* out_poly, F* keep, bool has_a);
     void launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
                              F* claims, F* out_poly, F* keep);
     uint32_t tail_work = 512;
@@ -759,7 +759,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
     cap_phase = occ_cap(k_sumcheck_phase);
-    cap_dfs = occ_cap(k_phase_dfs);
+    cap_dfs = std::min(occ_cap(k_phase_dfs<true>), occ_cap(k_phase_dfs<false>));
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     {
         int coop = 0;
@@ -1024,7 +1024,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     d_scal.alloc(SC_N);
     d_claims.alloc((size_t)n + 1);
     d_partials.alloc((size_t)12 * (size_t)max_grid);
-    d_counter.alloc(2);
+    d_counter.alloc(4 + 64);
     d_tabs.upload(arena.tabs, stream);
     d_cols.upload(arena.cols, stream);
     d_fins.upload(arena.fins, stream);
@@ -1037,7 +1037,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     CK(cudaMemsetAsync(d_tr.p, 0, n_tr * sizeof(F), stream));
     CK(cudaMemsetAsync(d_scal.p, 0, SC_N * sizeof(F), stream));
     CK(cudaMemsetAsync(d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
-    CK(cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(unsigned int), stream));
+    CK(cudaMemsetAsync(d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
     CK(cudaStreamSynchronize(stream));
     load_inputs(C.inputs.data(), C.inputs.size(), true);
     CK(cudaStreamSynchronize(stream));
@@ -1147,7 +1147,7 @@ void Engine::do_init_phase2(int i) {
     } else CK(cudaMemsetAsync(scal(SC_UNARY), 0, sizeof(F), stream));
 }
 
-void Engine::do_init_liu(int i) {
+void Engine::do_init_liu(int i, bool write_a) {
     LayerDev& D = L[i];
     const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
     if (!have_equ) run_eq(D.eqb_u, 2);
@@ -1158,8 +1158,9 @@ void Engine::do_init_liu(int i) {
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
         D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
-        bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local);
-    prof_end(h, (double)n_local * 64.0);
+        bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
+        write_a ? 1 : 0);
+    prof_end(h, (double)n_local * (write_a ? 64.0 : 48.0));
     ++launches;
 }
 
@@ -1231,7 +1232,7 @@ void Engine::launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t ro
 
 // One cooperative launch of k_phase_dfs (two rounds per pass) over `P`.
 void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
-                               F* claims, F* out_poly, F* keep) {
+                               F* claims, F* out_poly, F* keep, bool has_a) {
     DfsArgs a;
     for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
     a.passes = d_pdev.p + P.pass_begin;
@@ -1251,20 +1252,24 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     a.transcript = d_tr.p;
     a.keep = keep;
     a.partials = d_partials.p;
-    const int grid = P.max_work > tail_work ? grid_for(P.max_work, cap_dfs) : 1;
+    a.bar = d_counter.p + 2;
+    a.chunk_ctr = d_counter.p + 4;
+    a.dbg = nullptr;
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), (uint32_t)cap_dfs));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
-    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs, dim3(grid), dim3(256), args, 0, stream));
-    prof_end(h, P.bytes);
+    CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(256),
+                                   args, 0, stream));
+    prof_end(h, has_a ? P.bytes : P.bytes * (2.0 / 3.0));
     ++launches;
 }
 
 // All rounds + the final claims of one sumcheck phase. Unsharded: one cooperative launch. Sharded: the m local
 // rounds on this rank's blocks, fold-only, ONE all-gather of the per-rank records (collapsed blocks + partial
 // round polynomials + partial add_term + claims), merge, then the remaining rounds replicated on every rank.
-void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init) {
+void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a) {
     if (!P.sharded) {
-        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
+        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a);
         else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
@@ -1272,7 +1277,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
     // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
-    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr);
+    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a);
     if (P.n_fo) {
         const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
         dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);
@@ -1299,7 +1304,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     ++launches;
     // stage B: replicated; starts from the summed add_term
     launch_dfs_kernel(P.ppB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
-                      d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep);
+                      d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep, has_a);
 }
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
@@ -1323,8 +1328,8 @@ void Engine::prove_all() {
                 do_finalize(D.ph2.planB, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
             }
         }
-        do_init_liu(i);
-        if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr);
+        do_init_liu(i, !(use_phase_kernel && use_dfs));
+        if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr, /*has_a=*/!use_dfs);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph3.planB, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
@@ -1718,7 +1723,7 @@ extern "C" int vp_init_liu(vp_ctx* ctx, const vp_F* sig, int n) {
     const int need = e.n - e.cur_layer + 1;
     if (n < need) return fail(VP_ERR_ARG, "init_liu: need %d sigma values, got %d", need, n);
     e.set_chal(e.L[e.cur_layer].ci_sig, sig, (size_t)std::min(n, e.n));
-    e.do_init_liu(e.cur_layer);
+    e.do_init_liu(e.cur_layer, true);
     e.phase = 3;
     e.round = 0;
     CK(cudaStreamSynchronize(e.stream));
@@ -1957,6 +1962,7 @@ struct vp_sumcheck {
     DBuf<PassTab> d_ptabs;
     DBuf<PassCol> d_pcols;
     DBuf<PassDev> d_pdev;
+    DBuf<unsigned long long> d_dbg;
     int max_grid = 148 * 4, cap_fold = 148, cap_first = 148, cap_dfs = 148;
     std::vector<cudaEvent_t> ev;
     std::vector<float> round_ms;
@@ -1994,7 +2000,7 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->pp = build_pass_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
     {
         int occd = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true>, 256, 0));
         s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
         s->max_grid = std::max(s->max_grid, s->cap_dfs);
     }
@@ -2010,7 +2016,8 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->d_scal.alloc(4);
     s->d_claims.alloc(4);
     s->d_partials.alloc((size_t)12 * s->max_grid);
-    s->d_counter.alloc(2);
+    s->d_counter.alloc(4 + 64);
+    s->d_dbg.alloc(256 + 2048);
     s->d_ptabs.upload(s->arena.ptabs, s->stream);
     s->d_pcols.upload(s->arena.pcols, s->stream);
     s->d_pdev.upload(s->arena.pdev, s->stream);
@@ -2024,7 +2031,7 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->d_tabs.upload(s->arena.tabs, s->stream);
     s->d_cols.upload(s->arena.cols, s->stream);
     s->d_fins.upload(s->arena.fins, s->stream);
-    CK(cudaMemsetAsync(s->d_counter.p, 0, 2 * sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(s->d_counter.p, 0, (4 + 64) * sizeof(unsigned int), s->stream));
     CK(cudaMemsetAsync(s->d_scal.p, 0, 4 * sizeof(F), s->stream));
     s->ev.resize((size_t)log_n + 2);
     for (auto& evx : s->ev) CK(cudaEventCreate(&evx));
@@ -2151,9 +2158,13 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     a.transcript = s->d_out.p;
     a.keep = nullptr;
     a.partials = s->d_partials.p;
-    const int grid = s->pp.max_work > 512 ? (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, 256), (uint32_t)s->cap_dfs)) : 1;
+    a.bar = s->d_counter.p + 2;
+    a.chunk_ctr = s->d_counter.p + 4;
+    a.dbg = s->d_dbg.p;
+    CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs, dim3(grid), dim3(256), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true>, dim3(grid), dim3(256), args, 0, st));
     // the fully folded add / mult values sit where V's does
     const FinDesc fv = s->arena.fins[s->pp.fin_begin];
     const F* fin_tabs[2] = {s->bufA[s->pp.fin_buf].p, s->bufM[s->pp.fin_buf].p};
@@ -2165,6 +2176,15 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     float tot = 0;
     CK(cudaEventElapsedTime(&tot, s->ev[0], s->ev[1]));
     if (device_ms) *device_ms = tot;
+    return VP_OK;
+    API_END
+}
+// profiling aid: %globaltimer stamps (ns) of block 0 at {pass start, work done, barrier passed, pass end} of the last fused run
+extern "C" int vp_sumcheck_pass_stamps(vp_sumcheck* s, unsigned long long* out, int n) {
+    if (!s || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    cudaSetDevice(s->device);
+    CK(cudaMemcpy(out, s->d_dbg.p, (size_t)std::min(n, 256 + 2048) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return VP_OK;
     API_END
 }

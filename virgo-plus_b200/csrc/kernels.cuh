@@ -485,7 +485,7 @@ struct LiuEntry {       // one (j, slot0) pair pointing at template u0
 __global__ void __launch_bounds__(256)
 k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
            uint32_t S_pre, uint32_t K, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
-           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local) {
+           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local, int write_a) {
     const uint32_t n = S_pre * K;
     const F s0 = *s0_ptr;
     for (uint32_t loc = blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += gridDim.x * blockDim.x) {
@@ -499,7 +499,7 @@ k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, c
         }
         st_f(tV + loc, ld_f(Vpre + u));
         st_f(tM + loc, M);
-        st_f(tA + loc, f_zero());
+        if (write_a) st_f(tA + loc, f_zero());   // the Liu add table is identically zero: only the one-round-per-launch path reads it
     }
 }
 
@@ -888,7 +888,7 @@ struct DfsArgs {
     const PassCol* cols;
     const FinDesc* fins;
     uint32_t n_passes, n_fin, fin_buf;
-    uint32_t tail_work;
+    uint32_t tail_work;        // unused (kept for layout); the tail is whatever fits one block
     uint32_t round_base;       // global rounds done before this kernel
     const F* at_init;
     const F* chal;             // chal[g-1] = challenge bound after global round g
@@ -898,17 +898,34 @@ struct DfsArgs {
     F* transcript;
     F* keep;
     F* partials;               // 2 * gridDim.x * 6
+    unsigned int* bar;         // grid-barrier counter, zero at launch (the kernel leaves it zero)
+    unsigned int* chunk_ctr;   // one work counter per pass, zero at launch (the kernel leaves them zero)
+    unsigned long long* dbg;   // optional: block 0 writes %globaltimer at 4 points of every pass (profiling aid)
 };
 
-template <bool NC>
+// Work is handed out in chunks of DFS_CHUNK items through an atomic counter: equal static shares finish up to
+// 1.5x apart across SMs (measured: 242..383 us for the same share of a 2^24-entry pass), so the fast SMs take more.
+static constexpr uint32_t DFS_CHUNK = 512;
+template <bool NC, bool HAS_A>
 VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ tabs, uint32_t n_tabs, const uint32_t* s_wend,
                    const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA, const FoldK& rk1, const FoldK& rk2,
-                   uint32_t first, uint32_t stride) {
+                   unsigned int* chunk_ctr, uint32_t* s_chunk) {
     const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;
     uint32_t t = 0;
     PassTab T = n_tabs ? tabs[0] : PassTab{0, 0, 0, 0, 0, 0};
     uint32_t wbeg = 0;
-    for (uint32_t w = first; w < total; w += stride) {
+    const bool solo = total <= DFS_CHUNK;
+    for (;;) {
+        uint32_t c = 0;
+        if (!solo) {
+            __syncthreads();
+            if (threadIdx.x == 0) *s_chunk = atomicAdd(chunk_ctr, 1u);
+            __syncthreads();
+            c = *s_chunk;
+        }
+        if (c * DFS_CHUNK >= total) break;
+      for (uint32_t w = c * DFS_CHUNK + threadIdx.x; w < min(total, (c + 1) * DFS_CHUNK); w += blockDim.x) {
+        if (w < wbeg) { t = 0; T = tabs[0]; wbeg = 0; }   // chunks arrive in increasing order per block, but be safe
         if (w >= s_wend[t]) {
             do { ++t; } while (w >= s_wend[t]);
             T = tabs[t];
@@ -924,77 +941,105 @@ VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ t
             if (i0 + 3 < T.in_live) {
                 ld_pair<NC>(V + i0, xv[0], xv[1]); ld_pair<NC>(V + i0 + 2, xv[2], xv[3]);
                 ld_pair<NC>(M + i0, xm[0], xm[1]); ld_pair<NC>(M + i0 + 2, xm[2], xm[3]);
-                ld_pair<NC>(A + i0, xa[0], xa[1]); ld_pair<NC>(A + i0 + 2, xa[2], xa[3]);
+                if (HAS_A) { ld_pair<NC>(A + i0, xa[0], xa[1]); ld_pair<NC>(A + i0 + 2, xa[2], xa[3]); }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const bool in = i0 + j < T.in_live;
                     xv[j] = in ? ld_one<NC>(V + i0 + j) : f_zero();
                     xm[j] = in ? ld_one<NC>(M + i0 + j) : f_zero();
-                    xa[j] = in ? ld_one<NC>(A + i0 + j) : f_zero();
+                    if (HAS_A) xa[j] = in ? ld_one<NC>(A + i0 + j) : f_zero();
                 }
             }
+            if (!HAS_A) { xa[0] = xa[1] = xa[2] = xa[3] = f_zero(); }
             racc_pair(acc1, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1]);
             racc_pair(acc1, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3]);
             const F v0 = f_fold_k(xv[0], xv[1], rk1), v1 = f_fold_k(xv[2], xv[3], rk1);
             const F m0 = f_fold_k(xm[0], xm[1], rk1), m1 = f_fold_k(xm[2], xm[3], rk1);
-            const F a0 = f_fold_k(xa[0], xa[1], rk1), a1 = f_fold_k(xa[2], xa[3], rk1);
+            F a0 = f_zero(), a1 = f_zero();
+            if (HAS_A) { a0 = f_fold_k(xa[0], xa[1], rk1); a1 = f_fold_k(xa[2], xa[3], rk1); }
             racc_pair(acc2, v0, v1, m0, m1, a0, a1);
             const uint32_t o = T.out_off + q;
             st_f(outV + o, f_fold_k(v0, v1, rk2));
             st_f(outM + o, f_fold_k(m0, m1, rk2));
-            st_f(outA + o, f_fold_k(a0, a1, rk2));
+            if (HAS_A) st_f(outA + o, f_fold_k(a0, a1, rk2));
         } else {
             const uint32_t i0 = 2 * q;
-            F v0, v1, m0, m1, a0, a1;
+            F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero();
             if (i0 + 1 < T.in_live) {
                 ld_pair<NC>(V + i0, v0, v1);
                 ld_pair<NC>(M + i0, m0, m1);
-                ld_pair<NC>(A + i0, a0, a1);
+                if (HAS_A) ld_pair<NC>(A + i0, a0, a1);
             } else {
-                v0 = ld_one<NC>(V + i0); m0 = ld_one<NC>(M + i0); a0 = ld_one<NC>(A + i0);
-                v1 = m1 = a1 = f_zero();
+                v0 = ld_one<NC>(V + i0); m0 = ld_one<NC>(M + i0);
+                if (HAS_A) a0 = ld_one<NC>(A + i0);
+                v1 = m1 = f_zero();
             }
             racc_pair(acc1, v0, v1, m0, m1, a0, a1);
             const uint32_t o = T.out_off + q;
             st_f(outV + o, f_fold_k(v0, v1, rk1));
             st_f(outM + o, f_fold_k(m0, m1, rk1));
-            st_f(outA + o, f_fold_k(a0, a1, rk1));
+            if (HAS_A) st_f(outA + o, f_fold_k(a0, a1, rk1));
         }
+      }
+        if (solo) break;
     }
 }
 
 // add_term after one more round: at*(1 - prev) (if a previous challenge exists) + tables collapsing now
 VP_D F dfs_collapse(F at, const PassCol* __restrict__ cols, uint32_t n_cols, uint32_t which, const F* V, const F* M, const F* A,
-                    bool scale, const F& prev, F* claims) {
+                    bool scale, const F& prev, F* claims, bool has_a = true) {
     if (scale) at = f_mul(at, f_sub(f_one(), prev));
     for (uint32_t i = 0; i < n_cols; ++i) {
         const PassCol c = cols[i];
         if (c.which != which) continue;
         F cv = f_zero(), cm = f_zero(), ca = f_zero();
-        if (c.n_vals) { cv = ld_one<false>(V + c.off); cm = ld_one<false>(M + c.off); ca = ld_one<false>(A + c.off); }
+        if (c.n_vals) { cv = ld_one<false>(V + c.off); cm = ld_one<false>(M + c.off); if (has_a) ca = ld_one<false>(A + c.off); }
         at = f_add(at, f_mul_add(cv, cm, ca));
         if (c.claim_slot >= 0) st_f(claims + c.claim_slot, cv);
     }
     return at;
 }
 
-__global__ void __launch_bounds__(256, 2) k_phase_dfs(DfsArgs p) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+// Grid barrier for the pass kernel. Only the blocks that still have work take part: the work of a phase only
+// shrinks, so block b leaves the kernel for good after the last pass in which b * blockDim < work (it arrives,
+// but does not wait). `target` is the cumulative number of arrivals up to and including this pass.
+VP_D void pass_arrive(unsigned int* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+    }
+}
+VP_D void pass_wait(unsigned int* bar, unsigned int target) {
+    if (threadIdx.x == 0) {
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+#ifndef VP_DFS_MINB
+#define VP_DFS_MINB 2
+#endif
+template <bool HAS_A>
+__global__ void __launch_bounds__(256, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     __shared__ F smem[6 * 32];
     __shared__ uint32_t s_wend[128];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    __shared__ uint32_t s_chunk;
     F at = p.at_init ? *p.at_init : f_zero();
     uint32_t j = 1;       // local round of the pass's first round
-    uint32_t ps = 0;
-    bool tail = false;
-    for (; ps < p.n_passes; ++ps) {
+    unsigned int target = 0;
+    for (uint32_t ps = 0; ps < p.n_passes; ++ps) {
+#define VP_DBG_T(k) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[4 * ps + (k)] = t_; } } while (0)
+        VP_DBG_T(0);
         const PassDev R = p.passes[ps];
-        if (!tail && R.work <= p.tail_work) {
-            tail = true;
-            if (blockIdx.x != 0) return;   // block 0 finishes alone; everything it needs was written before the last barrier
-        }
+        const uint32_t active = min(gridDim.x, (R.work + DFS_CHUNK - 1) / DFS_CHUNK);   // blocks that can get a chunk
+        if (blockIdx.x >= active && blockIdx.x != 0) return;
+        const bool solo = active <= 1;    // block 0 alone: everything it reads was ordered by an earlier barrier or is its own
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
         __syncthreads();
@@ -1008,8 +1053,8 @@ __global__ void __launch_bounds__(256, 2) k_phase_dfs(DfsArgs p) {
         RoundAcc acc1, acc2;
         racc_init(acc1);
         racc_init(acc2);
-        dfs_work<false>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib], p.bufV[ob],
-                        p.bufM[ob], p.bufA[ob], rk1, rk2, tail ? threadIdx.x : gtid, tail ? blockDim.x : gstride);
+        dfs_work<false, HAS_A>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib], p.bufV[ob],
+                        p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
         F v[6];
         {
             F a[3], b[3];
@@ -1017,27 +1062,44 @@ __global__ void __launch_bounds__(256, 2) k_phase_dfs(DfsArgs p) {
             racc_finish(acc2, b);
             v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = b[0]; v[4] = b[1]; v[5] = b[2];
         }
+        VP_DBG_T(1);
+        if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
+            unsigned long long t_; unsigned int sm_;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+            p.dbg[256 + 2 * blockIdx.x] = t_;
+            p.dbg[256 + 2 * blockIdx.x + 1] = sm_;
+        }
         block_sum<6>(v, smem);
         F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
         const PassCol* cols = p.cols + R.col_begin;
         // tables that were already down to one value join add_term in the pass's first round; their value sits in the
         // IN buffer, which the next pass overwrites: read it before the barrier
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, prev1, p.claims);
-        if (!tail) {
-            if (threadIdx.x == 0) {
+            at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, prev1, p.claims, HAS_A);
+        if (!solo) {
+            if (threadIdx.x == 0 && blockIdx.x != 0) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
             }
-            grid.sync();
+            pass_arrive(p.bar);
+            target += active;
+            // does this block have work in a later pass? (block 0 always stays)
+            const uint32_t next_work = ps + 1 < p.n_passes ? p.passes[ps + 1].work : 0;
+            if (blockIdx.x != 0 && blockIdx.x * DFS_CHUNK >= next_work) return;
+            pass_wait(p.bar, target);
+            VP_DBG_T(2);
             if (blockIdx.x == 0) {
+                F t6[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) v[k] = f_zero();
-                for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+                for (int k = 0; k < 6; ++k) t6[k] = f_zero();
+                for (uint32_t b = 1 + threadIdx.x; b < active; b += blockDim.x) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) v[k] = f_add(v[k], ld_one<false>(part + (size_t)b * 6 + k));
+                    for (int k = 0; k < 6; ++k) t6[k] = f_add(t6[k], ld_one<false>(part + (size_t)b * 6 + k));
                 }
-                block_sum<6>(v, smem);
+                block_sum<6>(t6, smem);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) v[k] = f_add(v[k], t6[k]);   // thread 0: own block's sum + the others'
             }
         } else __syncthreads();   // this pass's outputs (a table reaching one value) are visible to thread 0
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1047,17 +1109,22 @@ __global__ void __launch_bounds__(256, 2) k_phase_dfs(DfsArgs p) {
             st_f(o + 2, f_add(v[2], at));
             if (R.n_rounds == 2) {
                 // tables that reached one value in this pass's first round join in its second round (OUT buffer)
-                at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, r1, p.claims);
+                at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, r1, p.claims, HAS_A);
                 st_f(o + 3, v[3]);
                 st_f(o + 4, f_sub(v[4], at));
                 st_f(o + 5, f_add(v[5], at));
             }
         }
+        VP_DBG_T(3);
         j += R.n_rounds;
     }
     if (blockIdx.x != 0) return;
     __syncthreads();
-    if (threadIdx.x == 0) st_f(p.add_term, at);
+    if (threadIdx.x == 0) {
+        st_f(p.add_term, at);
+        *p.bar = 0;   // every other block has arrived for the last time: ready for the next launch
+    }
+    for (uint32_t i = threadIdx.x; i < p.n_passes; i += blockDim.x) p.chunk_ctr[i] = 0;
     // final claims: a table alive to the end is down to its level-R value (prover.cpp:494-521)
     const F* V = p.bufV[p.fin_buf];
     for (uint32_t i = threadIdx.x; i < p.n_fin; i += blockDim.x) {

@@ -505,7 +505,7 @@ struct LayerDev {
     PhasePlan ph1, ph2, ph3;
     int max_dad_bl = -1;
     // eq build descriptor slices (indices into Engine::eq_descs)
-    uint32_t eqb_g = 0, eqb_u = 0, eqb_liu = 0, n_eqb_liu = 0;
+    uint32_t eqb_g = 0, eqb_u = 0, eqb_u1 = 0, eqb_liu = 0, n_eqb_liu = 0;
     DBuf<EqTab> liu_eqtabs;
     // challenge indices
     uint32_t ci_ru = 0, ci_assert = 0, ci_rv = 0, ci_sig = 0, ci_rliu = 0, ci_g = 0;
@@ -569,6 +569,25 @@ struct Engine {
     DBuf<PassTab> d_ptabs;
     DBuf<PassCol> d_pcols;
     DBuf<PassDev> d_pdev;
+    // second lane: the Liu phases only need the challenges, not the results of phase 1/2, so vp_prove runs them on
+    // their own stream with their own table buffers; the latency-bound tail of one phase then overlaps the bulk
+    // passes of an independent phase. swap_lane() exchanges the lane-specific members (host-side pointer swaps).
+    struct LaneRes {
+        cudaStream_t stream = nullptr;
+        DBuf<F> bufV[2], bufM[2], bufA[2], d_scal, d_partials;
+        DBuf<unsigned int> d_counter;
+    } lane1;
+    bool two_lanes = false, on_lane1 = false;
+    cudaEvent_t ev_eval = nullptr, ev_lane1 = nullptr;
+    uint32_t region_u_lane1 = 0;
+    void swap_lane() {
+        std::swap(stream, lane1.stream);
+        for (int b = 0; b < 2; ++b) { std::swap(bufV[b], lane1.bufV[b]); std::swap(bufM[b], lane1.bufM[b]); std::swap(bufA[b], lane1.bufA[b]); }
+        std::swap(d_scal, lane1.d_scal);
+        std::swap(d_partials, lane1.d_partials);
+        std::swap(d_counter, lane1.d_counter);
+        on_lane1 = !on_lane1;
+    }
     bool use_dfs = true;   // two rounds per pass in vp_prove (k_phase_dfs); false: one round per pass (k_sumcheck_phase)
     int cap_dfs = 0;
     int n = 0;            // layers
@@ -657,7 +676,11 @@ struct Engine {
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (on_lane1) swap_lane();
         if (stream && own_stream) cudaStreamDestroy(stream);
+        if (lane1.stream) cudaStreamDestroy(lane1.stream);
+        if (ev_eval) cudaEventDestroy(ev_eval);
+        if (ev_lane1) cudaEventDestroy(ev_lane1);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     }
 
@@ -797,7 +820,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
 
     // eq scratch: region 0 = beta_g, 1 = beta_u, 2 = output/input MLE, 3.. = Liu tables
     eq_half_cap = 1u << ((max_bl + 1) >> 1);
-    const uint32_t n_regions = 3 + (uint32_t)n;
+    const uint32_t n_regions = 4 + (uint32_t)n;
+    region_u_lane1 = 3 + (uint32_t)n;   // lane 1's own copy of beta_u
     d_eq.alloc((size_t)n_regions * 2 * eq_half_cap);
 
     // values
@@ -875,6 +899,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         add_eq_build(0, D.ci_g, C.bit_length(i), -1);
         D.eqb_u = (uint32_t)eq_descs.size();
         add_eq_build(1, D.ci_ru, pb, -1);
+        D.eqb_u1 = (uint32_t)eq_descs.size();
+        add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, -1);
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
@@ -1007,6 +1033,25 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         bufV[b].alloc(cap);
         bufM[b].alloc(cap);
         bufA[b].alloc(cap);
+    }
+    two_lanes = world == 1 && !getenv("VP_ONE_LANE");
+    if (two_lanes) {
+        uint32_t c0 = 4, c1 = 4;
+        for (int i = 1; i < n; ++i) { c0 = std::max(c0, L[i].ph3.cap0); c1 = std::max(c1, L[i].ph3.cap1); }
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t cap = b == 0 ? c0 : c1;
+            lane1.bufV[b].alloc(cap);
+            lane1.bufM[b].alloc(cap);
+            lane1.bufA[b].alloc(4);   // the Liu add table is never stored in whole-proof mode
+        }
+        lane1.d_scal.alloc(SC_N);
+        lane1.d_partials.alloc((size_t)12 * (size_t)max_grid);
+        lane1.d_counter.alloc(4 + 64);
+        CK(cudaMemsetAsync(lane1.d_scal.p, 0, SC_N * sizeof(F), stream));
+        CK(cudaMemsetAsync(lane1.d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
+        CK(cudaStreamCreateWithFlags(&lane1.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_eval, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_lane1, cudaEventDisableTiming));
     }
     d_rowpart.alloc(max_partial);
     if (world > 1) {
@@ -1150,14 +1195,18 @@ void Engine::do_init_phase2(int i) {
 void Engine::do_init_liu(int i, bool write_a) {
     LayerDev& D = L[i];
     const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
-    if (!have_equ) run_eq(D.eqb_u, 2);
-    have_equ = false;
+    const uint32_t reg_u = on_lane1 ? region_u_lane1 : 1;
+    if (on_lane1) run_eq(D.eqb_u1, 2);
+    else {
+        if (!have_equ) run_eq(D.eqb_u, 2);
+        have_equ = false;
+    }
     run_eq(D.eqb_liu, D.n_eqb_liu);
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
-        D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(1, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
+        D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
         bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
         write_a ? 1 : 0);
     prof_end(h, (double)n_local * (write_a ? 64.0 : 48.0));
@@ -1255,7 +1304,10 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     a.bar = d_counter.p + 2;
     a.chunk_ctr = d_counter.p + 4;
     a.dbg = nullptr;
-    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), (uint32_t)cap_dfs));
+    // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
+    // this one is down to its small passes
+    const uint32_t cap = two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), cap));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
     CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(256),
@@ -1310,6 +1362,10 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
     evaluate();
+    if (two_lanes && use_phase_kernel && use_dfs) {   // fork: lane 1 needs the circuit values (and the uploaded challenges)
+        CK(cudaEventRecord(ev_eval, stream));
+        CK(cudaStreamWaitEvent(lane1.stream, ev_eval, 0));
+    }
     do_vres();
     for (int i = n - 1; i >= 1; --i) {
         LayerDev& D = L[i];
@@ -1328,12 +1384,19 @@ void Engine::prove_all() {
                 do_finalize(D.ph2.planB, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
             }
         }
+        const bool lane = two_lanes && use_phase_kernel && use_dfs;
+        if (lane) swap_lane();
         do_init_liu(i, !(use_phase_kernel && use_dfs));
         if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr, /*has_a=*/!use_dfs);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph3.planB, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
         }
+        if (lane) swap_lane();
+    }
+    if (two_lanes && use_phase_kernel && use_dfs) {   // join: the input MLE and the transcript copy follow on lane 0
+        CK(cudaEventRecord(ev_lane1, lane1.stream));
+        CK(cudaStreamWaitEvent(stream, ev_lane1, 0));
     }
     do_input_mle();
     CK(cudaGetLastError());

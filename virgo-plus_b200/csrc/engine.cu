@@ -578,6 +578,7 @@ struct Engine {
         DBuf<unsigned int> d_counter;
     } lane1;
     bool two_lanes = false, on_lane1 = false;
+    bool direct_v = false;   // whole-proof, unsharded: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
     cudaEvent_t ev_eval = nullptr, ev_lane1 = nullptr;
     uint32_t region_u_lane1 = 0;
     void swap_lane() {
@@ -724,10 +725,11 @@ struct Engine {
     void do_init_phase2(int i);
     void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
-    void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a = true);
+    void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a = true,
+                  const F* v_first = nullptr);
     void do_init_liu(int i, bool write_a);
     void launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out, F* claims,
-                           F* out_poly, F* keep, bool has_a);
+                           F* out_poly, F* keep, bool has_a, const F* v_first = nullptr);
     void launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
                              F* claims, F* out_poly, F* keep);
     uint32_t tail_work = 512;
@@ -900,7 +902,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         D.eqb_u = (uint32_t)eq_descs.size();
         add_eq_build(1, D.ci_ru, pb, -1);
         D.eqb_u1 = (uint32_t)eq_descs.size();
-        add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, -1);
+        add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, (int)D.ci_sig);   // lane 1's copy is only used by Liu: bake s[0] in
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
@@ -1145,15 +1147,15 @@ void Engine::do_init_phase1(int i) {
     k_init_phase1<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1), 256, 0, stream>>>(
         D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
         d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
-        bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0]);
+        bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1);
     if (D.p1_long.n) {
         k_combine_phase1<<<grid_for((uint32_t)(D.p1_long.n * K), cap_comb), 256, 0, stream>>>(
             D.p1_long.p, (uint32_t)D.p1_long.n, S_pre, K, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0],
-            bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0]);
+            bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1);
         ++launches;
     }
     // per output: V read + 3 table writes; per gate: one gathered operand
-    prof_end(h, (double)tot * 64.0 + (double)D.S * K * 16.0);
+    prof_end(h, (double)tot * (direct_v ? 32.0 : 64.0) + (double)D.S * K * 16.0);
     ++launches;
     have_equ = false;
 }
@@ -1208,8 +1210,8 @@ void Engine::do_init_liu(int i, bool write_a) {
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
         D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
         bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
-        write_a ? 1 : 0);
-    prof_end(h, (double)n_local * (write_a ? 64.0 : 48.0));
+        write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1);
+    prof_end(h, (double)n_local * ((write_a ? 64.0 : 48.0) - (direct_v ? 32.0 : 0.0)));
     ++launches;
 }
 
@@ -1281,7 +1283,7 @@ void Engine::launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t ro
 
 // One cooperative launch of k_phase_dfs (two rounds per pass) over `P`.
 void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
-                               F* claims, F* out_poly, F* keep, bool has_a) {
+                               F* claims, F* out_poly, F* keep, bool has_a, const F* v_first) {
     DfsArgs a;
     for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
     a.passes = d_pdev.p + P.pass_begin;
@@ -1303,6 +1305,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     a.partials = d_partials.p;
     a.bar = d_counter.p + 2;
     a.chunk_ctr = d_counter.p + 4;
+    a.v_first = v_first;
     a.dbg = nullptr;
     // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
     // this one is down to its small passes
@@ -1319,9 +1322,10 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
 // All rounds + the final claims of one sumcheck phase. Unsharded: one cooperative launch. Sharded: the m local
 // rounds on this rank's blocks, fold-only, ONE all-gather of the per-rank records (collapsed blocks + partial
 // round polynomials + partial add_term + claims), merge, then the remaining rounds replicated on every rank.
-void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a) {
+void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a,
+                      const F* v_first) {
     if (!P.sharded) {
-        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a);
+        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a, v_first);
         else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
@@ -1361,6 +1365,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
+    direct_v = world == 1 && use_phase_kernel && use_dfs;
     evaluate();
     if (two_lanes && use_phase_kernel && use_dfs) {   // fork: lane 1 needs the circuit values (and the uploaded challenges)
         CK(cudaEventRecord(ev_eval, stream));
@@ -1371,7 +1376,7 @@ void Engine::prove_all() {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
         do_init_phase1(i);
-        if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, scal(SC_VU), nullptr);
+        if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, scal(SC_VU), nullptr, true, direct_v ? val[i - 1].p : nullptr);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph1.planB, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph1.planB, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
@@ -1387,7 +1392,7 @@ void Engine::prove_all() {
         const bool lane = two_lanes && use_phase_kernel && use_dfs;
         if (lane) swap_lane();
         do_init_liu(i, !(use_phase_kernel && use_dfs));
-        if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr, /*has_a=*/!use_dfs);
+        if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr, /*has_a=*/!use_dfs, direct_v ? val[i - 1].p : nullptr);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph3.planB, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
@@ -1399,6 +1404,7 @@ void Engine::prove_all() {
         CK(cudaStreamWaitEvent(stream, ev_lane1, 0));
     }
     do_input_mle();
+    direct_v = false;
     CK(cudaGetLastError());
 }
 
@@ -2223,6 +2229,7 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     a.partials = s->d_partials.p;
     a.bar = s->d_counter.p + 2;
     a.chunk_ctr = s->d_counter.p + 4;
+    a.v_first = nullptr;
     a.dbg = s->d_dbg.p;
     CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));

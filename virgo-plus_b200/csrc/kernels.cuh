@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256)
 k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
               EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
               const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
-              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm) {
+              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm, int write_v) {
     const uint64_t total = (uint64_t)n_items * K;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)k * n_items);
@@ -309,7 +309,7 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
         }
         const uint32_t slot = I.cnt_slot >> 8;
         if (slot == 0) {
-            st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));
+            if (write_v) st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));
             st_f(tM + loc, M);
             st_f(tA + loc, A);
         } else {
@@ -323,7 +323,7 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 __global__ void __launch_bounds__(256)
 k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
                  F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,
-                 ShardMap sm) {
+                 ShardMap sm, int write_v) {
     const uint64_t total = (uint64_t)n_rows * K;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)k * n_rows);
@@ -337,7 +337,7 @@ k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_p
             M = f_add(M, ld_f_cg(src));
             A = f_add(A, ld_f_cg(src + 1));
         }
-        st_f(tV + loc, ld_f(Vpre + u));
+        if (write_v) st_f(tV + loc, ld_f(Vpre + u));
         st_f(tM + loc, M);
         st_f(tA + loc, A);
     }
@@ -485,19 +485,21 @@ struct LiuEntry {       // one (j, slot0) pair pointing at template u0
 __global__ void __launch_bounds__(256)
 k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
            uint32_t S_pre, uint32_t K, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
-           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local, int write_a) {
+           F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local, int write_a,
+           int equ_scaled, int write_v) {
     const uint32_t n = S_pre * K;
     const F s0 = *s0_ptr;
     for (uint32_t loc = blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += gridDim.x * blockDim.x) {
         const uint32_t u = shard_global(sm, loc);
         if (u >= n) continue;
         const uint32_t k = u / S_pre, u0 = u - k * S_pre;
-        F M = f_mul(s0, eq_at(equ, u));
+        F M = eq_at(equ, u);                       // equ_scaled: its first half table already carries s[0]
+        if (!equ_scaled) M = f_mul(s0, M);
         for (uint32_t e = off[u0]; e < off[u0 + 1]; ++e) {
             const LiuEntry E = ent[e];
             M = f_add(M, eq_at(eqs[E.eq_id], (K - 1 - k) * E.D + E.slot0));
         }
-        st_f(tV + loc, ld_f(Vpre + u));
+        if (write_v) st_f(tV + loc, ld_f(Vpre + u));   // unsharded whole-proof mode reads V straight from circuitValue
         st_f(tM + loc, M);
         if (write_a) st_f(tA + loc, f_zero());   // the Liu add table is identically zero: only the one-round-per-launch path reads it
     }
@@ -900,6 +902,7 @@ struct DfsArgs {
     F* partials;               // 2 * gridDim.x * 6
     unsigned int* bar;         // grid-barrier counter, zero at launch (the kernel leaves it zero)
     unsigned int* chunk_ctr;   // one work counter per pass, zero at launch (the kernel leaves them zero)
+    const F* v_first;          // if set: the first pass reads its V table from here (circuitValue[i-1], no copy made)
     unsigned long long* dbg;   // optional: block 0 writes %globaltimer at 4 points of every pass (profiling aid)
 };
 
@@ -1053,7 +1056,8 @@ __global__ void __launch_bounds__(256, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
         RoundAcc acc1, acc2;
         racc_init(acc1);
         racc_init(acc2);
-        dfs_work<false, HAS_A>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, p.bufV[ib], p.bufM[ib], p.bufA[ib], p.bufV[ob],
+        dfs_work<false, HAS_A>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib],
+                               p.bufM[ib], p.bufA[ib], p.bufV[ob],
                         p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
         F v[6];
         {
@@ -1126,7 +1130,7 @@ __global__ void __launch_bounds__(256, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     }
     for (uint32_t i = threadIdx.x; i < p.n_passes; i += blockDim.x) p.chunk_ctr[i] = 0;
     // final claims: a table alive to the end is down to its level-R value (prover.cpp:494-521)
-    const F* V = p.bufV[p.fin_buf];
+    const F* V = (p.n_passes == 0 && p.v_first) ? p.v_first : p.bufV[p.fin_buf];   // zero rounds: the value was never copied
     for (uint32_t i = threadIdx.x; i < p.n_fin; i += blockDim.x) {
         const FinDesc f = p.fins[i];
         F c;

@@ -128,7 +128,8 @@ struct PassPlan {
     uint32_t pass_begin = 0, n_passes = 0, fin_begin = 0, n_fin = 0;
     int fin_buf = 0;
     uint32_t cap0 = 0, cap1 = 0, max_work = 0;
-    double bytes = 0;                          // algorithmic bytes: 48 B per live entry read + 48 B per entry written
+    double bytes = 0;                          // bytes this plan really moves: 48 B per live entry read + 48 B per entry written
+    double alg_bytes = 0;                      // SURVEY 8(d) model: 144 B per live table entry over the whole sumcheck
     std::vector<uint32_t> off0, end_off, end_live;
 };
 static PassPlan build_pass_plan(const std::vector<PlanTable>& tabs, int rounds, const std::vector<uint32_t>& fin_out,
@@ -146,6 +147,7 @@ static PassPlan build_pass_plan(const std::vector<PlanTable>& tabs, int rounds, 
     }
     P.off0 = off;
     P.cap0 = o;
+    for (size_t t = 0; t < nt; ++t) P.alg_bytes += 144.0 * tabs[t].live;
     P.pass_begin = (uint32_t)A.pdev.size();
     int cur = 0;
     for (int j = 1; j <= rounds;) {
@@ -1315,7 +1317,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     size_t h = prof_begin(KC_ROUND_FOLD);
     CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(256),
                                    args, 0, stream));
-    prof_end(h, has_a ? P.bytes : P.bytes * (2.0 / 3.0));
+    prof_end(h, P.alg_bytes);
     ++launches;
 }
 

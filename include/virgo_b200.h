@@ -84,6 +84,15 @@ int vp_draw_challenges(const vp_circuit* c, unsigned seed, vp_F* out /* vp_chall
  * bl(i-1) x (a,b,c), claim_liu; finally the input-layer MLE. */
 size_t vp_transcript_len(const vp_circuit* c);
 
+/* Transcript containers. GKRProof byte stream = the layout of GKRProof::write (src/GKRProof.hpp:23-58; the struct is
+ * dead code in the reference): members final_claims_u, final_claims, final_claims_v, polys_u, polys_v,
+ * polys, outer vectors indexed by layer id; the reference's undefined poly_proof part is replaced by a trailer
+ * {u64 2, Vres, input MLE}. out == NULL: only *len is set. Text dump: "TAG real img" lines. */
+int vp_transcript_to_gkrproof(const vp_circuit* c, const vp_F* transcript, unsigned char* out, size_t cap, size_t* len);
+int vp_gkrproof_to_transcript(const vp_circuit* c, const unsigned char* bytes, size_t len, vp_F* transcript);
+int vp_transcript_text(const vp_circuit* c, const vp_F* transcript, const vp_F* challenges, char* out, size_t cap,
+                       size_t* len);
+
 /* ------------------------------------------------------------------ prover
  * One context = one `prover` object (src/prover.h:12-67) on one GPU. */
 int vp_create(const vp_circuit* c, int device, vp_ctx** out);

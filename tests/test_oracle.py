@@ -211,3 +211,25 @@ def test_oracle_matches_compiled_reference_on_random_circuits(B, O, n_layers, lo
     want, _, _ = O.ref_prove(flat)
     got, _, _ = O.OracleCircuit(flat).prove()
     assert (got["re"] == want["re"]).all() and (got["im"] == want["im"]).all()
+
+
+# ------------------------------------------------------------------ transcript containers (host side of the product)
+def test_transcript_text_and_gkrproof_container(B, O, sha_circuit):
+    """the product's own text dump reproduces the reference's golden dump byte for byte, and the GKRProof byte
+    stream (src/GKRProof.hpp:23-58 layout) round-trips"""
+    import struct
+    tr, ch, _ = O.OracleCircuit(sha_circuit.flat()).prove()
+    assert sha_circuit.transcript_text(tr, ch) == H.golden_bytes("sha256_64.transcript.txt.xz").decode()
+    blob = sha_circuit.to_gkrproof(tr)
+    n = sha_circuit.n_layers
+    assert struct.unpack_from("<Q", blob, 0)[0] == n                       # final_claims_u: one slot per layer id
+    # layer 14's claim_u sits in slot 14 of final_claims_u
+    re, im = struct.unpack_from("<QQ", blob, 8 + 16 * (n - 1))
+    assert (re, im) == (int(tr[1 + 3 * sha_circuit.bit_length(n - 2)]["re"]), int(tr[1 + 3 * sha_circuit.bit_length(n - 2)]["im"]))
+    # 439 round polynomials x 48 B + claims: GKR part = reference proof size 22 976 B + the zero slots / length words
+    back = sha_circuit.from_gkrproof(blob)
+    assert (back["re"] == tr["re"]).all() and (back["im"] == tr["im"]).all()
+    with pytest.raises(B.VpError):
+        sha_circuit.from_gkrproof(blob[:-8])
+    with pytest.raises(B.VpError):
+        sha_circuit.from_gkrproof(blob + b"\\0" * 8)

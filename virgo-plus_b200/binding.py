@@ -70,6 +70,9 @@ def _declare(L):
     L.vp_draw_challenges.argtypes = [vp, C.c_uint, vp]
     L.vp_transcript_len.argtypes = [vp]
     L.vp_transcript_len.restype = C.c_size_t
+    L.vp_transcript_to_gkrproof.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.vp_gkrproof_to_transcript.argtypes = [vp, vp, C.c_size_t, vp]
+    L.vp_transcript_text.argtypes = [vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.vp_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.vp_nccl_unique_id.argtypes = [vp]
     L.vp_create_sharded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
@@ -269,6 +272,31 @@ class Circuit:
         out = np.zeros(self.challenge_count, F_DTYPE)
         _ck(lib().vp_draw_challenges(self.h, seed, _ptr(out)))
         return out
+
+    def to_gkrproof(self, transcript):
+        """bytes in the layout of GKRProof::write (src/GKRProof.hpp:23-58) + {Vres, input MLE} trailer"""
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        assert len(tr) == self.transcript_len
+        n = C.c_size_t()
+        _ck(lib().vp_transcript_to_gkrproof(self.h, _ptr(tr), None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        _ck(lib().vp_transcript_to_gkrproof(self.h, _ptr(tr), _ptr(buf), len(buf), C.byref(n)))
+        return buf.tobytes()
+
+    def from_gkrproof(self, data):
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        tr = np.zeros(self.transcript_len, F_DTYPE)
+        _ck(lib().vp_gkrproof_to_transcript(self.h, _ptr(buf), len(buf), _ptr(tr)))
+        return tr
+
+    def transcript_text(self, transcript, challenges=None):
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        ch = np.ascontiguousarray(self.draw_challenges() if challenges is None else challenges, dtype=F_DTYPE)
+        n = C.c_size_t()
+        _ck(lib().vp_transcript_text(self.h, _ptr(tr), _ptr(ch), None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        _ck(lib().vp_transcript_text(self.h, _ptr(tr), _ptr(ch), _ptr(buf), len(buf), C.byref(n)))
+        return buf.tobytes().decode()
 
     def flat(self):
         """Flat arrays of this circuit (instances must be 1), concatenated over layers (used by tests)."""

@@ -18,6 +18,7 @@
 
 #include "../../include/virgo_b200.h"
 #include "../host/circuit_model.h"
+#include "../host/proof_io.h"
 #include "kernels.cuh"
 
 using namespace vp;
@@ -1603,6 +1604,33 @@ extern "C" size_t vp_transcript_len(const vp_circuit* c) {
         t += 3 * (size_t)pb + 1;
     }
     return t + 1;
+}
+
+// ------------------------------------------------------------------ C ABI: transcript containers
+extern "C" int vp_transcript_to_gkrproof(const vp_circuit* c, const vp_F* transcript, unsigned char* out, size_t cap, size_t* len) {
+    if (!c || !transcript || !len) return fail(VP_ERR_ARG, "null argument");
+    std::vector<unsigned char> b = transcript_to_gkrproof(c->c, reinterpret_cast<const F*>(transcript));
+    *len = b.size();
+    if (!out) return VP_OK;   // size query
+    if (cap < b.size()) return fail(VP_ERR_ARG, "output buffer too small (%zu < %zu)", cap, b.size());
+    memcpy(out, b.data(), b.size());
+    return VP_OK;
+}
+extern "C" int vp_gkrproof_to_transcript(const vp_circuit* c, const unsigned char* bytes, size_t len, vp_F* transcript) {
+    if (!c || !bytes || !transcript) return fail(VP_ERR_ARG, "null argument");
+    std::string err = gkrproof_to_transcript(c->c, bytes, len, reinterpret_cast<F*>(transcript));
+    if (!err.empty()) return fail(VP_ERR_ARG, "%s", err.c_str());
+    return VP_OK;
+}
+extern "C" int vp_transcript_text(const vp_circuit* c, const vp_F* transcript, const vp_F* challenges, char* out, size_t cap,
+                                  size_t* len) {
+    if (!c || !transcript || !challenges || !len) return fail(VP_ERR_ARG, "null argument");
+    std::string t = transcript_text(c->c, reinterpret_cast<const F*>(transcript), reinterpret_cast<const F*>(challenges));
+    *len = t.size();
+    if (!out) return VP_OK;
+    if (cap < t.size()) return fail(VP_ERR_ARG, "output buffer too small");
+    memcpy(out, t.data(), t.size());
+    return VP_OK;
 }
 
 // ------------------------------------------------------------------ C ABI: prover

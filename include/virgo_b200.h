@@ -103,12 +103,12 @@ int vp_create_sharded(const vp_circuit* c, int device, int rank, int world, cons
                       vp_ctx** out);
 void vp_destroy(vp_ctx* ctx);
 /* Host-only: how phase (1, 2 = phase 2, 3 = Liu) of `layer` is dealt out to `rank` of `world` GPUs.
- * out: 10 values per table {bits, live, sharded, m, first, local_live, local_len, present, n_blocks, rot}. */
+ * out: 10 values per table {bits, live, sharded, m, row_lo, row_hi, local_len, present, n_blocks, reversed}:
+ * the rank holds the live table entries [row_lo, row_hi). */
 int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int phase, uint32_t* out, size_t cap,
                       size_t* n_tables);
-/* Host-only: block-cyclic index map (block 2^m, 2^logG ranks, this rank's residue `first`):
- * returns 1 and *local if idx belongs to the rank, 0 if not. */
-int vp_shard_map_index(uint32_t m, uint32_t logG, uint32_t first, uint32_t idx, uint32_t* local);
+/* Host-only: index map of a rank holding the table entries [lo, hi): returns 1 and *local if idx belongs to it. */
+int vp_shard_map_index(uint32_t lo, uint32_t hi, uint32_t idx, uint32_t* local);
 
 /* Upload the witness inputs (instances * layer_size(0) values < p); default: the circuit's own. */
 int vp_set_inputs(vp_ctx* ctx, const uint64_t* inputs, size_t n);

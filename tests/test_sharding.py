@@ -10,24 +10,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_block_cyclic_index_map_is_a_partition(B):
-    for m, logG in [(2, 1), (3, 2), (4, 3), (2, 3)]:
-        G = 1 << logG
-        n = (1 << m) * G * 5 + 3
-        seen = {}
-        for first in range(G):
-            locs = []
-            for idx in range(n):
-                mine, loc = B.shard_map_index(m, logG, first, idx)
-                if mine:
-                    assert idx not in seen
-                    seen[idx] = first
-                    locs.append(loc)
-            assert locs == sorted(locs) and len(set(locs)) == len(locs)   # order-preserving and injective
-            # local blocks are dense: block q of the rank starts at q * 2^m
-            assert all((l >> m) == (i >> m) for i, l in enumerate(locs) if (i & ((1 << m) - 1)) == 0 or True) or True
-        assert len(seen) == n
-    mine, loc = B.shard_map_index(31, 0, 0, 12345)   # world == 1: identity
+def test_range_index_map(B):
+    for lo, hi in [(0, 16), (16, 48), (48, 48), (1024, 4096)]:
+        for idx in list(range(0, 64)) + [1023, 1024, 4095, 4096]:
+            mine, loc = B.shard_map_index(lo, hi, idx)
+            assert mine == (lo <= idx < hi)
+            if mine:
+                assert loc == idx - lo
+    mine, loc = B.shard_map_index(0, 0xffffffff, 12345)   # world == 1: identity
     assert mine and loc == 12345
 
 
@@ -54,15 +44,28 @@ def _worker(rank, world, port, q):
             t0 = tabs[0]
             assert all(t["bits"] == t0["bits"] and t["live"] == t0["live"] and t["sharded"] == t0["sharded"] for t in tabs)
             if not t0["sharded"]:
-                ok &= all(t["local_live"] == t0["live"] and t["present"] == 1 for t in tabs)   # replicated
+                ok &= all(t["row_lo"] == 0 and t["row_hi"] == t0["live"] and t["present"] == 1 for t in tabs)   # replicated
                 continue
             n_sharded += 1
-            ok &= sum(t["local_live"] for t in tabs) == t0["live"]                    # every live entry has one owner
+            bs = 1 << t0["m"]
             if t0["bits"] >= t0["m"]:
-                ok &= sorted(t["first"] for t in tabs) == list(range(world))          # residues are a permutation
-                ok &= max(t["local_live"] for t in tabs) - min(t["local_live"] for t in tabs) <= (1 << t0["m"])  # balance
+                # the ranks' row ranges tile [0, live) without gaps or overlaps, block aligned, in rank order
+                # (reverse rank order for phase-2 tables), and differ by at most one block
+                order = sorted(tabs, key=lambda t: t["row_lo"] if t["row_hi"] > t["row_lo"] else 1 << 40)
+                pos = 0
+                for t in order:
+                    if t["row_hi"] == t["row_lo"]:
+                        continue
+                    ok &= t["row_lo"] == pos and t["row_lo"] % bs == 0
+                    pos = t["row_hi"]
+                ok &= pos == t0["live"]
+                sizes = [-(-(t["row_hi"] - t["row_lo"]) // bs) for t in tabs]
+                ok &= max(sizes) - min(sizes) <= 1
+                lows = [t["row_lo"] for t in tabs if t["row_hi"] > t["row_lo"]]
+                ok &= lows == sorted(lows, reverse=bool(t0["reversed"]))
             else:
                 ok &= sum(t["present"] for t in tabs) == 1                            # single block: one owner
+                ok &= sum(t["row_hi"] - t["row_lo"] for t in tabs) == t0["live"]
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, ok, n_sharded))

@@ -78,7 +78,7 @@ def _declare(L):
     L.vp_create_sharded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.vp_destroy.argtypes = [vp]
     L.vp_shard_describe.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
-    L.vp_shard_map_index.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
+    L.vp_shard_map_index.argtypes = [C.c_uint32] * 3 + [C.POINTER(C.c_uint32)]
     L.vp_destroy.restype = None
     L.vp_set_inputs.argtypes = [vp, vp, C.c_size_t]
     L.vp_evaluate.argtypes = [vp]
@@ -338,13 +338,13 @@ def shard_describe(circuit, world, rank, layer, phase):
     out = np.zeros(10 * 256, np.uint32)
     n = C.c_size_t()
     _ck(lib().vp_shard_describe(circuit.h, world, rank, layer, phase, _ptr(out), len(out), C.byref(n)))
-    keys = ("bits", "live", "sharded", "m", "first", "local_live", "local_len", "present", "n_blocks", "rot")
+    keys = ("bits", "live", "sharded", "m", "row_lo", "row_hi", "local_len", "present", "n_blocks", "reversed")
     return [dict(zip(keys, (int(x) for x in out[10 * t:10 * t + 10]))) for t in range(n.value)]
 
 
-def shard_map_index(m, logG, first, idx):
+def shard_map_index(lo, hi, idx):
     loc = C.c_uint32()
-    rc = lib().vp_shard_map_index(m, logG, first, idx, C.byref(loc))
+    rc = lib().vp_shard_map_index(lo, hi, idx, C.byref(loc))
     assert rc >= 0, "shard_global(shard_local(idx)) != idx"
     return (rc == 1), loc.value
 

@@ -227,6 +227,7 @@ struct PhasePlan {
     std::vector<ShardMap> maps;        // per global table
     std::vector<uint32_t> tab_off;     // offset of the table's level-0 values in buffer 0 on this rank
     std::vector<uint32_t> local_len;   // padded local length (multiple of the block size when sharded)
+    std::vector<uint32_t> row_lo, row_hi;  // live table entries [row_lo, row_hi) this rank holds (global indices)
     std::vector<uint8_t> present;
     uint32_t fo_begin = 0, n_fo = 0, mt_begin = 0, n_mt = 0;
     uint32_t rec_len = 0, sc_base = 0, n_poly = 0, n_claims = 0;
@@ -236,25 +237,22 @@ struct PhasePlan {
 
 static constexpr int CYC_BITS = 10;   // a sharded table is dealt out in 2^CYC_BITS blocks (the largest table of the phase)
 
-static uint32_t local_live_of(uint32_t n, int m, uint32_t G, uint32_t first, uint32_t* n_local_blocks) {
-    const uint32_t bs = 1u << m, n_blocks = (n + bs - 1) >> m;
-    const uint32_t cnt = n_blocks > first ? (n_blocks - first + G - 1) / G : 0;
-    if (n_local_blocks) *n_local_blocks = cnt;
-    if (!cnt) return 0;
-    const uint32_t last = first + (cnt - 1) * G, partial = n & (bs - 1);
-    return (cnt - 1) * bs + ((last == n_blocks - 1 && partial) ? partial : bs);
-}
+// slice s of G of a table with nb blocks: blocks [slice_begin(s), slice_begin(s+1))
+static inline uint32_t slice_begin(uint32_t nb, uint32_t G, uint32_t s) { return (uint32_t)((uint64_t)nb * s / G); }
 
 static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const std::vector<uint32_t>& fin_out,
                                PlanArena& A);
 
 // empty_fin_out: transcript slots of tables that never enter a plan (empty subsets): claim 0
 static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const std::vector<uint32_t>& empty_fin_out, int world,
-                            int rank, int n_claims, PlanArena& A) {
+                            int rank, int n_claims, PlanArena& A, bool rev = false) {
     PhasePlan P;
     P.rounds = rounds;
     const size_t nt = T.size();
-    P.maps.assign(nt, ShardMap{31, 0, 0, 0});
+    P.maps.assign(nt, ShardMap{0, 0xffffffffu});
+    P.row_lo.assign(nt, 0);
+    P.row_hi.assign(nt, 0);
+    for (size_t t = 0; t < nt; ++t) P.row_hi[t] = T[t].live;
     P.tab_off.assign(nt, 0);
     P.local_len.assign(nt, 0);
     P.present.assign(nt, 1);
@@ -303,25 +301,30 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
     std::vector<FinDesc> collapsed_fins;
     struct Dist { size_t t; uint32_t n_blocks, local_blocks, cnt; };
     std::vector<Dist> dist;
+    const uint32_t slice = rev ? G - 1 - (uint32_t)rank : (uint32_t)rank;   // phase-2 tables run in reverse instance order
     for (size_t t = 0; t < nt; ++t) {
-        const uint32_t rot = (uint32_t)(t % G), first = ((uint32_t)rank + G - rot) % G;
-        P.maps[t] = ShardMap{(uint32_t)m, (uint32_t)logG, first, 0};
+        const uint32_t nb = std::max<uint32_t>(1, (T[t].live + (1u << m) - 1) >> m);
+        const uint32_t b0 = slice_begin(nb, G, slice), b1 = slice_begin(nb, G, slice + 1);
+        const uint32_t lo = std::min<uint64_t>((uint64_t)b0 << m, T[t].live), hi = std::min<uint64_t>((uint64_t)b1 << m, T[t].live);
+        P.row_lo[t] = lo;
+        P.row_hi[t] = hi;
         if (T[t].bits >= m) {  // distributed: stays alive through the m local rounds
-            uint32_t lb = 0;
-            const uint32_t ll = local_live_of(T[t].live, m, G, first, &lb);
-            const uint32_t nb = (T[t].live + (1u << m) - 1) >> m;
+            P.maps[t] = ShardMap{b0 << m, (uint32_t)std::min<uint64_t>((uint64_t)b1 << m, 0xffffffffull)};
             idxA[t] = (uint32_t)tabsA.size();
-            tabsA.push_back(PlanTable{99, ll, -1, 0});
-            P.local_len[t] = lb << m;
-            dist.push_back(Dist{t, nb, lb, (nb + G - 1) / G});
+            tabsA.push_back(PlanTable{99, hi - lo, -1, 0});
+            P.local_len[t] = (b1 - b0) << m;
+            dist.push_back(Dist{t, nb, b1 - b0, (nb + G - 1) / G});
             tabsB.push_back(PlanTable{T[t].bits - m, nb, T[t].claim_slot, 0});
             finB.push_back(T[t].fin_out);
-        } else {               // a single block: lives (and collapses) entirely on its owner
-            P.present[t] = first == 0;
+        } else {               // a single block: lives (and collapses) entirely on the rank holding the last slice
+            P.present[t] = b1 > b0;
             if (P.present[t]) {
                 idxA[t] = (uint32_t)tabsA.size();
                 tabsA.push_back(PlanTable{T[t].bits, T[t].live, T[t].claim_slot, 0});
                 P.local_len[t] = T[t].live;
+            } else {
+                P.maps[t] = ShardMap{0, 0};
+                P.row_lo[t] = P.row_hi[t] = 0;
             }
             collapsed_fins.push_back(FinDesc{0, 0, T[t].claim_slot, T[t].fin_out});
         }
@@ -348,7 +351,15 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
         const uint32_t ia = idxA[d.t];
         // after the m local rounds every local block is down to one value: copy them into the record (fold = 0)
         A.fo.push_back(FoldOnlyDesc{P.ppA.end_off[ia], P.ppA.end_live[ia], d.local_blocks, base, d.cnt, 0});
-        A.mt.push_back(MergeTab{base, d.cnt, d.n_blocks, P.ppB.off0[q], (uint32_t)(d.t % G), 0});
+        MergeTab mt;
+        memset(&mt, 0, sizeof mt);
+        mt.rec_base = base;
+        mt.cnt = d.cnt;
+        mt.n_blocks = d.n_blocks;
+        mt.out_off = P.ppB.off0[q];
+        mt.rev = rev ? 1 : 0;
+        for (uint32_t sl = 0; sl <= G; ++sl) mt.sb[sl] = slice_begin(d.n_blocks, G, sl);
+        A.mt.push_back(mt);
         base += 3 * d.cnt;
     }
     P.n_fo = (uint32_t)dist.size();
@@ -488,6 +499,8 @@ struct LayerDev {
     DBuf<RowItem> p1_items;
     DBuf<LongRow> p1_long;
     uint32_t p1_nslots = 0;
+    uint32_t p1_k0 = 0, p1_k1 = 0;       // instance range of this rank's phase-1 rows
+    uint32_t p2_kk0 = 0, p2_kk1 = 0;     // reversed-instance range of this rank's phase-2 rows
     // phase 2
     DBuf<uint32_t> p2_dad_all, p2_g0, p2_u0;
     DBuf<uint8_t> p2_ty;
@@ -524,6 +537,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(vp_ncclComm_t*, int, /* ncclUniqueId by value: 128 bytes */ struct NcclId, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, vp_ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, vp_ncclComm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(vp_ncclComm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -548,6 +562,7 @@ static void nccl_load() {
     g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(vp_ncclComm_t*, int, NcclId, int))sym("ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, vp_ncclComm_t, cudaStream_t))sym("ncclAllGather");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, vp_ncclComm_t, cudaStream_t))sym("ncclBroadcast");
     g_nccl.CommDestroy = (int (*)(vp_ncclComm_t))sym("ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
 }
@@ -565,6 +580,8 @@ struct Engine {
     Circuit C;
     int device = 0;
     int world = 1, rank = 0;
+    uint32_t k_lo = 0, k_hi = 0;     // instances [k_lo, k_hi) this rank evaluates (all of them when world == 1)
+    uint32_t ko_lo = 0, ko_hi = 0;   // this rank's own slice of the instances (disjoint over the ranks): dot products, unary sums
     vp_ncclComm_t comm = nullptr;
     DBuf<F> d_send, d_recv;
     DBuf<FoldOnlyDesc> d_fo;
@@ -577,8 +594,9 @@ struct Engine {
     // passes of an independent phase. swap_lane() exchanges the lane-specific members (host-side pointer swaps).
     struct LaneRes {
         cudaStream_t stream = nullptr;
-        DBuf<F> bufV[2], bufM[2], bufA[2], d_scal, d_partials;
+        DBuf<F> bufV[2], bufM[2], bufA[2], d_scal, d_partials, d_send, d_recv, d_claims;
         DBuf<unsigned int> d_counter;
+        vp_ncclComm_t comm = nullptr;
     } lane1;
     bool two_lanes = false, on_lane1 = false;
     bool direct_v = false;   // whole-proof, unsharded: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
@@ -590,6 +608,10 @@ struct Engine {
         std::swap(d_scal, lane1.d_scal);
         std::swap(d_partials, lane1.d_partials);
         std::swap(d_counter, lane1.d_counter);
+        std::swap(d_claims, lane1.d_claims);
+        std::swap(d_send, lane1.d_send);
+        std::swap(d_recv, lane1.d_recv);
+        std::swap(comm, lane1.comm);
         on_lane1 = !on_lane1;
     }
     bool use_dfs = true;   // two rounds per pass in vp_prove (k_phase_dfs); false: one round per pass (k_sumcheck_phase)
@@ -686,6 +708,7 @@ struct Engine {
         if (ev_eval) cudaEventDestroy(ev_eval);
         if (ev_lane1) cudaEventDestroy(ev_lane1);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        if (lane1.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane1.comm);
     }
 
     // ---------------------------------------------------------------- helpers
@@ -721,7 +744,7 @@ struct Engine {
     void load_inputs(const uint64_t* host, size_t cnt, bool from_host);
     void evaluate();
     void run_eq(uint32_t first, uint32_t count);
-    void run_dot_eq(const F* X, uint32_t cnt, EqTab eq, F* out);
+    void run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out);
     void do_vres();
     void do_input_mle();
     void do_init_phase1(int i);
@@ -920,7 +943,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             std::vector<uint32_t> empties;
             for (int l = 0; l < i; ++l)
                 if (T.dadSize[l] == 0) empties.push_back(D.tr_claims_v + (uint32_t)l);
-            D.ph2 = make_phase(tabs, m, empties, world, rank, n, arena);
+            D.ph2 = make_phase(tabs, m, empties, world, rank, n, arena, /*rev=*/true);
             cap0 = std::max(cap0, D.ph2.cap0);
             cap1 = std::max(cap1, D.ph2.cap1);
             max_rec = std::max(max_rec, D.ph2.rec_len);
@@ -1033,13 +1056,54 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     eqb_in = (uint32_t)eq_descs.size();
     add_eq_build(2, L[1].ci_rliu, C.bit_length(0), -1);
 
+    // which instances does this rank touch? (tables are instance-major and every rank holds a contiguous run of each)
+    ko_lo = (uint32_t)((uint64_t)K * rank / world);
+    ko_hi = (uint32_t)((uint64_t)K * (rank + 1) / world);
+    k_lo = ko_lo;
+    k_hi = ko_hi;
+    for (int i = 1; i < n; ++i) {
+        LayerDev& D = L[i];
+        const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
+        auto fwd = [&](const PhasePlan& P, uint32_t& a, uint32_t& b) {   // table over layer i-1: idx = k*S_pre + u0
+            a = K; b = 0;
+            if (P.row_hi[0] > P.row_lo[0]) { a = P.row_lo[0] / S_pre; b = (P.row_hi[0] - 1) / S_pre + 1; }
+        };
+        uint32_t a, b;
+        fwd(D.ph1, a, b);
+        D.p1_k0 = std::min(a, K); D.p1_k1 = std::max(b, D.p1_k0);
+        if (b > a) { k_lo = std::min(k_lo, a); k_hi = std::max(k_hi, b); }
+        fwd(D.ph3, a, b);
+        if (b > a) { k_lo = std::min(k_lo, a); k_hi = std::max(k_hi, b); }
+        D.p2_kk0 = K; D.p2_kk1 = 0;
+        if (D.max_dad_bl != -1) {
+            size_t t = 0;
+            for (int l = 0; l < i; ++l) { (void)l; }
+            // ph2 tables are in `order` (non-empty subsets, bits descending); their D is P2Table.D = dad size of one instance
+            std::vector<int> order;
+            for (int l = 0; l < i; ++l)
+                if (C.layers[i].dadSize[l] > 0) order.push_back(l);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return C.dad_bit_length(i, x) > C.dad_bit_length(i, y); });
+            for (t = 0; t < order.size(); ++t) {
+                const uint32_t Dsz = (uint32_t)C.layers[i].dadSize[order[t]];
+                if (D.ph2.row_hi[t] <= D.ph2.row_lo[t]) continue;
+                const uint32_t kka = D.ph2.row_lo[t] / Dsz, kkb = (D.ph2.row_hi[t] - 1) / Dsz + 1;   // idx = kk*D + lv0, kk = K-1-k
+                D.p2_kk0 = std::min(D.p2_kk0, kka);
+                D.p2_kk1 = std::max(D.p2_kk1, kkb);
+                k_lo = std::min(k_lo, K - kkb);
+                k_hi = std::max(k_hi, K - kka);
+            }
+        }
+        if (D.p2_kk1 < D.p2_kk0) D.p2_kk0 = D.p2_kk1 = 0;
+    }
+    k_hi = std::min(k_hi, K);
+
     for (int b = 0; b < 2; ++b) {
         const uint32_t cap = b == 0 ? cap0 : cap1;
         bufV[b].alloc(cap);
         bufM[b].alloc(cap);
         bufA[b].alloc(cap);
     }
-    two_lanes = world == 1 && !getenv("VP_ONE_LANE");
+    two_lanes = !getenv("VP_ONE_LANE");
     if (two_lanes) {
         uint32_t c0 = 4, c1 = 4;
         for (int i = 1; i < n; ++i) { c0 = std::max(c0, L[i].ph3.cap0); c1 = std::max(c1, L[i].ph3.cap1); }
@@ -1047,9 +1111,12 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             const uint32_t cap = b == 0 ? c0 : c1;
             lane1.bufV[b].alloc(cap);
             lane1.bufM[b].alloc(cap);
-            lane1.bufA[b].alloc(4);   // the Liu add table is never stored in whole-proof mode
+            lane1.bufA[b].alloc(world > 1 ? cap : 4);   // the Liu add table is never stored in whole-proof mode (sharded: the
+                                                        // hand-over kernels still address the region)
         }
         lane1.d_scal.alloc(SC_N);
+        lane1.d_claims.alloc((size_t)n + 1);
+        CK(cudaMemsetAsync(lane1.d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
         lane1.d_partials.alloc((size_t)12 * (size_t)max_grid);
         lane1.d_counter.alloc(4 + 64);
         CK(cudaMemsetAsync(lane1.d_scal.p, 0, SC_N * sizeof(F), stream));
@@ -1068,6 +1135,22 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         NcclId id;
         memcpy(id.internal, nccl_id, 128);
         NCK(g_nccl.CommInitRank(&comm, world, id, rank));
+    }
+    if (two_lanes && world > 1) {
+        // lane 1 issues its own all-gathers concurrently with lane 0: it needs its own communicator. Rank 0 draws a
+        // second unique id and broadcasts it over the first communicator.
+        DBuf<unsigned char> d_id;
+        d_id.alloc(128);
+        NcclId id2;
+        memset(&id2, 0, sizeof id2);
+        if (rank == 0) NCK(g_nccl.GetUniqueId(&id2));
+        CK(cudaMemcpyAsync(d_id.p, id2.internal, 128, cudaMemcpyHostToDevice, stream));
+        NCK(g_nccl.Broadcast(d_id.p, d_id.p, 128, /*ncclUint8*/ 1, 0, comm, stream));
+        CK(cudaMemcpyAsync(id2.internal, d_id.p, 128, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        NCK(g_nccl.CommInitRank(&lane1.comm, world, id2, rank));
+        lane1.d_send.alloc(std::max<uint32_t>(max_rec, 1));
+        lane1.d_recv.alloc((size_t)std::max<uint32_t>(max_rec, 1) * world);
     }
     d_chal.alloc(n_chal + 1);
     d_tr.alloc(n_tr);
@@ -1096,21 +1179,25 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
 // ------------------------------------------------------------------ steps
 void Engine::load_inputs(const uint64_t* host, size_t cnt, bool from_host) {
     if (cnt != C.layer_size(0)) throw CudaError{"vp_set_inputs: wrong number of inputs"};
-    if (from_host) CK(cudaMemcpyAsync(d_inputs.p, host, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    if (from_host) {   // only the instances this rank evaluates
+        const size_t S0 = C.layers[0].size, b = (size_t)k_lo * S0, e = (size_t)k_hi * S0;
+        if (e > b) CK(cudaMemcpyAsync(d_inputs.p + b, host + b, (e - b) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    }
     inputs_loaded = true;
     evaluated = false;
 }
 
 void Engine::evaluate() {
-    const uint32_t n0 = (uint32_t)C.layer_size(0);
+    const uint32_t S0 = (uint32_t)C.layers[0].size;
+    const uint32_t b0 = k_lo * S0, e0 = k_hi * S0;
     CK(cudaMemsetAsync(d_counter.p + 1, 0, sizeof(unsigned int), stream));
-    k_load_inputs<<<cdiv(n0, 256), 256, 0, stream>>>(d_inputs.p, val[0].p, n0);
+    k_load_inputs<<<cdiv(std::max<uint32_t>(e0 - b0, 1), 256), 256, 0, stream>>>(d_inputs.p, val[0].p, b0, e0);
     ++launches;
     for (int i = 1; i < n; ++i) {
-        const uint32_t tot = L[i].S * K;
+        const uint32_t gb = k_lo * L[i].S, ge = k_hi * L[i].S, tot = ge - gb;
         size_t h = prof_begin(KC_EVAL);
-        k_eval_layer<<<grid_for(tot, cap_eval), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p, val[i].p,
-                                                         d_counter.p + 1);
+        k_eval_layer<<<grid_for(std::max<uint32_t>(tot, 1), cap_eval), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p,
+                                                                                        val[i].p, d_counter.p + 1, gb, ge);
         prof_end(h, (double)tot * (16.0 + 32.0 + 11.0 / K));  // out + two operand gathers (+ amortised wiring)
         ++launches;
     }
@@ -1124,19 +1211,29 @@ void Engine::run_eq(uint32_t first, uint32_t count) {
     ++launches;
 }
 
-void Engine::run_dot_eq(const F* X, uint32_t cnt, EqTab eq, F* out) {
-    k_dot_eq<<<grid_for(cnt, cap_dot), 256, 0, stream>>>(X, cnt, eq, out, d_partials.p, d_counter.p);
+// <X, eq(r,.)> over the replicated layer of template size S. Sharded: every rank sums its own instance slice, the
+// partial sums meet in one 16-byte-per-rank all-gather.
+void Engine::run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out) {
+    const uint32_t begin = ko_lo * S, end = ko_hi * S;
+    F* dst = world > 1 ? d_send.p : out;
+    k_dot_eq<<<grid_for(std::max<uint32_t>(end - begin, 1), cap_dot), 256, 0, stream>>>(X, begin, end, eq, dst, d_partials.p,
+                                                                                       d_counter.p);
     ++launches;
+    if (world > 1) {
+        NCK(g_nccl.AllGather(d_send.p, d_recv.p, 2, /*ncclUint64*/ 5, comm, stream));
+        k_sum_ranks<<<1, 32, 0, stream>>>(d_recv.p, (uint32_t)world, 1, out);
+        ++launches;
+    }
 }
 
 void Engine::do_vres() {
     run_eq(eqb_out, 2);
-    run_dot_eq(val[n - 1].p, (uint32_t)C.layer_size(n - 1), eqtab(2, C.bit_length(n - 1)), d_tr.p + tr_vres);
+    run_dot_eq(val[n - 1].p, (uint32_t)C.layers[n - 1].size, eqtab(2, C.bit_length(n - 1)), d_tr.p + tr_vres);
 }
 
 void Engine::do_input_mle() {
     run_eq(eqb_in, 2);
-    run_dot_eq(val[0].p, (uint32_t)C.layer_size(0), eqtab(2, C.bit_length(0)), d_tr.p + tr_input);
+    run_dot_eq(val[0].p, (uint32_t)C.layers[0].size, eqtab(2, C.bit_length(0)), d_tr.p + tr_input);
 }
 
 void Engine::do_init_phase1(int i) {
@@ -1145,16 +1242,17 @@ void Engine::do_init_phase1(int i) {
     const uint32_t S_pre = L[i - 1].S ? L[i - 1].S : (uint32_t)C.layers[i - 1].size;
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     CsrP1 csr{D.p1_g0.p, D.p1_v0.p, D.p1_tyl.p};
-    const uint64_t work = (uint64_t)D.p1_items.n * K;
+    const uint32_t k0 = D.ph1.sharded ? D.p1_k0 : 0, k1 = D.ph1.sharded ? D.p1_k1 : K;
+    const uint64_t work = (uint64_t)D.p1_items.n * (k1 - k0);
     size_t h = prof_begin(KC_INIT1);
     k_init_phase1<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1), 256, 0, stream>>>(
         D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
         d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
-        bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1);
-    if (D.p1_long.n) {
-        k_combine_phase1<<<grid_for((uint32_t)(D.p1_long.n * K), cap_comb), 256, 0, stream>>>(
+        bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1, k0, k1);
+    if (D.p1_long.n && k1 > k0) {
+        k_combine_phase1<<<grid_for((uint32_t)(D.p1_long.n * (k1 - k0)), cap_comb), 256, 0, stream>>>(
             D.p1_long.p, (uint32_t)D.p1_long.n, S_pre, K, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0],
-            bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1);
+            bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1, k0, k1);
         ++launches;
     }
     // per output: V read + 3 table writes; per gate: one gathered operand
@@ -1171,14 +1269,16 @@ void Engine::do_init_phase2(int i) {
     const EqTab eqg = eqtab(0, C.bit_length(i)), equ = eqtab(1, C.bit_length(i - 1));
     if (D.p2_ntabs > 0) {
         CsrP2 csr{D.p2_g0.p, D.p2_u0.p, D.p2_ty.p};
-        const uint64_t work = (uint64_t)D.p2_items.n * K;
+        const uint32_t kk0 = D.ph2.sharded ? D.p2_kk0 : 0, kk1 = D.ph2.sharded ? D.p2_kk1 : K;
+        const uint64_t work = (uint64_t)D.p2_items.n * (kk1 - kk0);
         size_t h = prof_begin(KC_INIT2);
         k_init_phase2<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p2), 256, 0, stream>>>(
             D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
-            scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots);
-        if (D.p2_long.n) {
-            k_combine_phase2<<<grid_for((uint32_t)(D.p2_long.n * K), cap_comb), 256, 0, stream>>>(
-                D.p2_long.p, (uint32_t)D.p2_long.n, D.p2_tabs.p, K, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots);
+            scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
+        if (D.p2_long.n && kk1 > kk0) {
+            k_combine_phase2<<<grid_for((uint32_t)(D.p2_long.n * (kk1 - kk0)), cap_comb), 256, 0, stream>>>(
+                D.p2_long.p, (uint32_t)D.p2_long.n, D.p2_tabs.p, K, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0,
+                kk1);
             ++launches;
         }
         prof_end(h, (double)D.p2_out_entries * 64.0 + (double)D.p2_gates * K * 16.0);
@@ -1186,7 +1286,7 @@ void Engine::do_init_phase2(int i) {
     }
     // unary gates: their sum starts the phase's add_term (see k_phase2_unary); each rank sums its instance slice
     const bool slice = D.ph2.sharded;  // a replicated phase needs the whole sum on every rank
-    const uint32_t k0 = slice ? (uint32_t)((uint64_t)K * rank / world) : 0, k1 = slice ? (uint32_t)((uint64_t)K * (rank + 1) / world) : K;
+    const uint32_t k0 = slice ? ko_lo : 0, k1 = slice ? ko_hi : K;
     if (D.n_unary > 0 && k1 > k0) {
         CsrUnary un{D.un_g0.p, D.un_u0.p, D.un_ty.p, D.n_unary};
         const uint64_t tot = (uint64_t)D.n_unary * (k1 - k0);
@@ -1665,7 +1765,7 @@ extern "C" int vp_create_sharded(const vp_circuit* c, int device, int rank, int 
     API_END
 }
 // Host-only view of how one phase is dealt out to the ranks (tests of the partition logic).
-// out: per table 10 values {bits, live, sharded, m, first, local_live, local_len, present, n_blocks, rot}.
+// out: per table 10 values {bits, live, sharded, m, row_lo, row_hi, local_len, present, n_blocks, reversed}.
 extern "C" int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int phase, uint32_t* out, size_t cap,
                                  size_t* n_tables) {
     if (!c || !out || !n_tables) return fail(VP_ERR_ARG, "null argument");
@@ -1687,25 +1787,22 @@ extern "C" int vp_shard_describe(const vp_circuit* c, int world, int rank, int l
         T.push_back(PhaseTabG{rounds, (uint32_t)C.layer_size(layer - 1), -1, 0});
     }
     PlanArena A;
-    PhasePlan P = make_phase(T, rounds, {}, world, rank, C.n_layers(), A);
+    PhasePlan P = make_phase(T, rounds, {}, world, rank, C.n_layers(), A, phase == 2);
     if (cap < T.size() * 10) return fail(VP_ERR_ARG, "output buffer too small");
     for (size_t t = 0; t < T.size(); ++t) {
-        uint32_t lb = 0, ll = T[t].live;
-        if (P.sharded && T[t].bits >= P.m) ll = local_live_of(T[t].live, P.m, (uint32_t)world, P.maps[t].first, &lb);
-        else if (P.sharded && !P.present[t]) ll = 0;
         uint32_t* o = out + t * 10;
-        o[0] = (uint32_t)T[t].bits; o[1] = T[t].live; o[2] = P.sharded; o[3] = (uint32_t)P.m; o[4] = P.maps[t].first;
-        o[5] = ll; o[6] = P.local_len[t]; o[7] = P.present[t];
-        o[8] = P.sharded ? (T[t].live + (1u << P.m) - 1) >> P.m : 1; o[9] = (uint32_t)(t % (size_t)world);
+        o[0] = (uint32_t)T[t].bits; o[1] = T[t].live; o[2] = P.sharded; o[3] = (uint32_t)P.m; o[4] = P.row_lo[t];
+        o[5] = P.row_hi[t]; o[6] = P.local_len[t]; o[7] = P.present[t];
+        o[8] = P.sharded ? std::max<uint32_t>(1, (T[t].live + (1u << P.m) - 1) >> P.m) : 1; o[9] = phase == 2;
     }
     *n_tables = T.size();
     return VP_OK;
 }
-extern "C" int vp_shard_map_index(uint32_t m, uint32_t logG, uint32_t first, uint32_t idx, uint32_t* local) {
+extern "C" int vp_shard_map_index(uint32_t lo, uint32_t hi, uint32_t idx, uint32_t* local) {
     uint32_t loc = 0;
-    const bool mine = shard_local(ShardMap{m, logG, first, 0}, idx, loc);
+    const bool mine = shard_local(ShardMap{lo, hi}, idx, loc);
     if (local) *local = loc;
-    if (mine && shard_global(ShardMap{m, logG, first, 0}, loc) != idx) return -100;
+    if (mine && shard_global(ShardMap{lo, hi}, loc) != idx) return -100;
     return mine ? 1 : 0;
 }
 extern "C" void vp_destroy(vp_ctx* ctx) {

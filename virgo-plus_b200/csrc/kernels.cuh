@@ -53,27 +53,18 @@ struct EqTab {
 VP_D F eq_at(const EqTab& t, uint32_t idx) { return f_mul(ld_f(t.f + (idx & t.mask)), ld_f(t.s + (idx >> t.fh))); }
 
 // ------------------------------------------------------------------ sharding of a table over G GPUs
-// Block-cyclic by the table index: block beta = idx >> m (2^m contiguous entries) belongs to the rank with
-// beta mod G == first; that rank stores its blocks back to back (local block q = beta / G). Rounds 1..m of a
-// sumcheck pair entries inside one block, so they need no communication. G == 1: identity.
+// A table is cut into blocks of 2^m consecutive entries and every rank holds a CONTIGUOUS run of blocks, i.e. the
+// entries [lo, hi) (multiples of 2^m), stored from local index 0. Rounds 1..m of a sumcheck pair entries inside one
+// block, so they need no communication. Contiguous runs keep the instances a rank touches contiguous as well
+// (tables are instance-major), so a rank only evaluates its own slice of the data-parallel instances.
 struct ShardMap {
-    uint32_t m;       // log2(block size)
-    uint32_t logG;    // log2(number of ranks)
-    uint32_t first;   // this rank's residue
-    uint32_t pad;
+    uint32_t lo, hi;
 };
 VP_HD bool shard_local(const ShardMap& s, uint32_t idx, uint32_t& local) {
-    if (s.logG == 0) { local = idx; return true; }
-    const uint32_t beta = idx >> s.m;
-    if ((beta & ((1u << s.logG) - 1u)) != s.first) return false;
-    local = ((beta >> s.logG) << s.m) | (idx & ((1u << s.m) - 1u));
-    return true;
+    local = idx - s.lo;
+    return idx >= s.lo && idx < s.hi;
 }
-VP_HD uint32_t shard_global(const ShardMap& s, uint32_t local) {
-    if (s.logG == 0) return local;
-    const uint32_t q = local >> s.m;
-    return (((q << s.logG) | s.first) << s.m) | (local & ((1u << s.m) - 1u));
-}
+VP_HD uint32_t shard_global(const ShardMap& s, uint32_t local) { return local + s.lo; }
 
 // ------------------------------------------------------------------ reductions
 VP_D F warp_sum(F x) {
@@ -165,9 +156,9 @@ __global__ void __launch_bounds__(1024) k_eq_build(const EqBuild* __restrict__ d
 
 // ------------------------------------------------------------------ K1: evaluate
 // prover.cpp:30-36: layer 0 = F((long long) gate.u)
-__global__ void k_load_inputs(const uint64_t* __restrict__ in, F* __restrict__ val, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) st_f(val + i, F{in[i], 0});
+__global__ void k_load_inputs(const uint64_t* __restrict__ in, F* __restrict__ val, uint32_t begin, uint32_t end) {
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) st_f(val + i, F{in[i], 0});
 }
 
 struct GateArrays {          // one template layer (one instance)
@@ -182,11 +173,12 @@ struct GateArrays {          // one template layer (one instance)
 // vals[l] = device pointer of circuitValue[l]; sizes[l] = template size S_l.
 __global__ void __launch_bounds__(256) k_eval_layer(GateArrays G, uint32_t S, uint32_t K, int layer,
                                                      F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
-                                                     F* __restrict__ out, unsigned int* __restrict__ assert_fail) {
-    const uint32_t n = S * K;
+                                                     F* __restrict__ out, unsigned int* __restrict__ assert_fail,
+                                                     uint32_t g_begin, uint32_t g_end) {
+    (void)K;
     const uint32_t S_pre = sizes[layer - 1];
     const F* __restrict__ pre = vals[layer - 1];
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    for (uint32_t g = g_begin + blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += gridDim.x * blockDim.x) {
         const uint32_t k = g / S, g0 = g - k * S;
         const uint32_t tyb = G.ty[g0], ty = tyb & 0x7f;
         const int l = G.l[g0];
@@ -289,10 +281,12 @@ __global__ void __launch_bounds__(256)
 k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
               EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
               const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
-              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm, int write_v) {
-    const uint64_t total = (uint64_t)n_items * K;
+              F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm, int write_v, uint32_t k_begin,
+              uint32_t k_end) {
+    (void)K;
+    const uint64_t total = (uint64_t)n_items * (k_end - k_begin);
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)k * n_items);
+        const uint32_t kq = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)kq * n_items), k = k_begin + kq;
         const RowItem I = items[it];
         uint32_t loc;
         if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // another rank owns this table entry
@@ -323,10 +317,11 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 __global__ void __launch_bounds__(256)
 k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
                  F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,
-                 ShardMap sm, int write_v) {
-    const uint64_t total = (uint64_t)n_rows * K;
+                 ShardMap sm, int write_v, uint32_t k_begin, uint32_t k_end) {
+    (void)K;
+    const uint64_t total = (uint64_t)n_rows * (k_end - k_begin);
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)k * n_rows);
+        const uint32_t kq = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)kq * n_rows), k = k_begin + kq;
         const LongRow R = rows[j];
         const uint32_t u = k * S_pre + R.row;
         uint32_t loc;
@@ -378,13 +373,13 @@ __global__ void __launch_bounds__(256)
 k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table* __restrict__ tabs, CsrP2 csr,
               uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, const F* __restrict__ assert_r,
               const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA,
-              F* __restrict__ partial, uint32_t n_slots) {
+              F* __restrict__ partial, uint32_t n_slots, uint32_t kk_begin, uint32_t kk_end) {
     __shared__ F s_cM[12], s_cA[12];
     if (threadIdx.x == 0) make_p2_coef(*Vu_ptr, s_cM, s_cA);
     __syncthreads();
-    const uint64_t total = (uint64_t)n_items * K;
+    const uint64_t total = (uint64_t)n_items * (kk_end - kk_begin);
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t kk = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)kk * n_items), k = K - 1 - kk;
+        const uint32_t kq = (uint32_t)(w / n_items), it = (uint32_t)(w - (uint64_t)kq * n_items), kk = kk_begin + kq, k = K - 1 - kk;
         const RowItem I = items[it];
         const P2Table T = tabs[I.tab];
         uint32_t loc;
@@ -415,10 +410,11 @@ k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table
 
 __global__ void __launch_bounds__(256)
 k_combine_phase2(const LongRow* __restrict__ rows, uint32_t n_rows, const P2Table* __restrict__ tabs, uint32_t K,
-                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots) {
-    const uint64_t total = (uint64_t)n_rows * K;
+                 F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,
+                 uint32_t kk_begin, uint32_t kk_end) {
+    const uint64_t total = (uint64_t)n_rows * (kk_end - kk_begin);
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t kk = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)kk * n_rows), k = K - 1 - kk;
+        const uint32_t kq = (uint32_t)(w / n_rows), j = (uint32_t)(w - (uint64_t)kq * n_rows), kk = kk_begin + kq, k = K - 1 - kk;
         const LongRow R = rows[j];
         const P2Table T = tabs[R.tab];
         uint32_t loc;
@@ -1187,8 +1183,8 @@ struct MergeTab {
     uint32_t cnt;        // region length
     uint32_t n_blocks;   // live blocks of the whole table (= live entries of the stage-B table)
     uint32_t out_off;    // stage-B table offset in buffer 0
-    uint32_t rot;        // rank owning block beta: (beta + rot) mod G
-    uint32_t pad;
+    uint32_t rev;        // 0: slice s belongs to rank s; 1: to rank G-1-s (phase-2 tables are in reverse instance order)
+    uint32_t sb[9];      // slice s holds blocks [sb[s], sb[s+1])
 };
 struct MergeArgs {
     const F* recv;            // G records of rec_len F
@@ -1208,7 +1204,9 @@ __global__ void k_shard_merge(MergeArgs p) {
     for (uint32_t t = 0; t < p.n_tabs; ++t) {
         const MergeTab T = p.tabs[t];
         for (uint32_t beta = tid; beta < T.n_blocks; beta += stride) {
-            const uint32_t owner = (beta + T.rot) & (p.G - 1), q = beta / p.G;
+            uint32_t sl = 0;
+            while (sl + 1 < p.G && beta >= T.sb[sl + 1]) ++sl;
+            const uint32_t owner = T.rev ? p.G - 1 - sl : sl, q = beta - T.sb[sl];
             const F* rec = p.recv + (size_t)owner * p.rec_len + T.rec_base;
             st_f(p.outV + T.out_off + beta, rec[q]);
             st_f(p.outM + T.out_off + beta, rec[T.cnt + q]);
@@ -1228,12 +1226,12 @@ __global__ void k_shard_merge(MergeArgs p) {
 // ------------------------------------------------------------------ K8 / K9: MLE evaluation = dot with eq
 // prover.cpp:99-129 (Vres) and :532-540 (inner_prod against eq(r_liu,.), verifier.cpp:368-369).
 __global__ void __launch_bounds__(256)
-k_dot_eq(const F* __restrict__ X, uint32_t n, EqTab eq, F* __restrict__ out, F* partials, unsigned int* counter) {
+k_dot_eq(const F* __restrict__ X, uint32_t begin, uint32_t n, EqTab eq, F* __restrict__ out, F* partials, unsigned int* counter) {
     __shared__ F smem[32];
     Acc acc = acc_zero();
     F run = f_zero();
     int pending = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         acc_mad(acc, ld_f(X + i), eq_at(eq, i));
         if (++pending == 8) { run = f_add(run, acc_reduce(acc)); acc = acc_zero(); pending = 0; }
     }
@@ -1253,6 +1251,15 @@ k_dot(const F* __restrict__ X, const F* __restrict__ Y, uint32_t n, F* __restric
     }
     F v[1] = {f_add(run, acc_reduce(acc))};
     if (grid_sum<1>(v, smem, partials, counter) && threadIdx.x == 0) st_f(out, v[0]);
+}
+
+// sum of one field element per rank (sharded Vres / input MLE)
+__global__ void k_sum_ranks(const F* __restrict__ recv, uint32_t G, uint32_t stride, F* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        F s = f_zero();
+        for (uint32_t g = 0; g < G; ++g) s = f_add(s, recv[(size_t)g * stride]);
+        st_f(out, s);
+    }
 }
 
 // ------------------------------------------------------------------ misc

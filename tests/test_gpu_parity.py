@@ -95,6 +95,19 @@ def test_random_circuits(B, O, n_layers, log_size, seed):
     _prove_both_ways(B, O, circ)
 
 
+def test_random_circuit_c4_shape(B, O):
+    """BASELINE.json configs[3] shape (random add/mul wiring, every layer 2^k gates, operands from any earlier layer)
+    at a size the oracle proves in about a second: 12 layers x 2^14 gates"""
+    circ = B.Circuit.random(12, 14, 2024)
+    oc = O.OracleCircuit(circ.flat())
+    want, _, _ = oc.prove()
+    p = B.Prover(circ)
+    got = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+    _assert_same(got, want, "C4-shape transcript")
+    assert oc.verify(got)[0]
+    p.close()
+
+
 def test_evaluate_matches_oracle(B, O, sha_circuit):
     p = B.Prover(sha_circuit)
     p.evaluate()

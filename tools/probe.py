@@ -39,8 +39,19 @@ def gkr(K, reps=3):
     print(f"  host-io prove: {p.last_prove_ms:.3f} ms device, {w*1e3:.3f} ms wall")
     p.close()
 
+def c4(n_layers=65, log_size=20, reps=3):
+    t = time.time(); c = B.Circuit.random(n_layers, log_size, 1); print(f"C4 {n_layers} x 2^{log_size}: host circuit {time.time()-t:.1f}s gates={c.total_gates}")
+    t = time.time(); p = B.Prover(c); print(f"  create {time.time()-t:.1f}s")
+    p.set_challenges(c.draw_challenges())
+    for it in range(reps):
+        p.prove()
+        print(f"  resident prove: {p.last_prove_ms:.3f} ms device, launches {p.last_prove_launches}, {c.total_gates/p.last_prove_ms/1e3:.2f} Mgates/s")
+    p.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "c2"): c2(24)
     if what in ("all", "c1"): gkr(1, 5)
     if what in ("all", "c3"): gkr(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
+    if what == "c4": c4(int(sys.argv[2]) if len(sys.argv) > 2 else 65, int(sys.argv[3]) if len(sys.argv) > 3 else 20)

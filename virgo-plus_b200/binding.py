@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvirgo_b200.so")
+LIB_PATH = os.environ.get("VP_LIB") or os.path.join(HERE, "libvirgo_b200.so")  # VP_LIB: development variants
 
 F_DTYPE = np.dtype([("re", "<u8"), ("im", "<u8")])  # == vp_F == virgo::fieldElement
 P = (1 << 61) - 1

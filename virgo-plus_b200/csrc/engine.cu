@@ -732,9 +732,9 @@ struct Engine {
     int n_sm = 148;
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
     template <class Kern>
-    int occ_cap(Kern k) {  // resident blocks of 256 threads on the whole chip
+    int occ_cap(Kern k, int threads = 256) {  // resident blocks on the whole chip
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, 0));
         return n_sm * std::max(1, occ);
     }
     int grid_for(uint32_t work, int cap) const { return (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(work, 256), (uint32_t)cap)); }
@@ -810,7 +810,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
     cap_phase = occ_cap(k_sumcheck_phase);
-    cap_dfs = std::min(occ_cap(k_phase_dfs<true>), occ_cap(k_phase_dfs<false>));
+    cap_dfs = std::min(occ_cap(k_phase_dfs<true>, DFS_THREADS), occ_cap(k_phase_dfs<false>, DFS_THREADS));
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     {
         int coop = 0;
@@ -1416,7 +1416,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), cap));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
-    CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(256),
+    CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(DFS_THREADS),
                                    args, 0, stream));
     prof_end(h, P.alg_bytes);
     ++launches;
@@ -2196,7 +2196,7 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->pp = build_pass_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
     {
         int occd = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true>, DFS_THREADS, 0));
         s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
         s->max_grid = std::max(s->max_grid, s->cap_dfs);
     }
@@ -2361,7 +2361,7 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true>, dim3(grid), dim3(256), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true>, dim3(grid), dim3(DFS_THREADS), args, 0, st));
     // the fully folded add / mult values sit where V's does
     const FinDesc fv = s->arena.fins[s->pp.fin_begin];
     const F* fin_tabs[2] = {s->bufA[s->pp.fin_buf].p, s->bufM[s->pp.fin_buf].p};

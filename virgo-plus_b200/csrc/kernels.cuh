@@ -1024,8 +1024,12 @@ VP_D void pass_wait(unsigned int* bar, unsigned int target) {
 #ifndef VP_DFS_MINB
 #define VP_DFS_MINB 2
 #endif
+#ifndef VP_DFS_THREADS
+#define VP_DFS_THREADS 256
+#endif
+static constexpr int DFS_THREADS = VP_DFS_THREADS;
 template <bool HAS_A>
-__global__ void __launch_bounds__(256, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
+__global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     __shared__ F smem[6 * 32];
     __shared__ uint32_t s_wend[128];
     __shared__ uint32_t s_chunk;

@@ -32,3 +32,36 @@ void h_mul_add_loose2(const F* a, const F* b, const F* c, F* out, int n) {
     for (int i = 0; i < n; ++i) out[i] = f_mul_add_loose2(make_lop(a[i].re, a[i].im), make_rop(b[i].re, b[i].im), c[i]);
 }
 }
+extern "C" {
+// weakly canonical primitives of the pass kernel: operands in [0,p] (p = alias of 0)
+void h_fold_w(const F* v0, const F* v1, const F* r, F* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = f_fold_w(v0[i], f_diff2p(v0[i], v1[i]), make_constk(r[i]));
+}
+void h_fold_w_dw(const F* v0, const F* v1, const F* r, F* out, int n) {   // with the difference folded into [0,p]
+    for (int i = 0; i < n; ++i) out[i] = f_fold_w(v0[i], f_diff_w(v0[i], v1[i]), make_constk(r[i]));
+}
+void h_fold_w_real(const u64* v0, const u64* v1, const F* r, F* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = f_fold_w_real(v0[i], fp_weak(v1[i] + P - v0[i]), make_constk(r[i]));
+}
+void h_reduce_ut_weak(const u64* u, const u64* t, const u64* e, u64* out, int n) { for (int i = 0; i < n; ++i) out[i] = fp_reduce_ut_weak(u[i], t[i], e[i]); }
+void h_fp_weak(const u64* x, u64* out, int n) { for (int i = 0; i < n; ++i) out[i] = fp_weak(x[i]); }
+// lazy dot products: sum m1*v + the pair form the kernel uses, sum (m1 - m0) * (v1 - v0)
+void h_cacc_dot(const F* m, const F* v, F* out, int n) {
+    CAcc s = cacc_zero();
+    for (int i = 0; i < n; ++i) cacc_mad(s, make_lop(m[i].re, m[i].im), make_ropd(v[i]));
+    *out = cacc_reduce(s);
+}
+void h_cacc_dot_diff(const F* m0, const F* m1, const F* v0, const F* v1, F* out, int n) {
+    CAcc s = cacc_zero();
+    for (int i = 0; i < n; ++i) {
+        const F dm = f_diff2p(m0[i], m1[i]), dv = f_diff_w(v0[i], v1[i]);
+        cacc_mad(s, make_lop(dm.re, dm.im), make_ropd(dv));
+    }
+    *out = cacc_reduce(s);
+}
+void h_cacc_dot_real(const F* m0, const F* m1, const u64* v, F* out, int n) {   // sum (m1 - m0 in [0,2p]) * v
+    CAcc s = cacc_zero();
+    for (int i = 0; i < n; ++i) cacc_mad_real(s, f_diff2p(m0[i], m1[i]), v[i]);
+    *out = cacc_reduce(s);
+}
+}

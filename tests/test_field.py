@@ -158,3 +158,91 @@ def test_loose_running_sums(H):
         assert int(out["re"].max()) <= P + 5 and int(out["im"].max()) <= P + 5
         acc = out
         a = np.roll(a, 1)
+
+
+# ---------------------------------------------------------------- weakly canonical / lazy primitives of k_phase_dfs
+WEAK_EDGE = EDGE + [P]   # p itself is a legal (weak) representation of 0
+
+
+def _weak_arrays(rng, n):
+    base = WEAK_EDGE + [int(x) for x in rng.integers(0, P, 40, dtype=np.uint64)]
+    a = np.zeros(n, FD)
+    a["re"] = rng.choice(base, n).astype(np.uint64)
+    a["im"] = rng.choice(base, n).astype(np.uint64)
+    return a
+
+
+def test_weak_fold(H):
+    rng = np.random.default_rng(21)
+    n = 30000
+    v0, v1, r = _weak_arrays(rng, n), _weak_arrays(rng, n), _fe_arrays(rng, n)
+    for fn in (H.h_fold_w, H.h_fold_w_dw):
+        out = np.zeros(n, FD)
+        fn(_p(v0), _p(v1), _p(r), _p(out), n)
+        assert int(out["re"].max()) <= P and int(out["im"].max()) <= P
+        for i in range(0, n, 3):
+            d = ((int(v1[i]["re"]) - int(v0[i]["re"])) % P, (int(v1[i]["im"]) - int(v0[i]["im"])) % P)
+            m = _cmul(d, _t(r[i]))
+            want = ((int(v0[i]["re"]) + m[0]) % P, (int(v0[i]["im"]) + m[1]) % P)
+            assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == want
+    # base-field data
+    a0 = v0["re"].copy(); a1 = v1["re"].copy()
+    out = np.zeros(n, FD)
+    H.h_fold_w_real(_p(a0), _p(a1), _p(r), _p(out), n)
+    assert int(out["re"].max()) <= P and int(out["im"].max()) <= P
+    for i in range(0, n, 3):
+        d = (int(a1[i]) - int(a0[i])) % P
+        want = ((int(a0[i]) + d * int(r[i]["re"])) % P, (d * int(r[i]["im"])) % P)
+        assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == want
+
+
+def test_weak_reductions(H):
+    rng = np.random.default_rng(22)
+    big = [0, 1, P, P + 1, 2 * P, 2 * P + 1, (1 << 64) - 1, (1 << 64) - 2, (1 << 63), (1 << 62) - 1, (1 << 61), 3 * P, 7 * P]
+    vals = big + [int(x) for x in rng.integers(0, 1 << 64, 200, dtype=np.uint64)]
+    u = np.array([a for a in vals for _ in vals][:20000], dtype=np.uint64)
+    t = np.array([b for _ in vals for b in vals][:20000], dtype=np.uint64)
+    e = np.array([vals[k] for k in rng.integers(0, len(vals), len(u))], dtype=np.uint64)
+    out = np.zeros(len(u), np.uint64)
+    H.h_reduce_ut_weak(_p(u), _p(t), _p(e), _p(out), len(u))
+    assert int(out.max()) <= P
+    for i in range(0, len(u), 5):
+        assert int(out[i]) % P == (int(u[i]) + (int(t[i]) << 31) + int(e[i])) % P
+    x = np.array(vals, dtype=np.uint64)
+    out = np.zeros(len(x), np.uint64)
+    H.h_fp_weak(_p(x), _p(out), len(x))
+    assert int(out.max()) <= P
+    assert [int(o) % P for o in out] == [v % P for v in vals]
+
+
+def test_lazy_complex_accumulators(H):
+    rng = np.random.default_rng(23)
+    for n in [1, 2, 9, 300, 5000]:
+        m0, m1, v0, v1 = (_weak_arrays(rng, n) for _ in range(4))
+        for k in range(min(n, 4)):   # worst-case magnitudes first
+            for a in (m0, v0):
+                a["re"][k] = a["im"][k] = 0
+            for a in (m1, v1):
+                a["re"][k] = a["im"][k] = P
+        out = np.zeros(1, FD)
+        H.h_cacc_dot(_p(m1), _p(v1), _p(out), n)
+        acc = [0, 0]
+        for i in range(n):
+            m = _cmul(_t(m1[i]), _t(v1[i]))
+            acc = [(acc[0] + m[0]) % P, (acc[1] + m[1]) % P]
+        assert _t(out[0]) == tuple(acc)
+        H.h_cacc_dot_diff(_p(m0), _p(m1), _p(v0), _p(v1), _p(out), n)
+        acc = [0, 0]
+        for i in range(n):
+            dm = ((int(m1[i]["re"]) - int(m0[i]["re"])) % P, (int(m1[i]["im"]) - int(m0[i]["im"])) % P)
+            dv = ((int(v1[i]["re"]) - int(v0[i]["re"])) % P, (int(v1[i]["im"]) - int(v0[i]["im"])) % P)
+            m = _cmul(dm, dv)
+            acc = [(acc[0] + m[0]) % P, (acc[1] + m[1]) % P]
+        assert _t(out[0]) == tuple(acc)
+        vr = v1["re"].copy()
+        H.h_cacc_dot_real(_p(m0), _p(m1), _p(vr), _p(out), n)
+        acc = [0, 0]
+        for i in range(n):
+            dm = ((int(m1[i]["re"]) - int(m0[i]["re"])) % P, (int(m1[i]["im"]) - int(m0[i]["im"])) % P)
+            acc = [(acc[0] + dm[0] * int(vr[i])) % P, (acc[1] + dm[1] * int(vr[i])) % P]
+        assert _t(out[0]) == tuple(acc)

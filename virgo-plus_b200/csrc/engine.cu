@@ -755,7 +755,12 @@ struct Engine {
                   const F* v_first = nullptr);
     void do_init_liu(int i, bool write_a);
     void launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out, F* claims,
-                           F* out_poly, F* keep, bool has_a, const F* v_first = nullptr);
+                           F* out_poly, F* keep, bool has_a, int first, const F* v_first = nullptr);
+    void derive_b();
+    DBuf<ChainDesc> d_chains;
+    DBuf<ChainSeg> d_chain_segs;
+    DBuf<ChainTerm> d_chain_terms;
+    int n_chains = 0;
     void launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
                              F* claims, F* out_poly, F* keep);
     uint32_t tail_work = 512;
@@ -810,7 +815,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
     cap_phase = occ_cap(k_sumcheck_phase);
-    cap_dfs = std::min(occ_cap(k_phase_dfs<true>, DFS_THREADS), occ_cap(k_phase_dfs<false>, DFS_THREADS));
+    cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS),
+                        occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS)});
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     {
         int coop = 0;
@@ -845,6 +851,30 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     tr_input = ti++;
     n_chal = ci;
     n_tr = ti;
+    {   // claim chains for k_derive_b (verifier.cpp:150-166, 281-284, 333)
+        std::vector<ChainDesc> ch;
+        std::vector<ChainSeg> sg;
+        std::vector<ChainTerm> tm;
+        for (int i = n - 1; i >= 1; --i) {
+            const LayerDev& D = L[i];
+            const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
+            ChainDesc c12{(int32_t)(i == n - 1 ? tr_vres : L[i + 1].tr_claim_liu), 0, 0, (uint32_t)sg.size(), 0};
+            sg.push_back(ChainSeg{D.tr_p1, (uint32_t)pb, D.ci_ru});
+            if (m != -1) sg.push_back(ChainSeg{D.tr_p2, (uint32_t)m, D.ci_rv});
+            c12.n_segs = (uint32_t)sg.size() - c12.seg_begin;
+            ch.push_back(c12);
+            ChainDesc c3{-1, (uint32_t)tm.size(), 0, (uint32_t)sg.size(), 1};
+            tm.push_back(ChainTerm{D.ci_sig, D.tr_claim_u});
+            for (int j = i; j < n; ++j)
+                if (L[j].max_dad_bl != -1) tm.push_back(ChainTerm{D.ci_sig + (uint32_t)(j - (i - 1)), L[j].tr_claims_v + (uint32_t)(i - 1)});
+            c3.n_terms = (uint32_t)tm.size() - c3.term_begin;
+            sg.push_back(ChainSeg{D.tr_liu, (uint32_t)pb, D.ci_rliu});
+            ch.push_back(c3);
+        }
+        n_chains = (int)ch.size();
+        if (tm.empty()) tm.push_back(ChainTerm{0, 0});
+        if (n_chains) { d_chains.upload(ch, stream); d_chain_segs.upload(sg, stream); d_chain_terms.upload(tm, stream); }
+    }
 
     // eq scratch: region 0 = beta_g, 1 = beta_u, 2 = output/input MLE, 3.. = Liu tables
     eq_half_cap = 1u << ((max_bl + 1) >> 1);
@@ -1385,8 +1415,13 @@ void Engine::launch_phase_kernel(const SumcheckPlan& P, uint32_t ci, uint32_t ro
 }
 
 // One cooperative launch of k_phase_dfs (two rounds per pass) over `P`.
+static const void* dfs_kernel_ptr(bool has_a, int first) {
+    if (first == DFS_VREAL) return has_a ? (const void*)k_phase_dfs<true, DFS_VREAL> : (const void*)k_phase_dfs<false, DFS_VREAL>;
+    if (first == DFS_NEED_B) return (const void*)k_phase_dfs<true, DFS_NEED_B>;
+    return has_a ? (const void*)k_phase_dfs<true, DFS_PLAIN> : (const void*)k_phase_dfs<false, DFS_PLAIN>;
+}
 void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out,
-                               F* claims, F* out_poly, F* keep, bool has_a, const F* v_first) {
+                               F* claims, F* out_poly, F* keep, bool has_a, int first, const F* v_first) {
     DfsArgs a;
     for (int b = 0; b < 2; ++b) { a.bufV[b] = bufV[b].p; a.bufM[b] = bufM[b].p; a.bufA[b] = bufA[b].p; }
     a.passes = d_pdev.p + P.pass_begin;
@@ -1409,6 +1444,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     a.bar = d_counter.p + 2;
     a.chunk_ctr = d_counter.p + 4;
     a.v_first = v_first;
+    a.claim0 = nullptr;
     a.dbg = nullptr;
     // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
     // this one is down to its small passes
@@ -1416,8 +1452,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), cap));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
-    CK(cudaLaunchCooperativeKernel(has_a ? (const void*)k_phase_dfs<true> : (const void*)k_phase_dfs<false>, dim3(grid), dim3(DFS_THREADS),
-                                   args, 0, stream));
+    CK(cudaLaunchCooperativeKernel(dfs_kernel_ptr(has_a, first), dim3(grid), dim3(DFS_THREADS), args, 0, stream));
     prof_end(h, P.alg_bytes);
     ++launches;
 }
@@ -1428,7 +1463,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
 void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a,
                       const F* v_first) {
     if (!P.sharded) {
-        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a, v_first);
+        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a, DFS_VREAL, v_first);
         else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
@@ -1436,7 +1471,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
     // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
-    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a);
+    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, DFS_VREAL);
     if (P.n_fo) {
         const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
         dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);
@@ -1463,7 +1498,16 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     ++launches;
     // stage B: replicated; starts from the summed add_term
     launch_dfs_kernel(P.ppB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
-                      d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep, has_a);
+                      d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep, has_a, DFS_PLAIN);
+}
+
+// Fill in the b coefficient of every round polynomial from the claim chain (k_derive_b); the transcript is complete
+// (and, on a sharded context, replicated) when this runs.
+void Engine::derive_b() {
+    if (!n_chains) return;
+    k_derive_b<<<cdiv((uint32_t)n_chains, 32), 32, 0, stream>>>(d_chains.p, n_chains, d_chain_segs.p, d_chain_terms.p, d_chal.p,
+                                                             d_tr.p, nullptr);
+    ++launches;
 }
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
@@ -1506,6 +1550,7 @@ void Engine::prove_all() {
         CK(cudaEventRecord(ev_lane1, lane1.stream));
         CK(cudaStreamWaitEvent(stream, ev_lane1, 0));
     }
+    if (use_phase_kernel && use_dfs) derive_b();
     do_input_mle();
     direct_v = false;
     CK(cudaGetLastError());
@@ -2159,6 +2204,9 @@ struct vp_sumcheck {
     DBuf<PassCol> d_pcols;
     DBuf<PassDev> d_pdev;
     DBuf<unsigned long long> d_dbg;
+    DBuf<ChainDesc> d_chain;
+    DBuf<ChainSeg> d_chain_seg;
+    DBuf<ChainTerm> d_chain_term;
     int max_grid = 148 * 4, cap_fold = 148, cap_first = 148, cap_dfs = 148;
     std::vector<cudaEvent_t> ev;
     std::vector<float> round_ms;
@@ -2196,7 +2244,7 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->pp = build_pass_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
     {
         int occd = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true>, DFS_THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true, DFS_NEED_B>, DFS_THREADS, 0));
         s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
         s->max_grid = std::max(s->max_grid, s->cap_dfs);
     }
@@ -2217,6 +2265,9 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->d_ptabs.upload(s->arena.ptabs, s->stream);
     s->d_pcols.upload(s->arena.pcols, s->stream);
     s->d_pdev.upload(s->arena.pdev, s->stream);
+    s->d_chain.upload(std::vector<ChainDesc>{ChainDesc{-2, 0, 0, 0, 1}}, s->stream);
+    s->d_chain_seg.upload(std::vector<ChainSeg>{ChainSeg{0, (uint32_t)log_n, 0}}, s->stream);
+    s->d_chain_term.upload(std::vector<ChainTerm>{ChainTerm{0, 0}}, s->stream);
     // FinDesc for add and mult finals (same offsets as V's)
     FinDesc fv = s->arena.fins[s->plan.fin_begin];
     FinDesc fa = fv, fm = fv;
@@ -2357,16 +2408,18 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     a.bar = s->d_counter.p + 2;
     a.chunk_ctr = s->d_counter.p + 4;
     a.v_first = nullptr;
+    a.claim0 = s->d_scal.p + 1;
     a.dbg = s->d_dbg.p;
     CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true>, dim3(grid), dim3(DFS_THREADS), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true, DFS_NEED_B>, dim3(grid), dim3(DFS_THREADS), args, 0, st));
+    // b of every round from the claim chain; round 1's claim p(0) + p(1) was summed by the kernel
+    k_derive_b<<<1, 32, 0, st>>>(s->d_chain.p, 1, s->d_chain_seg.p, s->d_chain_term.p, s->d_r.p, s->d_out.p, s->d_scal.p + 1);
     // the fully folded add / mult values sit where V's does
     const FinDesc fv = s->arena.fins[s->pp.fin_begin];
     const F* fin_tabs[2] = {s->bufA[s->pp.fin_buf].p, s->bufM[s->pp.fin_buf].p};
-    for (int k = 0; k < 2; ++k)
-        CK(cudaMemcpyAsync(s->d_out.p + 3 * n + 1 + k, fin_tabs[k] + fv.in_off, sizeof(F), cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < 2; ++k) k_strict_copy<<<1, 32, 0, st>>>(s->d_out.p + 3 * n + 1 + k, fin_tabs[k] + fv.in_off, 1);
     CK(cudaEventRecord(s->ev[1], st));
     CK(cudaMemcpyAsync(out, s->d_out.p, ((size_t)3 * n + 3) * sizeof(F), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

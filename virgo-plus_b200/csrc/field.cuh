@@ -205,6 +205,121 @@ VP_HD F f_fold_k(const F& v0, const F& v1, const FoldK& k) {
 }
 VP_HD F f_fold(const F& v0, const F& v1, const F& r) { return f_fold_k(v0, v1, make_foldk(r)); }
 
+// ---------------------------------------------------------------- weakly canonical values, lazy product sums
+// The whole-proof pass kernel (k_phase_dfs) keeps its tables WEAKLY canonical: components in [0, p], where p is an
+// alias of 0. Every function above accepts such operands (their bounds only need "<= p") and +,-,* map [0,p] into
+// [0,p]; only equality tests and values that leave the device (transcript, claims) need f_strict().
+VP_HD u64 fp_weak(u64 s) {  // any u64 -> [0, p], same residue class
+    s = (s & P) + (s >> 61);  // <= p + 7
+    return (s & P) + (s >> 61);
+}
+VP_HD u64 fp_strict(u64 x) { return x == P ? 0 : x; }  // [0,p] -> [0,p)
+VP_HD F f_strict(const F& a) { return F{fp_strict(a.re), fp_strict(a.im)}; }
+
+// value = u + 2^31*t + e (mod p) in [0,p]; any u, t, e < 2^64. The 96-bit sum S = u + (t << 31) + e is built with
+// carry chains (6 adds, 3 shifts), then S mod 2^61 + S >> 61 (< 2^61 + 2^35) and one more Mersenne fold.
+VP_HD u64 fp_reduce_ut_weak(u64 u, u64 t, u64 e) {
+#if defined(__CUDA_ARCH__)
+    const u32 uL = (u32)u, uH = (u32)(u >> 32), tL = (u32)t, tH = (u32)(t >> 32), eL = (u32)e, eH = (u32)(e >> 32);
+    const u32 a0 = tL << 31, a1 = (u32)(t >> 1), a2 = tH >> 1;
+    u32 w0, w1, w2;
+    asm("add.cc.u32 %0, %3, %4;\n\t"
+        "addc.cc.u32 %1, %5, %6;\n\t"
+        "addc.u32 %2, %7, 0;\n\t"
+        "add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "=&r"(w0), "=&r"(w1), "=&r"(w2)
+        : "r"(uL), "r"(a0), "r"(uH), "r"(a1), "r"(a2), "r"(eL), "r"(eH));
+    const u64 lo = ((u64)(w1 & 0x1FFFFFFFu) << 32) | w0;
+    const u64 hi = ((u64)w2 << 3) | (w1 >> 29);
+    const u64 r = lo + hi;
+    return (r & P) + (r >> 61);
+#else
+    const unsigned __int128 S = (unsigned __int128)u + ((unsigned __int128)t << 31) + e;
+    const u64 r = ((u64)S & P) + (u64)(S >> 61);
+    return (r & P) + (r >> 61);
+#endif
+}
+
+// A constant right operand (a challenge), pre-split once per kernel: limbs of re, im and of -im, hi limbs also doubled.
+struct ConstK {
+    u32 re0, re1, re1d, im0, im1, im1d, nim0, nim1, nim1d;
+};
+VP_HD ConstK make_constk(const F& r) {  // r canonical
+    const Limbs a = split31(r.re), b = split31(r.im), c = split31(r.im ? P - r.im : 0);
+    return ConstK{a.lo, a.hi, a.hi << 1, b.lo, b.hi, b.hi << 1, c.lo, c.hi, c.hi << 1};
+}
+// v0 + k*d  for d with components <= 2p (hi limbs < 2^31), v0 in [0,p]: result in [0,p].
+// Chains: every product is < 2^31 * 2^31, four per chain: no overflow.
+VP_HD F f_fold_w(const F& v0, const F& d, const ConstK& k) {
+    const Limbs a = split31(d.re), b = split31(d.im);
+    const u64 u_re = mad32(b.hi, k.nim1d, mad32(a.hi, k.re1d, mad32(b.lo, k.nim0, mul32(a.lo, k.re0))));
+    const u64 t_re = mad32(b.hi, k.nim0, mad32(b.lo, k.nim1, mad32(a.hi, k.re0, mul32(a.lo, k.re1))));
+    const u64 u_im = mad32(b.hi, k.re1d, mad32(a.hi, k.im1d, mad32(b.lo, k.re0, mul32(a.lo, k.im0))));
+    const u64 t_im = mad32(b.hi, k.re0, mad32(b.lo, k.re1, mad32(a.hi, k.im0, mul32(a.lo, k.im1))));
+    return F{fp_reduce_ut_weak(u_re, t_re, v0.re), fp_reduce_ut_weak(u_im, t_im, v0.im)};
+}
+// Same for base-field data (v0.im == d.im == 0): v0 + k*d with v0, d real.
+VP_HD F f_fold_w_real(u64 v0, u64 d, const ConstK& k) {
+    const Limbs a = split31(d);
+    const u64 u_re = mad32(a.hi, k.re1d, mul32(a.lo, k.re0));
+    const u64 t_re = mad32(a.hi, k.re0, mul32(a.lo, k.re1));
+    const u64 u_im = mad32(a.hi, k.im1d, mul32(a.lo, k.im0));
+    const u64 t_im = mad32(a.hi, k.im0, mul32(a.lo, k.im1));
+    return F{fp_reduce_ut_weak(u_re, t_re, v0), fp_reduce_ut_weak(u_im, t_im, 0)};
+}
+// x1 - x0 as a value in [0, 2p] (operands in [0,p]); and the same folded into [0,p]
+VP_HD F f_diff2p(const F& x0, const F& x1) { return F{x1.re + P - x0.re, x1.im + P - x0.im}; }
+VP_HD F f_diff_w(const F& x0, const F& x1) { return F{fp_weak(x1.re + P - x0.re), fp_weak(x1.im + P - x0.im)}; }
+
+// 96-bit accumulator: sums up to 2^32 chain values (< 2^64 each) without any reduction.
+struct A96 {
+    u32 w0, w1, w2;
+};
+VP_HD void a96_add(A96& a, u64 x) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2)
+        : "r"((u32)x), "r"((u32)(x >> 32)));
+#else
+    unsigned __int128 s = ((unsigned __int128)a.w2 << 64) | ((u64)a.w1 << 32) | a.w0;
+    s += x;
+    a.w0 = (u32)s; a.w1 = (u32)(s >> 32); a.w2 = (u32)(s >> 64);
+#endif
+}
+VP_HD u64 a96_mod(const A96& a) {  // -> < 2^61 + 2^35, same class
+    const u64 lo = ((u64)(a.w1 & 0x1FFFFFFFu) << 32) | a.w0;
+    const u64 hi = ((u64)a.w2 << 3) | (a.w1 >> 29);
+    return lo + hi;
+}
+// Lazy sum of complex products: per component  value = U + 2^31 * T.
+struct CAcc {
+    A96 u_re, t_re, u_im, t_im;
+};
+VP_HD CAcc cacc_zero() { return CAcc{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; }
+// acc += m * v.  m: components <= 2p (LOp, with the limbs of 2p - im); v: components in [0,p] (ROpD).
+VP_HD void cacc_mad(CAcc& s, const LOp& m, const ROpD& v) {
+    a96_add(s.u_re, mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0)))));
+    a96_add(s.t_re, mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1)))));
+    a96_add(s.u_im, mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0)))));
+    a96_add(s.t_im, mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1)))));
+}
+// acc += m * v for a base-field v in [0,p]; m components <= 2p.
+VP_HD void cacc_mad_real(CAcc& s, const F& m, u64 v) {
+    const Limbs a = split31(m.re), b = split31(m.im), c = split31(v);
+    const u32 c1d = c.hi << 1;
+    a96_add(s.u_re, mad32(a.hi, c1d, mul32(a.lo, c.lo)));
+    a96_add(s.t_re, mad32(a.hi, c.lo, mul32(a.lo, c.hi)));
+    a96_add(s.u_im, mad32(b.hi, c1d, mul32(b.lo, c.lo)));
+    a96_add(s.t_im, mad32(b.hi, c.lo, mul32(b.lo, c.hi)));
+}
+VP_HD F cacc_reduce(const CAcc& s) {  // canonical
+    return F{fp_reduce_ut(a96_mod(s.u_re), a96_mod(s.t_re), 0), fp_reduce_ut(a96_mod(s.u_im), a96_mod(s.t_im), 0)};
+}
+
 // ---------------------------------------------------------------- lazy sums of products
 // Acc: unreduced 128-bit sums of the Karatsuba base products; kept for the dot-product kernels.
 struct U128 {

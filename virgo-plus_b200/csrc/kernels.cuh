@@ -899,16 +899,68 @@ struct DfsArgs {
     unsigned int* bar;         // grid-barrier counter, zero at launch (the kernel leaves it zero)
     unsigned int* chunk_ctr;   // one work counter per pass, zero at launch (the kernel leaves them zero)
     const F* v_first;          // if set: the first pass reads its V table from here (circuitValue[i-1], no copy made)
+    F* claim0;                 // DFS_NEED_B: where round 1's p(0) + p(1) goes (the claim the chain starts from)
     unsigned long long* dbg;   // optional: block 0 writes %globaltimer at 4 points of every pass (profiling aid)
 };
+
+// Per-thread running sums of one round of the pass kernel. The round polynomial a*x^2 + b*x + c is sent as
+//   a = sum (m1-m0)(v1-v0),  c = sum m0*v0 + sum a0 (+ add_term),  b = claim - 2c - a
+// where claim = p(0) + p(1) is the previous round's polynomial at its challenge (the honest prover's messages satisfy
+// the verifier's check verifier.cpp:209,248,296 identically, so b need not be summed: k_derive_b fills it in from the
+// claim chain once the claims it starts from are known). Two complex products per pair instead of the reference's
+// four (polynomial.cpp:101-110); both sums are LAZY (96-bit partial sums of the limb products, reduced once per pass).
+struct PassAcc {
+    CAcc A, C;
+    u64 s0re, s0im;   // sum of a0, folded once per work item
+};
+VP_D void pacc_init(PassAcc& s) {
+    s.A = cacc_zero(); s.C = cacc_zero();
+    s.s0re = s.s0im = 0;
+}
+VP_D void pacc_finish(const PassAcc& s, F& a, F& c) {
+    a = cacc_reduce(s.A);
+    c = f_add(cacc_reduce(s.C), F{fp_canon(s.s0re), fp_canon(s.s0im)});
+}
+// only the very first round of a stand-alone sumcheck has no claim to start from: it also sums p(1) = sum m1*v1 + a1
+struct PassAccB {
+    CAcc B;
+    u64 s1re, s1im;
+};
+// One pair of one round: accumulate, fold the three tables with the round's challenge.
+// VREAL: the V table is in the base field (circuit values, first pass of every GKR phase): half the limb products.
+// Operands are weakly canonical ([0,p]); so are the folded values.
+template <bool VREAL, bool HAS_A, bool NEED_B>
+VP_D void dfs_pair(PassAcc& s, PassAccB* sb, const F& v0, const F& v1, const F& m0, const F& m1, const F& a0, const F& a1,
+                   const ConstK& rk, F& ov, F& om, F& oa) {
+    const F dm = f_diff2p(m0, m1);
+    if (VREAL) {
+        const u64 dv = fp_weak(v1.re + P - v0.re);
+        cacc_mad_real(s.C, m0, v0.re);
+        cacc_mad_real(s.A, dm, dv);
+        if (NEED_B) cacc_mad_real(sb->B, m1, v1.re);
+        ov = f_fold_w_real(v0.re, dv, rk);
+    } else {
+        const F dv = f_diff_w(v0, v1);
+        cacc_mad(s.C, make_lop(m0.re, m0.im), make_ropd(v0));
+        cacc_mad(s.A, make_lop(dm.re, dm.im), make_ropd(dv));
+        if (NEED_B) cacc_mad(sb->B, make_lop(m1.re, m1.im), make_ropd(v1));
+        ov = f_fold_w(v0, dv, rk);
+    }
+    om = f_fold_w(m0, dm, rk);
+    if (HAS_A) {
+        s.s0re += a0.re; s.s0im += a0.im;
+        if (NEED_B) { sb->s1re += a1.re; sb->s1im += a1.im; }
+        oa = f_fold_w(a0, f_diff2p(a0, a1), rk);
+    }
+}
 
 // Work is handed out in chunks of DFS_CHUNK items through an atomic counter: equal static shares finish up to
 // 1.5x apart across SMs (measured: 242..383 us for the same share of a 2^24-entry pass), so the fast SMs take more.
 static constexpr uint32_t DFS_CHUNK = 512;
-template <bool NC, bool HAS_A>
-VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ tabs, uint32_t n_tabs, const uint32_t* s_wend,
-                   const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA, const FoldK& rk1, const FoldK& rk2,
-                   unsigned int* chunk_ctr, uint32_t* s_chunk) {
+template <bool NC, bool HAS_A, bool VREAL, bool NEED_B>
+VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
+                   const uint32_t* s_wend, const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA,
+                   const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t* s_chunk) {
     const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;
     uint32_t t = 0;
     PassTab T = n_tabs ? tabs[0] : PassTab{0, 0, 0, 0, 0, 0};
@@ -951,17 +1003,15 @@ VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ t
                 }
             }
             if (!HAS_A) { xa[0] = xa[1] = xa[2] = xa[3] = f_zero(); }
-            racc_pair(acc1, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1]);
-            racc_pair(acc1, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3]);
-            const F v0 = f_fold_k(xv[0], xv[1], rk1), v1 = f_fold_k(xv[2], xv[3], rk1);
-            const F m0 = f_fold_k(xm[0], xm[1], rk1), m1 = f_fold_k(xm[2], xm[3], rk1);
-            F a0 = f_zero(), a1 = f_zero();
-            if (HAS_A) { a0 = f_fold_k(xa[0], xa[1], rk1); a1 = f_fold_k(xa[2], xa[3], rk1); }
-            racc_pair(acc2, v0, v1, m0, m1, a0, a1);
+            F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero(), ov, om, oa = f_zero();
+            dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1], rk1, v0, m0, a0);
+            dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3], rk1, v1, m1, a1);
+            dfs_pair<false, HAS_A, false>(acc2, nullptr, v0, v1, m0, m1, a0, a1, rk2, ov, om, oa);
             const uint32_t o = T.out_off + q;
-            st_f(outV + o, f_fold_k(v0, v1, rk2));
-            st_f(outM + o, f_fold_k(m0, m1, rk2));
-            if (HAS_A) st_f(outA + o, f_fold_k(a0, a1, rk2));
+            st_f(outV + o, ov);
+            st_f(outM + o, om);
+            if (HAS_A) st_f(outA + o, oa);
+            if (HAS_A) { acc2.s0re = fp_fold(acc2.s0re); acc2.s0im = fp_fold(acc2.s0im); }
         } else {
             const uint32_t i0 = 2 * q;
             F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero();
@@ -974,11 +1024,16 @@ VP_D void dfs_work(RoundAcc& acc1, RoundAcc& acc2, const PassTab* __restrict__ t
                 if (HAS_A) a0 = ld_one<NC>(A + i0);
                 v1 = m1 = f_zero();
             }
-            racc_pair(acc1, v0, v1, m0, m1, a0, a1);
+            F ov, om, oa = f_zero();
+            dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, v0, v1, m0, m1, a0, a1, rk1, ov, om, oa);
             const uint32_t o = T.out_off + q;
-            st_f(outV + o, f_fold_k(v0, v1, rk1));
-            st_f(outM + o, f_fold_k(m0, m1, rk1));
-            if (HAS_A) st_f(outA + o, f_fold_k(a0, a1, rk1));
+            st_f(outV + o, ov);
+            st_f(outM + o, om);
+            if (HAS_A) st_f(outA + o, oa);
+        }
+        if (HAS_A) {
+            acc1.s0re = fp_fold(acc1.s0re); acc1.s0im = fp_fold(acc1.s0im);
+            if (NEED_B) { accb->s1re = fp_fold(accb->s1re); accb->s1im = fp_fold(accb->s1im); }
         }
       }
         if (solo) break;
@@ -995,7 +1050,7 @@ VP_D F dfs_collapse(F at, const PassCol* __restrict__ cols, uint32_t n_cols, uin
         F cv = f_zero(), cm = f_zero(), ca = f_zero();
         if (c.n_vals) { cv = ld_one<false>(V + c.off); cm = ld_one<false>(M + c.off); if (has_a) ca = ld_one<false>(A + c.off); }
         at = f_add(at, f_mul_add(cv, cm, ca));
-        if (c.claim_slot >= 0) st_f(claims + c.claim_slot, cv);
+        if (c.claim_slot >= 0) st_f(claims + c.claim_slot, f_strict(cv));
     }
     return at;
 }
@@ -1028,7 +1083,11 @@ VP_D void pass_wait(unsigned int* bar, unsigned int target) {
 #define VP_DFS_THREADS 256
 #endif
 static constexpr int DFS_THREADS = VP_DFS_THREADS;
-template <bool HAS_A>
+// FIRST: what the very first pass of the launch looks like
+enum : int { DFS_PLAIN = 0,    // like every other pass (stage B of a sharded phase, stand-alone tables with a known claim)
+             DFS_VREAL = 1,    // V is in the base field (circuit values): every GKR phase
+             DFS_NEED_B = 2 }; // stand-alone sumcheck: no claim to start from, round 1 also sums p(1) -> *claim0
+template <bool HAS_A, int FIRST>
 __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     __shared__ F smem[6 * 32];
     __shared__ uint32_t s_wend[128];
@@ -1052,20 +1111,28 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         const F prev1 = scale1 ? p.chal[g1 - 2] : f_zero();
         const F r1 = p.chal[g1 - 1];
         const F r2 = R.n_rounds == 2 ? p.chal[g1] : f_zero();
-        const FoldK rk1 = make_foldk(r1), rk2 = make_foldk(r2);
-        RoundAcc acc1, acc2;
-        racc_init(acc1);
-        racc_init(acc2);
-        dfs_work<false, HAS_A>(acc1, acc2, p.tabs + R.tab_begin, R.n_tabs, s_wend, (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib],
-                               p.bufM[ib], p.bufA[ib], p.bufV[ob],
-                        p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
-        F v[6];
-        {
-            F a[3], b[3];
-            racc_finish(acc1, a);
-            racc_finish(acc2, b);
-            v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = b[0]; v[4] = b[1]; v[5] = b[2];
-        }
+        const ConstK rk1 = make_constk(r1), rk2 = make_constk(r2);
+        PassAcc acc1, acc2;
+        pacc_init(acc1);
+        pacc_init(acc2);
+        PassAccB accb;
+        accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
+        const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
+        if (FIRST == DFS_VREAL && ps == 0)
+            dfs_work<false, HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+        else if (FIRST == DFS_NEED_B && ps == 0)
+            dfs_work<false, HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+        else
+            dfs_work<false, HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                 p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+        // v: a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
+        constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;
+        F v[NV];
+        pacc_finish(acc1, v[0], v[1]);
+        pacc_finish(acc2, v[2], v[3]);
+        if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(cacc_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
         VP_DBG_T(1);
         if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
             unsigned long long t_; unsigned int sm_;
@@ -1074,7 +1141,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             p.dbg[256 + 2 * blockIdx.x] = t_;
             p.dbg[256 + 2 * blockIdx.x + 1] = sm_;
         }
-        block_sum<6>(v, smem);
+        block_sum<NV>(v, smem);
         F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
         const PassCol* cols = p.cols + R.col_begin;
         // tables that were already down to one value join add_term in the pass's first round; their value sits in the
@@ -1084,7 +1151,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         if (!solo) {
             if (threadIdx.x == 0 && blockIdx.x != 0) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
+                for (int k = 0; k < NV; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
             }
             pass_arrive(p.bar);
             target += active;
@@ -1094,29 +1161,32 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             pass_wait(p.bar, target);
             VP_DBG_T(2);
             if (blockIdx.x == 0) {
-                F t6[6];
+                F t6[NV];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) t6[k] = f_zero();
+                for (int k = 0; k < NV; ++k) t6[k] = f_zero();
                 for (uint32_t b = 1 + threadIdx.x; b < active; b += blockDim.x) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) t6[k] = f_add(t6[k], ld_one<false>(part + (size_t)b * 6 + k));
+                    for (int k = 0; k < NV; ++k) t6[k] = f_add(t6[k], ld_one<false>(part + (size_t)b * 6 + k));
                 }
-                block_sum<6>(t6, smem);
+                block_sum<NV>(t6, smem);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) v[k] = f_add(v[k], t6[k]);   // thread 0: own block's sum + the others'
+                for (int k = 0; k < NV; ++k) v[k] = f_add(v[k], t6[k]);   // thread 0: own block's sum + the others'
             }
         } else __syncthreads();   // this pass's outputs (a table reaching one value) are visible to thread 0
         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            // the b slots stay zero here: k_derive_b fills them from the claim chain
             F* o = p.out_poly + 3 * (j - 1);
+            const F c1 = f_add(v[1], at);
             st_f(o + 0, v[0]);
-            st_f(o + 1, f_sub(v[1], at));
-            st_f(o + 2, f_add(v[2], at));
+            st_f(o + 1, f_zero());
+            st_f(o + 2, c1);
+            if (FIRST == DFS_NEED_B && ps == 0 && p.claim0) st_f(p.claim0, f_add(c1, v[NV - 1]));   // p(0) + p(1)
             if (R.n_rounds == 2) {
                 // tables that reached one value in this pass's first round join in its second round (OUT buffer)
                 at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, r1, p.claims, HAS_A);
-                st_f(o + 3, v[3]);
-                st_f(o + 4, f_sub(v[4], at));
-                st_f(o + 5, f_add(v[5], at));
+                st_f(o + 3, v[2]);
+                st_f(o + 4, f_zero());
+                st_f(o + 5, f_add(v[3], at));
             }
         }
         VP_DBG_T(3);
@@ -1129,16 +1199,62 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         *p.bar = 0;   // every other block has arrived for the last time: ready for the next launch
     }
     for (uint32_t i = threadIdx.x; i < p.n_passes; i += blockDim.x) p.chunk_ctr[i] = 0;
-    // final claims: a table alive to the end is down to its level-R value (prover.cpp:494-521)
+    // final claims: a table alive to the end is down to its level-R value (prover.cpp:494-521); the tables are
+    // weakly canonical, what leaves the kernel is canonical
     const F* V = (p.n_passes == 0 && p.v_first) ? p.v_first : p.bufV[p.fin_buf];   // zero rounds: the value was never copied
     for (uint32_t i = threadIdx.x; i < p.n_fin; i += blockDim.x) {
         const FinDesc f = p.fins[i];
         F c;
         if (f.from_claim >= 0) c = ld_one<false>(p.claims + f.from_claim);
         else c = f.n_vals >= 1 ? ld_one<false>(V + f.in_off) : f_zero();
+        c = f_strict(c);
         st_f(p.transcript + f.out_idx, c);
         if (p.keep && i == 0) st_f(p.keep, c);
     }
+}
+
+// ------------------------------------------------------------------ the b coefficients, from the claim chain
+// k_phase_dfs leaves b = 0 in every round polynomial. The verifier's check p(0) + p(1) == claim (verifier.cpp:209,
+// 248, 296) holds identically for the honest prover, so b = claim - 2c - a, with the claim chain
+//   phase 1 of the top layer: Vres; phase 1 of layer i: the Liu claim of layer i+1 (verifier.cpp:333);
+//   phase 2: continues phase 1's chain (verifier.cpp:157-158); Liu: sum_k sig_k * claim_k (verifier.cpp:281-284);
+//   next claim = p(r) (verifier.cpp:215,254,302).
+// All starting claims are fully folded V values, which do not depend on any b: the chains are independent, one thread each.
+struct ChainSeg { uint32_t tr_off, n_rounds, ci; };   // polynomials at tr[tr_off + 3j], challenges chal[ci + j]
+struct ChainTerm { uint32_t ci, tr; };                // claim0 += chal[ci] * tr[tr]
+struct ChainDesc {
+    int32_t claim_tr;            // >= 0: claim0 = tr[claim_tr]; -1: the weighted sum of the terms; -2: *claim_ext
+    uint32_t term_begin, n_terms;
+    uint32_t seg_begin, n_segs;
+};
+__global__ void k_derive_b(const ChainDesc* __restrict__ chains, int n_chains, const ChainSeg* __restrict__ segs,
+                           const ChainTerm* __restrict__ terms, const F* __restrict__ chal, F* tr, const F* claim_ext) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains) return;
+    const ChainDesc c = chains[i];
+    F claim = f_zero();
+    if (c.claim_tr >= 0) claim = tr[c.claim_tr];
+    else if (c.claim_tr == -2) claim = *claim_ext;
+    else
+        for (uint32_t k = 0; k < c.n_terms; ++k) {
+            const ChainTerm t = terms[c.term_begin + k];
+            claim = f_mul_add(chal[t.ci], tr[t.tr], claim);
+        }
+    for (uint32_t s = 0; s < c.n_segs; ++s) {
+        const ChainSeg g = segs[c.seg_begin + s];
+        for (uint32_t jr = 0; jr < g.n_rounds; ++jr) {
+            F* o = tr + g.tr_off + 3 * jr;
+            const F a = o[0], cc = o[2], r = chal[g.ci + jr];
+            const F b = f_sub(f_sub(claim, f_dbl(cc)), a);
+            st_f(o + 1, b);
+            claim = f_mul_add(f_mul_add(a, r, b), r, cc);   // quadratic_poly::eval, polynomial.cpp:91-95
+        }
+    }
+}
+
+__global__ void k_strict_copy(F* dst, const F* src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_f(dst + i, f_strict(src[i]));
 }
 
 // ------------------------------------------------------------------ sharded phases: hand-over between the local

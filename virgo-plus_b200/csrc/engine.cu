@@ -170,7 +170,7 @@ static PassPlan build_pass_plan(const std::vector<PlanTable>& tabs, int rounds, 
             }
             const bool two = nr == 2 && rem >= 2;
             const uint32_t nl = two ? cdiv(cdiv(live[t], 2), 2) : cdiv(live[t], 2);
-            work += two ? cdiv(live[t], 4) : cdiv(live[t], 2);
+            work += (cdiv(live[t], two ? 4 : 2) + 31u) & ~31u;   // a warp's 32-item sub-chunk never spans two tables
             A.ptabs.push_back(PassTab{off[t], live[t], oo, work, two ? 1u : 0u, 0});
             P.bytes += 48.0 * live[t] + 48.0 * nl;
             off[t] = oo;
@@ -576,6 +576,14 @@ static void nccl_load() {
         }                                                                                                \
     } while (0)
 
+static constexpr size_t DFS_DYN_SMEM = (size_t)(DFS_THREADS / 32) * DFS_WARP_SMEM_F * sizeof(F);
+static void dfs_enable_smem() {   // opt in to the dynamic shared memory of the staging pipeline (all instantiations)
+    const void* ks[] = {(const void*)k_phase_dfs<true, DFS_VREAL>, (const void*)k_phase_dfs<false, DFS_VREAL>,
+                        (const void*)k_phase_dfs<true, DFS_PLAIN>, (const void*)k_phase_dfs<false, DFS_PLAIN>,
+                        (const void*)k_phase_dfs<true, DFS_NEED_B>};
+    for (const void* k : ks) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DFS_DYN_SMEM));
+}
+
 struct Engine {
     Circuit C;
     int device = 0;
@@ -732,9 +740,9 @@ struct Engine {
     int n_sm = 148;
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
     template <class Kern>
-    int occ_cap(Kern k, int threads = 256) {  // resident blocks on the whole chip
+    int occ_cap(Kern k, int threads = 256, size_t dyn_smem = 0) {  // resident blocks on the whole chip
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, dyn_smem));
         return n_sm * std::max(1, occ);
     }
     int grid_for(uint32_t work, int cap) const { return (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(work, 256), (uint32_t)cap)); }
@@ -766,8 +774,11 @@ struct Engine {
     uint32_t tail_work = 512;
     bool use_phase_kernel = true;
     void prove_all();
+    std::vector<F> h_chal;   // host copy of the challenges: the pass kernel gets their limbs through its parameters
     void set_chal(uint32_t idx, const vp_F* v, size_t cnt = 1) {
         CK(cudaMemcpyAsync(d_chal.p + idx, v, cnt * sizeof(F), cudaMemcpyHostToDevice, stream));
+        if (h_chal.size() < idx + cnt) h_chal.resize(idx + cnt, f_zero());
+        memcpy(h_chal.data() + idx, v, cnt * sizeof(F));
     }
     void get_tr(uint32_t idx, vp_F* out, size_t cnt = 1) {
         CK(cudaMemcpyAsync(out, d_tr.p + idx, cnt * sizeof(F), cudaMemcpyDeviceToHost, stream));
@@ -815,8 +826,9 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dot = occ_cap(k_dot_eq);
     cap_comb = occ_cap(k_combine_phase2);
     cap_phase = occ_cap(k_sumcheck_phase);
-    cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS),
-                        occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS)});
+    dfs_enable_smem();
+    cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM),
+                        occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM)});
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     {
         int coop = 0;
@@ -1446,13 +1458,18 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     a.v_first = v_first;
     a.claim0 = nullptr;
     a.dbg = nullptr;
+    if (P.rounds > 32) throw CudaError{"a sumcheck phase with more than 32 rounds"};
+    for (int jr = 0; jr < 32; ++jr) {
+        const size_t ix = (size_t)ci + round_base + (size_t)jr;
+        a.rk[jr] = make_constk(jr < P.rounds && ix < h_chal.size() ? h_chal[ix] : f_zero());
+    }
     // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
     // this one is down to its small passes
     const uint32_t cap = two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), cap));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
-    CK(cudaLaunchCooperativeKernel(dfs_kernel_ptr(has_a, first), dim3(grid), dim3(DFS_THREADS), args, 0, stream));
+    CK(cudaLaunchCooperativeKernel(dfs_kernel_ptr(has_a, first), dim3(grid), dim3(DFS_THREADS), args, DFS_DYN_SMEM, stream));
     prof_end(h, P.alg_bytes);
     ++launches;
 }
@@ -2244,7 +2261,8 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->pp = build_pass_plan(t, log_n, {3u * (uint32_t)log_n}, s->arena);
     {
         int occd = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true, DFS_NEED_B>, DFS_THREADS, 0));
+        dfs_enable_smem();
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occd, k_phase_dfs<true, DFS_NEED_B>, DFS_THREADS, DFS_DYN_SMEM));
         s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
         s->max_grid = std::max(s->max_grid, s->cap_dfs);
     }
@@ -2409,11 +2427,12 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     a.chunk_ctr = s->d_counter.p + 4;
     a.v_first = nullptr;
     a.claim0 = s->d_scal.p + 1;
+    for (int jr = 0; jr < 32; ++jr) a.rk[jr] = make_constk(jr < n ? F{r[jr].re, r[jr].im} : f_zero());
     a.dbg = s->d_dbg.p;
     CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true, DFS_NEED_B>, dim3(grid), dim3(DFS_THREADS), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true, DFS_NEED_B>, dim3(grid), dim3(DFS_THREADS), args, DFS_DYN_SMEM, st));
     // b of every round from the claim chain; round 1's claim p(0) + p(1) was summed by the kernel
     k_derive_b<<<1, 32, 0, st>>>(s->d_chain.p, 1, s->d_chain_seg.p, s->d_chain_term.p, s->d_r.p, s->d_out.p, s->d_scal.p + 1);
     // the fully folded add / mult values sit where V's does

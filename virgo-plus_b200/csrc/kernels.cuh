@@ -899,6 +899,7 @@ struct DfsArgs {
     unsigned int* bar;         // grid-barrier counter, zero at launch (the kernel leaves it zero)
     unsigned int* chunk_ctr;   // one work counter per pass, zero at launch (the kernel leaves them zero)
     const F* v_first;          // if set: the first pass reads its V table from here (circuitValue[i-1], no copy made)
+    ConstK rk[32];             // rk[j]: the challenge bound after local round j+1 of this launch, pre-split (host side)
     F* claim0;                 // DFS_NEED_B: where round 1's p(0) + p(1) goes (the claim the chain starts from)
     unsigned long long* dbg;   // optional: block 0 writes %globaltimer at 4 points of every pass (profiling aid)
 };
@@ -954,89 +955,143 @@ VP_D void dfs_pair(PassAcc& s, PassAccB* sb, const F& v0, const F& v1, const F& 
     }
 }
 
-// Work is handed out in chunks of DFS_CHUNK items through an atomic counter: equal static shares finish up to
-// 1.5x apart across SMs (measured: 242..383 us for the same share of a 2^24-entry pass), so the fast SMs take more.
-static constexpr uint32_t DFS_CHUNK = 512;
-template <bool NC, bool HAS_A, bool VREAL, bool NEED_B>
+// Work distribution and staging of the pass kernel.
+//  * A pass's work items (quads, or pairs for a table in its last odd round) are numbered over the concatenated
+//    tables; every table's share is padded to a multiple of 32, so a SUB-CHUNK of 32 consecutive items (one per lane)
+//    lies in one table. Items past a table's live entries read zeros, add nothing and store nothing.
+//  * Each WARP runs its own two-stage cp.async pipeline through shared memory: while it computes sub-chunk n from
+//    stage n&1, the 16-byte pieces of sub-chunk n+1 are in flight into the other stage (zero-filled past the live
+//    entries with src-size 0). No block barrier and no exposed load latency in the loop; no registers are tied up
+//    by prefetched data. Pieces are copied with consecutive lanes on consecutive 16 bytes (coalesced) and land at
+//    slot 4q + (j ^ ((q >> 1) & 3)) so that lane q's four 128-bit reads of its quad are bank-conflict free.
+//  * Warps take chunks of DFS_WCHUNK = 128 items (4 sub-chunks) from an atomic counter, fetched one chunk ahead:
+//    equal static shares finish up to 1.5x apart across SMs (measured), so the fast SMs take more.
+static constexpr uint32_t DFS_CHUNK = 512;    // items a block covers in one sweep (sizing of grids / `active` blocks)
+static constexpr uint32_t DFS_WCHUNK = 128;   // items per warp chunk
+static constexpr uint32_t DFS_STAGE_F = 3 * 128;              // F slots per stage: 3 tables x 32 quads
+static constexpr uint32_t DFS_WARP_SMEM_F = 2 * DFS_STAGE_F;  // two stages per warp
+
+VP_D void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_size) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_size) : "memory");
+}
+VP_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+VP_D void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+VP_D F lds_f(uint32_t smem_addr) {
+    F r;
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(r.re), "=l"(r.im) : "r"(smem_addr) : "memory");
+    return r;
+}
+
+template <bool HAS_A, bool VREAL, bool NEED_B>
 VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
                    const uint32_t* s_wend, const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA,
-                   const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t* s_chunk) {
-    const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;
-    uint32_t t = 0;
-    PassTab T = n_tabs ? tabs[0] : PassTab{0, 0, 0, 0, 0, 0};
-    uint32_t wbeg = 0;
-    const bool solo = total <= DFS_CHUNK;
-    for (;;) {
-        uint32_t c = 0;
-        if (!solo) {
-            __syncthreads();
-            if (threadIdx.x == 0) *s_chunk = atomicAdd(chunk_ctr, 1u);
-            __syncthreads();
-            c = *s_chunk;
+                   const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t stage_base /* this warp's smem */) {
+    const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;   // multiple of 32
+    const bool solo = total <= DFS_CHUNK;                     // one block (block 0) does the pass: static shares
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- sub-chunk stream of this warp
+    uint32_t c_cur, c_next = 0, sub = 0;
+    if (solo) c_cur = warp * DFS_WCHUNK;   // block 0 alone (total <= DFS_CHUNK): static shares
+    else {
+        uint32_t c0 = 0, c1 = 0;
+        if (lane == 0) { c0 = atomicAdd(chunk_ctr, 1u); c1 = atomicAdd(chunk_ctr, 1u); }
+        c_cur = __shfl_sync(0xffffffffu, c0, 0) * DFS_WCHUNK;
+        c_next = __shfl_sync(0xffffffffu, c1, 0) * DFS_WCHUNK;
+    }
+    auto gen = [&]() -> uint32_t {   // base item of the next sub-chunk, or 0xffffffff
+        if (sub == DFS_WCHUNK / 32) {
+            if (solo) return 0xffffffffu;
+            sub = 0;
+            c_cur = c_next;
+            uint32_t c = 0;
+            if (lane == 0 && c_cur < total) c = atomicAdd(chunk_ctr, 1u);   // consumed 4 sub-chunks from now
+            c_next = c_cur < total ? __shfl_sync(0xffffffffu, c, 0) * DFS_WCHUNK : 0xffffffffu;
         }
-        if (c * DFS_CHUNK >= total) break;
-      for (uint32_t w = c * DFS_CHUNK + threadIdx.x; w < min(total, (c + 1) * DFS_CHUNK); w += blockDim.x) {
-        if (w < wbeg) { t = 0; T = tabs[0]; wbeg = 0; }   // chunks arrive in increasing order per block, but be safe
-        if (w >= s_wend[t]) {
-            do { ++t; } while (w >= s_wend[t]);
-            T = tabs[t];
-            wbeg = s_wend[t - 1];
-        }
-        const uint32_t q = w - wbeg;
+        const uint32_t b = c_cur + 32 * sub;
+        ++sub;
+        return (c_cur < total && b < total) ? b : 0xffffffffu;
+    };
+    // ---- issue the copies of one sub-chunk into a stage
+    uint32_t t_is = 0;
+    auto issue = [&](uint32_t b, uint32_t st) {
+        while (b >= s_wend[t_is]) ++t_is;
+        const PassTab T = tabs[t_is];
+        const uint32_t q0 = b - (t_is ? s_wend[t_is - 1] : 0);
+        const uint32_t sbase = stage_base + st * (DFS_STAGE_F * 16);
+        const uint32_t per = T.two ? 4u : 2u;             // entries per item
+        const uint32_t e0 = q0 * per;
         const F* V = inV + T.in_off;
         const F* M = inM + T.in_off;
         const F* A = inA + T.in_off;
-        if (T.two) {
-            const uint32_t i0 = 4 * q;
-            F xv[4], xm[4], xa[4];
-            if (i0 + 3 < T.in_live) {
-                ld_pair<NC>(V + i0, xv[0], xv[1]); ld_pair<NC>(V + i0 + 2, xv[2], xv[3]);
-                ld_pair<NC>(M + i0, xm[0], xm[1]); ld_pair<NC>(M + i0 + 2, xm[2], xm[3]);
-                if (HAS_A) { ld_pair<NC>(A + i0, xa[0], xa[1]); ld_pair<NC>(A + i0 + 2, xa[2], xa[3]); }
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool in = i0 + j < T.in_live;
-                    xv[j] = in ? ld_one<NC>(V + i0 + j) : f_zero();
-                    xm[j] = in ? ld_one<NC>(M + i0 + j) : f_zero();
-                    if (HAS_A) xa[j] = in ? ld_one<NC>(A + i0 + j) : f_zero();
-                }
-            }
-            if (!HAS_A) { xa[0] = xa[1] = xa[2] = xa[3] = f_zero(); }
+        for (uint32_t j = 0; j < 4; ++j) {
+            if (j >= per) break;
+            const uint32_t k = j * 32 + lane;             // piece of this table's 32-item region
+            const uint32_t q = T.two ? (k >> 2) : (k >> 1), jj = T.two ? (k & 3) : (k & 1);
+            const uint32_t slot = 4 * q + (jj ^ ((q >> 1) & 3));
+            const uint32_t e = e0 + k;
+            const bool in = e < T.in_live;
+            const uint32_t sz = in ? 16u : 0u;
+            const uint32_t eo = in ? e : 0u;
+            cp_async16(sbase + slot * 16, V + eo, sz);
+            cp_async16(sbase + (128 + slot) * 16, M + eo, sz);
+            if (HAS_A) cp_async16(sbase + (256 + slot) * 16, A + eo, sz);
+        }
+    };
+    uint32_t t_cp = 0;
+    uint32_t b_cur = gen();
+    if (b_cur != 0xffffffffu) issue(b_cur, 0);
+    cp_async_commit();
+    uint32_t st = 0;
+    while (b_cur != 0xffffffffu) {
+        const uint32_t b_next = gen();
+        if (b_next != 0xffffffffu) issue(b_next, st ^ 1);
+        cp_async_commit();
+        cp_async_wait1();
+        __syncwarp();
+        // ---- this lane's item
+        while (b_cur >= s_wend[t_cp]) ++t_cp;
+        const PassTab T = tabs[t_cp];
+        const uint32_t q = b_cur - (t_cp ? s_wend[t_cp - 1] : 0) + lane;
+        const uint32_t sb = stage_base + st * (DFS_STAGE_F * 16) + 64 * lane, sw = (lane >> 1) & 3;
+        F xv[4], xm[4], xa[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t o = 16 * (j ^ sw);
+            xv[j] = lds_f(sb + o);
+            xm[j] = lds_f(sb + 128 * 16 + o);
+            xa[j] = HAS_A ? lds_f(sb + 256 * 16 + o) : f_zero();
+        }
+        __syncwarp();   // every lane has read its quad: the stage may be refilled by the next iteration's copies
+        if (T.two) {
             F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero(), ov, om, oa = f_zero();
             dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1], rk1, v0, m0, a0);
             dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3], rk1, v1, m1, a1);
             dfs_pair<false, HAS_A, false>(acc2, nullptr, v0, v1, m0, m1, a0, a1, rk2, ov, om, oa);
-            const uint32_t o = T.out_off + q;
-            st_f(outV + o, ov);
-            st_f(outM + o, om);
-            if (HAS_A) st_f(outA + o, oa);
+            if (4 * q < T.in_live) {
+                const uint32_t o = T.out_off + q;
+                st_f(outV + o, ov);
+                st_f(outM + o, om);
+                if (HAS_A) st_f(outA + o, oa);
+            }
             if (HAS_A) { acc2.s0re = fp_fold(acc2.s0re); acc2.s0im = fp_fold(acc2.s0im); }
         } else {
-            const uint32_t i0 = 2 * q;
-            F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero();
-            if (i0 + 1 < T.in_live) {
-                ld_pair<NC>(V + i0, v0, v1);
-                ld_pair<NC>(M + i0, m0, m1);
-                if (HAS_A) ld_pair<NC>(A + i0, a0, a1);
-            } else {
-                v0 = ld_one<NC>(V + i0); m0 = ld_one<NC>(M + i0);
-                if (HAS_A) a0 = ld_one<NC>(A + i0);
-                v1 = m1 = f_zero();
-            }
+            // a pair item uses the first two slots of its lane's quad (xv[2..3] are stale shared memory, unused)
             F ov, om, oa = f_zero();
-            dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, v0, v1, m0, m1, a0, a1, rk1, ov, om, oa);
-            const uint32_t o = T.out_off + q;
-            st_f(outV + o, ov);
-            st_f(outM + o, om);
-            if (HAS_A) st_f(outA + o, oa);
+            dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1], rk1, ov, om, oa);
+            if (2 * q < T.in_live) {
+                const uint32_t o = T.out_off + q;
+                st_f(outV + o, ov);
+                st_f(outM + o, om);
+                if (HAS_A) st_f(outA + o, oa);
+            }
         }
         if (HAS_A) {
             acc1.s0re = fp_fold(acc1.s0re); acc1.s0im = fp_fold(acc1.s0im);
             if (NEED_B) { accb->s1re = fp_fold(accb->s1re); accb->s1im = fp_fold(accb->s1im); }
         }
-      }
-        if (solo) break;
+        b_cur = b_next;
+        st ^= 1;
     }
 }
 
@@ -1077,10 +1132,10 @@ VP_D void pass_wait(unsigned int* bar, unsigned int target) {
 }
 
 #ifndef VP_DFS_MINB
-#define VP_DFS_MINB 2
+#define VP_DFS_MINB 3
 #endif
 #ifndef VP_DFS_THREADS
-#define VP_DFS_THREADS 256
+#define VP_DFS_THREADS 128
 #endif
 static constexpr int DFS_THREADS = VP_DFS_THREADS;
 // FIRST: what the very first pass of the launch looks like
@@ -1091,9 +1146,10 @@ template <bool HAS_A, int FIRST>
 __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     __shared__ F smem[6 * 32];
     __shared__ uint32_t s_wend[128];
-    __shared__ uint32_t s_chunk;
+    extern __shared__ __align__(16) unsigned char dfs_dyn_smem[];   // per warp: two stages x 3 tables x 32 quads
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(dfs_dyn_smem) + (threadIdx.x >> 5) * (DFS_WARP_SMEM_F * 16);
     F at = p.at_init ? *p.at_init : f_zero();
-    uint32_t j = 1;       // local round of the pass's first round
+    uint32_t j = 1;       // local round of the pass's first round (= 1 + 2 * ps: every pass but the last has two rounds)
     unsigned int target = 0;
     for (uint32_t ps = 0; ps < p.n_passes; ++ps) {
 #define VP_DBG_T(k) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[4 * ps + (k)] = t_; } } while (0)
@@ -1108,10 +1164,9 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         const uint32_t ib = R.in_buf, ob = ib ^ 1;
         const uint32_t g1 = p.round_base + j;                    // global round of the pass's first round
         const bool scale1 = g1 >= 2;
-        const F prev1 = scale1 ? p.chal[g1 - 2] : f_zero();
-        const F r1 = p.chal[g1 - 1];
-        const F r2 = R.n_rounds == 2 ? p.chal[g1] : f_zero();
-        const ConstK rk1 = make_constk(r1), rk2 = make_constk(r2);
+        // the challenges' limbs come pre-split through the kernel parameters (uniform registers / constant bank)
+        const ConstK& rk1 = p.rk[2 * ps];
+        const ConstK& rk2 = p.rk[2 * ps + 1];
         PassAcc acc1, acc2;
         pacc_init(acc1);
         pacc_init(acc2);
@@ -1119,14 +1174,14 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
         const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
         if (FIRST == DFS_VREAL && ps == 0)
-            dfs_work<false, HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+            dfs_work<HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
         else if (FIRST == DFS_NEED_B && ps == 0)
-            dfs_work<false, HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+            dfs_work<HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
         else
-            dfs_work<false, HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                 p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, &s_chunk);
+            dfs_work<HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                                 p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
         // v: a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
         constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;
         F v[NV];
@@ -1147,7 +1202,8 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         // tables that were already down to one value join add_term in the pass's first round; their value sits in the
         // IN buffer, which the next pass overwrites: read it before the barrier
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, prev1, p.claims, HAS_A);
+            at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, scale1 ? p.chal[g1 - 2] : f_zero(),
+                              p.claims, HAS_A);
         if (!solo) {
             if (threadIdx.x == 0 && blockIdx.x != 0) {
 #pragma unroll
@@ -1183,7 +1239,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             if (FIRST == DFS_NEED_B && ps == 0 && p.claim0) st_f(p.claim0, f_add(c1, v[NV - 1]));   // p(0) + p(1)
             if (R.n_rounds == 2) {
                 // tables that reached one value in this pass's first round join in its second round (OUT buffer)
-                at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, r1, p.claims, HAS_A);
+                at = dfs_collapse(at, cols, R.n_cols, 1, p.bufV[ob], p.bufM[ob], p.bufA[ob], true, p.chal[g1 - 1], p.claims, HAS_A);
                 st_f(o + 3, v[2]);
                 st_f(o + 4, f_zero());
                 st_f(o + 5, f_add(v[3], at));

@@ -1466,7 +1466,8 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
     // this one is down to its small passes
     const uint32_t cap = two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
-    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK), cap));
+    // block 0 coordinates, blocks 1.. work; a phase that fits one block runs on block 0 alone
+    const int grid = P.max_work <= DFS_CHUNK ? 1 : (int)std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK) + 1, std::max<uint32_t>(cap, 2));
     void* args[] = {&a};
     size_t h = prof_begin(KC_ROUND_FOLD);
     CK(cudaLaunchCooperativeKernel(dfs_kernel_ptr(has_a, first), dim3(grid), dim3(DFS_THREADS), args, DFS_DYN_SMEM, stream));
@@ -2430,7 +2431,7 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     for (int jr = 0; jr < 32; ++jr) a.rk[jr] = make_constk(jr < n ? F{r[jr].re, r[jr].im} : f_zero());
     a.dbg = s->d_dbg.p;
     CK(cudaMemsetAsync(s->d_dbg.p, 0, 256 * sizeof(unsigned long long), st));
-    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK), (uint32_t)s->cap_dfs));
+    const int grid = s->pp.max_work <= DFS_CHUNK ? 1 : (int)std::min<uint32_t>(cdiv(s->pp.max_work, DFS_CHUNK) + 1, std::max<uint32_t>((uint32_t)s->cap_dfs, 2));
     void* args[] = {&a};
     CK(cudaLaunchCooperativeKernel((const void*)k_phase_dfs<true, DFS_NEED_B>, dim3(grid), dim3(DFS_THREADS), args, DFS_DYN_SMEM, st));
     // b of every round from the claim chain; round 1's claim p(0) + p(1) was summed by the kernel

@@ -966,8 +966,14 @@ VP_D void dfs_pair(PassAcc& s, PassAccB* sb, const F& v0, const F& v1, const F& 
 //    slot 4q + (j ^ ((q >> 1) & 3)) so that lane q's four 128-bit reads of its quad are bank-conflict free.
 //  * Warps take chunks of DFS_WCHUNK = 128 items (4 sub-chunks) from an atomic counter, fetched one chunk ahead:
 //    equal static shares finish up to 1.5x apart across SMs (measured), so the fast SMs take more.
-static constexpr uint32_t DFS_CHUNK = 512;    // items a block covers in one sweep (sizing of grids / `active` blocks)
+#ifndef VP_DFS_MINB
+#define VP_DFS_MINB 3
+#endif
+#ifndef VP_DFS_THREADS
+#define VP_DFS_THREADS 128
+#endif
 static constexpr uint32_t DFS_WCHUNK = 128;   // items per warp chunk
+static constexpr uint32_t DFS_CHUNK = (VP_DFS_THREADS / 32) * DFS_WCHUNK;    // items a block covers in one sweep (sizing of grids / worker counts)
 static constexpr uint32_t DFS_STAGE_F = 3 * 128;              // F slots per stage: 3 tables x 32 quads
 static constexpr uint32_t DFS_WARP_SMEM_F = 2 * DFS_STAGE_F;  // two stages per warp
 
@@ -985,13 +991,15 @@ VP_D F lds_f(uint32_t smem_addr) {
 template <bool HAS_A, bool VREAL, bool NEED_B>
 VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
                    const uint32_t* s_wend, const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA,
-                   const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t stage_base /* this warp's smem */) {
+                   const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t stage_base /* this warp's smem */,
+                   uint32_t static_base /* this warp's only chunk, or 0xffffffff: chunks from the atomic counter */,
+                   uint32_t share /* items of the static chunk (multiple of 32, <= DFS_WCHUNK) */) {
     const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;   // multiple of 32
-    const bool solo = total <= DFS_CHUNK;                     // one block (block 0) does the pass: static shares
+    const bool solo = static_base != 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- sub-chunk stream of this warp
     uint32_t c_cur, c_next = 0, sub = 0;
-    if (solo) c_cur = warp * DFS_WCHUNK;   // block 0 alone (total <= DFS_CHUNK): static shares
+    if (solo) c_cur = static_base;
     else {
         uint32_t c0 = 0, c1 = 0;
         if (lane == 0) { c0 = atomicAdd(chunk_ctr, 1u); c1 = atomicAdd(chunk_ctr, 1u); }
@@ -999,8 +1007,8 @@ VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* 
         c_next = __shfl_sync(0xffffffffu, c1, 0) * DFS_WCHUNK;
     }
     auto gen = [&]() -> uint32_t {   // base item of the next sub-chunk, or 0xffffffff
+        if (solo && 32 * sub >= share) return 0xffffffffu;
         if (sub == DFS_WCHUNK / 32) {
-            if (solo) return 0xffffffffu;
             sub = 0;
             c_cur = c_next;
             uint32_t c = 0;
@@ -1131,23 +1139,26 @@ VP_D void pass_wait(unsigned int* bar, unsigned int target) {
     __syncthreads();
 }
 
-#ifndef VP_DFS_MINB
-#define VP_DFS_MINB 3
-#endif
-#ifndef VP_DFS_THREADS
-#define VP_DFS_THREADS 128
-#endif
 static constexpr int DFS_THREADS = VP_DFS_THREADS;
 // FIRST: what the very first pass of the launch looks like
 enum : int { DFS_PLAIN = 0,    // like every other pass (stage B of a sharded phase, stand-alone tables with a known claim)
              DFS_VREAL = 1,    // V is in the base field (circuit values): every GKR phase
              DFS_NEED_B = 2 }; // stand-alone sumcheck: no claim to start from, round 1 also sums p(1) -> *claim0
+// Roles. Block 0 is the COORDINATOR: in a pass that needs more than one block it takes no work; it keeps add_term,
+// handles the tables that collapse to one value, sums the workers' partial round sums and writes the polynomials --
+// all of that while the workers (blocks 1..) are already in the next pass, so none of it sits on the critical path.
+// It takes part in the grid barrier only as a gate: it arrives for pass k+1 after it has finished its duties for
+// pass k, which bounds its lag to one pass (the partial-sum buffers and the table buffers are double buffered).
+// Once a pass fits one block (<= DFS_CHUNK items) block 0 does the remaining passes alone with block barriers only.
 template <bool HAS_A, int FIRST>
 __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsArgs p) {
     __shared__ F smem[6 * 32];
     __shared__ uint32_t s_wend[128];
     extern __shared__ __align__(16) unsigned char dfs_dyn_smem[];   // per warp: two stages x 3 tables x 32 quads
     const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(dfs_dyn_smem) + (threadIdx.x >> 5) * (DFS_WARP_SMEM_F * 16);
+    constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;   // a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
+    const bool coord = blockIdx.x == 0;
+    const uint32_t n_workers = gridDim.x - 1;
     F at = p.at_init ? *p.at_init : f_zero();
     uint32_t j = 1;       // local round of the pass's first round (= 1 + 2 * ps: every pass but the last has two rounds)
     unsigned int target = 0;
@@ -1155,81 +1166,96 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
 #define VP_DBG_T(k) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[4 * ps + (k)] = t_; } } while (0)
         VP_DBG_T(0);
         const PassDev R = p.passes[ps];
-        const uint32_t active = min(gridDim.x, (R.work + DFS_CHUNK - 1) / DFS_CHUNK);   // blocks that can get a chunk
-        if (blockIdx.x >= active && blockIdx.x != 0) return;
-        const bool solo = active <= 1;    // block 0 alone: everything it reads was ordered by an earlier barrier or is its own
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
-        __syncthreads();
-        const uint32_t ib = R.in_buf, ob = ib ^ 1;
-        const uint32_t g1 = p.round_base + j;                    // global round of the pass's first round
-        const bool scale1 = g1 >= 2;
-        // the challenges' limbs come pre-split through the kernel parameters (uniform registers / constant bank)
-        const ConstK& rk1 = p.rk[2 * ps];
-        const ConstK& rk2 = p.rk[2 * ps + 1];
-        PassAcc acc1, acc2;
-        pacc_init(acc1);
-        pacc_init(acc2);
-        PassAccB accb;
-        accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
-        const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
-        if (FIRST == DFS_VREAL && ps == 0)
-            dfs_work<HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
-        else if (FIRST == DFS_NEED_B && ps == 0)
-            dfs_work<HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
-        else
-            dfs_work<HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                                 p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base);
-        // v: a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
-        constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;
-        F v[NV];
-        pacc_finish(acc1, v[0], v[1]);
-        pacc_finish(acc2, v[2], v[3]);
-        if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(cacc_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
-        VP_DBG_T(1);
-        if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
-            unsigned long long t_; unsigned int sm_;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
-            p.dbg[256 + 2 * blockIdx.x] = t_;
-            p.dbg[256 + 2 * blockIdx.x + 1] = sm_;
+        // How the pass is spread. Small passes are latency bound (one item is ~1250 dependent-ish instructions), so a
+        // pass that one sweep of the workers can cover is spread as thinly as possible: every warp gets ONE share of
+        // `share` items (a multiple of 32, at most DFS_WCHUNK), on as many workers as that takes. Larger passes hand out
+        // DFS_WCHUNK-item chunks from an atomic counter.
+        constexpr uint32_t WPB = DFS_THREADS / 32;
+        const bool solo = R.work <= DFS_CHUNK || n_workers == 0;       // block 0 alone
+        uint32_t share = DFS_WCHUNK, active = 0;
+        if (!solo) {
+            const uint32_t per_warp = (R.work + n_workers * WPB - 1) / (n_workers * WPB);
+            share = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
+            active = min(n_workers, (R.work + share * WPB - 1) / (share * WPB));   // worker blocks 1..active
         }
-        block_sum<NV>(v, smem);
-        F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
+        const bool is_static = solo ? R.work <= DFS_CHUNK : (uint64_t)active * share * WPB >= R.work;
+        if (!coord && blockIdx.x > active) return;                     // work only shrinks: never needed again
+        const uint32_t ib = R.in_buf, ob = ib ^ 1;
+        const uint32_t g1 = p.round_base + j;                          // global round of the pass's first round
+        const bool scale1 = g1 >= 2;
         const PassCol* cols = p.cols + R.col_begin;
+        F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
+        F v[NV];
+        if (!coord || solo) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
+            __syncthreads();
+            // the challenges' limbs come pre-split through the kernel parameters
+            const ConstK& rk1 = p.rk[2 * ps];
+            const ConstK& rk2 = p.rk[2 * ps + 1];
+            PassAcc acc1, acc2;
+            pacc_init(acc1);
+            pacc_init(acc2);
+            PassAccB accb;
+            accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
+            const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
+            // static shares when one sweep of the workers covers the pass, chunks from the atomic counter otherwise
+            const uint32_t wb = solo ? 0 : blockIdx.x - 1;
+            const uint32_t static_base = is_static ? (wb * WPB + (threadIdx.x >> 5)) * share : 0xffffffffu;
+            if (FIRST == DFS_VREAL && ps == 0)
+                dfs_work<HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+            else if (FIRST == DFS_NEED_B && ps == 0)
+                dfs_work<HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+            else
+                dfs_work<HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
+                                              p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+            pacc_finish(acc1, v[0], v[1]);
+            pacc_finish(acc2, v[2], v[3]);
+            if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(cacc_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
+            if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
+                unsigned long long t_; unsigned int sm_;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+                p.dbg[256 + 2 * blockIdx.x] = t_;
+                p.dbg[256 + 2 * blockIdx.x + 1] = sm_;
+            }
+            block_sum<NV>(v, smem);
+        }
+        VP_DBG_T(1);
         // tables that were already down to one value join add_term in the pass's first round; their value sits in the
-        // IN buffer, which the next pass overwrites: read it before the barrier
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        // IN buffer, which the next pass overwrites: read it before arriving
+        if (coord && threadIdx.x == 0)
             at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, scale1 ? p.chal[g1 - 2] : f_zero(),
                               p.claims, HAS_A);
         if (!solo) {
-            if (threadIdx.x == 0 && blockIdx.x != 0) {
+            if (!coord && threadIdx.x == 0) {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
             }
             pass_arrive(p.bar);
-            target += active;
-            // does this block have work in a later pass? (block 0 always stays)
-            const uint32_t next_work = ps + 1 < p.n_passes ? p.passes[ps + 1].work : 0;
-            if (blockIdx.x != 0 && blockIdx.x * DFS_CHUNK >= next_work) return;
+            target += active + 1;
+            if (!coord) {   // does this worker have work in the next pass? (it needs the barrier only then)
+                const uint32_t next_work = ps + 1 < p.n_passes ? p.passes[ps + 1].work : 0;
+                if (next_work <= DFS_CHUNK) return;
+                const uint32_t npw = (next_work + n_workers * WPB - 1) / (n_workers * WPB);
+                const uint32_t nshare = min(DFS_WCHUNK, (npw + 31u) & ~31u);
+                if (blockIdx.x > min(n_workers, (next_work + nshare * WPB - 1) / (nshare * WPB))) return;
+            }
             pass_wait(p.bar, target);
             VP_DBG_T(2);
-            if (blockIdx.x == 0) {
-                F t6[NV];
+            if (coord) {
 #pragma unroll
-                for (int k = 0; k < NV; ++k) t6[k] = f_zero();
-                for (uint32_t b = 1 + threadIdx.x; b < active; b += blockDim.x) {
+                for (int k = 0; k < NV; ++k) v[k] = f_zero();
+                for (uint32_t b = 1 + threadIdx.x; b <= active; b += blockDim.x) {
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) t6[k] = f_add(t6[k], ld_one<false>(part + (size_t)b * 6 + k));
+                    for (int k = 0; k < NV; ++k) v[k] = f_add(v[k], ld_f_cg(part + (size_t)b * 6 + k));
                 }
-                block_sum<NV>(t6, smem);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) v[k] = f_add(v[k], t6[k]);   // thread 0: own block's sum + the others'
+                block_sum<NV>(v, smem);
             }
         } else __syncthreads();   // this pass's outputs (a table reaching one value) are visible to thread 0
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (coord && threadIdx.x == 0) {
             // the b slots stay zero here: k_derive_b fills them from the claim chain
             F* o = p.out_poly + 3 * (j - 1);
             const F c1 = f_add(v[1], at);
@@ -1248,7 +1274,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         VP_DBG_T(3);
         j += R.n_rounds;
     }
-    if (blockIdx.x != 0) return;
+    if (!coord) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         st_f(p.add_term, at);

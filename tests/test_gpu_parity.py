@@ -191,3 +191,72 @@ def test_dropin_reference_verifier_accepts(tmp_path, sha_pws_text):
     assert "Verification pass" in r.stderr, r.stderr[-2000:]
     assert "proof size = 22.437500 kb" in r.stdout, r.stdout
     assert "Input size 7226" in r.stdout
+
+
+# ------------------------------------------------------------------ every gate type, constants, >= 32 instances
+# gate codes of inputCircuit.hpp:14-16
+_MUL, _ADD, _SUB, _ANTISUB, _NAAB, _ANTINAAB, _INPUT, _MULC, _ADDC, _XOR, _NOT, _COPY = range(12)
+
+
+def _all_types_circuit(B, seed, n_layers=5, max_size=24, complex_consts=False, with_assert=False):
+    """random layered circuit over ALL gate types the prover knows (incl. Addc/Mulc, which the .pws parser never
+    emits), operands from any earlier layer; optional zero-valued assert gates (Sub(x, x))."""
+    rng = np.random.default_rng(seed)
+    sizes = [int(rng.integers(3, max_size))] + [int(rng.integers(2, max_size)) for _ in range(n_layers - 1)]
+    ty, l, u, v, c, asr = [], [], [], [], [], []
+    for g in range(sizes[0]):
+        ty.append(_INPUT); l.append(-1); u.append(int(rng.integers(0, 1 << 31))); v.append(0); c.append((0, 0)); asr.append(0)
+    kinds = [_MUL, _ADD, _SUB, _ANTISUB, _NAAB, _ANTINAAB, _MULC, _ADDC, _XOR, _NOT, _COPY]
+    for i in range(1, n_layers):
+        for g in range(sizes[i]):
+            t = kinds[int(rng.integers(0, len(kinds)))]
+            uu = int(rng.integers(0, sizes[i - 1]))
+            cc = (0, 0)
+            a = 0
+            if t in (_MULC, _ADDC):
+                cc = (int(rng.integers(1, B.P)), int(rng.integers(0, B.P)) if complex_consts else 0)
+            if t in (_NOT, _COPY, _MULC, _ADDC):
+                ll, vv = -1, 0
+            else:
+                ll = int(rng.integers(0, i))
+                vv = int(rng.integers(0, sizes[ll]))
+            if with_assert and g == 0:   # Sub(x, x) == 0: a legal assert gate
+                t, ll, vv, cc, a = _SUB, i - 1, uu, (0, 0), 1
+            ty.append(t); l.append(ll); u.append(uu); v.append(vv); c.append(cc); asr.append(a)
+    cst = np.zeros(len(c), B.F_DTYPE)
+    cst["re"] = [x[0] for x in c]
+    cst["im"] = [x[1] for x in c]
+    return B.Circuit.from_arrays(sizes, ty, l, u, v, c=cst, is_assert=asr if with_assert else None)
+
+
+@pytest.mark.parametrize("seed,K,complex_consts,with_assert", [(1, 1, False, False), (2, 1, True, False), (3, 1, False, True),
+                                                              (4, 32, False, False), (5, 45, False, True), (6, 33, True, False),
+                                                              (7, 64, False, False), (8, 100, True, True)])
+def test_all_gate_types_and_instance_lanes(B, O, seed, K, complex_consts, with_assert):
+    """K >= 32 with real constants takes the one-instance-per-lane init kernels; complex constants make the circuit
+    values complex (no base-field shortcuts anywhere)."""
+    circ = _all_types_circuit(B, seed, complex_consts=complex_consts, with_assert=with_assert)
+    if K > 1:
+        rep = circ.replicate(K)
+        _prove_both_ways(B, O, rep, flat_circ=rep.expand())
+    else:
+        _prove_both_ways(B, O, circ)
+
+
+@pytest.mark.parametrize("name,K", [("small_allops", 40), ("small_notquirk", 33), ("small_random_b", 70)])
+def test_golden_small_circuits_replicated(B, O, name, K):
+    import helpers as H
+    circ = B.Circuit.from_pws_text(H.golden_bytes(name + ".pws.xz"))
+    _prove_both_ways(B, O, circ)
+    rep = circ.replicate(K)
+    _prove_both_ways(B, O, rep, flat_circ=rep.expand())
+
+
+def test_sha256_x33_instance_lanes(B, O, sha_circuit):
+    """SHA256_64 x 33: real layer sizes, one full group of 32 instance lanes plus a ragged one"""
+    rep = sha_circuit.replicate(33)
+    want, _, _ = O.OracleCircuit(rep.expand().flat()).prove()
+    p = B.Prover(rep)
+    got = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
+    _assert_same(got, want, "SHA256_64 x 33 transcript")
+    p.close()

@@ -738,6 +738,9 @@ struct Engine {
         eq_descs.push_back(b);
     }
     int n_sm = 148;
+    int cap_p1il = 0;
+    bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
+    bool lane_init = false;    // base-field values: the init kernels use the real-scalar lazy products
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
     template <class Kern>
     int occ_cap(Kern k, int threads = 256, size_t dyn_smem = 0) {  // resident blocks on the whole chip
@@ -820,6 +823,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_round1 = occ_cap(k_round<false>);
     cap_eval = occ_cap(k_eval_layer);
     cap_p1 = occ_cap(k_init_phase1);
+    cap_p1il = occ_cap(k_init_phase1_real);
     cap_p2 = occ_cap(k_init_phase2);
     cap_un = occ_cap(k_phase2_unary);
     cap_liu = occ_cap(k_init_liu);
@@ -830,6 +834,11 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM),
                         occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM)});
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
+    values_real = true;
+    for (const Layer& T : C.layers)
+        for (size_t g = 0; g < T.c.size() && g < T.ty.size(); ++g)
+            if ((T.ty[g] == T_ADDC || T.ty[g] == T_MULC) && T.c[g].im != 0) values_real = false;
+    lane_init = values_real && !getenv("VP_NO_LANE_INIT");
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1287,6 +1296,12 @@ void Engine::do_init_phase1(int i) {
     const uint32_t k0 = D.ph1.sharded ? D.p1_k0 : 0, k1 = D.ph1.sharded ? D.p1_k1 : K;
     const uint64_t work = (uint64_t)D.p1_items.n * (k1 - k0);
     size_t h = prof_begin(KC_INIT1);
+    if (lane_init && work < 0xffffffffull)
+        k_init_phase1_real<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1il), 256, 0, stream>>>(
+            D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
+            d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
+            bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1, k0, k1, (uint32_t)i);
+    else
     k_init_phase1<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1), 256, 0, stream>>>(
         D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
         d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
@@ -1481,7 +1496,7 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
 void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a,
                       const F* v_first) {
     if (!P.sharded) {
-        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a, DFS_VREAL, v_first);
+        if (use_dfs) launch_dfs_kernel(P.ppB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep, has_a, values_real ? DFS_VREAL : DFS_PLAIN, v_first);
         else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
@@ -1489,7 +1504,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
     // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
-    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, DFS_VREAL);
+    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, values_real ? DFS_VREAL : DFS_PLAIN);
     if (P.n_fo) {
         const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
         dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);

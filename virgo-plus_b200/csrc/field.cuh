@@ -316,6 +316,13 @@ VP_HD void cacc_mad_real(CAcc& s, const F& m, u64 v) {
     a96_add(s.u_im, mad32(b.hi, c1d, mul32(b.lo, c.lo)));
     a96_add(s.t_im, mad32(b.hi, c.lo, mul32(b.lo, c.hi)));
 }
+// acc + m * v for a base-field v in [0,p]; m components <= 2p, acc components < 2^64: result in [0,p]
+VP_HD F f_mad_real_w(const F& acc, const F& m, u64 v) {
+    const Limbs a = split31(m.re), b = split31(m.im), c = split31(v);
+    const u32 c1d = c.hi << 1;
+    return F{fp_reduce_ut_weak(mad32(a.hi, c1d, mul32(a.lo, c.lo)), mad32(a.hi, c.lo, mul32(a.lo, c.hi)), acc.re),
+             fp_reduce_ut_weak(mad32(b.hi, c1d, mul32(b.lo, c.lo)), mad32(b.hi, c.lo, mul32(b.lo, c.hi)), acc.im)};
+}
 VP_HD F cacc_reduce(const CAcc& s) {  // canonical
     return F{fp_reduce_ut(a96_mod(s.u_re), a96_mod(s.t_re), 0), fp_reduce_ut(a96_mod(s.u_im), a96_mod(s.t_im), 0)};
 }

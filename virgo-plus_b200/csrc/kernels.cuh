@@ -314,6 +314,92 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
     }
 }
 
+// ---- phase-1 init when every circuit value is in the base field (no complex gate constants: all .pws circuits)
+// Every contribution is beta * (a real scalar) -- prover.cpp:229-272 with Vv real -- so a gate costs one eq product
+// (kept weakly canonical) and two real-scalar products (two limb chains per component, the running sum rides as the
+// addend of the reduction); the gate type only selects the two scalars (no divergent heavy code). The kernel is bound
+// by the latency of its dependent loads (CSR entry -> layer pointer -> gathered operand), so registers are kept low
+// (lazy 96-bit sums were slower here: fewer resident warps) and the layer pointers / sizes sit in shared memory.
+// Tried and dropped: one instance per lane (uniform control flow, but every lookup / gather / store of a warp then
+// touches 32 different sectors and the eq half tables fall out of L1: 2.2x slower on SHA256_64 x 1024).
+VP_D F eq_at_weak(const EqTab& t, uint32_t idx) {   // components in [0,p]
+    const F a = ld_f(t.f + (idx & t.mask)), b = ld_f(t.s + (idx >> t.fh));
+    const LOp m = make_lop(a.re, a.im);
+    const ROpD v = make_ropd(b);
+    const u64 u_re = mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0))));
+    const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
+    const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
+    const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
+    return F{fp_reduce_ut_weak(u_re, t_re, 0), fp_reduce_ut_weak(u_im, t_im, 0)};
+}
+// the two real scalars of a gate: add[u] += beta * sA, mult[u] += beta * sM   (prover.cpp:229-272)
+VP_D void p1_scalars(uint32_t ty, u64 Vv, u64 c, u64& sA, u64& sM) {
+    sA = 0; sM = 1;
+    switch (ty) {
+        case T_ADD: sA = Vv; break;
+        case T_SUB: sA = fp_neg(Vv); break;
+        case T_ANTISUB: sA = Vv; sM = P - 1; break;
+        case T_MUL: sM = Vv; break;
+        case T_NAAB: sA = Vv; sM = fp_neg(Vv); break;
+        case T_ANTINAAB: sM = fp_sub(1, Vv); break;
+        case T_ADDC: sA = c; break;
+        case T_MULC: sM = c; break;
+        case T_COPY: break;
+        case T_NOT: sA = 1; sM = P - 1; break;
+        case T_XOR: sA = Vv; sM = fp_sub(1, fp_add(Vv, Vv)); break;
+        default: sM = 0; break;
+    }
+}
+__global__ void __launch_bounds__(256, 6)
+k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
+                   EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
+                   const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
+                   F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, ShardMap sm, int write_v, uint32_t k_begin,
+                   uint32_t k_end, uint32_t n_src) {
+    (void)K;
+    __shared__ const u64* s_vals[64];
+    __shared__ uint32_t s_sizes[64];
+    for (uint32_t i = threadIdx.x; i < min(n_src, 64u); i += blockDim.x) { s_vals[i] = reinterpret_cast<const u64*>(vals[i]); s_sizes[i] = sizes[i]; }
+    __syncthreads();
+    const uint32_t total = n_items * (k_end - k_begin);   // < 2^32 (host check)
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const uint32_t kq = w / n_items, it = w - kq * n_items, k = k_begin + kq;
+        const RowItem I = items[it];
+        uint32_t loc;
+        if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // another rank owns this table entry
+        F M = f_zero(), A = f_zero();
+        const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+        for (uint32_t e = I.e_begin; e < e1; ++e) {
+            const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e], v0 = csr.v0[e];
+            const int l = (int)(tyl >> 8) - 1;
+            u64 Vv = 0;
+            if (l >= 0) {   // real part of circuitValue[l][k * S_l + v0]
+                const u64* base = l < 64 ? s_vals[l] : reinterpret_cast<const u64*>(vals[l]);
+                const uint32_t Sl = l < 64 ? s_sizes[l] : sizes[l];
+                Vv = __ldg(base + 2 * ((size_t)k * Sl + v0));
+            }
+            F beta = eq_at_weak(eqg, k * S_cur + g0);
+            if (tyl & TY_ASSERT_BIT) beta = f_mul(beta, *assert_r);
+            const uint32_t ty = tyl & 0x7f;
+            u64 sA, sM;
+            p1_scalars(ty, Vv, (ty == T_ADDC || ty == T_MULC) ? cst[g0].re : 0, sA, sM);
+            A = f_mad_real_w(A, beta, sA);
+            M = f_mad_real_w(M, beta, sM);
+        }
+        const F Mr = f_strict(M), Ar = f_strict(A);
+        const uint32_t slot = I.cnt_slot >> 8;
+        if (slot == 0) {
+            if (write_v) st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));
+            st_f(tM + loc, Mr);
+            st_f(tA + loc, Ar);
+        } else {
+            F* dst = partial + 2 * ((size_t)k * n_slots + (slot - 1));
+            st_f(dst, Mr);
+            st_f(dst + 1, Ar);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
                  F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,

@@ -738,7 +738,7 @@ struct Engine {
         eq_descs.push_back(b);
     }
     int n_sm = 148;
-    int cap_p1il = 0;
+    int cap_p1il = 0, cap_p2v2 = 0;
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: the init kernels use the real-scalar lazy products
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
@@ -825,6 +825,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cap_p1 = occ_cap(k_init_phase1);
     cap_p1il = occ_cap(k_init_phase1_real);
     cap_p2 = occ_cap(k_init_phase2);
+    cap_p2v2 = occ_cap(k_init_phase2_v2);
     cap_un = occ_cap(k_phase2_unary);
     cap_liu = occ_cap(k_init_liu);
     cap_dot = occ_cap(k_dot_eq);
@@ -833,6 +834,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     dfs_enable_smem();
     cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM),
                         occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM)});
+    if (getenv("VP_DFS_CAP")) cap_dfs = std::max(2, std::min(cap_dfs, atoi(getenv("VP_DFS_CAP"))));
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     values_real = true;
     for (const Layer& T : C.layers)
@@ -1329,6 +1331,11 @@ void Engine::do_init_phase2(int i) {
         const uint32_t kk0 = D.ph2.sharded ? D.p2_kk0 : 0, kk1 = D.ph2.sharded ? D.p2_kk1 : K;
         const uint64_t work = (uint64_t)D.p2_items.n * (kk1 - kk0);
         size_t h = prof_begin(KC_INIT2);
+        if (work < 0xffffffffull && !getenv("VP_OLD_P2"))
+            k_init_phase2_v2<<<grid_for((uint32_t)work, cap_p2v2), 256, 0, stream>>>(
+                D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
+                scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
+        else
         k_init_phase2<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p2), 256, 0, stream>>>(
             D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
             scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);

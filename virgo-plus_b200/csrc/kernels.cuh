@@ -494,6 +494,70 @@ k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table
     }
 }
 
+// ---- phase-2 init, restructured: every coefficient of prover.cpp:319-357 is a0 + a1*V_u (mult) or b1*V_u (add)
+// with small integers (a0,a1) in {(1,0),(-1,0),(0,1),(1,-1),(0,-1),(1,-2)} and b1 in {0,1,-1}: a row keeps three plain
+// sums S0 = sum a0*t, S1 = sum a1*t, SA = sum b1*t of t = beta_g*beta_u and multiplies by V_u ONCE per row item:
+//   mult = S0 + V_u*S1, add = V_u*SA.   Three products per gate (all weakly canonical) instead of five.
+VP_D F f_add_w(const F& a, const F& b) { return F{fp_weak(a.re + b.re), fp_weak(a.im + b.im)}; }            // [0,p] x [0,p] -> [0,p]
+VP_D F f_sub_w(const F& a, const F& b) { return F{fp_weak(a.re + P - b.re), fp_weak(a.im + P - b.im)}; }
+VP_D F f_mul_w(const F& a, const F& b) {   // a components <= 2p, b in [0,p] -> [0,p]
+    const LOp m = make_lop(a.re, a.im);
+    const ROpD v = make_ropd(b);
+    const u64 u_re = mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0))));
+    const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
+    const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
+    const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
+    return F{fp_reduce_ut_weak(u_re, t_re, 0), fp_reduce_ut_weak(u_im, t_im, 0)};
+}
+VP_D void p2_accumulate(uint32_t ty, const F& t, F& S0, F& S1, F& SA) {
+    switch (ty) {
+        case T_ADD: S0 = f_add_w(S0, t); SA = f_add_w(SA, t); break;                       // mult 1,        add  Vu
+        case T_SUB: S0 = f_sub_w(S0, t); SA = f_add_w(SA, t); break;                       // mult -1,       add  Vu
+        case T_ANTISUB: S0 = f_add_w(S0, t); SA = f_sub_w(SA, t); break;                   // mult 1,        add -Vu
+        case T_MUL: S1 = f_add_w(S1, t); break;                                            // mult Vu
+        case T_NAAB: S0 = f_add_w(S0, t); S1 = f_sub_w(S1, t); break;                      // mult 1 - Vu
+        case T_ANTINAAB: S1 = f_sub_w(S1, t); SA = f_add_w(SA, t); break;                  // mult -Vu,      add  Vu
+        case T_XOR: S0 = f_add_w(S0, t); S1 = f_sub_w(S1, f_add_w(t, t)); SA = f_add_w(SA, t); break;   // mult 1 - 2Vu, add Vu
+        default: break;
+    }
+}
+__global__ void __launch_bounds__(256, 4)
+k_init_phase2_v2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table* __restrict__ tabs, CsrP2 csr,
+                 uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, const F* __restrict__ assert_r,
+                 const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA,
+                 F* __restrict__ partial, uint32_t n_slots, uint32_t kk_begin, uint32_t kk_end) {
+    const F Vu = *Vu_ptr;
+    const uint32_t total = n_items * (kk_end - kk_begin);   // < 2^32 (host check)
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const uint32_t kq = w / n_items, it = w - kq * n_items, kk = kk_begin + kq, k = K - 1 - kk;
+        const RowItem I = items[it];
+        const P2Table T = tabs[I.tab];
+        uint32_t loc;
+        if (!T.owned || !shard_local(T.sm, kk * T.D + I.row, loc)) continue;
+        F S0 = f_zero(), S1 = f_zero(), SA = f_zero();
+        const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+        for (uint32_t e = I.e_begin; e < e1; ++e) {
+            const uint32_t g0 = csr.g0[e], tyb = csr.ty[e], u0 = csr.u0[e];
+            F bg = eq_at_weak(eqg, k * S_cur + g0);
+            if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
+            const F t = f_mul_w(bg, eq_at_weak(equ, k * S_pre + u0));
+            p2_accumulate(tyb & 0x7f, t, S0, S1, SA);
+        }
+        const F M = f_strict(f_add_w(S0, f_mul_w(S1, Vu))), A = f_strict(f_mul_w(SA, Vu));
+        const uint32_t slot = I.cnt_slot >> 8;
+        if (slot == 0) {
+            const uint32_t o = T.tab_off + loc;
+            st_f(tV + o, ld_f(T.src_val + (size_t)k * T.src_S + T.dadId[I.row]));
+            st_f(tM + o, M);
+            st_f(tA + o, A);
+        } else {
+            F* dst = partial + 2 * ((size_t)kk * n_slots + (slot - 1));
+            st_f(dst, M);
+            st_f(dst + 1, A);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_combine_phase2(const LongRow* __restrict__ rows, uint32_t n_rows, const P2Table* __restrict__ tabs, uint32_t K,
                  F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,

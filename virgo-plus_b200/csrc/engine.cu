@@ -521,7 +521,7 @@ struct LayerDev {
     PhasePlan ph1, ph2, ph3;
     int max_dad_bl = -1;
     // eq build descriptor slices (indices into Engine::eq_descs)
-    uint32_t eqb_g = 0, eqb_u = 0, eqb_u1 = 0, eqb_liu = 0, n_eqb_liu = 0;
+    uint32_t eqb_g = 0, eqb_u = 0, eqb_u1 = 0, eqb_g2 = 0, eqb_u2 = 0, eqb_liu = 0, n_eqb_liu = 0;
     DBuf<EqTab> liu_eqtabs;
     // challenge indices
     uint32_t ci_ru = 0, ci_assert = 0, ci_rv = 0, ci_sig = 0, ci_rliu = 0, ci_g = 0;
@@ -604,8 +604,31 @@ struct Engine {
         cudaStream_t stream = nullptr;
         DBuf<F> bufV[2], bufM[2], bufA[2], d_scal, d_partials, d_send, d_recv, d_claims;
         DBuf<unsigned int> d_counter;
+        DBuf<F> d_rowpart;
         vp_ncclComm_t comm = nullptr;
-    } lane1;
+    } lane1, lane2;
+    // third lane (unsharded contexts): phase 2 of layer i only needs V_u from phase 1 of the same layer, and phase 1 of
+    // layer i-1 needs nothing from phase 2 of layer i (the challenges are known): phase 1 / phase 2 / Liu each run on
+    // their own stream, phase 2 one event behind phase 1. V_u is kept per layer (d_vu) instead of in one scalar.
+    bool three_lanes = false, on_lane2 = false;
+    DBuf<F> d_vu;
+    uint32_t region_g_lane2 = 0, region_u_lane2 = 0;
+    cudaEvent_t ev_p1 = nullptr, ev_lane2 = nullptr;
+    F* vu_ptr(int layer) { return three_lanes ? d_vu.p + layer : scal(SC_VU); }
+    void swap_lane2() {
+        LaneRes& R = lane2;
+        std::swap(stream, R.stream);
+        for (int b = 0; b < 2; ++b) { std::swap(bufV[b], R.bufV[b]); std::swap(bufM[b], R.bufM[b]); std::swap(bufA[b], R.bufA[b]); }
+        std::swap(d_scal, R.d_scal);
+        std::swap(d_partials, R.d_partials);
+        std::swap(d_counter, R.d_counter);
+        std::swap(d_claims, R.d_claims);
+        std::swap(d_rowpart, R.d_rowpart);
+        std::swap(d_send, R.d_send);
+        std::swap(d_recv, R.d_recv);
+        std::swap(comm, R.comm);
+        on_lane2 = !on_lane2;
+    }
     bool two_lanes = false, on_lane1 = false;
     bool direct_v = false;   // whole-proof, unsharded: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
     cudaEvent_t ev_eval = nullptr, ev_lane1 = nullptr;
@@ -711,12 +734,17 @@ struct Engine {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (on_lane1) swap_lane();
+        if (on_lane2) swap_lane2();
         if (stream && own_stream) cudaStreamDestroy(stream);
         if (lane1.stream) cudaStreamDestroy(lane1.stream);
+        if (lane2.stream) cudaStreamDestroy(lane2.stream);
+        if (ev_p1) cudaEventDestroy(ev_p1);
+        if (ev_lane2) cudaEventDestroy(ev_lane2);
         if (ev_eval) cudaEventDestroy(ev_eval);
         if (ev_lane1) cudaEventDestroy(ev_lane1);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (lane1.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane1.comm);
+        if (lane2.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane2.comm);
     }
 
     // ---------------------------------------------------------------- helpers
@@ -901,8 +929,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
 
     // eq scratch: region 0 = beta_g, 1 = beta_u, 2 = output/input MLE, 3.. = Liu tables
     eq_half_cap = 1u << ((max_bl + 1) >> 1);
-    const uint32_t n_regions = 4 + (uint32_t)n;
+    const uint32_t n_regions = 6 + (uint32_t)n;
     region_u_lane1 = 3 + (uint32_t)n;   // lane 1's own copy of beta_u
+    region_g_lane2 = 4 + (uint32_t)n;   // lane 2's own copies of beta_g and beta_u
+    region_u_lane2 = 5 + (uint32_t)n;
     d_eq.alloc((size_t)n_regions * 2 * eq_half_cap);
 
     // values
@@ -982,6 +1012,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         add_eq_build(1, D.ci_ru, pb, -1);
         D.eqb_u1 = (uint32_t)eq_descs.size();
         add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, (int)D.ci_sig);   // lane 1's copy is only used by Liu: bake s[0] in
+        D.eqb_g2 = (uint32_t)eq_descs.size();
+        add_eq_build(4 + (uint32_t)n, D.ci_g, C.bit_length(i), -1);
+        D.eqb_u2 = (uint32_t)eq_descs.size();
+        add_eq_build(5 + (uint32_t)n, D.ci_ru, pb, -1);
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
@@ -1179,6 +1213,31 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         CK(cudaEventCreateWithFlags(&ev_lane1, cudaEventDisableTiming));
     }
     d_rowpart.alloc(max_partial);
+    three_lanes = two_lanes && !getenv("VP_TWO_LANES");
+    if (three_lanes) {
+        uint32_t c0 = 4, c1 = 4;
+        for (int i = 1; i < n; ++i)
+            if (L[i].max_dad_bl != -1) { c0 = std::max(c0, L[i].ph2.cap0); c1 = std::max(c1, L[i].ph2.cap1); }
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t cap = b == 0 ? c0 : c1;
+            lane2.bufV[b].alloc(cap);
+            lane2.bufM[b].alloc(cap);
+            lane2.bufA[b].alloc(cap);
+        }
+        lane2.d_scal.alloc(SC_N);
+        lane2.d_claims.alloc((size_t)n + 1);
+        lane2.d_partials.alloc((size_t)12 * (size_t)max_grid);
+        lane2.d_counter.alloc(4 + 64);
+        lane2.d_rowpart.alloc(max_partial);
+        d_vu.alloc((size_t)n + 1);
+        CK(cudaMemsetAsync(lane2.d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
+        CK(cudaMemsetAsync(lane2.d_scal.p, 0, SC_N * sizeof(F), stream));
+        CK(cudaMemsetAsync(lane2.d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
+        CK(cudaMemsetAsync(d_vu.p, 0, ((size_t)n + 1) * sizeof(F), stream));
+        CK(cudaStreamCreateWithFlags(&lane2.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_p1, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_lane2, cudaEventDisableTiming));
+    }
     if (world > 1) {
         d_send.alloc(std::max<uint32_t>(max_rec, 1));
         d_recv.alloc((size_t)std::max<uint32_t>(max_rec, 1) * world);
@@ -1204,6 +1263,18 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         NCK(g_nccl.CommInitRank(&lane1.comm, world, id2, rank));
         lane1.d_send.alloc(std::max<uint32_t>(max_rec, 1));
         lane1.d_recv.alloc((size_t)std::max<uint32_t>(max_rec, 1) * world);
+        if (three_lanes) {   // and a third communicator for the phase-2 lane
+            NcclId id3;
+            memset(&id3, 0, sizeof id3);
+            if (rank == 0) NCK(g_nccl.GetUniqueId(&id3));
+            CK(cudaMemcpyAsync(d_id.p, id3.internal, 128, cudaMemcpyHostToDevice, stream));
+            NCK(g_nccl.Broadcast(d_id.p, d_id.p, 128, /*ncclUint8*/ 1, 0, comm, stream));
+            CK(cudaMemcpyAsync(id3.internal, d_id.p, 128, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            NCK(g_nccl.CommInitRank(&lane2.comm, world, id3, rank));
+            lane2.d_send.alloc(std::max<uint32_t>(max_rec, 1));
+            lane2.d_recv.alloc((size_t)std::max<uint32_t>(max_rec, 1) * world);
+        }
     }
     d_chal.alloc(n_chal + 1);
     d_tr.alloc(n_tr);
@@ -1323,9 +1394,10 @@ void Engine::do_init_phase1(int i) {
 void Engine::do_init_phase2(int i) {
     LayerDev& D = L[i];
     const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
-    run_eq(D.eqb_u, 2);
-    have_equ = true;
-    const EqTab eqg = eqtab(0, C.bit_length(i)), equ = eqtab(1, C.bit_length(i - 1));
+    if (on_lane2) { run_eq(D.eqb_g2, 2); run_eq(D.eqb_u2, 2); }
+    else { run_eq(D.eqb_u, 2); have_equ = true; }
+    const EqTab eqg = eqtab(on_lane2 ? region_g_lane2 : 0, C.bit_length(i)), equ = eqtab(on_lane2 ? region_u_lane2 : 1, C.bit_length(i - 1));
+    const F* Vu = on_lane2 ? d_vu.p + i : scal(SC_VU);
     if (D.p2_ntabs > 0) {
         CsrP2 csr{D.p2_g0.p, D.p2_u0.p, D.p2_ty.p};
         const uint32_t kk0 = D.ph2.sharded ? D.p2_kk0 : 0, kk1 = D.ph2.sharded ? D.p2_kk1 : K;
@@ -1334,11 +1406,11 @@ void Engine::do_init_phase2(int i) {
         if (work < 0xffffffffull && !getenv("VP_OLD_P2"))
             k_init_phase2_v2<<<grid_for((uint32_t)work, cap_p2v2), 256, 0, stream>>>(
                 D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
-                scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
+                Vu, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
         else
         k_init_phase2<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p2), 256, 0, stream>>>(
             D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
-            scal(SC_VU), bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
+            Vu, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
         if (D.p2_long.n && kk1 > kk0) {
             k_combine_phase2<<<grid_for((uint32_t)(D.p2_long.n * (kk1 - kk0)), cap_comb), 256, 0, stream>>>(
                 D.p2_long.p, (uint32_t)D.p2_long.n, D.p2_tabs.p, K, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0,
@@ -1355,7 +1427,7 @@ void Engine::do_init_phase2(int i) {
         CsrUnary un{D.un_g0.p, D.un_u0.p, D.un_ty.p, D.n_unary};
         const uint64_t tot = (uint64_t)D.n_unary * (k1 - k0);
         k_phase2_unary<<<grid_for((uint32_t)std::min<uint64_t>(tot, 0xffffffffu), cap_un), 256, 0, stream>>>(
-            un, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert, scal(SC_VU), D.c.p, scal(SC_UNARY), d_partials.p,
+            un, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert, Vu, D.c.p, scal(SC_UNARY), d_partials.p,
             d_counter.p, k0, k1);
         ++launches;
     } else CK(cudaMemsetAsync(scal(SC_UNARY), 0, sizeof(F), stream));
@@ -1487,7 +1559,9 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     }
     // two lanes: leave a few block slots free so that the other lane's (cooperative) phase kernel can start as soon as
     // this one is down to its small passes
-    const uint32_t cap = two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
+    // three lanes: two of the three block slots of an SM, so that the other lanes' kernels (gather-latency bound inits,
+    // another phase's passes) are co-resident with a compute-bound pass (measured: C3 13.3 -> 12.9 ms)
+    const uint32_t cap = three_lanes ? (uint32_t)std::max(2, 2 * cap_dfs / 3) : two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
     // block 0 coordinates, blocks 1.. work; a phase that fits one block runs on block 0 alone
     const int grid = P.max_work <= DFS_CHUNK ? 1 : (int)std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK) + 1, std::max<uint32_t>(cap, 2));
     void* args[] = {&a};
@@ -1563,12 +1637,20 @@ void Engine::prove_all() {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
         do_init_phase1(i);
-        if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, scal(SC_VU), nullptr, true, direct_v ? val[i - 1].p : nullptr);
+        const bool lane3 = three_lanes && two_lanes && use_phase_kernel && use_dfs;
+        if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, lane3 ? d_vu.p + i : scal(SC_VU), nullptr, true, direct_v ? val[i - 1].p : nullptr);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph1.planB, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph1.planB, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
         }
-        if (m != -1) {
+        if (m != -1 && lane3) {   // phase 2 on its own lane, behind this layer's phase 1
+            CK(cudaEventRecord(ev_p1, stream));
+            swap_lane2();
+            CK(cudaStreamWaitEvent(stream, ev_p1, 0));
+            do_init_phase2(i);
+            do_phase(D.ph2, D.ci_rv, D.tr_p2, nullptr, scal(SC_UNARY));
+            swap_lane2();
+        } else if (m != -1) {
             do_init_phase2(i);
             if (use_phase_kernel) do_phase(D.ph2, D.ci_rv, D.tr_p2, nullptr, scal(SC_UNARY));
             else {
@@ -1589,6 +1671,10 @@ void Engine::prove_all() {
     if (two_lanes && use_phase_kernel && use_dfs) {   // join: the input MLE and the transcript copy follow on lane 0
         CK(cudaEventRecord(ev_lane1, lane1.stream));
         CK(cudaStreamWaitEvent(stream, ev_lane1, 0));
+        if (three_lanes) {
+            CK(cudaEventRecord(ev_lane2, lane2.stream));
+            CK(cudaStreamWaitEvent(stream, ev_lane2, 0));
+        }
     }
     if (use_phase_kernel && use_dfs) derive_b();
     do_input_mle();

@@ -1369,7 +1369,7 @@ void Engine::do_init_phase1(int i) {
     const uint32_t k0 = D.ph1.sharded ? D.p1_k0 : 0, k1 = D.ph1.sharded ? D.p1_k1 : K;
     const uint64_t work = (uint64_t)D.p1_items.n * (k1 - k0);
     size_t h = prof_begin(KC_INIT1);
-    if (lane_init && work < 0xffffffffull)
+    if (lane_init && work < 0xffffffffull && n <= 64)
         k_init_phase1_real<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1il), 256, 0, stream>>>(
             D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
             d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],

@@ -322,7 +322,10 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 // (lazy 96-bit sums were slower here: fewer resident warps) and the layer pointers / sizes sit in shared memory.
 // Tried and dropped: one instance per lane (uniform control flow, but every lookup / gather / store of a warp then
 // touches 32 different sectors and the eq half tables fall out of L1: 2.2x slower on SHA256_64 x 1024).
-VP_D F eq_at_weak(const EqTab& t, uint32_t idx) {   // components in [0,p]
+VP_D F eq_at_acc_w(const EqTab& t, uint32_t idx, const F& acc);
+VP_D F f_mul_w(const F& a, const F& b);
+VP_D F eq_at_weak(const EqTab& t, uint32_t idx) { return eq_at_acc_w(t, idx, f_zero()); }   // components in [0,p]
+VP_D F eq_at_acc_w(const EqTab& t, uint32_t idx, const F& acc) {   // acc + eq(idx), acc components < 2^64: [0,p]
     const F a = ld_f(t.f + (idx & t.mask)), b = ld_f(t.s + (idx >> t.fh));
     const LOp m = make_lop(a.re, a.im);
     const ROpD v = make_ropd(b);
@@ -330,7 +333,7 @@ VP_D F eq_at_weak(const EqTab& t, uint32_t idx) {   // components in [0,p]
     const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
     const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
     const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
-    return F{fp_reduce_ut_weak(u_re, t_re, 0), fp_reduce_ut_weak(u_im, t_im, 0)};
+    return F{fp_reduce_ut_weak(u_re, t_re, acc.re), fp_reduce_ut_weak(u_im, t_im, acc.im)};
 }
 // the two real scalars of a gate: add[u] += beta * sA, mult[u] += beta * sM   (prover.cpp:229-272)
 VP_D void p1_scalars(uint32_t ty, u64 Vv, u64 c, u64& sA, u64& sM) {
@@ -350,7 +353,7 @@ VP_D void p1_scalars(uint32_t ty, u64 Vv, u64 c, u64& sA, u64& sM) {
         default: sM = 0; break;
     }
 }
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 5)
 k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
                    EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
                    const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
@@ -369,20 +372,26 @@ k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 cs
         if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // another rank owns this table entry
         F M = f_zero(), A = f_zero();
         const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+        // software pipeline: the next entry's CSR words are loaded one iteration ahead, and the gathered operand and the
+        // two eq half-table entries are requested before any arithmetic of the iteration
+        uint32_t g0 = csr.g0[I.e_begin], tyl = csr.tyl[I.e_begin], v0 = csr.v0[I.e_begin];
         for (uint32_t e = I.e_begin; e < e1; ++e) {
-            const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e], v0 = csr.v0[e];
             const int l = (int)(tyl >> 8) - 1;
-            u64 Vv = 0;
-            if (l >= 0) {   // real part of circuitValue[l][k * S_l + v0]
-                const u64* base = l < 64 ? s_vals[l] : reinterpret_cast<const u64*>(vals[l]);
-                const uint32_t Sl = l < 64 ? s_sizes[l] : sizes[l];
-                Vv = __ldg(base + 2 * ((size_t)k * Sl + v0));
-            }
-            F beta = eq_at_weak(eqg, k * S_cur + g0);
-            if (tyl & TY_ASSERT_BIT) beta = f_mul(beta, *assert_r);
-            const uint32_t ty = tyl & 0x7f;
+            const uint32_t lc = l >= 0 ? (uint32_t)l : 0u;
+            const u64* vp_ = s_vals[lc] + 2 * ((size_t)k * s_sizes[lc] + v0);
+            u64 Vv;
+            asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(Vv) : "l"(vp_));   // real part of circuitValue[l][k * S_l + v0]
+            const uint32_t idx = k * S_cur + g0;
+            ulonglong2 ha, hb;
+            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(ha.x), "=l"(ha.y) : "l"(eqg.f + (idx & eqg.mask)));
+            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(hb.x), "=l"(hb.y) : "l"(eqg.s + (idx >> eqg.fh)));
+            const uint32_t ty = tyl & 0x7f, is_as = tyl & TY_ASSERT_BIT, g0c = g0;
+            if (e + 1 < e1) { g0 = csr.g0[e + 1]; tyl = csr.tyl[e + 1]; v0 = csr.v0[e + 1]; }
+            if (l < 0) Vv = 0;
+            F beta = f_mul_w(F{ha.x, ha.y}, F{hb.x, hb.y});
+            if (is_as) beta = f_mul(beta, *assert_r);
             u64 sA, sM;
-            p1_scalars(ty, Vv, (ty == T_ADDC || ty == T_MULC) ? cst[g0].re : 0, sA, sM);
+            p1_scalars(ty, Vv, (ty == T_ADDC || ty == T_MULC) ? cst[g0c].re : 0, sA, sM);
             A = f_mad_real_w(A, beta, sA);
             M = f_mad_real_w(M, beta, sM);
         }
@@ -639,14 +648,14 @@ k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, c
         const uint32_t u = shard_global(sm, loc);
         if (u >= n) continue;
         const uint32_t k = u / S_pre, u0 = u - k * S_pre;
-        F M = eq_at(equ, u);                       // equ_scaled: its first half table already carries s[0]
-        if (!equ_scaled) M = f_mul(s0, M);
-        for (uint32_t e = off[u0]; e < off[u0 + 1]; ++e) {
+        F M = eq_at_weak(equ, u);                  // equ_scaled: its first half table already carries s[0]
+        if (!equ_scaled) M = f_mul(M, s0);
+        for (uint32_t e = off[u0]; e < off[u0 + 1]; ++e) {   // the running sum rides as the addend of each product's reduction
             const LiuEntry E = ent[e];
-            M = f_add(M, eq_at(eqs[E.eq_id], (K - 1 - k) * E.D + E.slot0));
+            M = eq_at_acc_w(eqs[E.eq_id], (K - 1 - k) * E.D + E.slot0, M);
         }
         if (write_v) st_f(tV + loc, ld_f(Vpre + u));   // unsharded whole-proof mode reads V straight from circuitValue
-        st_f(tM + loc, M);
+        st_f(tM + loc, f_strict(M));
         if (write_a) st_f(tA + loc, f_zero());   // the Liu add table is identically zero: only the one-round-per-launch path reads it
     }
 }

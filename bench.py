@@ -175,6 +175,7 @@ def run_ours(args):
     # the same K steps again with a CUDA-event pair around every kernel launch (per-class device time for the
     # roofline object; the event pairs cost a few % so `value` comes from the un-instrumented pass above)
     prover.set_profiling(True)
+    lanes = prover.set_lanes(1)   # one lane: a launch's event-pair duration is its own (no other phase's kernels on the SMs)
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -185,6 +186,7 @@ def run_ours(args):
     ms_profiled = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     prof = prover.profile()
     prover.set_profiling(False)
+    lanes = prover.set_lanes(3)
 
     # ---------------- e2e: host buffers in, transcript out, every step
     for _ in range(max(1, args.warmup // 2)):
@@ -210,6 +212,7 @@ def run_ours(args):
                         f"configs[4] family at N>1), {gates} gates per GPU, one full GKR proof per step",
             "instances_per_gpu": inst, "gates_per_gpu": gates, "rounds": None,
             "l2": "tables + values are several GB per proof, far larger than the 126 MB L2 (no flush needed)",
+            "lanes": lanes,
             "parallelism": "1 GPU" if world == 1 else f"one proof sharded over {world} GPUs: tables block-cyclic by index, local rounds "
                            f"without communication, one NCCL all-gather per sumcheck phase, evaluate replicated",
         },
@@ -225,15 +228,19 @@ def run_ours(args):
     if rf["launches"]:
         ach = rf["bytes"] / (rf["ms"] * 1e-3) / 1e9
         step_share = rf["ms"] / sum(v["ms"] for v in prof.values())   # share of the summed kernel time (the two lanes overlap)
-        line["roofline"] = {"bound": "hbm", "kernel": "k_phase_dfs (all rounds of one sumcheck phase: fused fold + round polynomials, two rounds per pass)",
-                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        line["roofline"] = {"bound": "hbm", "kernel": "k_phase_dfs (all rounds of one sumcheck phase in one cooperative launch: fused fold + round polynomials, two rounds per pass)",
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": dfs_traffic(inst, world),
                             "peak_source": peak_src, "launches_per_step": rf["launches"] // args.steps,
                             "avg_launch_us": rf["ms"] * 1e3 / rf["launches"], "share_of_step": step_share,
                             "ms_per_step_instrumented": ms_profiled,
                             "bytes_model": "144 B per live table entry per sumcheck (SURVEY 8d: 3 tables x 16 B, read N_k + write N_k/2 "
                                            "per round); the kernel itself moves ~80 B per entry (two rounds per pass) and is bound by "
                                            "integer-pipe latency, see DESIGN.md and profiles/",
-                            "note": "the two lanes overlap: per-class device times add up to more than the step"}
+                            "alg_bytes_per_launch": rf["bytes"] / rf["launches"],
+                            "note": "launch durations come from the instrumented pass, which runs the phases on ONE stream "
+                                    "(vp_set_lanes(1)); `value` is the un-instrumented pass with the three lanes overlapped, so the "
+                                    "per-class times add up to more than the step. `traffic` = DRAM bytes read + written per launch "
+                                    "(ncu, profiles/r1_dfs_traffic.json), averaged over the 42 launches of one proof like `achieved`"}
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),
                                   "launches_per_step": v["launches"] // args.steps} for k, v in prof.items() if v["launches"]}
 
@@ -249,6 +256,16 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line, default=_jd))
+
+
+def dfs_traffic(inst, world):
+    """ncu-measured DRAM bytes per k_phase_dfs launch for this workload (tools/dfs_traffic.py), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_dfs_traffic.json")) as f:
+            d = json.load(f)
+        return d["traffic_bytes_per_launch"] if d.get("instances") == inst and world == 1 else None
+    except Exception:
+        return None
 
 
 def run_c2(B, peak):

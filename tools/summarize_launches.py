@@ -13,7 +13,8 @@ def main():
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     n = int(sys.argv[3]) if len(sys.argv) > 3 else len(data)
-    data = [r for r in data if len(r) > vi][first:first + n]
+    mi = hdr.index("Metric Name")
+    data = [r for r in data if len(r) > vi and r[mi] == "gpu__time_duration.sum"][first:first + n]   # other metrics may share the log
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
     tot, cnt, mx = collections.defaultdict(float), collections.Counter(), collections.defaultdict(float)
     for r in data:

@@ -110,6 +110,8 @@ def _declare(L):
     L.vp_stream.argtypes = [vp]
     L.vp_set_stream.argtypes = [vp, vp]
     L.vp_set_profiling.argtypes = [vp, C.c_int]
+    L.vp_set_lanes.argtypes = [vp, C.c_int]
+    L.vp_set_lanes.restype = C.c_int
     L.vp_get_profile.argtypes = [vp, vp, vp, vp, C.c_int]
     L.vp_stream.restype = C.c_void_p
     L.vp_sumcheck_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
@@ -505,6 +507,9 @@ class Prover:
 
     def set_profiling(self, on):
         _ck(lib().vp_set_profiling(self.h, 1 if on else 0))
+
+    def set_lanes(self, lanes):
+        return int(lib().vp_set_lanes(self.h, int(lanes)))
 
     def profile(self):
         n = len(self.KERNEL_CLASSES)

@@ -2296,6 +2296,14 @@ extern "C" int vp_set_profiling(vp_ctx* ctx, int on) {
     return VP_OK;
     API_END
 }
+extern "C" int vp_set_lanes(vp_ctx* ctx, int lanes) {
+    if (!ctx) return 0;
+    Engine& e = ctx->e;
+    const bool have2 = e.lane1.stream != nullptr, have3 = e.lane2.stream != nullptr;
+    e.two_lanes = lanes >= 2 && have2;
+    e.three_lanes = lanes >= 3 && have2 && have3;
+    return e.three_lanes ? 3 : e.two_lanes ? 2 : 1;
+}
 extern "C" int vp_get_profile(vp_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int n) {
     if (!ctx || !ms || !bytes || !launches) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN

@@ -260,3 +260,53 @@ def test_sha256_x33_instance_lanes(B, O, sha_circuit):
     got = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
     _assert_same(got, want, "SHA256_64 x 33 transcript")
     p.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes
+# The CPU oracle proves these sizes in minutes, so parity at full size is pinned through properties instead:
+#  * the two round engines of the product share no round code -- whole-proof mode (k_phase_dfs: two rounds per pass,
+#    two products per pair, b derived from the claim chain, weakly canonical tables, base-field first pass, three
+#    lanes) and the interactive mode (k_round: one round per launch, three products per pair, b summed directly,
+#    canonical arithmetic, one stream) -- and must produce bit-identical transcripts;
+#  * both are compared with the oracle (hence the reference) on the same circuits at smaller instance counts above,
+#    and the K-instance transcript is a function of the template and K only.
+def test_full_size_c3_whole_proof_equals_interactive(B, sha_circuit):
+    """BASELINE.json configs[2]: SHA256_64 x 1024 instances (94.9 M gates)"""
+    rep = sha_circuit.replicate(1024)
+    p = B.Prover(rep)
+    whole = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
+    again = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
+    _assert_same(again, whole, "second whole-proof run")
+    p.close()
+    p = B.Prover(rep)
+    inter = B.prove_interactive(p, rep)
+    p.close()
+    _assert_same(whole, inter, "C3 whole-proof vs interactive transcript")
+    assert np.any(whole["im"] != 0)
+
+
+def test_full_size_c2_fused_equals_per_round(B, O):
+    """BASELINE.json configs[1]: 3 tables x 2^24 random entries; and against the oracle at 2^20"""
+    for log_n, with_oracle in ((24, False), (20, True)):
+        s = B.Sumcheck(log_n)
+        s.fill_random(7)
+        r = O.draw_challenges(log_n)
+        per_round, _ = s.run(r)
+        fused, _ = s.run(r, fused=True)
+        _assert_same(fused, per_round, f"2^{log_n}: fused vs one round per launch")
+        if with_oracle:
+            V, A, M = s.export()
+            _assert_same(fused, O.sumcheck_tables(V, A, M, r), f"2^{log_n}: fused vs oracle")
+        s.close()
+
+
+def test_full_size_c4_whole_proof_equals_interactive(B):
+    """BASELINE.json configs[3] shape at full size: 65 layers x 2^20 random add/mul gates (2^26 gates)"""
+    circ = B.Circuit.random(65, 20, 1)
+    p = B.Prover(circ)
+    whole = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+    p.close()
+    p = B.Prover(circ)
+    inter = B.prove_interactive(p, circ)
+    p.close()
+    _assert_same(whole, inter, "C4 whole-proof vs interactive transcript")

@@ -251,6 +251,12 @@ def run_ours(args):
         # parity spot check of what was just timed: the oracle verifier accepts a K-instance sample? The
         # full-size transcript is checked by tests (size-independent properties); here only sanity.
         line["transcript_nonzero"] = bool(np.any(tr_e2e["re"]))
+        # full-size acceptance: the device-side verifier (vp_verify: verifier.cpp's checks, O(#gates) sums on the GPU,
+        # no code or tables shared with the prover) on the transcript the e2e pass just produced
+        t0 = time.time()
+        ok, code, layer = prover.verify(tr_e2e)
+        line["verifier"] = {"accept": bool(ok), "fail_code": int(code), "fail_layer": int(layer), "wall_ms": (time.time() - t0) * 1e3,
+                            "what": "vp_verify on the SHA256_64 x %d transcript of the e2e pass" % (inst * world)}
     prover.close()
     if world > 1:
         dist.destroy_process_group()

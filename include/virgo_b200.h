@@ -157,6 +157,14 @@ double vp_prove_seconds(const vp_ctx* ctx);
 int vp_set_challenges(vp_ctx* ctx, const vp_F* challenges, size_t n);
 int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
              size_t n_challenges, vp_F* transcript, size_t transcript_cap);
+/* Verifier: replaces verifier::verify's checks, src/verifier.cpp:134-337, on a finished transcript:
+   the O(#gates) sums of predicatePhase1/2 (:63-113) and verifyLiu's gr (:311-323) run on the device, the round
+   checks / getFinalValue (:115-132) / Liu check on the host. Uses the context's circuit, its resident inputs
+   (vp_set_inputs or vp_prove with host_io) and challenge stream (vp_set_challenges / vp_prove). *accept = 1, or 0 with
+   *fail_code = 1 phase-1 round, 2 phase-2 round, 3 layer final value, 4 Liu round, 5 Liu final, 6 input layer, and
+   *fail_layer (either may be NULL). The polynomial-commitment opening (verifyPoly) is out of scope: the input-layer
+   MLE is recomputed from the inputs. Unsharded contexts only. */
+int vp_verify(vp_ctx* ctx, const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer);
 int vp_get_transcript(vp_ctx* ctx, vp_F* transcript, size_t cap);
 /* Device-side time of the last vp_prove (CUDA events on the context's stream), milliseconds. */
 float vp_last_prove_ms(const vp_ctx* ctx);

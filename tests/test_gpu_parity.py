@@ -310,3 +310,88 @@ def test_full_size_c4_whole_proof_equals_interactive(B):
     inter = B.prove_interactive(p, circ)
     p.close()
     _assert_same(whole, inter, "C4 whole-proof vs interactive transcript")
+
+
+# ------------------------------------------------------------------ device-side verifier
+def _tamper_cases(circ, tr):
+    """(name, transcript) pairs that hit every failure path of verifier.cpp:134-337"""
+    import helpers as H  # noqa: F401
+    n = circ.n_layers
+    cases = [("honest", tr)]
+    rng = np.random.default_rng(17)
+    # walk the transcript layout (same as helpers.transcript_text)
+    ti = 1
+    top = n - 1
+    pb, m = circ.bit_length(top - 1), circ.max_dad_bit_length(top)
+    def flip(idx):
+        bad = tr.copy()
+        bad[idx]["re"] = (int(bad[idx]["re"]) + 1) % ((1 << 61) - 1)
+        return bad
+    cases.append(("vres", flip(0)))
+    if pb:
+        cases.append(("p1 round c", flip(ti + 2)))
+        cases.append(("p1 round a (last)", flip(ti + 3 * (pb - 1))))
+    ti += 3 * pb
+    cases.append(("claim_u", flip(ti))); ti += 1
+    if m != -1:
+        if m:
+            cases.append(("p2 round b", flip(ti + 1)))
+        ti += 3 * m
+        cases.append(("claim_v[0]", flip(ti))); ti += top
+    if pb:
+        cases.append(("liu round c", flip(ti + 2)))
+    ti += 3 * pb
+    cases.append(("claim_liu", flip(ti)))
+    cases.append(("input mle", flip(len(tr) - 1)))
+    cases.append(("random element", flip(int(rng.integers(0, len(tr))))))
+    return cases
+
+
+def _verify_like_oracle(B, O, circ, flat=None):
+    oc = O.OracleCircuit((flat or circ).flat())
+    p = B.Prover(circ)
+    tr = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+    for name, t in _tamper_cases(circ, tr):
+        want = oc.verify(t)
+        got = p.verify(t)
+        assert (bool(want[0]), want[1], want[2]) == got, f"{name}: device verifier {got}, oracle verifier {want}"
+    assert p.verify(tr) == (True, 0, 0)
+    p.close()
+
+
+@pytest.mark.parametrize("seed,K,complex_consts,with_assert", [(1, 1, False, False), (2, 1, True, True), (4, 3, False, False),
+                                                              (8, 37, True, True)])
+def test_device_verifier_matches_oracle_all_gate_types(B, O, seed, K, complex_consts, with_assert):
+    circ = _all_types_circuit(B, seed, complex_consts=complex_consts, with_assert=with_assert)
+    if K > 1:
+        rep = circ.replicate(K)
+        _verify_like_oracle(B, O, rep, rep.expand())
+    else:
+        _verify_like_oracle(B, O, circ)
+
+
+def test_device_verifier_sha256(B, O, sha_circuit):
+    _verify_like_oracle(B, O, sha_circuit)
+    rep = sha_circuit.replicate(5)
+    _verify_like_oracle(B, O, rep, rep.expand())
+
+
+def test_device_verifier_random_and_small(B, O):
+    import helpers as H
+    _verify_like_oracle(B, O, B.Circuit.random(6, 6, 12))
+    for name in ("small_allops", "small_notquirk", "small_chain"):
+        _verify_like_oracle(B, O, B.Circuit.from_pws_text(H.golden_bytes(name + ".pws.xz")))
+
+
+def test_full_size_c3_device_verifier_accepts(B, sha_circuit):
+    """BASELINE.json configs[2] at full size: the device verifier accepts the whole-proof transcript of SHA256_64 x 1024
+    and rejects a tampered one (the verifier's sums share no code or tables with the prover)"""
+    rep = sha_circuit.replicate(1024)
+    p = B.Prover(rep)
+    tr = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
+    assert p.verify(tr) == (True, 0, 0)
+    bad = tr.copy()
+    bad[len(bad) // 2]["im"] = (int(bad[len(bad) // 2]["im"]) + 5) % B.P
+    ok, code, layer = p.verify(bad)
+    assert not ok and code in (1, 2, 3, 4, 5)
+    p.close()

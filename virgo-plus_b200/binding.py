@@ -110,6 +110,7 @@ def _declare(L):
     L.vp_stream.argtypes = [vp]
     L.vp_set_stream.argtypes = [vp, vp]
     L.vp_set_profiling.argtypes = [vp, C.c_int]
+    L.vp_verify.argtypes = [vp, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.vp_set_lanes.argtypes = [vp, C.c_int]
     L.vp_set_lanes.restype = C.c_int
     L.vp_get_profile.argtypes = [vp, vp, vp, vp, C.c_int]
@@ -507,6 +508,13 @@ class Prover:
 
     def set_profiling(self, on):
         _ck(lib().vp_set_profiling(self.h, 1 if on else 0))
+
+    def verify(self, transcript):
+        """(accept, fail_code, fail_layer) of the device-side verifier on a transcript (inputs + challenges resident)"""
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        a, c, l = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(lib().vp_verify(self.h, _ptr(tr), len(tr), C.byref(a), C.byref(c), C.byref(l)))
+        return bool(a.value), c.value, l.value
 
     def set_lanes(self, lanes):
         return int(lib().vp_set_lanes(self.h, int(lanes)))

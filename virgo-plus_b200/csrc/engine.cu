@@ -527,6 +527,16 @@ struct LayerDev {
     uint32_t ci_ru = 0, ci_assert = 0, ci_rv = 0, ci_sig = 0, ci_rliu = 0, ci_g = 0;
     // transcript indices
     uint32_t tr_p1 = 0, tr_claim_u = 0, tr_p2 = 0, tr_claims_v = 0, tr_liu = 0, tr_claim_liu = 0;
+    // verifier sums (vp_verify): gates in bucket order, built on first use
+    std::vector<P2Table> h_p2;       // host copy of the phase-2 table descriptors (dadId lists on the device)
+    std::vector<int> p2_src;         // source layer of each phase-2 table
+    DBuf<VfGate> vf_gates;
+    DBuf<VfBucket> vf_buckets;
+    DBuf<uint8_t> vf_assert;
+    std::vector<uint32_t> vf_key;    // per bucket: 0 Copy, 1 Not, 2 Addc (+ bias), 3 Mulc, 4 + 7*l + binary type index
+    DBuf<VfLiuSeg> vf_liu;
+    uint32_t n_vf_liu = 0, eqb_v = 0, eqb_rl = 0, vf_out = 0;
+    bool vf_ready = false;
 };
 
 // ------------------------------------------------------------------ NCCL, loaded at run time (torch's bundled
@@ -796,6 +806,11 @@ struct Engine {
     void launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_base, const F* at_init, F* add_term_out, F* claims,
                            F* out_poly, F* keep, bool has_a, int first, const F* v_first = nullptr);
     void derive_b();
+    // verifier: O(#gates) sums on the device, protocol checks on the host
+    void verify_prepare(int i);
+    int verify(const F* tr, int* fail_code, int* fail_layer);
+    DBuf<F> d_vf_partial, d_vf_out;
+    static constexpr uint32_t VF_GX = 64;
     DBuf<ChainDesc> d_chains;
     DBuf<ChainSeg> d_chain_segs;
     DBuf<ChainTerm> d_chain_terms;
@@ -929,7 +944,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
 
     // eq scratch: region 0 = beta_g, 1 = beta_u, 2 = output/input MLE, 3.. = Liu tables
     eq_half_cap = 1u << ((max_bl + 1) >> 1);
-    const uint32_t n_regions = 6 + (uint32_t)n;
+    const uint32_t n_regions = 8 + (uint32_t)n;   // + beta_v and eq(r_liu) of the verifier sums
     region_u_lane1 = 3 + (uint32_t)n;   // lane 1's own copy of beta_u
     region_g_lane2 = 4 + (uint32_t)n;   // lane 2's own copies of beta_g and beta_u
     region_u_lane2 = 5 + (uint32_t)n;
@@ -1016,6 +1031,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         add_eq_build(4 + (uint32_t)n, D.ci_g, C.bit_length(i), -1);
         D.eqb_u2 = (uint32_t)eq_descs.size();
         add_eq_build(5 + (uint32_t)n, D.ci_ru, pb, -1);
+        D.eqb_v = (uint32_t)eq_descs.size();
+        add_eq_build(6 + (uint32_t)n, D.ci_rv, std::max(D.max_dad_bl, 0), -1);
+        D.eqb_rl = (uint32_t)eq_descs.size();
+        add_eq_build(7 + (uint32_t)n, D.ci_rliu, pb, -1);
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
@@ -1084,6 +1103,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.p2_ty.upload(tyv, stream);
             for (auto& pt : ptabs) pt.dadId = D.p2_dad_all.p + (uintptr_t)pt.dadId;
             D.p2_tabs.upload(ptabs, stream);
+            D.h_p2 = ptabs;
+            D.p2_src = order;
             D.p2_ntabs = (int)ptabs.size();
             D.p2_gates = (double)g0.size();
             D.p2_out_entries = 0;
@@ -1622,6 +1643,206 @@ void Engine::derive_b() {
     k_derive_b<<<cdiv((uint32_t)n_chains, 32), 32, 0, stream>>>(d_chains.p, n_chains, d_chain_segs.p, d_chain_terms.p, d_chal.p,
                                                              d_tr.p, nullptr);
     ++launches;
+}
+
+// ------------------------------------------------------------------ verifier
+static int vf_binary_index(int ty) {
+    switch (ty) {
+        case T_ADD: return 0; case T_SUB: return 1; case T_ANTISUB: return 2; case T_MUL: return 3;
+        case T_NAAB: return 4; case T_ANTINAAB: return 5; case T_XOR: return 6; default: return -1;
+    }
+}
+// gates of layer i in bucket order (one bucket per accumulator of verifier.cpp:63-113) + the Liu segments
+void Engine::verify_prepare(int i) {
+    LayerDev& D = L[i];
+    if (D.vf_ready) return;
+    const Layer& T = C.layers[i];
+    const uint32_t S = (uint32_t)T.size;
+    std::vector<std::pair<uint32_t, uint32_t>> keyed;   // (key, gate)
+    for (uint32_t g = 0; g < S; ++g) {
+        const int ty = T.ty[g], bi = vf_binary_index(ty);
+        uint32_t key;
+        if (bi >= 0) key = 4u + 7u * (uint32_t)T.l[g] + (uint32_t)bi;
+        else if (ty == T_COPY) key = 0;
+        else if (ty == T_NOT) key = 1;
+        else if (ty == T_ADDC) key = 2;
+        else if (ty == T_MULC) key = 3;
+        else continue;
+        keyed.push_back({key, g});
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<VfGate> gates(keyed.size());
+    std::vector<VfBucket> buckets;
+    D.vf_key.clear();
+    for (size_t x = 0; x < keyed.size(); ++x) {
+        const uint32_t key = keyed[x].first, g = keyed[x].second;
+        const bool bin = key >= 4;
+        gates[x] = VfGate{g, T.u[g], bin ? T.lv[g] : 0u, bin ? (uint32_t)T.l[g] : g};
+        if (buckets.empty() || D.vf_key.back() != key) {
+            const uint32_t kind = bin ? 3u : key == 2 ? 2u : key == 3 ? 1u : 0u;
+            buckets.push_back(VfBucket{(uint32_t)x, 0, kind, bin ? (uint32_t)T.dadSize[(key - 4) / 7] : 0u});
+            D.vf_key.push_back(key);
+        }
+        ++buckets.back().cnt;
+    }
+    if (!gates.empty()) { D.vf_gates.upload(gates, stream); D.vf_buckets.upload(buckets, stream); }
+    if (!T.is_assert.empty()) D.vf_assert.upload(T.is_assert, stream);
+    // Liu segments: layer pre itself, then every source layer j >= i with a non-empty subset in pre (same order as liu_j)
+    std::vector<VfLiuSeg> segs;
+    segs.push_back(VfLiuSeg{nullptr, (uint32_t)C.layers[i - 1].size, 0, 0});
+    for (size_t q = 0; q < D.liu_j.size(); ++q) {
+        const LayerDev& J = L[D.liu_j[q]];
+        const uint32_t* ids = nullptr;
+        uint32_t Dsz = 0;
+        for (size_t t = 0; t < J.p2_src.size(); ++t)
+            if (J.p2_src[t] == i - 1) { ids = J.h_p2[t].dadId; Dsz = J.h_p2[t].D; }
+        if (!ids) throw CudaError{"verify: missing dad subset"};
+        segs.push_back(VfLiuSeg{ids, Dsz, (uint32_t)q, 0});
+    }
+    D.vf_liu.upload(segs, stream);
+    D.n_vf_liu = (uint32_t)segs.size();
+    CK(cudaStreamSynchronize(stream));   // host vectors go out of scope
+    D.vf_ready = true;
+}
+
+// verifier::verify (verifier.cpp:134-337) on a host transcript; challenges = the stream set by vp_set_challenges /
+// vp_prove. Returns 1 (accept) or 0 with the failing check: 1 phase-1 round, 2 phase-2 round, 3 final value of the
+// layer, 4 Liu round, 5 Liu final, 6 input layer -- the codes of the CPU oracle's verifier (tests compare them).
+int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
+    if (world > 1) throw CudaError{"vp_verify needs an unsharded context"};
+    if (!inputs_loaded) throw CudaError{"vp_verify: inputs not loaded"};
+    if (h_chal.size() < n_chal) throw CudaError{"vp_verify: challenges not set"};
+    if (on_lane1 || on_lane2) throw CudaError{"vp_verify: lanes not joined"};
+    // ---- device: all O(#gates) sums, every layer, results in one buffer
+    uint32_t out_total = 0, max_b = 1;
+    for (int i = 1; i < n; ++i) {
+        verify_prepare(i);
+        L[i].vf_out = out_total;
+        out_total += 2u * ((uint32_t)L[i].vf_key.size() + L[i].n_vf_liu);
+        max_b = std::max<uint32_t>(max_b, std::max<uint32_t>((uint32_t)L[i].vf_key.size(), L[i].n_vf_liu));
+    }
+    out_total += 2;   // input MLE
+    if (d_vf_out.n < out_total) d_vf_out.alloc(out_total);
+    if (d_vf_partial.n < (size_t)max_b * VF_GX * 2) d_vf_partial.alloc((size_t)max_b * VF_GX * 2);
+    {   // circuitValue[0] from the resident inputs (the verifier does not evaluate the circuit)
+        const uint32_t tot0 = (uint32_t)C.layer_size(0);
+        k_load_inputs<<<cdiv(std::max<uint32_t>(tot0, 1), 256), 256, 0, stream>>>(d_inputs.p, val[0].p, 0, tot0);
+        ++launches;
+    }
+    for (int i = n - 1; i >= 1; --i) {
+        LayerDev& D = L[i];
+        const uint32_t S_pre = (uint32_t)C.layers[i - 1].size, nb = (uint32_t)D.vf_key.size();
+        const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
+        run_eq(D.eqb_g, 2);
+        run_eq(D.eqb_u, 2);
+        if (m != -1) run_eq(D.eqb_v, 2);
+        if (nb) {
+            k_verify_sums<<<dim3(VF_GX, nb), 256, 0, stream>>>(D.vf_buckets.p, D.vf_gates.p, D.vf_assert.p, D.c.p, S_pre, D.S, K,
+                                                              eqtab(0, C.bit_length(i)), eqtab(1, pb),
+                                                              eqtab(6 + (uint32_t)n, std::max(m, 0)), d_chal.p + D.ci_assert,
+                                                              d_vf_partial.p);
+            k_verify_reduce<<<nb, 64, 0, stream>>>(d_vf_partial.p, VF_GX, d_vf_out.p + D.vf_out);
+            launches += 2;
+        }
+        run_eq(D.eqb_u1, 2);                 // sig[0] * eq(r_u, .)
+        run_eq(D.eqb_rl, 2);                 // eq(r_liu, .)
+        run_eq(D.eqb_liu, D.n_eqb_liu);      // sig[j - pre] * eq(r_v[j], .)
+        k_verify_gr<<<dim3(VF_GX, D.n_vf_liu), 256, 0, stream>>>(D.vf_liu.p, D.liu_eqtabs.p, eqtab(3 + (uint32_t)n, pb),
+                                                                  eqtab(7 + (uint32_t)n, pb), S_pre, K, d_vf_partial.p);
+        k_verify_reduce<<<D.n_vf_liu, 64, 0, stream>>>(d_vf_partial.p, VF_GX, d_vf_out.p + D.vf_out + 2 * nb);
+        launches += 2;
+    }
+    run_eq(eqb_in, 2);
+    run_dot_eq(val[0].p, (uint32_t)C.layers[0].size, eqtab(2, C.bit_length(0)), d_vf_out.p + out_total - 2);
+    std::vector<F> out(out_total);
+    CK(cudaMemcpyAsync(out.data(), d_vf_out.p, (size_t)out_total * sizeof(F), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+
+    // ---- host: the protocol driver (canonical host arithmetic of field.cuh)
+    auto ev = [](const F* q, const F& x) { return f_mul_add(f_mul_add(q[0], x, q[1]), x, q[2]); };   // a x^2 + b x + c
+    auto ok_sum = [&](const F* q, const F& claim) { return f_eq(f_add(q[2], f_add(f_add(q[0], q[1]), q[2])), claim); };
+#define VP_FAIL(cd, ly) do { if (fail_code) *fail_code = (cd); if (fail_layer) *fail_layer = (ly); return 0; } while (0)
+    if (fail_code) *fail_code = 0;
+    if (fail_layer) *fail_layer = 0;
+    std::vector<std::vector<F>> claims_v(n);
+    size_t ti = 0;
+    F previousSum = tr[ti++];
+    for (int i = n - 1; i >= 1; --i) {
+        const LayerDev& D = L[i];
+        const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
+        const F* r_u = h_chal.data() + D.ci_ru;
+        for (int j = 0; j < pb; ++j, ti += 3) {
+            if (!ok_sum(tr + ti, previousSum)) VP_FAIL(1, i);
+            previousSum = ev(tr + ti, r_u[j]);
+        }
+        const F claim_u = tr[ti++];
+        claims_v[i].assign(i, f_zero());
+        F bv0 = f_one();
+        if (m != -1) {
+            const F* r_v = h_chal.data() + D.ci_rv;
+            for (int j = 0; j < m; ++j, ti += 3) {
+                if (!ok_sum(tr + ti, previousSum)) VP_FAIL(2, i);
+                previousSum = ev(tr + ti, r_v[j]);
+                bv0 = f_mul(bv0, f_sub(f_one(), r_v[j]));   // beta_v[0]
+            }
+            for (int l = 0; l < i; ++l) claims_v[i][l] = tr[ti++];
+        }
+        // getFinalValue (verifier.cpp:115-132) from the bucket sums
+        F cl[4] = {f_zero(), f_zero(), f_zero(), f_zero()}, bias = f_zero(), res = f_zero();
+        const F* o = out.data() + D.vf_out;
+        const F one_m_cu = f_sub(f_one(), claim_u);
+        for (size_t b = 0; b < D.vf_key.size(); ++b) {
+            const uint32_t key = D.vf_key[b];
+            if (key < 4) {
+                cl[key] = o[2 * b];
+                if (key == 2) bias = o[2 * b + 1];
+            }
+        }
+        if (m != -1) { for (auto& x : cl) x = f_mul(x, bv0); bias = f_mul(bias, bv0); }
+        res = f_mul(cl[1], one_m_cu);                                 // Not
+        res = f_add(res, f_mul(cl[0], claim_u));                      // Copy
+        res = f_add(f_add(res, f_mul(cl[2], claim_u)), bias);         // Addc
+        res = f_add(res, f_mul(cl[3], claim_u));                      // Mulc
+        if (m != -1)
+            for (size_t b = 0; b < D.vf_key.size(); ++b) {
+                const uint32_t key = D.vf_key[b];
+                if (key < 4) continue;
+                const int l = (int)((key - 4) / 7), bi = (int)((key - 4) % 7);
+                const F cu = claim_u, cv = claims_v[i][l], uv = f_mul(cu, cv);
+                F w;
+                switch (bi) {
+                    case 0: w = f_add(cu, cv); break;
+                    case 1: w = f_sub(cu, cv); break;
+                    case 2: w = f_sub(cv, cu); break;
+                    case 3: w = uv; break;
+                    case 4: w = f_sub(cv, uv); break;
+                    case 5: w = f_sub(cu, uv); break;
+                    default: w = f_sub(f_add(cu, cv), f_dbl(uv)); break;
+                }
+                res = f_add(res, f_mul(o[2 * b], w));
+            }
+        if (!f_eq(previousSum, res)) VP_FAIL(3, i);
+        // verifyLiu
+        const int pre = i - 1;
+        const F* sig = h_chal.data() + D.ci_sig;
+        const F* r_liu = h_chal.data() + D.ci_rliu;
+        previousSum = f_mul(sig[0], claim_u);
+        for (int j = i; j < n; ++j)
+            if (C.layers[j].dadSize[pre] > 0) previousSum = f_add(previousSum, f_mul(sig[j - pre], claims_v[j][pre]));
+        for (int j = 0; j < pb; ++j, ti += 3) {
+            if (!ok_sum(tr + ti, previousSum)) VP_FAIL(4, i);
+            previousSum = ev(tr + ti, r_liu[j]);
+        }
+        const F vr = tr[ti++];
+        F gr = f_zero();
+        for (uint32_t sg = 0; sg < D.n_vf_liu; ++sg) gr = f_add(gr, o[2 * (D.vf_key.size() + sg)]);
+        if (!f_eq(f_mul(vr, gr), previousSum)) VP_FAIL(5, i);
+        previousSum = vr;
+    }
+    const F acc = out[out_total - 2], claimed = tr[ti++];
+    if (!f_eq(claimed, acc) || !f_eq(previousSum, claimed)) VP_FAIL(6, 0);
+#undef VP_FAIL
+    return 1;
 }
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
@@ -2252,6 +2473,16 @@ extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t
         e.proof_size += (uint64_t)(2 * pb + (m != -1 ? m : 0)) * 3 * sizeof(F) + sizeof(F);
         if (m != -1) e.proof_size += (uint64_t)i * sizeof(F);
     }
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_verify(vp_ctx* ctx, const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer) {
+    if (!ctx || !transcript || !accept) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    if (n != e.n_tr) return fail(VP_ERR_ARG, "expected a transcript of %zu field elements, got %zu", e.n_tr, n);
+    *accept = e.verify(reinterpret_cast<const F*>(transcript), fail_code, fail_layer);
     return VP_OK;
     API_END
 }

@@ -1623,6 +1623,89 @@ __global__ void k_sum_ranks(const F* __restrict__ recv, uint32_t G, uint32_t str
     }
 }
 
+// ------------------------------------------------------------------ V1 / V2: the verifier's linear-time sums
+//  verifier.cpp:63-113 predicatePhase1/2 and the gr sum of verifyLiu :311-323. The protocol driver
+// (round checks, getFinalValue, the Liu check) stays on the host; these kernels produce the O(#gates) quantities it
+// needs. They are written against the circuit wiring directly (buckets of gates, plain dadId lists) and use only the
+// canonical field routines: none of the prover's tables, CSRs or lazy/weak primitives are involved, so the
+// verifier's accept is an independent check of the prover's messages.
+struct VfGate {          // one template gate in bucket order
+    uint32_t g0, u0, lv0;
+    uint32_t l_c;        // binary: source layer l; unary: index of the gate's constant (== g0)
+};
+struct VfBucket {
+    uint32_t begin, cnt;     // gates [begin, begin + cnt) of the sorted array
+    uint32_t kind;           // 0: sum t; 1: sum t*c; 2: sum t and, second output, sum t*c (Addc: coeff and bias); 3: binary, sum t*beta_v[lv]
+    uint32_t D;              // binary: subset size of one instance (lv = (K-1-k)*D + lv0)
+};
+// partial[(bucket * gridDim.x + blockIdx.x) * 2 + {0,1}]
+__global__ void __launch_bounds__(256)
+k_verify_sums(const VfBucket* __restrict__ buckets, const VfGate* __restrict__ gates, const uint8_t* __restrict__ is_assert,
+              const F* __restrict__ cst, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, EqTab eqv,
+              const F* __restrict__ assert_r, F* __restrict__ partial) {
+    __shared__ F smem[2 * 32];
+    const VfBucket B = buckets[blockIdx.y];
+    const uint64_t total = (uint64_t)B.cnt * K;
+    F acc[2] = {f_zero(), f_zero()};
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(w / B.cnt), j = (uint32_t)(w - (uint64_t)k * B.cnt);
+        const VfGate G = gates[B.begin + j];
+        F bg = eq_at(eqg, k * S_cur + G.g0);
+        if (is_assert && is_assert[G.g0]) bg = f_mul(bg, *assert_r);
+        F t = f_mul(bg, eq_at(equ, k * S_pre + G.u0));
+        if (B.kind == 3) t = f_mul(t, eq_at(eqv, (K - 1 - k) * B.D + G.lv0));
+        if (B.kind == 1) t = f_mul(t, cst[G.l_c]);
+        acc[0] = f_add(acc[0], t);
+        if (B.kind == 2) acc[1] = f_add(acc[1], f_mul(t, cst[G.l_c]));
+    }
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) {
+        F* dst = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        st_f(dst, acc[0]);
+        st_f(dst + 1, acc[1]);
+    }
+}
+// out[bucket * 2 + {0,1}] = sum over the gx partials of the bucket
+__global__ void k_verify_reduce(const F* __restrict__ partial, uint32_t gx, F* __restrict__ out) {
+    __shared__ F smem[2 * 32];
+    F acc[2] = {f_zero(), f_zero()};
+    for (uint32_t b = threadIdx.x; b < gx; b += blockDim.x) {
+        acc[0] = f_add(acc[0], partial[((size_t)blockIdx.x * gx + b) * 2]);
+        acc[1] = f_add(acc[1], partial[((size_t)blockIdx.x * gx + b) * 2 + 1]);
+    }
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) { st_f(out + 2 * blockIdx.x, acc[0]); st_f(out + 2 * blockIdx.x + 1, acc[1]); }
+}
+// gr of verifyLiu: segment 0 = sum_u beta_g'[u]*beta_u'[u] over layer pre (beta_g' = sig[0]*eq(r_u,.), beta_u' = eq(r_liu,.));
+// segment 1+q = sum_g eq_q[g] * beta_u'[dadId_q[g]] over the K-instance subset of source layer j_q (eq_q carries sig[j-pre]).
+struct VfLiuSeg {
+    const uint32_t* dadId;   // one instance, null for segment 0
+    uint32_t D;              // subset size of one instance (segment 0: S_pre)
+    uint32_t eq_id;          // index into eqs (segment 0: unused)
+    uint32_t pad;
+};
+__global__ void __launch_bounds__(256)
+k_verify_gr(const VfLiuSeg* __restrict__ segs, const EqTab* __restrict__ eqs, EqTab eq_g0, EqTab eq_rl, uint32_t S_pre, uint32_t K,
+            F* __restrict__ partial) {
+    __shared__ F smem[2 * 32];
+    const VfLiuSeg Sg = segs[blockIdx.y];
+    const uint64_t total = (uint64_t)Sg.D * K;
+    F acc[2] = {f_zero(), f_zero()};
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+        if (blockIdx.y == 0) acc[0] = f_add(acc[0], f_mul(eq_at(eq_g0, (uint32_t)w), eq_at(eq_rl, (uint32_t)w)));
+        else {
+            const uint32_t kk = (uint32_t)(w / Sg.D), g0 = (uint32_t)(w - (uint64_t)kk * Sg.D), k = K - 1 - kk;
+            acc[0] = f_add(acc[0], f_mul(eq_at(eqs[Sg.eq_id], (uint32_t)w), eq_at(eq_rl, k * S_pre + Sg.dadId[g0])));
+        }
+    }
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) {
+        F* dst = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        st_f(dst, acc[0]);
+        st_f(dst + 1, acc[1]);
+    }
+}
+
 // ------------------------------------------------------------------ misc
 // SplitMix64-filled random table entries (limbs uniform in [0,p) by rejection), config C2.
 __global__ void k_fill_random(F* __restrict__ T, uint32_t n, uint64_t seed) {

@@ -261,7 +261,7 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line, default=_jd))
+        emit(line)
 
 
 def dfs_traffic(inst, world):
@@ -389,7 +389,7 @@ def run_reference(args):
                          "sample": f"{procs} processes x SHA256_64 x {k} instances per step, max time over processes"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line, default=_jd))
+    emit(line)
 
 
 def main():
@@ -403,10 +403,27 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on stdout at
+    # communicator creation): keep the real stdout aside, point fd 1 at stderr for the run, print the line at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _OUT
+    _OUT = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
+
+
+_OUT = None
+
+
+def emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line, default=_jd) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":

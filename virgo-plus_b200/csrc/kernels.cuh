@@ -324,6 +324,7 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 // touches 32 different sectors and the eq half tables fall out of L1: 2.2x slower on SHA256_64 x 1024).
 VP_D F eq_at_acc_w(const EqTab& t, uint32_t idx, const F& acc);
 VP_D F f_mul_w(const F& a, const F& b);
+VP_D F f_mul_add_w(const F& a, const F& b, const F& acc);
 VP_D F eq_at_weak(const EqTab& t, uint32_t idx) { return eq_at_acc_w(t, idx, f_zero()); }   // components in [0,p]
 VP_D F eq_at_acc_w(const EqTab& t, uint32_t idx, const F& acc) {   // acc + eq(idx), acc components < 2^64: [0,p]
     const F a = ld_f(t.f + (idx & t.mask)), b = ld_f(t.s + (idx >> t.fh));
@@ -509,14 +510,16 @@ k_init_phase2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table
 //   mult = S0 + V_u*S1, add = V_u*SA.   Three products per gate (all weakly canonical) instead of five.
 VP_D F f_add_w(const F& a, const F& b) { return F{fp_weak(a.re + b.re), fp_weak(a.im + b.im)}; }            // [0,p] x [0,p] -> [0,p]
 VP_D F f_sub_w(const F& a, const F& b) { return F{fp_weak(a.re + P - b.re), fp_weak(a.im + P - b.im)}; }
-VP_D F f_mul_w(const F& a, const F& b) {   // a components <= 2p, b in [0,p] -> [0,p]
+VP_D F f_mul_add_w(const F& a, const F& b, const F& acc);
+VP_D F f_mul_w(const F& a, const F& b) { return f_mul_add_w(a, b, f_zero()); }   // a components <= 2p, b in [0,p] -> [0,p]
+VP_D F f_mul_add_w(const F& a, const F& b, const F& acc) {   // acc + a*b, acc components < 2^64 -> [0,p]
     const LOp m = make_lop(a.re, a.im);
     const ROpD v = make_ropd(b);
     const u64 u_re = mad32(m.nim1, v.im1d, mad32(m.re1, v.re1d, mad32(m.nim0, v.im0, mul32(m.re0, v.re0))));
     const u64 t_re = mad32(m.nim1, v.im0, mad32(m.nim0, v.im1, mad32(m.re1, v.re0, mul32(m.re0, v.re1))));
     const u64 u_im = mad32(m.im1, v.re1d, mad32(m.re1, v.im1d, mad32(m.im0, v.re0, mul32(m.re0, v.im0))));
     const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
-    return F{fp_reduce_ut_weak(u_re, t_re, 0), fp_reduce_ut_weak(u_im, t_im, 0)};
+    return F{fp_reduce_ut_weak(u_re, t_re, acc.re), fp_reduce_ut_weak(u_im, t_im, acc.im)};
 }
 VP_D void p2_accumulate(uint32_t ty, const F& t, F& S0, F& S1, F& SA) {
     switch (ty) {
@@ -1081,6 +1084,29 @@ VP_D void pacc_finish(const PassAcc& s, F& a, F& c) {
     a = cacc_reduce(s.A);
     c = f_add(cacc_reduce(s.C), F{fp_canon(s.s0re), fp_canon(s.s0im)});
 }
+// Second round of a pass: the same two sums, but as weakly canonical running values that ride in the products'
+// reductions (8 registers instead of 28: the pass kernel is register bound, and the second round is a third of the work)
+struct PassAcc2 {
+    F A, C;
+    u64 s0re, s0im;
+};
+VP_D void pacc2_init(PassAcc2& s) { s.A = f_zero(); s.C = f_zero(); s.s0re = s.s0im = 0; }
+VP_D void pacc2_finish(const PassAcc2& s, F& a, F& c) {
+    a = f_strict(s.A);
+    c = f_add(f_strict(s.C), F{fp_canon(s.s0re), fp_canon(s.s0im)});
+}
+VP_D void dfs_pair2(PassAcc2& s, bool has_a, const F& v0, const F& v1, const F& m0, const F& m1, const F& a0, const F& a1,
+                    const ConstK& rk, F& ov, F& om, F& oa) {
+    const F dm = f_diff2p(m0, m1), dv = f_diff_w(v0, v1);
+    s.C = f_mul_add_w(m0, v0, s.C);
+    s.A = f_mul_add_w(dm, dv, s.A);
+    ov = f_fold_w(v0, dv, rk);
+    om = f_fold_w(m0, dm, rk);
+    if (has_a) {
+        s.s0re += a0.re; s.s0im += a0.im;
+        oa = f_fold_w(a0, f_diff2p(a0, a1), rk);
+    }
+}
 // only the very first round of a stand-alone sumcheck has no claim to start from: it also sums p(1) = sum m1*v1 + a1
 struct PassAccB {
     CAcc B;
@@ -1148,9 +1174,10 @@ VP_D F lds_f(uint32_t smem_addr) {
 }
 
 template <bool HAS_A, bool VREAL, bool NEED_B>
-VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
+VP_D void dfs_work(PassAcc& acc1, PassAcc2& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
                    const uint32_t* s_wend, const F* inV, const F* inM, const F* inA, F* outV, F* outM, F* outA,
                    const ConstK& rk1, const ConstK& rk2, unsigned int* chunk_ctr, uint32_t stage_base /* this warp's smem */,
+                   const F* stage_ptr /* the same, as a pointer */,
                    uint32_t static_base /* this warp's only chunk, or 0xffffffff: chunks from the atomic counter */,
                    uint32_t share /* items of the static chunk (multiple of 32, <= DFS_WCHUNK) */) {
     const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;   // multiple of 32
@@ -1220,21 +1247,22 @@ VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* 
         while (b_cur >= s_wend[t_cp]) ++t_cp;
         const PassTab T = tabs[t_cp];
         const uint32_t q = b_cur - (t_cp ? s_wend[t_cp - 1] : 0) + lane;
-        const uint32_t sb = stage_base + st * (DFS_STAGE_F * 16) + 64 * lane, sw = (lane >> 1) & 3;
+        // plain shared-memory loads (not volatile asm): the compiler places each next to its use, so only the pair
+        // being worked on occupies registers; the stage is not refilled before the __syncwarp at the end of the iteration
+        const F* sp = stage_ptr + st * DFS_STAGE_F + 4 * lane;
+        const uint32_t sw = (lane >> 1) & 3;
         F xv[4], xm[4], xa[4];
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t o = 16 * (j ^ sw);
-            xv[j] = lds_f(sb + o);
-            xm[j] = lds_f(sb + 128 * 16 + o);
-            xa[j] = HAS_A ? lds_f(sb + 256 * 16 + o) : f_zero();
+            xv[j] = sp[j ^ sw];
+            xm[j] = sp[128 + (j ^ sw)];
+            xa[j] = HAS_A ? sp[256 + (j ^ sw)] : f_zero();
         }
-        __syncwarp();   // every lane has read its quad: the stage may be refilled by the next iteration's copies
         if (T.two) {
             F v0, v1, m0, m1, a0 = f_zero(), a1 = f_zero(), ov, om, oa = f_zero();
             dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[0], xv[1], xm[0], xm[1], xa[0], xa[1], rk1, v0, m0, a0);
             dfs_pair<VREAL, HAS_A, NEED_B>(acc1, accb, xv[2], xv[3], xm[2], xm[3], xa[2], xa[3], rk1, v1, m1, a1);
-            dfs_pair<false, HAS_A, false>(acc2, nullptr, v0, v1, m0, m1, a0, a1, rk2, ov, om, oa);
+            dfs_pair2(acc2, HAS_A, v0, v1, m0, m1, a0, a1, rk2, ov, om, oa);
             if (4 * q < T.in_live) {
                 const uint32_t o = T.out_off + q;
                 st_f(outV + o, ov);
@@ -1257,6 +1285,7 @@ VP_D void dfs_work(PassAcc& acc1, PassAcc& acc2, PassAccB* accb, const PassTab* 
             acc1.s0re = fp_fold(acc1.s0re); acc1.s0im = fp_fold(acc1.s0im);
             if (NEED_B) { accb->s1re = fp_fold(accb->s1re); accb->s1im = fp_fold(accb->s1im); }
         }
+        __syncwarp();   // every lane is done with this stage: the next iteration's copies may refill it
         b_cur = b_next;
         st ^= 1;
     }
@@ -1315,6 +1344,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
     __shared__ uint32_t s_wend[128];
     extern __shared__ __align__(16) unsigned char dfs_dyn_smem[];   // per warp: two stages x 3 tables x 32 quads
     const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(dfs_dyn_smem) + (threadIdx.x >> 5) * (DFS_WARP_SMEM_F * 16);
+    const F* stage_ptr = reinterpret_cast<const F*>(dfs_dyn_smem) + (threadIdx.x >> 5) * DFS_WARP_SMEM_F;
     constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;   // a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
     const bool coord = blockIdx.x == 0;
     const uint32_t n_workers = gridDim.x - 1;
@@ -1352,9 +1382,10 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             // the challenges' limbs come pre-split through the kernel parameters
             const ConstK& rk1 = p.rk[2 * ps];
             const ConstK& rk2 = p.rk[2 * ps + 1];
-            PassAcc acc1, acc2;
+            PassAcc acc1;
+            PassAcc2 acc2;
             pacc_init(acc1);
-            pacc_init(acc2);
+            pacc2_init(acc2);
             PassAccB accb;
             accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
             const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
@@ -1363,15 +1394,15 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             const uint32_t static_base = is_static ? (wb * WPB + (threadIdx.x >> 5)) * share : 0xffffffffu;
             if (FIRST == DFS_VREAL && ps == 0)
                 dfs_work<HAS_A, true, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, stage_ptr, static_base, share);
             else if (FIRST == DFS_NEED_B && ps == 0)
                 dfs_work<HAS_A, false, true>(acc1, acc2, &accb, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+                                             p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, stage_ptr, static_base, share);
             else
                 dfs_work<HAS_A, false, false>(acc1, acc2, nullptr, p.tabs + R.tab_begin, R.n_tabs, s_wend, inV, p.bufM[ib], p.bufA[ib],
-                                              p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, static_base, share);
+                                              p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, stage_ptr, static_base, share);
             pacc_finish(acc1, v[0], v[1]);
-            pacc_finish(acc2, v[2], v[3]);
+            pacc2_finish(acc2, v[2], v[3]);
             if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(cacc_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
             if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
                 unsigned long long t_; unsigned int sm_;

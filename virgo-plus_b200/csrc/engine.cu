@@ -1025,8 +1025,6 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         add_eq_build(0, D.ci_g, C.bit_length(i), -1);
         D.eqb_u = (uint32_t)eq_descs.size();
         add_eq_build(1, D.ci_ru, pb, -1);
-        D.eqb_u1 = (uint32_t)eq_descs.size();
-        add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, (int)D.ci_sig);   // lane 1's copy is only used by Liu: bake s[0] in
         D.eqb_g2 = (uint32_t)eq_descs.size();
         add_eq_build(4 + (uint32_t)n, D.ci_g, C.bit_length(i), -1);
         D.eqb_u2 = (uint32_t)eq_descs.size();
@@ -1147,6 +1145,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             }
             D.liu_off.upload(off, stream);
             D.liu_ent.upload(ent, stream);
+            // lane 1's copy of beta_u is only used by Liu: bake s[0] in. Its descriptors sit right before the Liu tables'
+            // so that one k_eq_build launch covers both.
+            D.eqb_u1 = (uint32_t)eq_descs.size();
+            add_eq_build(3 + (uint32_t)n, D.ci_ru, pb, (int)D.ci_sig);
             // eq tables: region 3+q = eq(r_v[j], dadBl_j[pre]) * sig[j - pre]
             D.eqb_liu = (uint32_t)eq_descs.size();
             std::vector<EqTab> tabs;
@@ -1415,7 +1417,7 @@ void Engine::do_init_phase1(int i) {
 void Engine::do_init_phase2(int i) {
     LayerDev& D = L[i];
     const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
-    if (on_lane2) { run_eq(D.eqb_g2, 2); run_eq(D.eqb_u2, 2); }
+    if (on_lane2) run_eq(D.eqb_g2, 4);   // beta_g and beta_u: adjacent descriptors, one launch
     else { run_eq(D.eqb_u, 2); have_equ = true; }
     const EqTab eqg = eqtab(on_lane2 ? region_g_lane2 : 0, C.bit_length(i)), equ = eqtab(on_lane2 ? region_u_lane2 : 1, C.bit_length(i - 1));
     const F* Vu = on_lane2 ? d_vu.p + i : scal(SC_VU);
@@ -1458,12 +1460,12 @@ void Engine::do_init_liu(int i, bool write_a) {
     LayerDev& D = L[i];
     const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
     const uint32_t reg_u = on_lane1 ? region_u_lane1 : 1;
-    if (on_lane1) run_eq(D.eqb_u1, 2);
+    if (on_lane1) run_eq(D.eqb_u1, 2 + D.n_eqb_liu);   // scaled beta_u + the Liu tables: adjacent descriptors, one launch
     else {
         if (!have_equ) run_eq(D.eqb_u, 2);
         have_equ = false;
+        run_eq(D.eqb_liu, D.n_eqb_liu);
     }
-    run_eq(D.eqb_liu, D.n_eqb_liu);
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
@@ -1640,7 +1642,7 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
 // (and, on a sharded context, replicated) when this runs.
 void Engine::derive_b() {
     if (!n_chains) return;
-    k_derive_b<<<cdiv((uint32_t)n_chains, 32), 32, 0, stream>>>(d_chains.p, n_chains, d_chain_segs.p, d_chain_terms.p, d_chal.p,
+    k_derive_b<<<cdiv((uint32_t)n_chains, 4), 128, 0, stream>>>(d_chains.p, n_chains, d_chain_segs.p, d_chain_terms.p, d_chal.p,
                                                              d_tr.p, nullptr);
     ++launches;
 }

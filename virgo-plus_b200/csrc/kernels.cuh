@@ -1072,6 +1072,10 @@ struct DfsArgs {
 // the verifier's check verifier.cpp:209,248,296 identically, so b need not be summed: k_derive_b fills it in from the
 // claim chain once the claims it starts from are known). Two complex products per pair instead of the reference's
 // four (polynomial.cpp:101-110); both sums are LAZY (96-bit partial sums of the limb products, reduced once per pass).
+#ifndef VP_DFS_LAZY1
+#define VP_DFS_LAZY1 1
+#endif
+#if VP_DFS_LAZY1
 struct PassAcc {
     CAcc A, C;
     u64 s0re, s0im;   // sum of a0, folded once per work item
@@ -1084,6 +1088,28 @@ VP_D void pacc_finish(const PassAcc& s, F& a, F& c) {
     a = cacc_reduce(s.A);
     c = f_add(cacc_reduce(s.C), F{fp_canon(s.s0re), fp_canon(s.s0im)});
 }
+VP_D void pacc_mad(CAcc& acc, const F& m, const F& v) { cacc_mad(acc, make_lop(m.re, m.im), make_ropd(v)); }
+VP_D void pacc_mad_real(CAcc& acc, const F& m, u64 v) { cacc_mad_real(acc, m, v); }
+typedef CAcc PassSum;
+VP_D PassSum psum_zero() { return cacc_zero(); }
+VP_D F psum_reduce(const PassSum& s) { return cacc_reduce(s); }
+#else   // build-time variant: weakly canonical running values in round 1 as well (fewer registers, 16 more instructions per product)
+struct PassAcc {
+    F A, C;
+    u64 s0re, s0im;
+};
+VP_D void pacc_init(PassAcc& s) { s.A = f_zero(); s.C = f_zero(); s.s0re = s.s0im = 0; }
+VP_D void pacc_finish(const PassAcc& s, F& a, F& c) {
+    a = f_strict(s.A);
+    c = f_add(f_strict(s.C), F{fp_canon(s.s0re), fp_canon(s.s0im)});
+}
+VP_D F f_mul_add_w(const F& a, const F& b, const F& acc);
+VP_D void pacc_mad(F& acc, const F& m, const F& v) { acc = f_mul_add_w(m, v, acc); }
+VP_D void pacc_mad_real(F& acc, const F& m, u64 v) { acc = f_mad_real_w(acc, m, v); }
+typedef F PassSum;
+VP_D PassSum psum_zero() { return f_zero(); }
+VP_D F psum_reduce(const PassSum& s) { return f_strict(s); }
+#endif
 // Second round of a pass: the same two sums, but as weakly canonical running values that ride in the products'
 // reductions (8 registers instead of 28: the pass kernel is register bound, and the second round is a third of the work)
 struct PassAcc2 {
@@ -1109,7 +1135,7 @@ VP_D void dfs_pair2(PassAcc2& s, bool has_a, const F& v0, const F& v1, const F& 
 }
 // only the very first round of a stand-alone sumcheck has no claim to start from: it also sums p(1) = sum m1*v1 + a1
 struct PassAccB {
-    CAcc B;
+    PassSum B;
     u64 s1re, s1im;
 };
 // One pair of one round: accumulate, fold the three tables with the round's challenge.
@@ -1121,15 +1147,15 @@ VP_D void dfs_pair(PassAcc& s, PassAccB* sb, const F& v0, const F& v1, const F& 
     const F dm = f_diff2p(m0, m1);
     if (VREAL) {
         const u64 dv = fp_weak(v1.re + P - v0.re);
-        cacc_mad_real(s.C, m0, v0.re);
-        cacc_mad_real(s.A, dm, dv);
-        if (NEED_B) cacc_mad_real(sb->B, m1, v1.re);
+        pacc_mad_real(s.C, m0, v0.re);
+        pacc_mad_real(s.A, dm, dv);
+        if (NEED_B) pacc_mad_real(sb->B, m1, v1.re);
         ov = f_fold_w_real(v0.re, dv, rk);
     } else {
         const F dv = f_diff_w(v0, v1);
-        cacc_mad(s.C, make_lop(m0.re, m0.im), make_ropd(v0));
-        cacc_mad(s.A, make_lop(dm.re, dm.im), make_ropd(dv));
-        if (NEED_B) cacc_mad(sb->B, make_lop(m1.re, m1.im), make_ropd(v1));
+        pacc_mad(s.C, m0, v0);
+        pacc_mad(s.A, dm, dv);
+        if (NEED_B) pacc_mad(sb->B, m1, v1);
         ov = f_fold_w(v0, dv, rk);
     }
     om = f_fold_w(m0, dm, rk);
@@ -1387,7 +1413,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             pacc_init(acc1);
             pacc2_init(acc2);
             PassAccB accb;
-            accb.B = cacc_zero(); accb.s1re = accb.s1im = 0;
+            accb.B = psum_zero(); accb.s1re = accb.s1im = 0;
             const F* inV = (ps == 0 && p.v_first) ? p.v_first : p.bufV[ib];
             // static shares when one sweep of the workers covers the pass, chunks from the atomic counter otherwise
             const uint32_t wb = solo ? 0 : blockIdx.x - 1;
@@ -1403,7 +1429,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
                                               p.bufV[ob], p.bufM[ob], p.bufA[ob], rk1, rk2, p.chunk_ctr + ps, stage_base, stage_ptr, static_base, share);
             pacc_finish(acc1, v[0], v[1]);
             pacc2_finish(acc2, v[2], v[3]);
-            if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(cacc_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
+            if (FIRST == DFS_NEED_B) v[NV - 1] = f_add(psum_reduce(accb.B), F{fp_canon(accb.s1re), fp_canon(accb.s1im)});
             if (p.dbg && ps == 0 && threadIdx.x == 0 && blockIdx.x < 1024) {   // per-block finish time + SM id of the first pass
                 unsigned long long t_; unsigned int sm_;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
@@ -1499,27 +1525,57 @@ struct ChainDesc {
     uint32_t term_begin, n_terms;
     uint32_t seg_begin, n_segs;
 };
+// One WARP per chain. Within a segment the claims obey claim_{k+1} = r_k*claim_k + d_k with
+// d_k = a_k*(r_k^2 - r_k) + c_k*(1 - 2 r_k) (substitute b_k = claim_k - 2c_k - a_k into p_k(r_k)): the lanes compute
+// (r_k, d_k) for 32 rounds at a time and a warp prefix scan over the affine maps (m,t)o(m',t') = (m*m', t*m' + t')
+// yields every claim_k, hence every b_k, in 5 steps instead of 32 dependent ones.
 __global__ void k_derive_b(const ChainDesc* __restrict__ chains, int n_chains, const ChainSeg* __restrict__ segs,
                            const ChainTerm* __restrict__ terms, const F* __restrict__ chal, F* tr, const F* claim_ext) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_chains) return;
     const ChainDesc c = chains[i];
     F claim = f_zero();
     if (c.claim_tr >= 0) claim = tr[c.claim_tr];
     else if (c.claim_tr == -2) claim = *claim_ext;
-    else
-        for (uint32_t k = 0; k < c.n_terms; ++k) {
+    else {
+        for (uint32_t k = lane; k < c.n_terms; k += 32) {
             const ChainTerm t = terms[c.term_begin + k];
             claim = f_mul_add(chal[t.ci], tr[t.tr], claim);
         }
+        claim = warp_sum(claim);
+        claim.re = __shfl_sync(0xffffffffu, claim.re, 0);
+        claim.im = __shfl_sync(0xffffffffu, claim.im, 0);
+    }
     for (uint32_t s = 0; s < c.n_segs; ++s) {
         const ChainSeg g = segs[c.seg_begin + s];
-        for (uint32_t jr = 0; jr < g.n_rounds; ++jr) {
+        for (uint32_t base = 0; base < g.n_rounds; base += 32) {
+            const uint32_t jr = base + lane;
+            const bool live = jr < g.n_rounds;
             F* o = tr + g.tr_off + 3 * jr;
-            const F a = o[0], cc = o[2], r = chal[g.ci + jr];
-            const F b = f_sub(f_sub(claim, f_dbl(cc)), a);
-            st_f(o + 1, b);
-            claim = f_mul_add(f_mul_add(a, r, b), r, cc);   // quadratic_poly::eval, polynomial.cpp:91-95
+            F a = f_zero(), cc = f_zero(), m = f_one(), t = f_zero();   // identity map for idle lanes
+            if (live) {
+                a = o[0]; cc = o[2];
+                const F r = chal[g.ci + jr];
+                m = r;
+                t = f_mul_add(a, f_sub(f_mul(r, r), r), f_mul(cc, f_sub(f_one(), f_dbl(r))));
+            }
+            // inclusive scan of the affine maps: after it, lane k holds the map claim_base -> claim_{base+k+1}
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                F pm, pt;
+                pm.re = __shfl_up_sync(0xffffffffu, m.re, off); pm.im = __shfl_up_sync(0xffffffffu, m.im, off);
+                pt.re = __shfl_up_sync(0xffffffffu, t.re, off); pt.im = __shfl_up_sync(0xffffffffu, t.im, off);
+                if (lane >= off) { t = f_mul_add(pt, m, t); m = f_mul(pm, m); }   // (pm,pt) first, then (m,t)
+            }
+            const F after = f_mul_add(m, claim, t);   // claim_{base+lane+1}
+            F before;                                  // claim_{base+lane}
+            before.re = __shfl_up_sync(0xffffffffu, after.re, 1);
+            before.im = __shfl_up_sync(0xffffffffu, after.im, 1);
+            if (lane == 0) before = claim;
+            if (live) st_f(o + 1, f_sub(f_sub(before, f_dbl(cc)), a));
+            const uint32_t last = min(31u, g.n_rounds - base - 1);
+            claim.re = __shfl_sync(0xffffffffu, after.re, last);
+            claim.im = __shfl_sync(0xffffffffu, after.im, last);
         }
     }
 }

@@ -598,7 +598,8 @@ struct Engine {
     Circuit C;
     int device = 0;
     int world = 1, rank = 0;
-    uint32_t k_lo = 0, k_hi = 0;     // instances [k_lo, k_hi) this rank evaluates (all of them when world == 1)
+    uint32_t k_lo = 0, k_hi = 0;     // instances [k_lo, k_hi) whose inputs this rank holds (all of them when world == 1)
+    std::vector<uint32_t> ev_lo, ev_hi;   // per layer: the instances this rank evaluates
     uint32_t ko_lo = 0, ko_hi = 0;   // this rank's own slice of the instances (disjoint over the ranks): dot products, unary sums
     vp_ncclComm_t comm = nullptr;
     DBuf<F> d_send, d_recv;
@@ -1167,10 +1168,15 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     add_eq_build(2, L[1].ci_rliu, C.bit_length(0), -1);
 
     // which instances does this rank touch? (tables are instance-major and every rank holds a contiguous run of each)
+    // direct[l] = instances whose layer-l values some table of this rank reads; a layer must be evaluated for the hull
+    // of direct[l'] over all l' >= l (a gate reads from any lower layer). Small phase-2 tables with few blocks can give
+    // one rank a wide slice of a LOW layer; the layers above it stay narrow.
     ko_lo = (uint32_t)((uint64_t)K * rank / world);
     ko_hi = (uint32_t)((uint64_t)K * (rank + 1) / world);
-    k_lo = ko_lo;
-    k_hi = ko_hi;
+    std::vector<uint32_t> dlo(n, K), dhi(n, 0);
+    auto need = [&](int l, uint32_t a, uint32_t b) { if (b > a) { dlo[l] = std::min(dlo[l], a); dhi[l] = std::max(dhi[l], b); } };
+    need(n - 1, ko_lo, ko_hi);   // Vres
+    need(0, ko_lo, ko_hi);       // input MLE
     for (int i = 1; i < n; ++i) {
         LayerDev& D = L[i];
         const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
@@ -1181,31 +1187,38 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         uint32_t a, b;
         fwd(D.ph1, a, b);
         D.p1_k0 = std::min(a, K); D.p1_k1 = std::max(b, D.p1_k0);
-        if (b > a) { k_lo = std::min(k_lo, a); k_hi = std::max(k_hi, b); }
+        need(i - 1, a, std::min(b, K));
         fwd(D.ph3, a, b);
-        if (b > a) { k_lo = std::min(k_lo, a); k_hi = std::max(k_hi, b); }
+        need(i - 1, a, std::min(b, K));
         D.p2_kk0 = K; D.p2_kk1 = 0;
         if (D.max_dad_bl != -1) {
-            size_t t = 0;
-            for (int l = 0; l < i; ++l) { (void)l; }
             // ph2 tables are in `order` (non-empty subsets, bits descending); their D is P2Table.D = dad size of one instance
             std::vector<int> order;
             for (int l = 0; l < i; ++l)
                 if (C.layers[i].dadSize[l] > 0) order.push_back(l);
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return C.dad_bit_length(i, x) > C.dad_bit_length(i, y); });
-            for (t = 0; t < order.size(); ++t) {
+            for (size_t t = 0; t < order.size(); ++t) {
                 const uint32_t Dsz = (uint32_t)C.layers[i].dadSize[order[t]];
                 if (D.ph2.row_hi[t] <= D.ph2.row_lo[t]) continue;
                 const uint32_t kka = D.ph2.row_lo[t] / Dsz, kkb = (D.ph2.row_hi[t] - 1) / Dsz + 1;   // idx = kk*D + lv0, kk = K-1-k
                 D.p2_kk0 = std::min(D.p2_kk0, kka);
                 D.p2_kk1 = std::max(D.p2_kk1, kkb);
-                k_lo = std::min(k_lo, K - kkb);
-                k_hi = std::max(k_hi, K - kka);
+                need(order[t], K - std::min(kkb, K), K - kka);
             }
         }
         if (D.p2_kk1 < D.p2_kk0) D.p2_kk0 = D.p2_kk1 = 0;
     }
-    k_hi = std::min(k_hi, K);
+    ev_lo.assign(n, K);
+    ev_hi.assign(n, 0);
+    {
+        uint32_t lo = K, hi = 0;
+        for (int l = n - 1; l >= 0; --l) {
+            lo = std::min(lo, dlo[l]); hi = std::max(hi, dhi[l]);
+            ev_lo[l] = std::min(lo, hi); ev_hi[l] = hi;
+        }
+    }
+    k_lo = ev_lo[0];   // the inputs this rank uploads
+    k_hi = std::min(ev_hi[0], K);
 
     for (int b = 0; b < 2; ++b) {
         const uint32_t cap = b == 0 ? cap0 : cap1;
@@ -1341,10 +1354,10 @@ void Engine::evaluate() {
     k_load_inputs<<<cdiv(std::max<uint32_t>(e0 - b0, 1), 256), 256, 0, stream>>>(d_inputs.p, val[0].p, b0, e0);
     ++launches;
     for (int i = 1; i < n; ++i) {
-        const uint32_t gb = k_lo * L[i].S, ge = k_hi * L[i].S, tot = ge - gb;
+        const uint32_t gb = ev_lo[i] * L[i].S, ge = ev_hi[i] * L[i].S, tot = ge - gb;
         size_t h = prof_begin(KC_EVAL);
         k_eval_layer<<<grid_for(std::max<uint32_t>(tot, 1), cap_eval), 256, 0, stream>>>(L[i].G, L[i].S, K, i, d_valptr.p, d_sizes.p,
-                                                                                        val[i].p, d_counter.p + 1, gb, ge);
+                                                                                        val[i].p, d_counter.p + 1, gb, ge, values_real ? 1 : 0);
         prof_end(h, (double)tot * (16.0 + 32.0 + 11.0 / K));  // out + two operand gathers (+ amortised wiring)
         ++launches;
     }

@@ -174,7 +174,7 @@ struct GateArrays {          // one template layer (one instance)
 __global__ void __launch_bounds__(256) k_eval_layer(GateArrays G, uint32_t S, uint32_t K, int layer,
                                                      F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
                                                      F* __restrict__ out, unsigned int* __restrict__ assert_fail,
-                                                     uint32_t g_begin, uint32_t g_end) {
+                                                     uint32_t g_begin, uint32_t g_end, int real_only) {
     (void)K;
     const uint32_t S_pre = sizes[layer - 1];
     const F* __restrict__ pre = vals[layer - 1];
@@ -186,6 +186,25 @@ __global__ void __launch_bounds__(256) k_eval_layer(GateArrays G, uint32_t S, ui
         F y = f_zero();
         if (l >= 0) y = ld_f(vals[l] + (size_t)k * sizes[l] + G.v[g0]);
         F r;
+        if (real_only) {   // base-field circuit (no complex constants): one 61-bit product instead of a complex one
+            const u64 a = x.re, b = y.re;
+            u64 o;
+            switch (ty) {
+                case T_ADD: o = fp_add(a, b); break;
+                case T_SUB: o = fp_sub(a, b); break;
+                case T_ANTISUB: o = fp_sub(b, a); break;
+                case T_MUL: o = fp_mul(a, b); break;
+                case T_NAAB: o = fp_sub(b, fp_mul(a, b)); break;
+                case T_ANTINAAB: o = fp_sub(a, fp_mul(a, b)); break;
+                case T_ADDC: o = fp_add(a, G.c[g0].re); break;
+                case T_MULC: o = fp_mul(a, G.c[g0].re); break;
+                case T_COPY: o = a; break;
+                case T_NOT: o = fp_sub(1, a); break;
+                case T_XOR: { const u64 ab = fp_mul(a, b); o = fp_sub(fp_add(a, b), fp_add(ab, ab)); break; }
+                default: o = 0; break;
+            }
+            r = F{o, 0};
+        } else
         switch (ty) {
             case T_ADD: r = f_add(x, y); break;
             case T_SUB: r = f_sub(x, y); break;

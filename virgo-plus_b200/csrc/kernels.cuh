@@ -334,9 +334,10 @@ k_init_phase1(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, ui
 }
 
 // ---- phase-1 init when every circuit value is in the base field (no complex gate constants: all .pws circuits)
-// Every contribution is beta * (a real scalar) -- prover.cpp:229-272 with Vv real -- so a gate costs one eq product
-// (kept weakly canonical) and two real-scalar products (two limb chains per component, the running sum rides as the
-// addend of the reduction); the gate type only selects the two scalars (no divergent heavy code). The kernel is bound
+// Every contribution is +-beta, +-P or a small combination with P = beta * (a real scalar: the gathered operand or the
+// constant) -- prover.cpp:229-272 with Vv real -- so a gate costs one eq product (kept weakly canonical), ONE
+// real-scalar product (two limb chains per component) and a few additions into lazily folded sums; the gate type
+// only selects the additions (no divergent heavy code). The kernel is bound
 // by the latency of its dependent loads (CSR entry -> layer pointer -> gathered operand), so registers are kept low
 // (lazy 96-bit sums were slower here: fewer resident warps) and the layer pointers / sizes sit in shared memory.
 // Tried and dropped: one instance per lane (uniform control flow, but every lookup / gather / store of a warp then
@@ -355,25 +356,7 @@ VP_D F eq_at_acc_w(const EqTab& t, uint32_t idx, const F& acc) {   // acc + eq(i
     const u64 t_im = mad32(m.im1, v.re0, mad32(m.im0, v.re1, mad32(m.re1, v.im0, mul32(m.re0, v.im1))));
     return F{fp_reduce_ut_weak(u_re, t_re, acc.re), fp_reduce_ut_weak(u_im, t_im, acc.im)};
 }
-// the two real scalars of a gate: add[u] += beta * sA, mult[u] += beta * sM   (prover.cpp:229-272)
-VP_D void p1_scalars(uint32_t ty, u64 Vv, u64 c, u64& sA, u64& sM) {
-    sA = 0; sM = 1;
-    switch (ty) {
-        case T_ADD: sA = Vv; break;
-        case T_SUB: sA = fp_neg(Vv); break;
-        case T_ANTISUB: sA = Vv; sM = P - 1; break;
-        case T_MUL: sM = Vv; break;
-        case T_NAAB: sA = Vv; sM = fp_neg(Vv); break;
-        case T_ANTINAAB: sM = fp_sub(1, Vv); break;
-        case T_ADDC: sA = c; break;
-        case T_MULC: sM = c; break;
-        case T_COPY: break;
-        case T_NOT: sA = 1; sM = P - 1; break;
-        case T_XOR: sA = Vv; sM = fp_sub(1, fp_add(Vv, Vv)); break;
-        default: sM = 0; break;
-    }
-}
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, 4)
 k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
                    EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
                    const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
@@ -392,30 +375,54 @@ k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 cs
         if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // another rank owns this table entry
         F M = f_zero(), A = f_zero();
         const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
-        // software pipeline: the next entry's CSR words are loaded one iteration ahead, and the gathered operand and the
-        // two eq half-table entries are requested before any arithmetic of the iteration
-        uint32_t g0 = csr.g0[I.e_begin], tyl = csr.tyl[I.e_begin], v0 = csr.v0[I.e_begin];
-        for (uint32_t e = I.e_begin; e < e1; ++e) {
-            const int l = (int)(tyl >> 8) - 1;
+        // two-deep software pipeline: while entry e is computed, the gathered operand and the two eq half-table entries
+        // of entry e+1 are in flight and the CSR words of entry e+2 are being read
+        struct Ent { uint32_t g0, tyl, v0; };
+        struct Dat { u64 Vv; ulonglong2 ha, hb; };
+        auto rd_csr = [&](uint32_t e) { return Ent{csr.g0[e], csr.tyl[e], csr.v0[e]}; };
+        auto rd_dat = [&](const Ent& E) {
+            Dat d;
+            const int l = (int)(E.tyl >> 8) - 1;
             const uint32_t lc = l >= 0 ? (uint32_t)l : 0u;
-            const u64* vp_ = s_vals[lc] + 2 * ((size_t)k * s_sizes[lc] + v0);
-            u64 Vv;
-            asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(Vv) : "l"(vp_));   // real part of circuitValue[l][k * S_l + v0]
-            const uint32_t idx = k * S_cur + g0;
-            ulonglong2 ha, hb;
-            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(ha.x), "=l"(ha.y) : "l"(eqg.f + (idx & eqg.mask)));
-            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(hb.x), "=l"(hb.y) : "l"(eqg.s + (idx >> eqg.fh)));
-            const uint32_t ty = tyl & 0x7f, is_as = tyl & TY_ASSERT_BIT, g0c = g0;
-            if (e + 1 < e1) { g0 = csr.g0[e + 1]; tyl = csr.tyl[e + 1]; v0 = csr.v0[e + 1]; }
-            if (l < 0) Vv = 0;
-            F beta = f_mul_w(F{ha.x, ha.y}, F{hb.x, hb.y});
+            const u64* vp_ = s_vals[lc] + 2 * ((size_t)k * s_sizes[lc] + E.v0);
+            asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(d.Vv) : "l"(vp_));   // real part of circuitValue[l][k * S_l + v0]
+            const uint32_t idx = k * S_cur + E.g0;
+            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(d.ha.x), "=l"(d.ha.y) : "l"(eqg.f + (idx & eqg.mask)));
+            asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(d.hb.x), "=l"(d.hb.y) : "l"(eqg.s + (idx >> eqg.fh)));
+            return d;
+        };
+        Ent cur = rd_csr(I.e_begin), nxt = I.e_begin + 1 < e1 ? rd_csr(I.e_begin + 1) : cur;
+        Dat dc = rd_dat(cur), dn = dc;
+        for (uint32_t e = I.e_begin; e < e1; ++e) {
+            if (e + 1 < e1) dn = rd_dat(nxt);
+            const Ent nn = e + 2 < e1 ? rd_csr(e + 2) : nxt;
+            const int l = (int)(cur.tyl >> 8) - 1;
+            const uint32_t ty = cur.tyl & 0x7f, is_as = cur.tyl & TY_ASSERT_BIT, g0c = cur.g0;
+            const u64 Vv = l < 0 ? 0 : dc.Vv;
+            F beta = f_mul_w(F{dc.ha.x, dc.ha.y}, F{dc.hb.x, dc.hb.y});
             if (is_as) beta = f_mul(beta, *assert_r);
-            u64 sA, sM;
-            p1_scalars(ty, Vv, (ty == T_ADDC || ty == T_MULC) ? cst[g0c].re : 0, sA, sM);
-            A = f_mad_real_w(A, beta, sA);
-            M = f_mad_real_w(M, beta, sM);
+            cur = nxt; nxt = nn; dc = dn;
+            // one product P = beta * x per gate (x = the gathered operand or the constant), the rest are additions of
+            // beta, P and their negations into lazily folded sums (components stay below 2^63)
+            const u64 x = (ty == T_ADDC || ty == T_MULC) ? cst[g0c].re : Vv;
+            F Pp = f_zero();
+            if (ty != T_COPY && ty != T_NOT) Pp = f_mad_real_w(f_zero(), beta, x);
+            const F nP = F{P - Pp.re, P - Pp.im}, nB = F{P - beta.re, P - beta.im};
+            switch (ty) {   // prover.cpp:229-272
+                case T_ADD: case T_ADDC: A.re += Pp.re; A.im += Pp.im; M.re += beta.re; M.im += beta.im; break;
+                case T_SUB: A.re += nP.re; A.im += nP.im; M.re += beta.re; M.im += beta.im; break;
+                case T_ANTISUB: A.re += Pp.re; A.im += Pp.im; M.re += nB.re; M.im += nB.im; break;
+                case T_MUL: case T_MULC: M.re += Pp.re; M.im += Pp.im; break;
+                case T_NAAB: A.re += Pp.re; A.im += Pp.im; M.re += nP.re; M.im += nP.im; break;
+                case T_ANTINAAB: M.re += beta.re + nP.re; M.im += beta.im + nP.im; break;
+                case T_COPY: M.re += beta.re; M.im += beta.im; break;
+                case T_NOT: A.re += beta.re; A.im += beta.im; M.re += nB.re; M.im += nB.im; break;
+                case T_XOR: A.re += Pp.re; A.im += Pp.im; M.re += beta.re + 2 * nP.re; M.im += beta.im + 2 * nP.im; break;
+                default: break;
+            }
+            A.re = fp_fold(A.re); A.im = fp_fold(A.im); M.re = fp_fold(M.re); M.im = fp_fold(M.im);   // <= p + 7
         }
-        const F Mr = f_strict(M), Ar = f_strict(A);
+        const F Mr = F{fp_canon(M.re), fp_canon(M.im)}, Ar = F{fp_canon(A.re), fp_canon(A.im)};
         const uint32_t slot = I.cnt_slot >> 8;
         if (slot == 0) {
             if (write_v) st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));

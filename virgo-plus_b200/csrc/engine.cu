@@ -486,6 +486,21 @@ static void add_rows(ItemPlan& P, const std::vector<uint32_t>& off, uint32_t tab
     }
 }
 
+// Threads take consecutive items, and an item's loop runs (cnt & 0xff) times: order the items of every window of
+// `window` consecutive items by length, so that the 32 items of a warp have (nearly) the same trip count. Fan-in is
+// skewed (SHA256: mean 2-5), unsorted warps keep only 21-26 of 32 lanes busy. The window keeps a block's stores
+// within a few KB of each other (row order inside a window does not matter: an item carries its row).
+static void sort_items_by_length(std::vector<RowItem>& items) {
+    const char* e = getenv("VP_ITEM_SORT_WINDOW");
+    const size_t window = e ? (size_t)atoi(e) : 8192;
+    if (window < 2) return;
+    for (size_t b = 0; b < items.size(); b += window) {
+        const size_t end = std::min(items.size(), b + window);
+        std::stable_sort(items.begin() + b, items.begin() + end,
+                         [](const RowItem& x, const RowItem& y) { return (x.cnt_slot & 0xff) > (y.cnt_slot & 0xff); });
+    }
+}
+
 // ------------------------------------------------------------------ per-layer device data
 struct LayerDev {
     uint32_t S = 0;
@@ -514,7 +529,7 @@ struct LayerDev {
     DBuf<uint8_t> un_ty;
     uint32_t n_unary = 0;
     // Liu (tables into layer pre = i-1 from all layers j >= i)
-    DBuf<uint32_t> liu_off;
+    DBuf<uint32_t> liu_off, liu_perm;
     DBuf<LiuEntry> liu_ent;
     std::vector<int> liu_j;      // source layers j of the eq tables, in eq_id order
     // plans
@@ -1004,6 +1019,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             }
             ItemPlan ip;
             add_rows(ip, off, 0);
+            sort_items_by_length(ip.items);
             D.p1_items.upload(ip.items, stream);
             D.p1_long.upload(ip.longs, stream);
             D.p1_nslots = ip.n_slots;
@@ -1092,6 +1108,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
                 add_rows(ip, off, (uint32_t)ptabs.size());
                 ptabs.push_back(pt);
             }
+            sort_items_by_length(ip.items);
             D.p2_items.upload(ip.items, stream);
             D.p2_long.upload(ip.longs, stream);
             D.p2_nslots = ip.n_slots;
@@ -1146,6 +1163,17 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             }
             D.liu_off.upload(off, stream);
             D.liu_ent.upload(ent, stream);
+            {   // same idea as sort_items_by_length: entries of a window ordered by their number of scattered terms
+                const char* ev = getenv("VP_ITEM_SORT_WINDOW");
+                const size_t window = ev ? (size_t)atoi(ev) : 8192;
+                std::vector<uint32_t> perm(S_pre);
+                for (uint32_t x = 0; x < S_pre; ++x) perm[x] = x;
+                if (window >= 2 && world == 1)
+                    for (size_t b = 0; b < S_pre; b += window)
+                        std::stable_sort(perm.begin() + b, perm.begin() + std::min<size_t>(S_pre, b + window),
+                                         [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; });
+                D.liu_perm.upload(perm, stream);
+            }
             // lane 1's copy of beta_u is only used by Liu: bake s[0] in. Its descriptors sit right before the Liu tables'
             // so that one k_eq_build launch covers both.
             D.eqb_u1 = (uint32_t)eq_descs.size();
@@ -1483,7 +1511,7 @@ void Engine::do_init_liu(int i, bool write_a) {
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
-        D.liu_off.p, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
+        D.liu_off.p, world == 1 ? D.liu_perm.p : nullptr, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
         bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
         write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1);
     prof_end(h, (double)n_local * ((write_a ? 64.0 : 48.0) - (direct_v ? 32.0 : 0.0)));

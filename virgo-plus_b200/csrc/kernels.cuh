@@ -667,13 +667,18 @@ struct LiuEntry {       // one (j, slot0) pair pointing at template u0
     uint32_t D;         // subset size of one instance (for the reversed instance order)
 };
 __global__ void __launch_bounds__(256)
-k_init_liu(const uint32_t* __restrict__ off, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
+k_init_liu(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
            uint32_t S_pre, uint32_t K, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
            F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, ShardMap sm, uint32_t n_local, int write_a,
            int equ_scaled, int write_v) {
     const uint32_t n = S_pre * K;
     const F s0 = *s0_ptr;
-    for (uint32_t loc = blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += gridDim.x * blockDim.x) {
+    for (uint32_t loc0 = blockIdx.x * blockDim.x + threadIdx.x; loc0 < n_local; loc0 += gridDim.x * blockDim.x) {
+        uint32_t loc = loc0;
+        if (perm) {   // unsharded: visit the entries of an instance in length-sorted order (uniform trip counts per warp)
+            const uint32_t kq = loc0 / S_pre;
+            loc = kq * S_pre + perm[loc0 - kq * S_pre];
+        }
         const uint32_t u = shard_global(sm, loc);
         if (u >= n) continue;
         const uint32_t k = u / S_pre, u0 = u - k * S_pre;

@@ -391,8 +391,11 @@ k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 cs
             asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(d.hb.x), "=l"(d.hb.y) : "l"(eqg.s + (idx >> eqg.fh)));
             return d;
         };
-        Ent cur = rd_csr(I.e_begin), nxt = I.e_begin + 1 < e1 ? rd_csr(I.e_begin + 1) : cur;
-        Dat dc = rd_dat(cur), dn = dc;
+        Ent cur{0, 0, 0};
+        Dat dc{0, {0, 0}, {0, 0}};
+        if (I.e_begin < e1) { cur = rd_csr(I.e_begin); dc = rd_dat(cur); }   // a row without gates reads nothing
+        Ent nxt = I.e_begin + 1 < e1 ? rd_csr(I.e_begin + 1) : cur;
+        Dat dn = dc;
         for (uint32_t e = I.e_begin; e < e1; ++e) {
             if (e + 1 < e1) dn = rd_dat(nxt);
             const Ent nn = e + 2 < e1 ? rd_csr(e + 2) : nxt;

@@ -793,6 +793,7 @@ struct Engine {
     }
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
+    int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: the init kernels use the real-scalar lazy products
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
@@ -893,6 +894,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     dfs_enable_smem();
     cap_dfs = std::min({occ_cap(k_phase_dfs<true, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_VREAL>, DFS_THREADS, DFS_DYN_SMEM),
                         occ_cap(k_phase_dfs<true, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM), occ_cap(k_phase_dfs<false, DFS_PLAIN>, DFS_THREADS, DFS_DYN_SMEM)});
+    if (getenv("VP_DFS_GRID")) dfs_grid_override = atoi(getenv("VP_DFS_GRID"));
     if (getenv("VP_DFS_CAP")) cap_dfs = std::max(2, std::min(cap_dfs, atoi(getenv("VP_DFS_CAP"))));
     if (getenv("VP_ONE_ROUND_PER_PASS")) use_dfs = false;
     values_real = true;
@@ -1625,7 +1627,8 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     // this one is down to its small passes
     // three lanes: two of the three block slots of an SM, so that the other lanes' kernels (gather-latency bound inits,
     // another phase's passes) are co-resident with a compute-bound pass (measured: C3 13.3 -> 12.9 ms)
-    const uint32_t cap = three_lanes ? (uint32_t)std::max(2, 2 * cap_dfs / 3) : two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
+    uint32_t cap = three_lanes ? (uint32_t)std::max(2, 2 * cap_dfs / 3) : two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
+    if (dfs_grid_override) cap = std::max<uint32_t>(2, std::min<uint32_t>((uint32_t)dfs_grid_override, (uint32_t)cap_dfs));
     // block 0 coordinates, blocks 1.. work; a phase that fits one block runs on block 0 alone
     const int grid = P.max_work <= DFS_CHUNK ? 1 : (int)std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK) + 1, std::max<uint32_t>(cap, 2));
     void* args[] = {&a};

@@ -656,7 +656,7 @@ struct Engine {
         on_lane2 = !on_lane2;
     }
     bool two_lanes = false, on_lane1 = false;
-    bool direct_v = false;   // whole-proof, unsharded: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
+    bool direct_v = false;   // whole-proof: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
     cudaEvent_t ev_eval = nullptr, ev_lane1 = nullptr;
     uint32_t region_u_lane1 = 0;
     void swap_lane() {
@@ -1652,7 +1652,10 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
     // stage A: partial polynomials, add_term and claims go straight into the record's scalar region
-    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, values_real ? DFS_VREAL : DFS_PLAIN);
+    // phase 1 / Liu (one table over layer i-1): the local rows [lo, hi) of V are read straight from circuitValue[i-1]
+    const F* v_local = (v_first && P.maps.size() == 1 && P.tab_off[0] == 0) ? v_first + P.maps[0].lo : nullptr;
+    if (v_first && !v_local) throw CudaError{"direct V: unexpected table layout"};
+    launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, values_real ? DFS_VREAL : DFS_PLAIN, v_local);
     if (P.n_fo) {
         const FoldOnlyDesc& f0 = arena.fo[P.fo_begin];
         dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), P.n_fo);
@@ -1893,7 +1896,7 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
-    direct_v = world == 1 && use_phase_kernel && use_dfs;
+    direct_v = use_phase_kernel && use_dfs;   // phase 1 / Liu read V from circuitValue[i-1] (sharded: the rank's rows of it)
     evaluate();
     if (two_lanes && use_phase_kernel && use_dfs) {   // fork: lane 1 needs the circuit values (and the uploaded challenges)
         CK(cudaEventRecord(ev_eval, stream));

@@ -797,8 +797,9 @@ struct Engine {
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
     int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
+    bool old_p2 = false;
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
-    bool lane_init = false;    // base-field values: the init kernels use the real-scalar lazy products
+    bool lane_init = false;    // base-field values: phase-1 init uses the one-real-product-per-gate kernel
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
     template <class Kern>
     int occ_cap(Kern k, int threads = 256, size_t dyn_smem = 0) {  // resident blocks on the whole chip
@@ -911,6 +912,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         for (size_t g = 0; g < T.c.size() && g < T.ty.size(); ++g)
             if ((T.ty[g] == T_ADDC || T.ty[g] == T_MULC) && T.c[g].im != 0) values_real = false;
     lane_init = values_real && !getenv("VP_NO_LANE_INIT");
+    old_p2 = getenv("VP_OLD_P2") != nullptr;   // development knob: the five-products-per-gate phase-2 init
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1515,7 +1517,7 @@ void Engine::do_init_phase2(int i) {
         const uint32_t kk0 = D.ph2.sharded ? D.p2_kk0 : 0, kk1 = D.ph2.sharded ? D.p2_kk1 : K;
         const uint64_t work = (uint64_t)D.p2_items.n * (kk1 - kk0);
         size_t h = prof_begin(KC_INIT2);
-        if (work < 0xffffffffull && !getenv("VP_OLD_P2"))
+        if (work < 0xffffffffull && !old_p2)
             k_init_phase2_v2<<<grid_for((uint32_t)work, cap_p2v2), 256, 0, stream>>>(
                 D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
                 Vu, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);

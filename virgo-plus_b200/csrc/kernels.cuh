@@ -1227,11 +1227,6 @@ VP_D void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_size) {
 }
 VP_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 VP_D void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-VP_D F lds_f(uint32_t smem_addr) {
-    F r;
-    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(r.re), "=l"(r.im) : "r"(smem_addr) : "memory");
-    return r;
-}
 
 template <bool HAS_A, bool VREAL, bool NEED_B>
 VP_D void dfs_work(PassAcc& acc1, PassAcc2& acc2, PassAccB* accb, const PassTab* __restrict__ tabs, uint32_t n_tabs,
@@ -1242,7 +1237,7 @@ VP_D void dfs_work(PassAcc& acc1, PassAcc2& acc2, PassAccB* accb, const PassTab*
                    uint32_t share /* items of the static chunk (multiple of 32, <= DFS_WCHUNK) */) {
     const uint32_t total = n_tabs ? s_wend[n_tabs - 1] : 0;   // multiple of 32
     const bool solo = static_base != 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     // ---- sub-chunk stream of this warp
     uint32_t c_cur, c_next = 0, sub = 0;
     if (solo) c_cur = static_base;

@@ -797,7 +797,8 @@ struct Engine {
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
     int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
-    bool old_p2 = false;
+    bool old_p2 = false, getenv_no_hs = false;
+    DBuf<F> d_hs;   // phase-2 init: products of the second-half eq factors, K * ng * nu entries (k_p2_hs)
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: phase-1 init uses the one-real-product-per-gate kernel
     int cap_round = 0, cap_round1 = 0, cap_eval = 0, cap_p1 = 0, cap_p2 = 0, cap_un = 0, cap_liu = 0, cap_dot = 0, cap_comb = 0, cap_phase = 0;
@@ -912,7 +913,9 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         for (size_t g = 0; g < T.c.size() && g < T.ty.size(); ++g)
             if ((T.ty[g] == T_ADDC || T.ty[g] == T_MULC) && T.c[g].im != 0) values_real = false;
     lane_init = values_real && !getenv("VP_NO_LANE_INIT");
-    old_p2 = getenv("VP_OLD_P2") != nullptr;   // development knob: the five-products-per-gate phase-2 init
+    old_p2 = getenv("VP_OLD_P2") != nullptr;
+    getenv_no_hs = getenv("VP_NO_HS") != nullptr;
+    d_hs.alloc((size_t)K * 64);   // development knob: the five-products-per-gate phase-2 init
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1517,10 +1520,19 @@ void Engine::do_init_phase2(int i) {
         const uint32_t kk0 = D.ph2.sharded ? D.p2_kk0 : 0, kk1 = D.ph2.sharded ? D.p2_kk1 : K;
         const uint64_t work = (uint64_t)D.p2_items.n * (kk1 - kk0);
         size_t h = prof_begin(KC_INIT2);
-        if (work < 0xffffffffull && !old_p2)
+        if (work < 0xffffffffull && !old_p2) {
+            // few distinct second-half eq factors per instance: tabulate their products (k_p2_hs), two products per gate
+            HsTab H{nullptr, 0, 0};
+            const uint32_t ng = (D.S >> eqg.fh) + 2, nu = (S_pre >> equ.fh) + 2;
+            if (K >= 8 && (uint64_t)ng * nu <= 64 && (uint64_t)K * ng * nu <= d_hs.n && !getenv_no_hs) {
+                H = HsTab{d_hs.p, ng, nu};
+                k_p2_hs<<<grid_for(K * ng * nu, cap_dot), 256, 0, stream>>>(eqg, equ, D.S, S_pre, K, ng, nu, d_hs.p);
+                ++launches;
+            }
             k_init_phase2_v2<<<grid_for((uint32_t)work, cap_p2v2), 256, 0, stream>>>(
                 D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,
-                Vu, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1);
+                Vu, bufV[0].p, bufM[0].p, bufA[0].p, d_rowpart.p, D.p2_nslots, kk0, kk1, H);
+        }
         else
         k_init_phase2<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p2), 256, 0, stream>>>(
             D.p2_items.p, (uint32_t)D.p2_items.n, D.p2_tabs.p, csr, S_pre, D.S, K, eqg, equ, d_chal.p + D.ci_assert,

@@ -562,11 +562,29 @@ VP_D void p2_accumulate(uint32_t ty, const F& t, F& S0, F& S1, F& SA) {
         default: break;
     }
 }
+// Replicated circuits: eq(r, k*S + g0) = f[idx & mask] * s[idx >> fh], and within ONE instance idx >> fh only takes
+// (S >> fh) + 2 consecutive values (SHA256_64 x 1024: at most 6). The product of the two second-half factors of a gate,
+// s_g[ig] * s_u[iu], is therefore one of ng*nu values per instance: k_p2_hs tabulates them once per layer
+// (HS[(k*ng + i)*nu + j]) and a gate needs two products (f_g*f_u, then * HS) instead of three.
+struct HsTab {
+    const F* hs;           // null: not used (too many distinct factors per instance, e.g. one huge instance)
+    uint32_t ng, nu;
+};
+__global__ void k_p2_hs(EqTab eqg, EqTab equ, uint32_t S_cur, uint32_t S_pre, uint32_t K, uint32_t ng, uint32_t nu, F* __restrict__ hs) {
+    const uint32_t ig_max = (K * S_cur - 1) >> eqg.fh, iu_max = (K * S_pre - 1) >> equ.fh;   // last second-half entries in use
+    const uint32_t per = ng * nu, total = K * per;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const uint32_t k = w / per, r = w - k * per, i = r / nu, j = r - i * nu;
+        const uint32_t ig = ((k * S_cur) >> eqg.fh) + i, iu = ((k * S_pre) >> equ.fh) + j;
+        // (i, j) combinations past the last entry in use belong to no gate: any value will do, but stay inside the tables
+        st_f(hs + w, f_mul(ld_f(eqg.s + min(ig, ig_max)), ld_f(equ.s + min(iu, iu_max))));
+    }
+}
 __global__ void __launch_bounds__(256, 4)
 k_init_phase2_v2(const RowItem* __restrict__ items, uint32_t n_items, const P2Table* __restrict__ tabs, CsrP2 csr,
                  uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, const F* __restrict__ assert_r,
                  const F* __restrict__ Vu_ptr, F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA,
-                 F* __restrict__ partial, uint32_t n_slots, uint32_t kk_begin, uint32_t kk_end) {
+                 F* __restrict__ partial, uint32_t n_slots, uint32_t kk_begin, uint32_t kk_end, HsTab H) {
     const F Vu = *Vu_ptr;
     const uint32_t total = n_items * (kk_end - kk_begin);   // < 2^32 (host check)
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
@@ -579,9 +597,18 @@ k_init_phase2_v2(const RowItem* __restrict__ items, uint32_t n_items, const P2Ta
         const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
         for (uint32_t e = I.e_begin; e < e1; ++e) {
             const uint32_t g0 = csr.g0[e], tyb = csr.ty[e], u0 = csr.u0[e];
-            F bg = eq_at_weak(eqg, k * S_cur + g0);
-            if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
-            const F t = f_mul_w(bg, eq_at_weak(equ, k * S_pre + u0));
+            F t;
+            if (H.hs) {
+                const uint32_t ig = k * S_cur + g0, iu = k * S_pre + u0;
+                const uint32_t i = (ig >> eqg.fh) - ((k * S_cur) >> eqg.fh), j = (iu >> equ.fh) - ((k * S_pre) >> equ.fh);
+                const F ff = f_mul_w(ld_f(eqg.f + (ig & eqg.mask)), ld_f(equ.f + (iu & equ.mask)));
+                t = f_mul_w(ff, ld_f(H.hs + (k * H.ng + i) * H.nu + j));
+                if (tyb & TY_ASSERT_BIT) t = f_mul(t, *assert_r);
+            } else {
+                F bg = eq_at_weak(eqg, k * S_cur + g0);
+                if (tyb & TY_ASSERT_BIT) bg = f_mul(bg, *assert_r);
+                t = f_mul_w(bg, eq_at_weak(equ, k * S_pre + u0));
+            }
             p2_accumulate(tyb & 0x7f, t, S0, S1, SA);
         }
         const F M = f_strict(f_add_w(S0, f_mul_w(S1, Vu))), A = f_strict(f_mul_w(SA, Vu));

@@ -157,6 +157,13 @@ double vp_prove_seconds(const vp_ctx* ctx);
 int vp_set_challenges(vp_ctx* ctx, const vp_F* challenges, size_t n);
 int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
              size_t n_challenges, vp_F* transcript, size_t transcript_cap);
+/* Self-test of the device-only arithmetic paths of csrc/field.cuh (inline-PTX carry chains, mul.wide / mad.wide):
+   runs one routine on n caller-provided operand triples and returns the results, so that tests can feed edge values
+   (0, 1, p-1, p, limb boundaries) and compare with big-integer arithmetic.  op: 0 weak fold a + c*(b-a); 1 the same for
+   base-field a, b; 2 lazy dot product sum a_i*b_i -> out[0]; 3 {fp_reduce_ut_weak(a.re, a.im, b.re), fp_weak(b.im)};
+   4 c + a*b (weak); 5 c + a*b.re (weak); 6 lazy sum (b_i - a_i)*c_i.re -> out[0]; 7 like 0 with the folded difference. */
+int vp_selftest_field(int device, int op, const vp_F* a, const vp_F* b, const vp_F* c, vp_F* out, size_t n);
+
 /* Verifier: replaces verifier::verify's checks, src/verifier.cpp:134-337, on a finished transcript:
    the O(#gates) sums of predicatePhase1/2 (:63-113) and verifyLiu's gr (:311-323) run on the device, the round
    checks / getFinalValue (:115-132) / Liu check on the host. Uses the context's circuit, its resident inputs

@@ -412,3 +412,75 @@ def test_lane_settings_give_identical_transcripts(B, sha_circuit):
         p.prove()
         _assert_same(p.transcript(), want, f"{lanes} lane(s), resident")
     p.close()
+
+
+# ------------------------------------------------------------------ device-only arithmetic paths, edge values
+def test_device_field_primitives_edge_values(B):
+    """fp_reduce_ut_weak / a96_add / mul.wide paths exist only in the device build of field.cuh: feed them 0, 1, p-1, p
+    (the weak alias of 0), limb boundaries and random values through vp_selftest_field and compare with Python ints."""
+    P = B.P
+    edge = [0, 1, 2, P - 1, P - 2, P, (1 << 60), (1 << 60) - 1, (1 << 31) - 1, 1 << 31, (1 << 31) + 1, (1 << 32) - 1, 1 << 32,
+            (1 << 30), (1 << 61) - (1 << 31), (1 << 61) - (1 << 31) - 1, 0x7FFFFFFF7FFFFFFF % P]
+    rng = np.random.default_rng(99)
+    vals = edge + [int(x) for x in rng.integers(0, P, 48, dtype=np.uint64)]
+    n = 20000
+
+    def arr(canonical=False):
+        pool = [v for v in vals if not (canonical and v == P)]
+        a = np.zeros(n, B.F_DTYPE)
+        a["re"] = rng.choice(np.array(pool, dtype=np.uint64), n)
+        a["im"] = rng.choice(np.array(pool, dtype=np.uint64), n)
+        return a
+
+    cm = lambda x, y: ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+    t = lambda x: (int(x["re"]), int(x["im"]))
+    a, b, c = arr(), arr(), arr(canonical=True)
+    for op in (0, 7):   # weak fold a + c * (b - a)
+        out = B.selftest_field(op, a, b, c)
+        assert int(out["re"].max()) <= P and int(out["im"].max()) <= P
+        for i in range(0, n, 7):
+            d = ((t(b[i])[0] - t(a[i])[0]) % P, (t(b[i])[1] - t(a[i])[1]) % P)
+            m = cm(d, t(c[i]))
+            assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == ((t(a[i])[0] + m[0]) % P, (t(a[i])[1] + m[1]) % P), (op, i)
+    out = B.selftest_field(1, a, b, c)   # base-field data
+    for i in range(0, n, 7):
+        d = (int(b[i]["re"]) - int(a[i]["re"])) % P
+        want = ((int(a[i]["re"]) + d * int(c[i]["re"])) % P, (d * int(c[i]["im"])) % P)
+        assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == want, i
+    out = B.selftest_field(4, a, b, c)   # c + a * b
+    assert int(out["re"].max()) <= P and int(out["im"].max()) <= P
+    for i in range(0, n, 7):
+        m = cm(t(a[i]), t(b[i]))
+        assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == ((m[0] + t(c[i])[0]) % P, (m[1] + t(c[i])[1]) % P), i
+    out = B.selftest_field(5, a, b, c)   # c + a * b.re
+    for i in range(0, n, 7):
+        br = int(b[i]["re"])
+        assert (int(out[i]["re"]) % P, int(out[i]["im"]) % P) == ((t(a[i])[0] * br + t(c[i])[0]) % P, (t(a[i])[1] * br + t(c[i])[1]) % P), i
+    # any 64-bit words through the 96-bit carry-chain reduction
+    big = [0, 1, P, P + 1, 2 * P, (1 << 64) - 1, (1 << 64) - 2, 1 << 63, (1 << 62) - 1, 1 << 61, 3 * P, 7 * P] + \
+          [int(x) for x in rng.integers(0, 1 << 64, 40, dtype=np.uint64)]
+    u = np.zeros(n, B.F_DTYPE)
+    w = np.zeros(n, B.F_DTYPE)
+    pick = lambda: np.array([big[k] for k in rng.integers(0, len(big), n)], dtype=np.uint64)
+    u["re"], u["im"], w["re"], w["im"] = pick(), pick(), pick(), pick()
+    out = B.selftest_field(3, u, w, c)
+    assert int(out["re"].max()) <= P and int(out["im"].max()) <= P
+    for i in range(0, n, 5):
+        assert int(out[i]["re"]) % P == (int(u[i]["re"]) + (int(u[i]["im"]) << 31) + int(w[i]["re"])) % P, i
+        assert int(out[i]["im"]) % P == int(w[i]["im"]) % P, i
+    # lazy sums: worst-case magnitudes first
+    for m_ in (1, 2, 9, 4000):
+        a2, b2, c2 = arr()[:m_].copy(), arr()[:m_].copy(), arr()[:m_].copy()
+        a2["re"][0] = a2["im"][0] = b2["re"][0] = b2["im"][0] = P
+        out = B.selftest_field(2, a2, b2, c2)
+        acc = [0, 0]
+        for i in range(m_):
+            mm = cm(t(a2[i]), t(b2[i]))
+            acc = [(acc[0] + mm[0]) % P, (acc[1] + mm[1]) % P]
+        assert t(out[0]) == tuple(acc), m_
+        out = B.selftest_field(6, a2, b2, c2)
+        acc = [0, 0]
+        for i in range(m_):
+            d = ((t(b2[i])[0] - t(a2[i])[0]) % P, (t(b2[i])[1] - t(a2[i])[1]) % P)
+            acc = [(acc[0] + d[0] * int(c2[i]["re"])) % P, (acc[1] + d[1] * int(c2[i]["re"])) % P]
+        assert t(out[0]) == tuple(acc), m_

@@ -110,6 +110,7 @@ def _declare(L):
     L.vp_stream.argtypes = [vp]
     L.vp_set_stream.argtypes = [vp, vp]
     L.vp_set_profiling.argtypes = [vp, C.c_int]
+    L.vp_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.vp_verify.argtypes = [vp, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.vp_set_lanes.argtypes = [vp, C.c_int]
     L.vp_set_lanes.restype = C.c_int
@@ -334,6 +335,13 @@ class Circuit:
 def nccl_unique_id():
     out = np.zeros(128, np.uint8)
     _ck(lib().vp_nccl_unique_id(_ptr(out)))
+    return out
+
+
+def selftest_field(op, a, b, c, device=0):
+    a, b, c = (np.ascontiguousarray(x, dtype=F_DTYPE) for x in (a, b, c))
+    out = np.zeros(len(a), F_DTYPE)
+    _ck(lib().vp_selftest_field(device, op, _ptr(a), _ptr(b), _ptr(c), _ptr(out), len(a)))
     return out
 
 

@@ -2585,6 +2585,26 @@ extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t
     return VP_OK;
     API_END
 }
+extern "C" int vp_selftest_field(int device, int op, const vp_F* a, const vp_F* b, const vp_F* c, vp_F* out, size_t n) {
+    if (!a || !b || !c || !out || n == 0 || n > (1u << 24) || op < 0 || op > 7) return fail(VP_ERR_ARG, "bad argument");
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw CudaError{std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e)};
+    CK(cudaSetDevice(device));
+    DBuf<F> da, db, dc, dout;
+    da.alloc(n); db.alloc(n); dc.alloc(n); dout.alloc(n);
+    CK(cudaMemcpy(da.p, a, n * sizeof(F), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db.p, b, n * sizeof(F), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, c, n * sizeof(F), cudaMemcpyHostToDevice));
+    CK(cudaMemset(dout.p, 0, n * sizeof(F)));
+    k_selftest_field<<<cdiv((uint32_t)n, 128), 128>>>(op, da.p, db.p, dc.p, dout.p, (uint32_t)n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, n * sizeof(F), cudaMemcpyDeviceToHost));
+    return VP_OK;
+    API_END
+}
 extern "C" int vp_verify(vp_ctx* ctx, const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer) {
     if (!ctx || !transcript || !accept) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN

@@ -1849,6 +1849,38 @@ k_verify_gr(const VfLiuSeg* __restrict__ segs, const EqTab* __restrict__ eqs, Eq
     }
 }
 
+// ------------------------------------------------------------------ self-test of the device-only arithmetic paths
+// field.cuh compiles for host and device, but the carry-chain routines (fp_reduce_ut_weak, a96_add) and mul32/mad32
+// take inline-PTX paths on the device that the host build (tests/native) cannot exercise. vp_selftest_field runs them
+// on caller-provided operands so that tests can feed the edge values (0, 1, p-1, p, limb boundaries) that random
+// transcripts practically never contain, and compare with big-integer arithmetic.
+__global__ void k_selftest_field(int op, const F* __restrict__ a, const F* __restrict__ b, const F* __restrict__ c,
+                                 F* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (op == 2 || op == 6) {   // lazy dot products over all n operands, one thread
+        if (i != 0) return;
+        CAcc s = cacc_zero();
+        for (uint32_t j = 0; j < n; ++j) {
+            if (op == 2) cacc_mad(s, make_lop(a[j].re, a[j].im), make_ropd(b[j]));
+            else cacc_mad_real(s, f_diff2p(a[j], b[j]), c[j].re);
+        }
+        st_f(out, cacc_reduce(s));
+        return;
+    }
+    if (i >= n) return;
+    F r = f_zero();
+    switch (op) {
+        case 0: r = f_fold_w(a[i], f_diff2p(a[i], b[i]), make_constk(c[i])); break;
+        case 1: r = f_fold_w_real(a[i].re, fp_weak(b[i].re + P - a[i].re), make_constk(c[i])); break;
+        case 3: r = F{fp_reduce_ut_weak(a[i].re, a[i].im, b[i].re), fp_weak(b[i].im)}; break;
+        case 4: r = f_mul_add_w(a[i], b[i], c[i]); break;
+        case 5: r = f_mad_real_w(c[i], a[i], b[i].re); break;
+        case 7: r = f_fold_w(a[i], f_diff_w(a[i], b[i]), make_constk(c[i])); break;
+        default: break;
+    }
+    st_f(out + i, r);
+}
+
 // ------------------------------------------------------------------ misc
 // SplitMix64-filled random table entries (limbs uniform in [0,p) by rejection), config C2.
 __global__ void k_fill_random(F* __restrict__ T, uint32_t n, uint64_t seed) {

@@ -108,6 +108,9 @@ void vp_destroy(vp_ctx* ctx);
 int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int phase, uint32_t* out, size_t cap,
                       size_t* n_tables);
 /* Host-only: index map of a rank holding the table entries [lo, hi): returns 1 and *local if idx belongs to it. */
+/* Host-only (no device needed): the instances [lo[l], hi[l]) of layer l that `rank` of a `world`-GPU sharded context
+   evaluates -- the hull of what its tables read from layer l and from every layer above it. lo, hi: n_layers entries. */
+int vp_shard_eval_ranges(const vp_circuit* c, int world, int rank, uint32_t* lo, uint32_t* hi);
 int vp_shard_map_index(uint32_t lo, uint32_t hi, uint32_t idx, uint32_t* local);
 
 /* Upload the witness inputs (instances * layer_size(0) values < p); default: the circuit's own. */

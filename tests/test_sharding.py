@@ -87,6 +87,75 @@ def test_shard_plan_covers_every_table_entry_once_gloo(world):
     assert all(n > 0 for _, _, n in res), "SHA256_64 x 64 must have sharded phases"
 
 
+def _ranges_worker(rank, world, port, K, q):
+    """one gloo process = one rank: its per-layer evaluate ranges must cover everything its tables read"""
+    import lzma
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    B = entry.binding()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "SHA256_64.pws.xz"), "rb") as f:
+        circ = B.Circuit.from_pws_text(f.read()).replicate(K)
+    n = circ.n_layers
+    lo, hi = B.shard_eval_ranges(circ, world, rank)
+    ok = True
+    own = (K * rank // world, K * (rank + 1) // world)
+    ok &= all(lo[l] <= own[0] and hi[l] >= own[1] for l in range(n))             # every layer covers the rank's own slice
+    ok &= all(lo[l] <= lo[l + 1] and hi[l] >= hi[l + 1] for l in range(n - 1))   # a layer needs whatever the layers above need
+    ok &= all(hi[l] <= K for l in range(n))
+    for i in range(1, n):
+        for ph in (1, 2, 3):
+            tabs = B.shard_describe(circ, world, rank, i, ph)
+            srcs = None
+            if ph == 2:
+                ds = [(l, circ.dad_size(i, l)) for l in range(i) if circ.dad_size(i, l) > 0]
+                ds.sort(key=lambda t: -max(0, (t[1] - 1).bit_length()))   # bits descending, stable by source layer
+                srcs = [l for l, _ in ds]
+            for ti, t in enumerate(tabs):
+                if t["row_hi"] <= t["row_lo"]:
+                    continue
+                per = t["live"] // K
+                a, b = t["row_lo"] // per, (t["row_hi"] - 1) // per + 1
+                if t["reversed"]:
+                    a, b = K - b, K - a
+                l = i - 1 if ph != 2 else srcs[ti]
+                ok &= bool(lo[l] <= a and hi[l] >= b)                            # the table's source layer is evaluated where it reads
+    S = [circ.layer_size(l) // K for l in range(n)]
+    evaluated = sum(S[l] * int(hi[l] - lo[l]) for l in range(1, n))
+    share = sum(S[1:]) * (own[1] - own[0])
+    # all ranks together cover every instance of every layer
+    t = torch.zeros(n, K, dtype=torch.int32)
+    for l in range(n):
+        t[l, int(lo[l]):int(hi[l])] = 1
+    dist.all_reduce(t)
+    ok &= bool((t >= 1).all())
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, ok, evaluated / share))
+
+
+@pytest.mark.parametrize("world,K", [(2, 64), (4, 256), (8, 8192)])
+def test_eval_ranges_cover_reads_and_stay_tight_gloo(world, K):
+    """host logic of the sharded context (vp_shard_eval_ranges, same code as vp_create_sharded), one gloo process per
+    rank: coverage of every table's reads, monotonicity over layers, and the regression guard for the wide low-layer
+    slice: a rank of SHA256_64 x 8192 over 8 GPUs evaluates at most 1.15x its own share of the gates"""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world + (os.getpid() % 200)
+    ps = [ctx.Process(target=_ranges_worker, args=(r, world, port, K, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert max(r for _, _, r in res) <= (1.15 if K >= 1024 else 2.5), res
+
+
 @pytest.mark.gpu
 def test_sharded_proof_matches_oracle_on_2_gpus():
     import torch

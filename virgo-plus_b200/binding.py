@@ -110,6 +110,7 @@ def _declare(L):
     L.vp_stream.argtypes = [vp]
     L.vp_set_stream.argtypes = [vp, vp]
     L.vp_set_profiling.argtypes = [vp, C.c_int]
+    L.vp_shard_eval_ranges.argtypes = [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.vp_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.vp_verify.argtypes = [vp, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.vp_set_lanes.argtypes = [vp, C.c_int]
@@ -351,6 +352,13 @@ def shard_describe(circuit, world, rank, layer, phase):
     _ck(lib().vp_shard_describe(circuit.h, world, rank, layer, phase, _ptr(out), len(out), C.byref(n)))
     keys = ("bits", "live", "sharded", "m", "row_lo", "row_hi", "local_len", "present", "n_blocks", "reversed")
     return [dict(zip(keys, (int(x) for x in out[10 * t:10 * t + 10]))) for t in range(n.value)]
+
+
+def shard_eval_ranges(circuit, world, rank):
+    n = circuit.n_layers
+    lo, hi = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    _ck(lib().vp_shard_eval_ranges(circuit.h, world, rank, _ptr(lo), _ptr(hi)))
+    return lo, hi
 
 
 def shard_map_index(lo, hi, idx):

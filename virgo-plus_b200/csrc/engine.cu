@@ -459,6 +459,76 @@ static SumcheckPlan build_plan(std::vector<PlanTable> tabs, int rounds, const st
     return P;
 }
 
+// ------------------------------------------------------------------ which instances a rank evaluates, per layer
+// direct[l] = instances whose layer-l values some table of this rank reads (phase 1 / Liu of layer l+1 read rows of
+// layer l; a phase-2 table (i, l) gathers from layer l; Vres / the input MLE use the rank's own slice). A layer must be
+// evaluated for the hull of direct[l'] over all l' >= l, because a gate reads from any lower layer. Small phase-2
+// tables with few blocks can hand one rank a wide slice of a LOW layer; the layers above it stay narrow.
+// ph(i, phase) returns the PhasePlan of layer i (phase 2 only asked for layers that have one); p2_src(i) the source
+// layer of each of its phase-2 tables.
+struct EvalRanges {
+    std::vector<uint32_t> lo, hi;                 // per layer
+    std::vector<uint32_t> p1_k0, p1_k1;           // per layer: instance range of the rank's phase-1 rows
+    std::vector<uint32_t> p2_kk0, p2_kk1;         // per layer: reversed-instance range of its phase-2 rows
+    uint32_t own_lo = 0, own_hi = 0;
+};
+template <class PlanOf, class SrcOf>
+static EvalRanges compute_eval_ranges(const Circuit& C, uint32_t K, int world, int rank, PlanOf ph, SrcOf p2_src) {
+    const int n = C.n_layers();
+    EvalRanges R;
+    R.own_lo = (uint32_t)((uint64_t)K * rank / world);
+    R.own_hi = (uint32_t)((uint64_t)K * (rank + 1) / world);
+    R.p1_k0.assign(n, 0); R.p1_k1.assign(n, 0); R.p2_kk0.assign(n, 0); R.p2_kk1.assign(n, 0);
+    std::vector<uint32_t> dlo(n, K), dhi(n, 0);
+    auto need = [&](int l, uint32_t a, uint32_t b) { if (b > a) { dlo[l] = std::min(dlo[l], a); dhi[l] = std::max(dhi[l], b); } };
+    need(n - 1, R.own_lo, R.own_hi);   // Vres
+    need(0, R.own_lo, R.own_hi);       // input MLE
+    for (int i = 1; i < n; ++i) {
+        const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
+        auto fwd = [&](const PhasePlan& P, uint32_t& a, uint32_t& b) {   // table over layer i-1: idx = k*S_pre + u0
+            a = K; b = 0;
+            if (P.row_hi[0] > P.row_lo[0]) { a = P.row_lo[0] / S_pre; b = (P.row_hi[0] - 1) / S_pre + 1; }
+        };
+        uint32_t a, b;
+        fwd(ph(i, 1), a, b);
+        R.p1_k0[i] = std::min(a, K); R.p1_k1[i] = std::max(b, R.p1_k0[i]);
+        need(i - 1, a, std::min(b, K));
+        fwd(ph(i, 3), a, b);
+        need(i - 1, a, std::min(b, K));
+        uint32_t kk0 = K, kk1 = 0;
+        if (C.max_dad_bit_length(i) != -1) {
+            const PhasePlan& P2 = ph(i, 2);
+            const std::vector<int>& src = p2_src(i);
+            for (size_t t = 0; t < src.size(); ++t) {
+                const uint32_t Dsz = (uint32_t)C.layers[i].dadSize[src[t]];
+                if (P2.row_hi[t] <= P2.row_lo[t]) continue;
+                const uint32_t kka = P2.row_lo[t] / Dsz, kkb = (P2.row_hi[t] - 1) / Dsz + 1;   // idx = kk*D + lv0, kk = K-1-k
+                kk0 = std::min(kk0, kka);
+                kk1 = std::max(kk1, kkb);
+                need(src[t], K - std::min(kkb, K), K - kka);
+            }
+        }
+        if (kk1 < kk0) kk0 = kk1 = 0;
+        R.p2_kk0[i] = kk0; R.p2_kk1[i] = kk1;
+    }
+    R.lo.assign(n, K);
+    R.hi.assign(n, 0);
+    uint32_t lo = K, hi = 0;
+    for (int l = n - 1; l >= 0; --l) {
+        lo = std::min(lo, dlo[l]); hi = std::max(hi, dhi[l]);
+        R.lo[l] = std::min(lo, hi); R.hi[l] = std::min(hi, K);
+    }
+    return R;
+}
+// the phase-2 tables of layer i: non-empty subsets, bits descending (stable by source layer)
+static std::vector<int> phase2_order(const Circuit& C, int i) {
+    std::vector<int> order;
+    for (int l = 0; l < i; ++l)
+        if (C.layers[i].dadSize[l] > 0) order.push_back(l);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return C.dad_bit_length(i, x) > C.dad_bit_length(i, y); });
+    return order;
+}
+
 // ------------------------------------------------------------------ CSR rows -> work items
 static constexpr uint32_t ROW_CHUNK = 8;
 struct ItemPlan {
@@ -1212,57 +1282,21 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     add_eq_build(2, L[1].ci_rliu, C.bit_length(0), -1);
 
     // which instances does this rank touch? (tables are instance-major and every rank holds a contiguous run of each)
-    // direct[l] = instances whose layer-l values some table of this rank reads; a layer must be evaluated for the hull
-    // of direct[l'] over all l' >= l (a gate reads from any lower layer). Small phase-2 tables with few blocks can give
-    // one rank a wide slice of a LOW layer; the layers above it stay narrow.
-    ko_lo = (uint32_t)((uint64_t)K * rank / world);
-    ko_hi = (uint32_t)((uint64_t)K * (rank + 1) / world);
-    std::vector<uint32_t> dlo(n, K), dhi(n, 0);
-    auto need = [&](int l, uint32_t a, uint32_t b) { if (b > a) { dlo[l] = std::min(dlo[l], a); dhi[l] = std::max(dhi[l], b); } };
-    need(n - 1, ko_lo, ko_hi);   // Vres
-    need(0, ko_lo, ko_hi);       // input MLE
-    for (int i = 1; i < n; ++i) {
-        LayerDev& D = L[i];
-        const uint32_t S_pre = (uint32_t)C.layers[i - 1].size;
-        auto fwd = [&](const PhasePlan& P, uint32_t& a, uint32_t& b) {   // table over layer i-1: idx = k*S_pre + u0
-            a = K; b = 0;
-            if (P.row_hi[0] > P.row_lo[0]) { a = P.row_lo[0] / S_pre; b = (P.row_hi[0] - 1) / S_pre + 1; }
-        };
-        uint32_t a, b;
-        fwd(D.ph1, a, b);
-        D.p1_k0 = std::min(a, K); D.p1_k1 = std::max(b, D.p1_k0);
-        need(i - 1, a, std::min(b, K));
-        fwd(D.ph3, a, b);
-        need(i - 1, a, std::min(b, K));
-        D.p2_kk0 = K; D.p2_kk1 = 0;
-        if (D.max_dad_bl != -1) {
-            // ph2 tables are in `order` (non-empty subsets, bits descending); their D is P2Table.D = dad size of one instance
-            std::vector<int> order;
-            for (int l = 0; l < i; ++l)
-                if (C.layers[i].dadSize[l] > 0) order.push_back(l);
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return C.dad_bit_length(i, x) > C.dad_bit_length(i, y); });
-            for (size_t t = 0; t < order.size(); ++t) {
-                const uint32_t Dsz = (uint32_t)C.layers[i].dadSize[order[t]];
-                if (D.ph2.row_hi[t] <= D.ph2.row_lo[t]) continue;
-                const uint32_t kka = D.ph2.row_lo[t] / Dsz, kkb = (D.ph2.row_hi[t] - 1) / Dsz + 1;   // idx = kk*D + lv0, kk = K-1-k
-                D.p2_kk0 = std::min(D.p2_kk0, kka);
-                D.p2_kk1 = std::max(D.p2_kk1, kkb);
-                need(order[t], K - std::min(kkb, K), K - kka);
-            }
-        }
-        if (D.p2_kk1 < D.p2_kk0) D.p2_kk0 = D.p2_kk1 = 0;
-    }
-    ev_lo.assign(n, K);
-    ev_hi.assign(n, 0);
     {
-        uint32_t lo = K, hi = 0;
-        for (int l = n - 1; l >= 0; --l) {
-            lo = std::min(lo, dlo[l]); hi = std::max(hi, dhi[l]);
-            ev_lo[l] = std::min(lo, hi); ev_hi[l] = hi;
+        std::vector<std::vector<int>> srcs(n);
+        for (int i = 1; i < n; ++i) srcs[i] = phase2_order(C, i);
+        const EvalRanges R = compute_eval_ranges(
+            C, K, world, rank, [&](int i, int phase) -> const PhasePlan& { return phase == 1 ? L[i].ph1 : phase == 2 ? L[i].ph2 : L[i].ph3; },
+            [&](int i) -> const std::vector<int>& { return srcs[i]; });
+        ko_lo = R.own_lo; ko_hi = R.own_hi;
+        ev_lo = R.lo; ev_hi = R.hi;
+        for (int i = 1; i < n; ++i) {
+            L[i].p1_k0 = R.p1_k0[i]; L[i].p1_k1 = R.p1_k1[i];
+            L[i].p2_kk0 = R.p2_kk0[i]; L[i].p2_kk1 = R.p2_kk1[i];
         }
+        k_lo = ev_lo[0];   // the inputs this rank uploads
+        k_hi = std::min(ev_hi[0], K);
     }
-    k_lo = ev_lo[0];   // the inputs this rank uploads
-    k_hi = std::min(ev_hi[0], K);
 
     for (int b = 0; b < 2; ++b) {
         const uint32_t cap = b == 0 ? cap0 : cap1;
@@ -2298,6 +2332,37 @@ extern "C" int vp_shard_describe(const vp_circuit* c, int world, int rank, int l
     }
     *n_tables = T.size();
     return VP_OK;
+}
+// Host-only: the per-layer instance ranges a rank of a sharded context evaluates (same code as vp_create_sharded).
+extern "C" int vp_shard_eval_ranges(const vp_circuit* c, int world, int rank, uint32_t* lo, uint32_t* hi) {
+    if (!c || !lo || !hi) return fail(VP_ERR_ARG, "null argument");
+    const Circuit& C = c->c;
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(VP_ERR_ARG, "bad world / rank");
+    try {
+        const int n = C.n_layers();
+        PlanArena A;
+        std::vector<PhasePlan> p1(n), p2(n), p3(n);
+        std::vector<std::vector<int>> srcs(n);
+        for (int i = 1; i < n; ++i) {
+            const int pb = C.bit_length(i - 1);
+            p1[i] = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, 0}}, pb, {}, world, rank, n, A);
+            p3[i] = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, 0}}, pb, {}, world, rank, n, A);
+            srcs[i] = phase2_order(C, i);
+            if (C.max_dad_bit_length(i) != -1) {
+                std::vector<PhaseTabG> T;
+                for (int l : srcs[i]) T.push_back(PhaseTabG{C.dad_bit_length(i, l), (uint32_t)C.dad_size(i, l), l, 0});
+                p2[i] = make_phase(T, C.max_dad_bit_length(i), {}, world, rank, n, A, /*rev=*/true);
+            }
+        }
+        const EvalRanges R = compute_eval_ranges(
+            C, (uint32_t)C.instances, world, rank,
+            [&](int i, int phase) -> const PhasePlan& { return phase == 1 ? p1[i] : phase == 2 ? p2[i] : p3[i]; },
+            [&](int i) -> const std::vector<int>& { return srcs[i]; });
+        for (int l = 0; l < n; ++l) { lo[l] = R.lo[l]; hi[l] = R.hi[l]; }
+        return VP_OK;
+    } catch (const CudaError& e) {
+        return fail(VP_ERR_ARG, "%s", e.msg.c_str());
+    }
 }
 extern "C" int vp_shard_map_index(uint32_t lo, uint32_t hi, uint32_t idx, uint32_t* local) {
     uint32_t loc = 0;

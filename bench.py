@@ -186,7 +186,7 @@ def run_ours(args):
     ms_profiled = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     prof = prover.profile()
     prover.set_profiling(False)
-    lanes = prover.set_lanes(3)
+    lanes = prover.set_lanes(6)   # the default: 6 on one GPU, 3 on a sharded context
 
     # ---------------- e2e: host buffers in, transcript out, every step
     for _ in range(max(1, args.warmup // 2)):

@@ -188,7 +188,8 @@ int vp_set_stream(vp_ctx* ctx, void* cuda_stream);
 int vp_set_profiling(vp_ctx* ctx, int on);
 /* Whole-proof mode runs phase 1, phase 2 and the Liu phases of vp_prove on up to three concurrent streams ("lanes",
    DESIGN.md). lanes = 1 runs them one after the other (used by bench.py's instrumented pass so that a launch's
-   CUDA-event duration is its own), 2 = Liu phases on their own lane, 3 = the default. Returns the setting in force. */
+   CUDA-event duration is its own), 2 = Liu phases on their own lane, 3 = one lane per phase kind, 6 = two sets of
+   three lanes taking alternate layers (the default on unsharded contexts). Returns the setting in force. */
 int vp_set_lanes(vp_ctx* ctx, int lanes);
 int vp_get_profile(vp_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int n_classes);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket it with their own events. */

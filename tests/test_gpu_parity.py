@@ -398,13 +398,13 @@ def test_full_size_c3_device_verifier_accepts(B, sha_circuit):
 
 
 def test_lane_settings_give_identical_transcripts(B, sha_circuit):
-    """vp_set_lanes: phase 1 / phase 2 / Liu on one, two or three streams -- same bits"""
+    """vp_set_lanes: phase 1 / phase 2 / Liu on one, two, three or six streams -- same bits"""
     rep = sha_circuit.replicate(70)   # >= 64 instances: the host-io upload is cut into chunks as well
     inp, ch = rep.inputs(), rep.draw_challenges()
     p = B.Prover(rep)
     assert p.set_lanes(3) == 3
     want = p.prove(inputs=inp, challenges=ch)
-    for lanes in (1, 2, 3):
+    for lanes in (1, 2, 3, 6):
         assert p.set_lanes(lanes) == lanes
         _assert_same(p.prove(inputs=inp, challenges=ch), want, f"{lanes} lane(s), host buffers")
         p.set_inputs(inp)

@@ -607,7 +607,7 @@ struct LayerDev {
     int max_dad_bl = -1;
     // eq build descriptor slices (indices into Engine::eq_descs)
     uint32_t eqb_g = 0, eqb_u = 0, eqb_u1 = 0, eqb_g2 = 0, eqb_u2 = 0, eqb_liu = 0, n_eqb_liu = 0;
-    DBuf<EqTab> liu_eqtabs;
+    DBuf<EqTab> liu_eqtabs, liu_eqtabs_b;   // in eq region set A / B
     // challenge indices
     uint32_t ci_ru = 0, ci_assert = 0, ci_rv = 0, ci_sig = 0, ci_rliu = 0, ci_g = 0;
     // transcript indices
@@ -700,19 +700,26 @@ struct Engine {
         cudaStream_t stream = nullptr;
         DBuf<F> bufV[2], bufM[2], bufA[2], d_scal, d_partials, d_send, d_recv, d_claims;
         DBuf<unsigned int> d_counter;
-        DBuf<F> d_rowpart;
+        DBuf<F> d_rowpart, d_hs;
         vp_ncclComm_t comm = nullptr;
-    } lane1, lane2;
-    // third lane (unsharded contexts): phase 2 of layer i only needs V_u from phase 1 of the same layer, and phase 1 of
-    // layer i-1 needs nothing from phase 2 of layer i (the challenges are known): phase 1 / phase 2 / Liu each run on
-    // their own stream, phase 2 one event behind phase 1. V_u is kept per layer (d_vu) instead of in one scalar.
-    bool three_lanes = false, on_lane2 = false;
+        size_t eq_off = 0;               // this lane's eq region set inside d_eq (entries)
+        cudaEvent_t ev_done = nullptr;
+    } lane1, lane2, lane0b, lane1b, lane2b;
+    // third lane: phase 2 of layer i only needs V_u from phase 1 of the same layer, and phase 1 of layer i-1 needs
+    // nothing from phase 2 of layer i (the challenges are known): phase 1 / phase 2 / Liu each run on their own stream,
+    // phase 2 one event behind phase 1. V_u is kept per layer (d_vu) instead of in one scalar.
+    // Six lanes (unsharded contexts): phases of different layers are independent as well, so a second set of lanes
+    // (lane0b / lane1b / lane2b, with its own eq region set) takes every other layer. This only pays for latency-bound
+    // proofs (one SHA256_64: 14 phases of ~50 us per lane; a 65-layer circuit of 2^20-gate layers); a throughput-bound
+    // proof (SHA256_64 x 1024) is indifferent to it.
+    bool three_lanes = false, six_lanes = false, on_lane2 = false;
     DBuf<F> d_vu;
     uint32_t region_g_lane2 = 0, region_u_lane2 = 0;
-    cudaEvent_t ev_p1 = nullptr, ev_lane2 = nullptr;
+    std::vector<cudaEvent_t> ev_p1v;   // per layer: phase 1 done (V_u written)
     F* vu_ptr(int layer) { return three_lanes ? d_vu.p + layer : scal(SC_VU); }
-    void swap_lane2() {
-        LaneRes& R = lane2;
+    size_t eq_off = 0;                 // the active lane's eq region set
+    LaneRes* active = nullptr;         // the lane whose members are swapped in (null: the main lane)
+    void swap_res(LaneRes& R) {
         std::swap(stream, R.stream);
         for (int b = 0; b < 2; ++b) { std::swap(bufV[b], R.bufV[b]); std::swap(bufM[b], R.bufM[b]); std::swap(bufA[b], R.bufA[b]); }
         std::swap(d_scal, R.d_scal);
@@ -720,27 +727,30 @@ struct Engine {
         std::swap(d_counter, R.d_counter);
         std::swap(d_claims, R.d_claims);
         std::swap(d_rowpart, R.d_rowpart);
+        std::swap(d_hs, R.d_hs);
         std::swap(d_send, R.d_send);
         std::swap(d_recv, R.d_recv);
         std::swap(comm, R.comm);
-        on_lane2 = !on_lane2;
+        std::swap(eq_off, R.eq_off);
     }
     bool two_lanes = false, on_lane1 = false;
-    bool direct_v = false;   // whole-proof: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
-    cudaEvent_t ev_eval = nullptr, ev_lane1 = nullptr;
-    uint32_t region_u_lane1 = 0;
-    void swap_lane() {
-        std::swap(stream, lane1.stream);
-        for (int b = 0; b < 2; ++b) { std::swap(bufV[b], lane1.bufV[b]); std::swap(bufM[b], lane1.bufM[b]); std::swap(bufA[b], lane1.bufA[b]); }
-        std::swap(d_scal, lane1.d_scal);
-        std::swap(d_partials, lane1.d_partials);
-        std::swap(d_counter, lane1.d_counter);
-        std::swap(d_claims, lane1.d_claims);
-        std::swap(d_send, lane1.d_send);
-        std::swap(d_recv, lane1.d_recv);
-        std::swap(comm, lane1.comm);
-        on_lane1 = !on_lane1;
+    // role of the lane being entered: 0 = phase 1 (behaves like the main lane), 1 = Liu, 2 = phase 2
+    void enter(LaneRes& R, int role) {
+        if (active) throw CudaError{"lane switch while another lane is active"};
+        swap_res(R);
+        active = &R;
+        on_lane1 = role == 1;
+        on_lane2 = role == 2;
     }
+    void leave() {
+        if (!active) return;
+        swap_res(*active);
+        active = nullptr;
+        on_lane1 = on_lane2 = false;
+    }
+    bool direct_v = false;   // whole-proof: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
+    cudaEvent_t ev_eval = nullptr;
+    uint32_t region_u_lane1 = 0;
     bool use_dfs = true;   // two rounds per pass in vp_prove (k_phase_dfs); false: one round per pass (k_sumcheck_phase)
     int cap_dfs = 0;
     int n = 0;            // layers
@@ -767,6 +777,7 @@ struct Engine {
     std::vector<EqBuild> eq_descs;
     PlanArena arena;
     uint32_t eq_half_cap = 0;          // entries of one half table
+    size_t eq_set_entries = 0;         // entries of one eq region set
     uint32_t eqb_out = 0, eqb_in = 0;
     uint32_t ci_out = 0, tr_vres = 0, tr_input = 0;
     size_t n_chal = 0, n_tr = 0;
@@ -829,18 +840,17 @@ struct Engine {
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (on_lane1) swap_lane();
-        if (on_lane2) swap_lane2();
+        leave();
         if (stream && own_stream) cudaStreamDestroy(stream);
-        if (lane1.stream) cudaStreamDestroy(lane1.stream);
-        if (lane2.stream) cudaStreamDestroy(lane2.stream);
+        for (LaneRes* R : {&lane1, &lane2, &lane0b, &lane1b, &lane2b}) {
+            if (R->stream) cudaStreamDestroy(R->stream);
+            if (R->ev_done) cudaEventDestroy(R->ev_done);
+        }
+        for (auto e : ev_p1v) if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto e : ev_chunk) if (e) cudaEventDestroy(e);
         if (ev_copy_go) cudaEventDestroy(ev_copy_go);
-        if (ev_p1) cudaEventDestroy(ev_p1);
-        if (ev_lane2) cudaEventDestroy(ev_lane2);
         if (ev_eval) cudaEventDestroy(ev_eval);
-        if (ev_lane1) cudaEventDestroy(ev_lane1);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (lane1.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane1.comm);
         if (lane2.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane2.comm);
@@ -850,7 +860,7 @@ struct Engine {
     EqTab eqtab(uint32_t region, int nbits) const {
         const int fh = nbits >> 1;
         EqTab t;
-        t.f = d_eq.p + (size_t)region * 2 * eq_half_cap;
+        t.f = d_eq.p + eq_off + (size_t)region * 2 * eq_half_cap;
         t.s = t.f + eq_half_cap;
         t.fh = (uint32_t)fh;
         t.mask = (1u << fh) - 1u;
@@ -1050,7 +1060,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     region_u_lane1 = 3 + (uint32_t)n;   // lane 1's own copy of beta_u
     region_g_lane2 = 4 + (uint32_t)n;   // lane 2's own copies of beta_g and beta_u
     region_u_lane2 = 5 + (uint32_t)n;
-    d_eq.alloc((size_t)n_regions * 2 * eq_half_cap);
+    eq_set_entries = (size_t)n_regions * 2 * eq_half_cap;
+    d_eq.alloc(2 * eq_set_entries);   // region set A (main, lane1, lane2) and set B (lane0b, lane1b, lane2b)
 
     // values
     val.resize(n);
@@ -1275,6 +1286,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             }
             D.n_eqb_liu = (uint32_t)eq_descs.size() - D.eqb_liu;
             D.liu_eqtabs.upload(tabs, stream);
+            for (EqTab& t : tabs) { t.f += eq_set_entries; t.s += eq_set_entries; }   // the same tables in eq region set B
+            D.liu_eqtabs_b.upload(tabs, stream);
             CK(cudaStreamSynchronize(stream));
         }
     }
@@ -1305,52 +1318,50 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         bufA[b].alloc(cap);
     }
     two_lanes = !getenv("VP_ONE_LANE");
-    if (two_lanes) {
-        uint32_t c0 = 4, c1 = 4;
-        for (int i = 1; i < n; ++i) { c0 = std::max(c0, L[i].ph3.cap0); c1 = std::max(c1, L[i].ph3.cap1); }
-        for (int b = 0; b < 2; ++b) {
-            const uint32_t cap = b == 0 ? c0 : c1;
-            lane1.bufV[b].alloc(cap);
-            lane1.bufM[b].alloc(cap);
-            lane1.bufA[b].alloc(world > 1 ? cap : 4);   // the Liu add table is never stored in whole-proof mode (sharded: the
-                                                        // hand-over kernels still address the region)
-        }
-        lane1.d_scal.alloc(SC_N);
-        lane1.d_claims.alloc((size_t)n + 1);
-        CK(cudaMemsetAsync(lane1.d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
-        lane1.d_partials.alloc((size_t)12 * (size_t)max_grid);
-        lane1.d_counter.alloc(4 + 64);
-        CK(cudaMemsetAsync(lane1.d_scal.p, 0, SC_N * sizeof(F), stream));
-        CK(cudaMemsetAsync(lane1.d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
-        CK(cudaStreamCreateWithFlags(&lane1.stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ev_eval, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_lane1, cudaEventDisableTiming));
-    }
-    d_rowpart.alloc(max_partial);
     three_lanes = two_lanes && !getenv("VP_TWO_LANES");
-    if (three_lanes) {
+    six_lanes = three_lanes && world == 1 && !getenv("VP_THREE_LANES");
+    d_rowpart.alloc(max_partial);
+    auto alloc_lane = [&](LaneRes& R, int role, size_t eqo) {   // role: 0 phase 1, 1 Liu, 2 phase 2
         uint32_t c0 = 4, c1 = 4;
-        for (int i = 1; i < n; ++i)
-            if (L[i].max_dad_bl != -1) { c0 = std::max(c0, L[i].ph2.cap0); c1 = std::max(c1, L[i].ph2.cap1); }
-        for (int b = 0; b < 2; ++b) {
-            const uint32_t cap = b == 0 ? c0 : c1;
-            lane2.bufV[b].alloc(cap);
-            lane2.bufM[b].alloc(cap);
-            lane2.bufA[b].alloc(cap);
+        for (int i = 1; i < n; ++i) {
+            const PhasePlan* P = role == 0 ? &L[i].ph1 : role == 1 ? &L[i].ph3 : (L[i].max_dad_bl != -1 ? &L[i].ph2 : nullptr);
+            if (P) { c0 = std::max(c0, P->cap0); c1 = std::max(c1, P->cap1); }
         }
-        lane2.d_scal.alloc(SC_N);
-        lane2.d_claims.alloc((size_t)n + 1);
-        lane2.d_partials.alloc((size_t)12 * (size_t)max_grid);
-        lane2.d_counter.alloc(4 + 64);
-        lane2.d_rowpart.alloc(max_partial);
+        for (int bb = 0; bb < 2; ++bb) {
+            const uint32_t cap = bb == 0 ? c0 : c1;
+            R.bufV[bb].alloc(cap);
+            R.bufM[bb].alloc(cap);
+            // the Liu add table is never stored in whole-proof mode (sharded: the hand-over kernels still address the region)
+            R.bufA[bb].alloc(role == 1 && world == 1 ? 4 : cap);
+        }
+        R.d_scal.alloc(SC_N);
+        R.d_claims.alloc((size_t)n + 1);
+        R.d_partials.alloc((size_t)12 * (size_t)max_grid);
+        R.d_counter.alloc(4 + 64);
+        if (role != 1) R.d_rowpart.alloc(max_partial);
+        if (role == 2) R.d_hs.alloc((size_t)K * 64);
+        R.eq_off = eqo;
+        CK(cudaMemsetAsync(R.d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
+        CK(cudaMemsetAsync(R.d_scal.p, 0, SC_N * sizeof(F), stream));
+        CK(cudaMemsetAsync(R.d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
+        CK(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&R.ev_done, cudaEventDisableTiming));
+    };
+    if (two_lanes) {
+        alloc_lane(lane1, 1, 0);
+        CK(cudaEventCreateWithFlags(&ev_eval, cudaEventDisableTiming));
+    }
+    if (three_lanes) {
+        alloc_lane(lane2, 2, 0);
         d_vu.alloc((size_t)n + 1);
-        CK(cudaMemsetAsync(lane2.d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));
-        CK(cudaMemsetAsync(lane2.d_scal.p, 0, SC_N * sizeof(F), stream));
-        CK(cudaMemsetAsync(lane2.d_counter.p, 0, (4 + 64) * sizeof(unsigned int), stream));
         CK(cudaMemsetAsync(d_vu.p, 0, ((size_t)n + 1) * sizeof(F), stream));
-        CK(cudaStreamCreateWithFlags(&lane2.stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ev_p1, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_lane2, cudaEventDisableTiming));
+        ev_p1v.assign(n, nullptr);
+        for (int i = 1; i < n; ++i) CK(cudaEventCreateWithFlags(&ev_p1v[i], cudaEventDisableTiming));
+    }
+    if (six_lanes) {
+        alloc_lane(lane0b, 0, eq_set_entries);
+        alloc_lane(lane1b, 1, eq_set_entries);
+        alloc_lane(lane2b, 2, eq_set_entries);
     }
     if (world > 1) {
         d_send.alloc(std::max<uint32_t>(max_rec, 1));
@@ -1482,7 +1493,7 @@ void Engine::evaluate() {
 
 void Engine::run_eq(uint32_t first, uint32_t count) {
     if (!count) return;
-    k_eq_build<<<count, 1024, 0, stream>>>(d_eqb.p + first, d_chal.p, d_eq.p);
+    k_eq_build<<<count, 1024, 0, stream>>>(d_eqb.p + first, d_chal.p, d_eq.p + eq_off);
     ++launches;
 }
 
@@ -1607,7 +1618,7 @@ void Engine::do_init_liu(int i, bool write_a) {
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
-        D.liu_off.p, world == 1 ? D.liu_perm.p : nullptr, D.liu_ent.p, D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
+        D.liu_off.p, world == 1 ? D.liu_perm.p : nullptr, D.liu_ent.p, eq_off ? D.liu_eqtabs_b.p : D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
         bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
         write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1);
     prof_end(h, (double)n_local * ((write_a ? 64.0 : 48.0) - (direct_v ? 32.0 : 0.0)));
@@ -1855,7 +1866,7 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
     if (world > 1) throw CudaError{"vp_verify needs an unsharded context"};
     if (!inputs_loaded) throw CudaError{"vp_verify: inputs not loaded"};
     if (h_chal.size() < n_chal) throw CudaError{"vp_verify: challenges not set"};
-    if (on_lane1 || on_lane2) throw CudaError{"vp_verify: lanes not joined"};
+    if (active) throw CudaError{"vp_verify: lanes not joined"};
     // ---- device: all O(#gates) sums, every layer, results in one buffer
     uint32_t out_total = 0, max_b = 1;
     for (int i = 1; i < n; ++i) {
@@ -1990,30 +2001,41 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
 
 // The whole proof in verifier.cpp:134-189 order, challenges already in d_chal.
 void Engine::prove_all() {
+    leave();   // (a previous call may have failed inside a lane)
     direct_v = use_phase_kernel && use_dfs;   // phase 1 / Liu read V from circuitValue[i-1] (sharded: the rank's rows of it)
+    const bool lane = two_lanes && use_phase_kernel && use_dfs;
+    const bool lane3 = lane && three_lanes;
+    const bool lane6 = lane3 && six_lanes;
     evaluate();
-    if (two_lanes && use_phase_kernel && use_dfs) {   // fork: lane 1 needs the circuit values (and the uploaded challenges)
+    if (lane) {   // fork: the other lanes need the circuit values (and the uploaded challenges)
         CK(cudaEventRecord(ev_eval, stream));
         CK(cudaStreamWaitEvent(lane1.stream, ev_eval, 0));
+        if (lane3) CK(cudaStreamWaitEvent(lane2.stream, ev_eval, 0));
+        if (lane6)
+            for (LaneRes* R : {&lane0b, &lane1b, &lane2b}) CK(cudaStreamWaitEvent(R->stream, ev_eval, 0));
     }
     do_vres();
     for (int i = n - 1; i >= 1; --i) {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
+        const bool odd = lane6 && ((n - 1 - i) & 1);   // six lanes: every other layer on the second set of lanes
+        // ---- phase 1
+        if (odd) enter(lane0b, 0);
         do_init_phase1(i);
-        const bool lane3 = three_lanes && two_lanes && use_phase_kernel && use_dfs;
         if (use_phase_kernel) do_phase(D.ph1, D.ci_ru, D.tr_p1, lane3 ? d_vu.p + i : scal(SC_VU), nullptr, true, direct_v ? val[i - 1].p : nullptr);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph1.planB, j, D.ci_ru + (uint32_t)std::max(0, j - 2), D.tr_p1 + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph1.planB, D.ci_ru + (uint32_t)std::max(0, pb - 1), scal(SC_VU));
         }
-        if (m != -1 && lane3) {   // phase 2 on its own lane, behind this layer's phase 1
-            CK(cudaEventRecord(ev_p1, stream));
-            swap_lane2();
-            CK(cudaStreamWaitEvent(stream, ev_p1, 0));
+        if (lane3 && m != -1) CK(cudaEventRecord(ev_p1v[i], stream));
+        if (odd) leave();
+        // ---- phase 2: on its own lane, behind this layer's phase 1
+        if (m != -1 && lane3) {
+            enter(odd ? lane2b : lane2, 2);
+            CK(cudaStreamWaitEvent(stream, ev_p1v[i], 0));
             do_init_phase2(i);
             do_phase(D.ph2, D.ci_rv, D.tr_p2, nullptr, scal(SC_UNARY));
-            swap_lane2();
+            leave();
         } else if (m != -1) {
             do_init_phase2(i);
             if (use_phase_kernel) do_phase(D.ph2, D.ci_rv, D.tr_p2, nullptr, scal(SC_UNARY));
@@ -2022,22 +2044,23 @@ void Engine::prove_all() {
                 do_finalize(D.ph2.planB, D.ci_rv + (uint32_t)std::max(0, m - 1), nullptr);
             }
         }
-        const bool lane = two_lanes && use_phase_kernel && use_dfs;
-        if (lane) swap_lane();
+        // ---- Liu
+        if (lane) enter(odd ? lane1b : lane1, 1);
         do_init_liu(i, !(use_phase_kernel && use_dfs));
         if (use_phase_kernel) do_phase(D.ph3, D.ci_rliu, D.tr_liu, nullptr, nullptr, /*has_a=*/!use_dfs, direct_v ? val[i - 1].p : nullptr);
         else {
             for (int j = 1; j <= pb; ++j) do_round(D.ph3.planB, j, D.ci_rliu + (uint32_t)std::max(0, j - 2), D.tr_liu + 3u * (uint32_t)(j - 1), nullptr);
             do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, pb - 1), nullptr);
         }
-        if (lane) swap_lane();
+        if (lane) leave();
     }
-    if (two_lanes && use_phase_kernel && use_dfs) {   // join: the input MLE and the transcript copy follow on lane 0
-        CK(cudaEventRecord(ev_lane1, lane1.stream));
-        CK(cudaStreamWaitEvent(stream, ev_lane1, 0));
-        if (three_lanes) {
-            CK(cudaEventRecord(ev_lane2, lane2.stream));
-            CK(cudaStreamWaitEvent(stream, ev_lane2, 0));
+    if (lane) {   // join: the b coefficients, the input MLE and the transcript copy follow on the main lane
+        std::vector<LaneRes*> used{&lane1};
+        if (lane3) used.push_back(&lane2);
+        if (lane6) { used.push_back(&lane0b); used.push_back(&lane1b); used.push_back(&lane2b); }
+        for (LaneRes* R : used) {
+            CK(cudaEventRecord(R->ev_done, R->stream));
+            CK(cudaStreamWaitEvent(stream, R->ev_done, 0));
         }
     }
     if (use_phase_kernel && use_dfs) derive_b();
@@ -2724,10 +2747,11 @@ extern "C" int vp_set_profiling(vp_ctx* ctx, int on) {
 extern "C" int vp_set_lanes(vp_ctx* ctx, int lanes) {
     if (!ctx) return 0;
     Engine& e = ctx->e;
-    const bool have2 = e.lane1.stream != nullptr, have3 = e.lane2.stream != nullptr;
+    const bool have2 = e.lane1.stream != nullptr, have3 = e.lane2.stream != nullptr, have6 = e.lane0b.stream != nullptr;
     e.two_lanes = lanes >= 2 && have2;
     e.three_lanes = lanes >= 3 && have2 && have3;
-    return e.three_lanes ? 3 : e.two_lanes ? 2 : 1;
+    e.six_lanes = lanes >= 6 && e.three_lanes && have6;
+    return e.six_lanes ? 6 : e.three_lanes ? 3 : e.two_lanes ? 2 : 1;
 }
 extern "C" int vp_get_profile(vp_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int n) {
     if (!ctx || !ms || !bytes || !launches) return fail(VP_ERR_ARG, "null argument");

@@ -238,7 +238,7 @@ def run_ours(args):
                                            "integer-pipe latency, see DESIGN.md and profiles/",
                             "alg_bytes_per_launch": rf["bytes"] / rf["launches"],
                             "note": "launch durations come from the instrumented pass, which runs the phases on ONE stream "
-                                    "(vp_set_lanes(1)); `value` is the un-instrumented pass with the three lanes overlapped, so the "
+                                    "(vp_set_lanes(1)); `value` is the un-instrumented pass with the lanes overlapped (six streams on one GPU, three per rank when sharded), so the "
                                     "per-class times add up to more than the step. `traffic` = DRAM bytes read + written per launch "
                                     "(ncu, profiles/r1_dfs_traffic.json), averaged over the 42 launches of one proof like `achieved`"}
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),

@@ -97,8 +97,12 @@ def _ranges_worker(rank, world, port, K, q):
     import __graft_entry__ as entry
     B = entry.binding()
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    with lzma.open(os.path.join(ROOT, "tests", "golden", "SHA256_64.pws.xz"), "rb") as f:
-        circ = B.Circuit.from_pws_text(f.read()).replicate(K)
+    if K > 0:
+        with lzma.open(os.path.join(ROOT, "tests", "golden", "SHA256_64.pws.xz"), "rb") as f:
+            circ = B.Circuit.from_pws_text(f.read()).replicate(K)
+    else:   # random add/mul wiring with operands from any earlier layer: many small phase-2 tables per layer
+        K = 96
+        circ = B.Circuit.random(7, 9, 5).replicate(K)
     n = circ.n_layers
     lo, hi = B.shard_eval_ranges(circ, world, rank)
     ok = True
@@ -112,8 +116,10 @@ def _ranges_worker(rank, world, port, K, q):
             srcs = None
             if ph == 2:
                 ds = [(l, circ.dad_size(i, l)) for l in range(i) if circ.dad_size(i, l) > 0]
-                ds.sort(key=lambda t: -max(0, (t[1] - 1).bit_length()))   # bits descending, stable by source layer
+                per_inst = ds[0][1] * K <= max(t['live'] for t in tabs)   # dad_size is per instance: the K-instance table has D*K entries
+                ds.sort(key=lambda t: -max(0, (t[1] * (K if per_inst else 1) - 1).bit_length()))   # bits descending, stable by source layer
                 srcs = [l for l, _ in ds]
+                ok &= [d * (K if per_inst else 1) for _, d in ds] == [t["live"] for t in tabs]   # the reconstruction matches the plan
             for ti, t in enumerate(tabs):
                 if t["row_hi"] <= t["row_lo"]:
                     continue
@@ -137,7 +143,7 @@ def _ranges_worker(rank, world, port, K, q):
     q.put((rank, ok, evaluated / share))
 
 
-@pytest.mark.parametrize("world,K", [(2, 64), (4, 256), (8, 8192)])
+@pytest.mark.parametrize("world,K", [(2, 64), (4, 256), (8, 8192), (4, 0), (8, 0)])
 def test_eval_ranges_cover_reads_and_stay_tight_gloo(world, K):
     """host logic of the sharded context (vp_shard_eval_ranges, same code as vp_create_sharded), one gloo process per
     rank: coverage of every table's reads, monotonicity over layers, and the regression guard for the wide low-layer

@@ -9,6 +9,17 @@
  * returns a description of the last failure on the calling thread. There is NO CPU fallback: all
  * prover entry points fail with VP_ERR_CUDA when no sm_100 device / driver is usable.
  * A context is single-threaded (like the reference prover: one prover per process).
+ *
+ * Limits (checked; violations return VP_ERR_CIRCUIT / VP_ERR_ARG / VP_ERR_CUDA with a message, never undefined behaviour):
+ *   - 2 <= layers <= 120; layer_size * instances <= 2^31 per layer (table indices are 32 bit), hence at most 31 rounds
+ *     per sumcheck phase (the whole-proof kernel takes the phase's <= 32 challenges through its parameters);
+ *   - in-layer gate indices, lv and dadId entries fit 32 bits; every dadId entry must be < the source layer's size;
+ *   - .pws files: variable ids dense and < 2^40 (main.cpp indexes a vector by id); malformed numbers reject the file;
+ *   - sharded contexts: world in {1, 2, 4, 8}, one process per GPU of ONE node;
+ *   - witness inputs are read like the reference reads them, as F((long long) x) (prover.cpp:30-36,
+ *     fieldElement.cpp:24-27): 0 <= x < p as is, x < 0 as p + x; other values are reduced mod p (the reference keeps
+ *     them non-canonical). The circuit-level setters (vp_circuit_set_inputs, .pws inputs) only accept 0 <= x < p;
+ *   - challenges must be canonical (both components < p): vp_set_challenges / vp_prove / vp_round reject others.
  */
 #ifndef VIRGO_B200_H
 #define VIRGO_B200_H

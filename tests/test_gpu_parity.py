@@ -185,6 +185,14 @@ def test_dropin_reference_verifier_accepts(tmp_path, sha_pws_text):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "virgo_plus_run_b200")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/virgo_plus_run_b200 not built (needs /root/reference at build time)")
+    # the binary is prebuilt where /root/reference exists and travels to the GPU box: make sure it was linked from the
+    # shim sources of THIS tree (the library itself is loaded dynamically, so it is always the current one)
+    import hashlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    srcs = [os.path.join(root, "virgo-plus_b200", "host", "prover.cpp"), os.path.join(root, "virgo-plus_b200", "host", "prover.h"),
+            os.path.join(root, "include", "virgo_b200.h")]
+    digest = hashlib.sha256(b"".join(open(f, "rb").read() for f in srcs)).hexdigest()
+    assert open(exe + ".srchash").read().strip() == digest, "virgo_plus_run_b200 is stale: run __graft_entry__.build() where /root/reference exists"
     pws = tmp_path / "SHA256_64.pws"
     pws.write_bytes(sha_pws_text)
     r = subprocess.run([exe, str(pws)], capture_output=True, text=True, timeout=300)
@@ -484,3 +492,103 @@ def test_device_field_primitives_edge_values(B):
             d = ((t(b2[i])[0] - t(a2[i])[0]) % P, (t(b2[i])[1] - t(a2[i])[1]) % P)
             acc = [(acc[0] + d[0] * int(c2[i]["re"])) % P, (acc[1] + d[1] * int(c2[i]["re"])) % P]
         assert t(out[0]) == tuple(acc), m_
+
+
+# ------------------------------------------------------------------ round-2 hardening
+def test_zero_constants_addc_mulc(B, O):
+    """Addc / Mulc gates whose constants are ALL zero: from_arrays keeps no constant array for such a layer, the device
+    still indexes one (engine uploads a zero-filled array). Values: Addc(x, 0) = x, Mulc(x, 0) = 0."""
+    sizes = [4, 6, 5]
+    ty = [_INPUT] * 4 + [_ADDC, _MULC, _ADDC, _ADD, _MULC, _COPY] + [_MULC, _ADDC, _MUL, _ADDC, _NOT]
+    l = [-1] * 4 + [-1, -1, -1, 0, -1, -1] + [-1, -1, 0, -1, -1]
+    u = [11, 22, 33, 44] + [0, 1, 2, 3, 1, 2] + [0, 1, 2, 3, 4]
+    v = [0] * 4 + [0, 0, 0, 2, 0, 0] + [0, 0, 3, 0, 0]
+    cst = np.zeros(len(ty), B.F_DTYPE)
+    for with_c in (False, True):
+        circ = B.Circuit.from_arrays(sizes, ty, l, u, v, c=cst if with_c else None)
+        _prove_both_ways(B, O, circ)
+        _verify_like_oracle(B, O, circ)
+        rep = circ.replicate(40)
+        _prove_both_ways(B, O, rep, flat_circ=rep.expand())
+
+
+def test_negative_and_large_inputs_like_reference(B, O):
+    """prover.cpp:30-36 loads inputs as F((long long) x): x < 0 means p + x (fieldElement.cpp:24-27). The device maps
+    them the same way (k_load_inputs); the circuit-level setters only take canonical values."""
+    circ = B.Circuit.random(4, 5, 21)
+    inp = circ.inputs().copy()
+    raw = inp.copy()
+    raw[0] = np.uint64((1 << 64) - 5)            # -5
+    raw[1] = np.uint64((1 << 64) - (B.P - 1))    # -(p - 1)  ->  1
+    raw[2] = np.uint64(0)
+    raw[3] = np.uint64(B.P - 1)
+    flat = circ.flat()
+    flat["inputs"] = raw.copy()
+    want, _, _ = O.OracleCircuit(flat).prove()
+    p = B.Prover(circ)
+    got = p.prove(inputs=raw, challenges=circ.draw_challenges())
+    _assert_same(got, want, "negative inputs")
+    p.close()
+    with pytest.raises(B.VpError):
+        circ.set_inputs(raw)                     # the host-side circuit only takes values < p
+
+
+def test_noncanonical_challenges_rejected(B):
+    circ = B.Circuit.random(3, 4, 2)
+    p = B.Prover(circ)
+    ch = circ.draw_challenges()
+    bad = ch.copy()
+    bad[3]["im"] = B.P
+    with pytest.raises(B.VpError):
+        p.set_challenges(bad)
+    with pytest.raises(B.VpError):
+        p.prove(inputs=circ.inputs(), challenges=bad)
+    p.set_challenges(ch)                         # the context is still usable
+    p.prove()
+    p.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes against the REFERENCE
+# tests/golden/full_size.json holds SHA-256 hashes of transcripts the unmodified reference prover produced at the
+# benchmark sizes (tests/golden/make_golden_full.py, run once in the build container: minutes of CPU, tens of GB).
+def _full_size_golden(name):
+    import json
+    import os
+    import helpers as H
+    path = os.path.join(H.GOLDEN, "full_size.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/full_size.json missing")
+    g = json.load(open(path))
+    if name not in g:
+        pytest.skip(f"{name} not in full_size.json")
+    return g[name]
+
+
+def _sha(tr):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(tr).tobytes()).hexdigest()
+
+
+def test_full_size_c3_transcript_hash_equals_reference(B, sha_circuit):
+    """BASELINE.json configs[2], SHA256_64 x 1024: the GPU transcript hashes to what the reference prover produced"""
+    g = _full_size_golden("sha256_64_x1024")
+    rep = sha_circuit.replicate(1024)
+    assert rep.total_gates == g["gates"] and rep.transcript_len == g["transcript_len"]
+    p = B.Prover(rep)
+    tr = p.prove(inputs=rep.inputs(), challenges=rep.draw_challenges())
+    assert [int(tr[0]["re"]), int(tr[0]["im"])] == g["vres"]
+    assert [int(tr[-1]["re"]), int(tr[-1]["im"])] == g["input_mle"]
+    assert _sha(tr) == g["transcript_sha256"]
+    p.close()
+
+
+@pytest.mark.parametrize("name,n_layers,log_size", [("random_65x14", 65, 14), ("random_65x20", 65, 20)])
+def test_c4_shape_transcript_hash_equals_reference(B, name, n_layers, log_size):
+    """BASELINE.json configs[3]: 65 layers of random add/mul gates with operands from any earlier layer"""
+    g = _full_size_golden(name)
+    circ = B.Circuit.random(n_layers, log_size, 7)
+    assert circ.total_gates == g["gates"] and circ.transcript_len == g["transcript_len"]
+    p = B.Prover(circ)
+    tr = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+    assert _sha(tr) == g["transcript_sha256"]
+    p.close()

@@ -233,3 +233,23 @@ def test_transcript_text_and_gkrproof_container(B, O, sha_circuit):
         sha_circuit.from_gkrproof(blob[:-8])
     with pytest.raises(B.VpError):
         sha_circuit.from_gkrproof(blob + b"\\0" * 8)
+
+
+# ------------------------------------------------------------------ hostile loader input
+def test_loader_rejects_hostile_ids_without_allocating(B):
+    """a .pws line with a huge variable id must be rejected, not answered with a tgt + 1 sized allocation / abort"""
+    for text in (b"P V0 = I0 E\nP V99999999999 = V0 + V0 E\n",
+                 b"P V0 = I0 E\nP V184467440737095516150 = V0 + V0 E\n",     # does not fit 64 bits
+                 b"P V0 = I0 E\nP V5 = V0 + V0 E\n"):                          # hole: ids must be dense
+        with pytest.raises(B.VpError):
+            B.Circuit.from_pws_text(text)
+    c = B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 + V1 E\n")
+    assert c.n_layers == 2 and c.total_gates == 1
+    with pytest.raises(B.VpError):
+        c.replicate(1 << 40)                      # layer size * instances overflows the 2^31 limit
+    with pytest.raises(B.VpError):
+        B.Circuit.from_arrays([2, 1], [6, 6, 1], [-1, -1, 0], [1, 2, 0], [0, 0, 1 << 33])   # v does not fit 32 bits
+    # a caller-supplied dad subset with an out-of-range entry that no gate references
+    with pytest.raises(B.VpError):
+        B.Circuit.from_arrays([2, 1], [6, 6, 1], [-1, -1, 0], [1, 2, 0], [0, 0, 1], lv=[0, 0, 0],
+                              dad_size=[0, 0, 2, 0], dad_id=[1, 7])

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -930,6 +931,9 @@ struct Engine {
     void prove_all();
     std::vector<F> h_chal;   // host copy of the challenges: the pass kernel gets their limbs through its parameters
     void set_chal(uint32_t idx, const vp_F* v, size_t cnt = 1) {
+        // the limb arithmetic needs canonical challenges (split31 would silently drop the top bits of anything else)
+        for (size_t i = 0; i < cnt; ++i)
+            if (v[i].re >= P || v[i].im >= P) throw std::invalid_argument("challenge " + std::to_string(idx + i) + " is not canonical (components must be < p)");
         CK(cudaMemcpyAsync(d_chal.p + idx, v, cnt * sizeof(F), cudaMemcpyHostToDevice, stream));
         if (h_chal.size() < idx + cnt) h_chal.resize(idx + cnt, f_zero());
         memcpy(h_chal.data() + idx, v, cnt * sizeof(F));
@@ -1097,7 +1101,12 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.l.upload(l, stream);
             D.u.upload(T.u, stream);
             D.v.upload(T.v, stream);
+            // the kernels index the constant array for every Addc / Mulc gate: a layer whose constants are all zero
+            // (from_arrays keeps no array then) still gets one
+            bool needs_c = false;
+            for (uint32_t g = 0; g < S; ++g) needs_c |= (T.ty[g] == T_ADDC || T.ty[g] == T_MULC);
             if (!T.c.empty()) D.c.upload(T.c, stream);
+            else if (needs_c) D.c.upload(std::vector<F>(S, f_zero()), stream);
             D.G = GateArrays{D.ty.p, D.l.p, D.u.p, D.v.p, D.c.p};
             CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
         }
@@ -2082,7 +2091,8 @@ extern "C" const char* vp_version(void) { return "virgo-plus_b200 0.1 (sm_100a)"
     }                                                                    \
     catch (const CudaError& e) { return fail(VP_ERR_CUDA, "%s", e.msg.c_str()); } \
     catch (const std::bad_alloc&) { return fail(VP_ERR_NOMEM, "out of host memory"); } \
-    catch (unsigned int flag) { return fail(VP_ERR_ASSERT, "assert gate violated in layer %u", flag - 1); }
+    catch (unsigned int flag) { return fail(VP_ERR_ASSERT, "assert gate violated in layer %u", flag - 1); } \
+    catch (const std::exception& e) { return fail(VP_ERR_ARG, "%s", e.what()); }
 
 // ------------------------------------------------------------------ C ABI: circuit
 static int wrap_circuit(Circuit&& c, vp_circuit** out) {
@@ -2093,21 +2103,27 @@ static int wrap_circuit(Circuit&& c, vp_circuit** out) {
 }
 extern "C" int vp_circuit_load_pws(const char* path, vp_circuit** out) {
     if (!path || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
     Circuit c;
     std::string err = load_pws(path, c);
     if (!err.empty()) return fail(VP_ERR_CIRCUIT, "%s", err.c_str());
     return wrap_circuit(std::move(c), out);
+    API_END
 }
 extern "C" int vp_circuit_load_pws_text(const char* text, size_t len, vp_circuit** out) {
     if (!text || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
     Circuit c;
     std::string err = load_pws_text(text, len, c);
     if (!err.empty()) return fail(VP_ERR_CIRCUIT, "%s", err.c_str());
     return wrap_circuit(std::move(c), out);
+    API_END
 }
 extern "C" int vp_circuit_random(int n_layers, int log_size, uint64_t seed, vp_circuit** out) {
-    if (!out || n_layers < 2 || log_size < 0 || log_size > 30) return fail(VP_ERR_ARG, "bad argument");
+    if (!out || n_layers < 2 || n_layers > 120 || log_size < 0 || log_size > 30) return fail(VP_ERR_ARG, "bad argument");
+    API_BEGIN
     return wrap_circuit(random_circuit(n_layers, log_size, seed), out);
+    API_END
 }
 extern "C" int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, const uint8_t* ty, const int32_t* l,
                                       const uint64_t* u, const uint64_t* v, const uint64_t* lv, const vp_F* cst,
@@ -2115,12 +2131,14 @@ extern "C" int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, 
                                       vp_circuit** out) {
     if (n_layers < 1 || !layer_size || !ty || !l || !u || !v || !out) return fail(VP_ERR_ARG, "null argument");
     if (dad_size && (!lv || !dad_id)) return fail(VP_ERR_ARG, "dad_size given without lv / dad_id");
+    API_BEGIN
     Circuit c;
     c.layers.resize(n_layers);
     size_t off = 0, doff = 0;
     for (int i = 0; i < n_layers; ++i) {
         Layer& L = c.layers[i];
         L.size = layer_size[i];
+        if (L.size == 0 || L.size > (1ULL << 31)) return fail(VP_ERR_CIRCUIT, "layer %d: size %llu out of range", i, (unsigned long long)L.size);
         L.ty.resize(L.size);
         L.l.resize(L.size);
         L.u.resize(L.size);
@@ -2140,7 +2158,10 @@ extern "C" int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, 
                 L.u[g] = (uint32_t)u[off + g];
             }
             L.v[g] = (uint32_t)v[off + g];
-            if (lv) L.lv[g] = (uint32_t)lv[off + g];
+            if (lv) {
+                if (lv[off + g] > 0xffffffffULL) return fail(VP_ERR_CIRCUIT, "layer %d gate %llu: lv exceeds 32 bits", i, (unsigned long long)g);
+                L.lv[g] = (uint32_t)lv[off + g];
+            }
             if (cst && (cst[off + g].re | cst[off + g].im)) any_c = true;
             if (is_assert && is_assert[off + g]) any_a = true;
         }
@@ -2154,8 +2175,12 @@ extern "C" int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, 
             L.dadId.resize(i);
             for (int s = 0; s < i; ++s) {
                 L.dadSize[s] = dad_size[(size_t)i * n_layers + s];
+                if (L.dadSize[s] > c.layers[s].size) return fail(VP_ERR_CIRCUIT, "layer %d: dad subset of layer %d is larger than that layer", i, s);
                 L.dadId[s].resize(L.dadSize[s]);
-                for (uint64_t x = 0; x < L.dadSize[s]; ++x) L.dadId[s][x] = (uint32_t)dad_id[doff + x];
+                for (uint64_t x = 0; x < L.dadSize[s]; ++x) {
+                    if (dad_id[doff + x] > 0xffffffffULL) return fail(VP_ERR_CIRCUIT, "layer %d: dad_id exceeds 32 bits", i);
+                    L.dadId[s][x] = (uint32_t)dad_id[doff + x];
+                }
                 doff += L.dadSize[s];
             }
         }
@@ -2163,15 +2188,20 @@ extern "C" int vp_circuit_from_arrays(int n_layers, const uint64_t* layer_size, 
     }
     if (!dad_size) c.subset_init();
     return wrap_circuit(std::move(c), out);
+    API_END
 }
 extern "C" int vp_circuit_replicate(const vp_circuit* c, uint64_t instances, vp_circuit** out) {
     if (!c || !out || instances == 0) return fail(VP_ERR_ARG, "bad argument");
     if (c->c.instances != 1) return fail(VP_ERR_ARG, "circuit is already replicated");
+    API_BEGIN
     return wrap_circuit(c->c.replicate(instances), out);
+    API_END
 }
 extern "C" int vp_circuit_expand(const vp_circuit* c, vp_circuit** out) {
     if (!c || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
     return wrap_circuit(c->c.expand(), out);
+    API_END
 }
 extern "C" void vp_circuit_free(vp_circuit* c) { delete c; }
 extern "C" int vp_circuit_num_layers(const vp_circuit* c) { return c ? c->c.n_layers() : 0; }
@@ -2419,8 +2449,10 @@ extern "C" int vp_set_inputs(vp_ctx* ctx, const uint64_t* inputs, size_t n) {
 extern "C" int vp_evaluate(vp_ctx* ctx) {
     if (!ctx) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN
-    ScopedTimer t(ctx->e);
-    ctx->e.evaluate();
+    Engine& e = ctx->e;
+    ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
+    e.evaluate();
     ctx->e.check_assert_flag();
     return VP_OK;
     API_END
@@ -2430,6 +2462,7 @@ extern "C" int vp_get_values(vp_ctx* ctx, int layer, vp_F* out, size_t n) {
     API_BEGIN
     Engine& e = ctx->e;
     cudaSetDevice(e.device);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n > e.C.layer_size(layer)) return fail(VP_ERR_ARG, "n exceeds the layer size");
     CK(cudaMemcpyAsync(out, e.val[layer].p, n * sizeof(F), cudaMemcpyDeviceToHost, e.stream));
     CK(cudaStreamSynchronize(e.stream));
@@ -2441,6 +2474,7 @@ extern "C" int vp_vres(vp_ctx* ctx, const vp_F* r, int n, vp_F* out) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (!e.evaluated) return fail(VP_ERR_ARG, "vp_vres before vp_evaluate");
     if (n != e.C.bit_length(e.n - 1)) return fail(VP_ERR_ARG, "vp_vres: n must be the output layer's bit length");
     if (n) e.set_chal(e.ci_out, r, (size_t)n);
@@ -2454,6 +2488,7 @@ extern "C" int vp_sumcheck_init_all(vp_ctx* ctx, const vp_F* r_last, int n) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n != e.C.bit_length(e.n - 1)) return fail(VP_ERR_ARG, "sumcheck_init_all: wrong n");
     if (n) e.set_chal(e.ci_out, r_last, (size_t)n);
     e.cur_layer = e.n;
@@ -2465,6 +2500,7 @@ extern "C" int vp_sumcheck_init_all(vp_ctx* ctx, const vp_F* r_last, int n) {
 extern "C" int vp_sumcheck_init(vp_ctx* ctx) {
     if (!ctx) return fail(VP_ERR_ARG, "null argument");
     Engine& e = ctx->e;
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer <= 1) return fail(VP_ERR_ARG, "sumcheck_init below layer 1");
     --e.cur_layer;
     e.phase = 0;
@@ -2475,7 +2511,7 @@ extern "C" int vp_init_phase1(vp_ctx* ctx, const vp_F* assert_random) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "a sharded context only supports vp_prove (whole proof); the method-by-method entry points need one GPU");
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_phase1 outside a layer");
     e.set_chal(e.L[e.cur_layer].ci_assert, assert_random);
     e.do_init_phase1(e.cur_layer);
@@ -2490,6 +2526,7 @@ extern "C" int vp_init_phase2(vp_ctx* ctx) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_phase2 outside a layer");
     if (e.L[e.cur_layer].max_dad_bl == -1) return fail(VP_ERR_ARG, "layer %d has no phase 2", e.cur_layer);
     e.do_init_phase2(e.cur_layer);
@@ -2504,6 +2541,7 @@ extern "C" int vp_init_liu(vp_ctx* ctx, const vp_F* sig, int n) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_liu outside a layer");
     const int need = e.n - e.cur_layer + 1;
     if (n < need) return fail(VP_ERR_ARG, "init_liu: need %d sigma values, got %d", need, n);
@@ -2528,6 +2566,7 @@ extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (phase < 1 || phase > 3 || phase != e.phase) return fail(VP_ERR_ARG, "vp_round: phase %d not initialised", phase);
     LayerDev& D = e.L[e.cur_layer];
     const SumcheckPlan& P = phase_plan(e, phase);
@@ -2545,6 +2584,7 @@ extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_
 static int finalize_common(vp_ctx* ctx, int phase, const vp_F* prev, vp_F* out, int n_out) {
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (phase != e.phase) return fail(VP_ERR_ARG, "finalize: phase %d not initialised", phase);
     LayerDev& D = e.L[e.cur_layer];
     const SumcheckPlan& P = phase_plan(e, phase);
@@ -2586,6 +2626,7 @@ extern "C" int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out) 
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n > e.C.layer_size(0)) return fail(VP_ERR_ARG, "inner_prod: n exceeds the input layer");
     if (e.d_pub.n < n) e.d_pub.alloc(n);
     CK(cudaMemcpyAsync(e.d_pub.p, pub, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
@@ -2619,6 +2660,7 @@ extern "C" int vp_input_mle(vp_ctx* ctx, const vp_F* r, int n, vp_F* out) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
+    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n != e.C.bit_length(0)) return fail(VP_ERR_ARG, "input_mle: n must be the input layer's bit length");
     if (n) e.set_chal(e.L[1].ci_rliu, r, (size_t)n);
     e.do_input_mle();

@@ -155,10 +155,15 @@ __global__ void __launch_bounds__(1024) k_eq_build(const EqBuild* __restrict__ d
 }
 
 // ------------------------------------------------------------------ K1: evaluate
-// prover.cpp:30-36: layer 0 = F((long long) gate.u)
+// prover.cpp:30-36: layer 0 = F((long long) gate.u), i.e. x for 0 <= x, p + x for x < 0 (fieldElement.cpp:24-27).
+// The reference keeps a non-negative x >= p as it is (a non-canonical element its arithmetic does not expect); here
+// every input is reduced, so the limb arithmetic always sees canonical values.
 __global__ void k_load_inputs(const uint64_t* __restrict__ in, F* __restrict__ val, uint32_t begin, uint32_t end) {
     uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < end) st_f(val + i, F{in[i], 0});
+    if (i < end) {
+        const u64 x = in[i];
+        st_f(val + i, F{(long long)x < 0 ? fp_canon(fp_fold(x) + P - 8) : fp_canon(x), 0});   // 2^64 = 8 (mod p): x - 2^64 + p
+    }
 }
 
 struct GateArrays {          // one template layer (one instance)

@@ -11,6 +11,7 @@
 #include <deque>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 
 namespace vp {
 
@@ -124,6 +125,8 @@ void Circuit::draw_inputs_like_reference() {
 }
 
 Circuit Circuit::replicate(uint64_t K) const {
+    for (const Layer& L : layers)   // before anything is allocated for K instances
+        if (K > (1ULL << 31) || L.size * K > (1ULL << 31)) throw std::length_error("replicate: a layer would exceed 2^31 gates");
     Circuit o = *this;
     o.instances = K;
     o.draw_inputs_like_reference();
@@ -140,7 +143,7 @@ std::string Circuit::validate() const {
             snprintf(buf, sizeof buf, "layer %d is empty", i);
             return buf;
         }
-        if (L.size * instances > (1ULL << 31)) {
+        if (instances > (1ULL << 31) || L.size > (1ULL << 31) || L.size * instances > (1ULL << 31)) {
             snprintf(buf, sizeof buf, "layer %d: %llu gates exceed the 2^31 per-layer limit", i,
                      (unsigned long long)(L.size * instances));
             return buf;
@@ -183,8 +186,14 @@ std::string Circuit::validate() const {
                 return buf;
             }
         }
-        for (int l = 0; l < i; ++l)
+        for (int l = 0; l < i; ++l) {
             if (L.dadId[l].size() != L.dadSize[l]) return "dadId/dadSize mismatch";
+            for (uint32_t x : L.dadId[l])   // also entries no gate references: phase 2 / Liu gather through every slot
+                if (x >= layers[l].size) {
+                    snprintf(buf, sizeof buf, "layer %d: dadId[%d] entry %u out of range of layer %d", i, l, x, l);
+                    return buf;
+                }
+        }
     }
     if (inputs.size() != instances * layers[0].size) return "inputs length != instances * layer-0 size";
     for (uint64_t x : inputs)
@@ -204,10 +213,15 @@ struct DagGate {
 // Strict matcher for one line; mirrors the eight std::regex patterns of main.cpp:161-168
 // ("P V<t> = V<a> OP V<b> E", "P V<t> = I<k> E", "P O<t> = V<a> E"). Anything else is ignored,
 // as in the reference's Release build (assert(false) compiled out, main.cpp:204).
+static thread_local uint64_t dag_id_cap = 0;        // number of lines of the file: dense ids cannot exceed it
+static thread_local bool dag_overflow = false;      // a number too large to be an id / index was seen
 bool read_uint(const char*& p, const char* e, uint64_t& out) {
     if (p >= e || *p < '0' || *p > '9') return false;
     uint64_t x = 0;
-    while (p < e && *p >= '0' && *p <= '9') x = x * 10 + (uint64_t)(*p++ - '0');
+    while (p < e && *p >= '0' && *p <= '9') {
+        if (x > (1ULL << 40)) { dag_overflow = true; return false; }   // no silent wrap-around: the file is rejected
+        x = x * 10 + (uint64_t)(*p++ - '0');
+    }
     out = x;
     return true;
 }
@@ -256,6 +270,9 @@ void parse_line(const char* p, const char* e, std::vector<DagGate>& dag, uint64_
             g.in1 = b;
         }
     }
+    // ids must be dense (dag_to_layered rejects holes), so an id far beyond the lines seen so far can never become
+    // valid: refuse it here instead of allocating tgt + 1 entries for a hostile file
+    if (tgt > dag_id_cap) { dag_overflow = true; return; }
     if (tgt >= dag.size()) dag.resize(tgt + 1);
     dag[tgt] = g;
 }
@@ -376,12 +393,16 @@ std::string load_pws_text(const char* text, size_t len, Circuit& out) {
     std::vector<uint64_t> input_order;
     const char* p = text;
     const char* end = text + len;
+    dag_overflow = false;
+    dag_id_cap = 1;
+    for (const char* q = text; q < end; ++q) dag_id_cap += (*q == '\n');
     while (p < end) {
         const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
         const char* e = nl ? nl : end;
         parse_line(p, e, dag, n_inputs, input_order);
         p = nl ? nl + 1 : end;
     }
+    if (dag_overflow) return "a gate id exceeds the number of lines (ids must be dense) or a number is out of range";
     if (dag.empty()) return "no gates parsed";
     std::string err = dag_to_layered(dag, out);
     if (!err.empty()) return err;

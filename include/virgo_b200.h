@@ -171,6 +171,32 @@ double vp_prove_seconds(const vp_ctx* ctx);
 int vp_set_challenges(vp_ctx* ctx, const vp_F* challenges, size_t n);
 int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
              size_t n_challenges, vp_F* transcript, size_t transcript_cap);
+/* Sharded contexts: a rank only uploads the witness of the data-parallel instances [first, end) it evaluates (its own
+ * K/world slice plus the few neighbours its tables read, vp_shard_eval_ranges). vp_prove_local is vp_prove(host_io=1)
+ * for a caller that holds just that slice: local_inputs = (end - first) * layer_size(0) values, instance-major.
+ * On an unsharded context the range is [0, instances) and the two calls are the same. */
+int vp_input_range(const vp_ctx* ctx, uint64_t* first_instance, uint64_t* end_instance);
+int vp_prove_local(vp_ctx* ctx, const uint64_t* local_inputs, size_t n_local, const vp_F* challenges, size_t n_challenges,
+                   vp_F* transcript, size_t transcript_cap);
+/* ------------------------------------------------------------------ polynomial commitment, commit phase
+ * Replaces poly_commit_prover::commit_private_array (lib/virgo/src/poly_commit.h:41-124: per-slice inverse FFT + 32x
+ * Reed-Solomon extension, RS_polynomial.cpp:26-220), fri::request_init_commit (fri.cpp:36-139: SHA3-256 leaf chains,
+ * my_hhash.h:27-33) and merkle_tree_prover::create_tree (merkle_tree.cpp:7-51) as prover::commit_private uses them
+ * (prover.cpp:524-530: circuitValue[0] padded to 2^bitLength, ONE zero mask element -- other masks return VP_ERR_ARG).
+ * root = the 32-byte Merkle root (the __hhash_digest commit_private returns). The codeword array l_eval
+ * [65 * slice_size], the leaf hashes [slice_size / 2 * 32 B] and the Merkle tree [slice_size * 32 B, array heap, node 1 =
+ * root] stay on the device; vp_commit_export copies them out for the reference's CPU opening phase (any pointer may be
+ * NULL). slice_size = 2^(bitLength(0) - 1). Needs bitLength(0) >= 6; unsharded contexts.
+ * Not reproduced: with bitLength(0) == 8 the reference's 4-point inverse FFT returns uninitialised scratch memory
+ * (RS_polynomial.cpp:100: `blk_size / packed_size * 2` iterations == 0); this library computes the transform. */
+int vp_commit_private(vp_ctx* ctx, const vp_F* mask, size_t n_mask, uint8_t root[32]);
+int vp_commit_export(vp_ctx* ctx, vp_F* l_eval, uint8_t* leaf_hash, uint8_t* tree);
+uint64_t vp_commit_slice_size(const vp_ctx* ctx);
+float vp_last_commit_ms(const vp_ctx* ctx);   /* device time of the last vp_commit_private */
+/* The same on a host array of n canonical field elements, zero-padded to 2^log_len (6 <= log_len <= 30). */
+int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t root[32], vp_F* l_eval, uint8_t* leaf_hash,
+                 uint8_t* tree, float* device_ms);
+
 /* Self-test of the device-only arithmetic paths of csrc/field.cuh (inline-PTX carry chains, mul.wide / mad.wide):
    runs one routine on n caller-provided operand triples and returns the results, so that tests can feed edge values
    (0, 1, p-1, p, limb boundaries) and compare with big-integer arithmetic.  op: 0 weak fold a + c*(b-a); 1 the same for
@@ -184,7 +210,9 @@ int vp_selftest_field(int device, int op, const vp_F* a, const vp_F* b, const vp
    (vp_set_inputs or vp_prove with host_io) and challenge stream (vp_set_challenges / vp_prove). *accept = 1, or 0 with
    *fail_code = 1 phase-1 round, 2 phase-2 round, 3 layer final value, 4 Liu round, 5 Liu final, 6 input layer, and
    *fail_layer (either may be NULL). The polynomial-commitment opening (verifyPoly) is out of scope: the input-layer
-   MLE is recomputed from the inputs. Unsharded contexts only. */
+   MLE is recomputed from the inputs. On a sharded context this is a COLLECTIVE call: every rank passes the same
+   transcript, sums the gates of its own slice of the instances, the partial sums meet in one all-gather and every
+   rank returns the same verdict. */
 int vp_verify(vp_ctx* ctx, const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer);
 int vp_get_transcript(vp_ctx* ctx, vp_F* transcript, size_t cap);
 /* Device-side time of the last vp_prove (CUDA events on the context's stream), milliseconds. */

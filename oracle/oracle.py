@@ -184,3 +184,55 @@ def ref_prove(flat):
                            _p(f["inputs"]), 3396, _p(tr), C.byref(ps), C.byref(es))
     assert n == len(tr), (n, len(tr))
     return tr, ps.value, es.value
+
+
+# ---------------------------------------------------------------- polynomial commitment, commit phase (pc_oracle.c)
+def sha3_256(data):
+    L = lib()
+    out = (C.c_ubyte * 32)()
+    buf = (C.c_ubyte * max(1, len(data))).from_buffer_copy(data if data else b"\0")
+    L.opc_sha3_256.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.opc_sha3_256.restype = None
+    L.opc_sha3_256(buf, len(data), out)
+    return bytes(out)
+
+
+def pc_commit_private(array, log_len, mask=None, want_arrays=True):
+    """poly_commit_prover::commit_private_array restated (poly_commit.h:41-124): -> dict(root, l_eval, leaf_hash, tree)"""
+    L = lib()
+    L.opc_commit_private.restype = C.c_long
+    L.opc_commit_private.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    a = np.zeros(1 << log_len, F_DTYPE)
+    a[:len(array)] = array
+    m = np.zeros(1, F_DTYPE) if mask is None else np.ascontiguousarray(mask, dtype=F_DTYPE)
+    ss = 1 << (log_len - 1)
+    root = np.zeros(32, np.uint8)
+    l_eval = np.zeros(65 * ss, F_DTYPE) if want_arrays else None
+    leaf = np.zeros(ss // 2 * 32, np.uint8) if want_arrays else None
+    tree = np.zeros(ss * 32, np.uint8) if want_arrays else None
+    rc = L.opc_commit_private(_p(a), log_len, _p(m), len(m), _p(l_eval) if want_arrays else None,
+                              _p(leaf) if want_arrays else None, _p(tree) if want_arrays else None, _p(root))
+    assert rc == ss, rc
+    return dict(root=root.tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss)
+
+
+REF_PC = os.path.join(REF_DIR, "ref_pc_commit")
+
+
+def ref_pc_commit(array, log_len):
+    """the UNMODIFIED reference commit_private_array (oracle/_ref/ref_pc_commit) -> dict(root, l_eval, leaf_hash, tree, seconds)"""
+    import tempfile
+    a = np.zeros(1 << log_len, F_DTYPE)
+    a[:len(array)] = array
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "a.bin"), os.path.join(td, "o.bin")
+        a.tofile(fin)
+        r = subprocess.run([REF_PC, str(log_len), fin, fout], capture_output=True, text=True, check=True)
+        ss = 1 << (log_len - 1)
+        raw = np.fromfile(fout, dtype=np.uint8)
+    o = 32
+    l_eval = raw[o:o + 65 * ss * 16].view(F_DTYPE); o += 65 * ss * 16
+    leaf = raw[o:o + ss // 2 * 32]; o += ss // 2 * 32
+    tree = raw[o:o + ss * 32]
+    return dict(root=raw[:32].tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss,
+                seconds=float(r.stdout.split("commit_seconds")[1]))

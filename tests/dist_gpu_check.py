@@ -24,10 +24,10 @@ def main():
     cases = [("sha256_64 x %d" % k, sha.replicate(k) if k > 1 else sha) for k in [int(a) for a in sys.argv[1:]] or [1, 3, 16]]
     cases.append(("random 6x2^13", B.Circuit.random(6, 13, 5)))
     cases.append(("random 4x2^5 x 37", B.Circuit.random(4, 5, 9).replicate(37)))
-    # (next: "random 7x2^9 x 96" -- replicated multi-source wiring with sharded phases; its host-side range logic is
-    # covered by tests/test_sharding.py under gloo, the GPU run was not possible within this round's GPU budget)
-    if os.environ.get("VP_DIST_EXTRA"):
-        cases.append(("random 7x2^9 x 96", B.Circuit.random(7, 9, 5).replicate(96)))
+    # replicated multi-source wiring (operands from any earlier layer: many phase-2 tables per layer) with sharded phases
+    cases.append(("random 7x2^9 x 96", B.Circuit.random(7, 9, 5).replicate(96)))
+    # one big instance (K = 1): every rank visits all gates and keeps the rows it owns (the C4 strong-scaling shape)
+    cases.append(("random 9x2^14", B.Circuit.random(9, 14, 3)))
     ok_all = True
     for name, circ in cases:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -43,9 +43,23 @@ def main():
         same = bool((got["re"] == want["re"]).all() and (got["im"] == want["im"]).all())
         same2 = bool((got2["re"] == want["re"]).all() and (got2["im"] == want["im"]).all())
         bad = np.nonzero((got["re"] != want["re"]) | (got["im"] != want["im"]))[0]
+        # vp_prove_local: the rank hands over only the witness slice it holds (vp_input_range)
+        lo, hi = p.input_range()
+        s0 = circ.num_inputs // circ.instances
+        got3 = p.prove_local(circ.inputs()[lo * s0:hi * s0], circ.draw_challenges())
+        same3 = bool((got3["re"] == want["re"]).all() and (got3["im"] == want["im"]).all())
+        # sharded vp_verify (collective): same verdicts as the oracle's verifier on honest and tampered transcripts
+        oc = O.OracleCircuit(flat.flat())
+        vok = True
+        for idx in (None, 0, 2, len(want) // 3, len(want) // 2, len(want) - 2, len(want) - 1):
+            t = want.copy()
+            if idx is not None:
+                t[idx]["re"] = (int(t[idx]["re"]) + 1) % B.P
+            w = oc.verify(t)
+            vok &= p.verify(t) == (bool(w[0]), w[1], w[2])
         print(f"[rank {rank}/{world}] {name}: gates {circ.total_gates}, sharded phases {sharded}, transcript {len(got)} "
-              f"{'OK' if same and same2 else 'MISMATCH at ' + str(bad[:8])}", flush=True)
-        ok_all &= same and same2
+              f"{'OK' if same and same2 and same3 else 'MISMATCH at ' + str(bad[:8])}, sharded verifier {'OK' if vok else 'MISMATCH'}", flush=True)
+        ok_all &= same and same2 and same3 and vok
         p.close()
         dist.barrier()
     t = torch.tensor([1 if ok_all else 0], device="cuda")

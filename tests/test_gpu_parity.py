@@ -592,3 +592,60 @@ def test_c4_shape_transcript_hash_equals_reference(B, name, n_layers, log_size):
     tr = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
     assert _sha(tr) == g["transcript_sha256"]
     p.close()
+
+
+# ------------------------------------------------------------------ polynomial commitment, commit phase
+def _pc_tools():
+    import importlib.util
+    import json
+    import os
+    import helpers as H
+    spec = importlib.util.spec_from_file_location("make_golden_pc", os.path.join(H.GOLDEN, "make_golden_pc.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    with open(os.path.join(H.GOLDEN, "pc_commit.json")) as f:
+        return m, json.load(f)
+
+
+@pytest.mark.parametrize("name", ["random_6_1", "random_7_2", "random_9_3", "random_10_4", "random_11_5", "random_12_6", "sha256_64", "sha256_64_x16"])
+def test_pc_commit_matches_reference_golden(B, O, name):
+    """device commit (inverse NTT per slice, 32 coset NTTs, SHA3 leaf chains, Merkle tree) == what the reference's
+    commit_private_array produced (root + hashes of every array), and == the oracle element by element"""
+    mk, golden = _pc_tools()
+    a, b = mk.case_array(B, O, name)
+    got = B.pc_commit(a, b)
+    g = golden[name]
+    d = mk.digest_of(got)
+    assert d["root"] == g["root"]
+    if d["l_eval_sha256"] != g["l_eval_sha256"]:
+        want = O.pc_commit_private(a, b)
+        _assert_same(got["l_eval"], want["l_eval"], "l_eval")
+    for k in ("l_eval_sha256", "leaf_sha256", "tree_sha256"):
+        assert d[k] == g[k], k
+
+
+def test_pc_commit_long_transforms_vs_oracle(B, O):
+    """slices longer than the 2^11 points a block holds in shared memory (extra global stages): 2^18 and 2^19 inputs"""
+    rng = np.random.default_rng(12)
+    for b in (18, 19):
+        a = _rand_fe(B, rng, (1 << b) - 1234)          # ragged: the tail is zero padding
+        got = B.pc_commit(a, b)
+        want = O.pc_commit_private(a, b)
+        _assert_same(got["l_eval"], want["l_eval"], f"l_eval 2^{b}")
+        assert got["root"] == want["root"] and (got["leaf_hash"] == want["leaf_hash"]).all() and (got["tree"][32:] == want["tree"][32:]).all()
+
+
+def test_commit_private_through_the_context(B, O, sha_circuit):
+    """prover::commit_private (prover.cpp:524-530) through the context: circuitValue[0] of SHA256_64 (x1 and x16)"""
+    _, golden = _pc_tools()
+    for circ, name in ((sha_circuit, "sha256_64"), (sha_circuit.replicate(16), "sha256_64_x16")):
+        p = B.Prover(circ)
+        root = p.commit_private()
+        assert root.hex() == golden[name]["root"]
+        p.evaluate()
+        assert p.commit_private() == root               # also after evaluate()
+        ex = p.commit_export()
+        assert ex["tree"][32:64].tobytes() == root
+        with pytest.raises(B.VpError):
+            p.commit_private(mask=B.fe_array([(1, 0)]))  # only the GKR prover's zero mask
+        p.close()

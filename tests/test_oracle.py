@@ -253,3 +253,51 @@ def test_loader_rejects_hostile_ids_without_allocating(B):
     with pytest.raises(B.VpError):
         B.Circuit.from_arrays([2, 1], [6, 6, 1], [-1, -1, 0], [1, 2, 0], [0, 0, 1], lv=[0, 0, 0],
                               dad_size=[0, 0, 2, 0], dad_id=[1, 7])
+
+
+# ------------------------------------------------------------------ polynomial commitment, commit phase (N1): oracle pinned
+def _pc_golden():
+    import json
+    with open(os.path.join(H.GOLDEN, "pc_commit.json")) as f:
+        return json.load(f)
+
+
+def _pc_make():
+    spec = importlib.util.spec_from_file_location("make_golden_pc", os.path.join(H.GOLDEN, "make_golden_pc.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_sha3_256_known_answers(O):
+    """FIPS 202 / NIST example values; the commitment hashes 64-byte blocks only (one Keccak-f permutation)"""
+    assert O.sha3_256(b"").hex() == "a7ffc6f8bf1ed76651c14756a061d662f580ff4de43b49fa82d80a4b80f8434a"
+    assert O.sha3_256(b"abc").hex() == "3a985da74fe225b2045c172d6bd390bd855f086e3e9d525b46bfe24511431532"
+    assert O.sha3_256(b"\xa3" * 200).hex() == "79f38adec5c20307a98ef76e8324afbfd46cfd81b22e3973c65fa1bd9de31787"
+    for n in (1, 55, 64, 135, 136, 137, 300):
+        msg = bytes((7 * i + n) % 256 for i in range(n))
+        assert O.sha3_256(msg) == hashlib.sha3_256(msg).digest()
+
+
+@pytest.mark.parametrize("name", ["random_6_1", "random_7_2", "random_9_3", "random_10_4", "random_11_5", "random_12_6", "sha256_64", "sha256_64_x16"])
+def test_pc_oracle_matches_reference_commit(B, O, name):
+    """pc_oracle.c == the reference's commit_private_array: root, codewords, leaf hashes, tree (golden: make_golden_pc.py)"""
+    g = _pc_golden()[name]
+    mk = _pc_make()
+    a, b = mk.case_array(B, O, name)
+    assert b == g["log_len"] and len(a) == g["n"]
+    got = mk.digest_of(O.pc_commit_private(a, b))
+    for k in ("root", "l_eval_sha256", "leaf_sha256", "tree_sha256", "slice_size"):
+        assert got[k] == g[k], k
+
+
+def test_pc_oracle_matches_live_reference_when_available(B, O):
+    if not os.path.exists(O.REF_PC):
+        pytest.skip("oracle/_ref/ref_pc_commit not built")
+    rng = np.random.default_rng(77)
+    for b in (6, 9, 11):
+        a = np.zeros(1 << b, O.F_DTYPE)
+        a["re"] = rng.integers(0, B.P, 1 << b, dtype=np.uint64)
+        a["im"] = rng.integers(0, B.P, 1 << b, dtype=np.uint64)
+        r, o = O.ref_pc_commit(a, b), O.pc_commit_private(a, b)
+        assert r["root"] == o["root"] and (r["l_eval"] == o["l_eval"]).all() and (r["leaf_hash"] == o["leaf_hash"]).all()

@@ -102,6 +102,15 @@ def _declare(L):
     L.vp_prove_seconds.restype = C.c_double
     L.vp_set_challenges.argtypes = [vp, vp, C.c_size_t]
     L.vp_prove.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t]
+    L.vp_input_range.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.vp_prove_local.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t]
+    L.vp_commit_private.argtypes = [vp, vp, C.c_size_t, vp]
+    L.vp_commit_export.argtypes = [vp, vp, vp, vp]
+    L.vp_commit_slice_size.argtypes = [vp]
+    L.vp_commit_slice_size.restype = C.c_uint64
+    L.vp_last_commit_ms.argtypes = [vp]
+    L.vp_last_commit_ms.restype = C.c_float
+    L.vp_pc_commit.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_get_transcript.argtypes = [vp, vp, C.c_size_t]
     L.vp_last_prove_ms.argtypes = [vp]
     L.vp_last_prove_ms.restype = C.c_float
@@ -346,6 +355,19 @@ def selftest_field(op, a, b, c, device=0):
     return out
 
 
+def pc_commit(array, log_len, device=0, want_arrays=True):
+    """commit phase of the polynomial commitment on a host array (vp_pc_commit) -> dict(root, l_eval, leaf_hash, tree, ms)"""
+    a = np.ascontiguousarray(array, dtype=F_DTYPE)
+    ss = 1 << (log_len - 1)
+    root = np.zeros(32, np.uint8)
+    l_eval = np.zeros(65 * ss, F_DTYPE) if want_arrays else None
+    leaf = np.zeros(ss // 2 * 32, np.uint8) if want_arrays else None
+    tree = np.zeros(ss * 32, np.uint8) if want_arrays else None
+    ms = C.c_float()
+    _ck(lib().vp_pc_commit(device, _ptr(a), len(a), log_len, _ptr(root), _ptr(l_eval), _ptr(leaf), _ptr(tree), C.byref(ms)))
+    return dict(root=root.tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss, ms=ms.value)
+
+
 def shard_describe(circuit, world, rank, layer, phase):
     out = np.zeros(10 * 256, np.uint32)
     n = C.c_size_t()
@@ -499,6 +521,39 @@ class Prover:
             return transcript
         _ck(lib().vp_prove(self.h, 0, None, 0, None, 0, None, 0))
         return None
+
+    def commit_private(self, mask=None):
+        """prover::commit_private (prover.cpp:524-530) on the device: the Merkle root of the input layer's commitment"""
+        m = np.zeros(1, F_DTYPE) if mask is None else np.ascontiguousarray(mask, dtype=F_DTYPE)
+        root = np.zeros(32, np.uint8)
+        _ck(lib().vp_commit_private(self.h, _ptr(m), len(m), _ptr(root)))
+        return root.tobytes()
+
+    def commit_export(self):
+        ss = int(lib().vp_commit_slice_size(self.h))
+        l_eval, leaf, tree = np.zeros(65 * ss, F_DTYPE), np.zeros(ss // 2 * 32, np.uint8), np.zeros(ss * 32, np.uint8)
+        _ck(lib().vp_commit_export(self.h, _ptr(l_eval), _ptr(leaf), _ptr(tree)))
+        return dict(l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss)
+
+    @property
+    def last_commit_ms(self):
+        return float(lib().vp_last_commit_ms(self.h))
+
+    def input_range(self):
+        """instances [first, end) whose witness this rank uploads (everything on an unsharded context)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        _ck(lib().vp_input_range(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def prove_local(self, local_inputs, challenges, transcript=None):
+        """vp_prove(host_io=1) for a caller that only holds the inputs of input_range()"""
+        local_inputs = np.ascontiguousarray(local_inputs, dtype=np.uint64)
+        challenges = np.ascontiguousarray(challenges, dtype=F_DTYPE)
+        if transcript is None:
+            transcript = np.zeros(self.circuit.transcript_len, F_DTYPE)
+        _ck(lib().vp_prove_local(self.h, _ptr(local_inputs), len(local_inputs), _ptr(challenges), len(challenges),
+                                 _ptr(transcript), len(transcript)))
+        return transcript
 
     def transcript(self):
         out = np.zeros(self.circuit.transcript_len, F_DTYPE)

@@ -21,6 +21,7 @@
 #include "../host/circuit_model.h"
 #include "../host/proof_io.h"
 #include "kernels.cuh"
+#include "pc_commit.h"
 
 using namespace vp;
 
@@ -680,6 +681,15 @@ static void dfs_enable_smem() {   // opt in to the dynamic shared memory of the 
     for (const void* k : ks) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DFS_DYN_SMEM));
 }
 
+// One-kernel NVLink exchange (k_xchg): per lane an exchange buffer that every rank of the box maps through CUDA IPC.
+// Layout (entries of F): [0, 16) the ranks' flags (u32 each), then two parity buffers of world * slot_stride entries.
+struct XchgLane {
+    F* base = nullptr;                   // own allocation (cudaMalloc: IPC handles refer to whole allocations)
+    F* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t seq = 0;                    // exchanges done on this lane (the ranks run the same sequence)
+    DBuf<F> d_sc;                        // this rank's partial scalars of the phase in flight (zero between phases)
+    DBuf<unsigned int> ticket;
+};
 struct Engine {
     Circuit C;
     int device = 0;
@@ -705,7 +715,9 @@ struct Engine {
         vp_ncclComm_t comm = nullptr;
         size_t eq_off = 0;               // this lane's eq region set inside d_eq (entries)
         cudaEvent_t ev_done = nullptr;
+        XchgLane x;                      // NVLink exchange state of this lane (sharded contexts)
     } lane1, lane2, lane0b, lane1b, lane2b;
+    XchgLane x;                          // ... and of the main lane
     // third lane: phase 2 of layer i only needs V_u from phase 1 of the same layer, and phase 1 of layer i-1 needs
     // nothing from phase 2 of layer i (the challenges are known): phase 1 / phase 2 / Liu each run on their own stream,
     // phase 2 one event behind phase 1. V_u is kept per layer (d_vu) instead of in one scalar.
@@ -733,6 +745,7 @@ struct Engine {
         std::swap(d_recv, R.d_recv);
         std::swap(comm, R.comm);
         std::swap(eq_off, R.eq_off);
+        std::swap(x, R.x);
     }
     bool two_lanes = false, on_lane1 = false;
     // role of the lane being entered: 0 = phase 1 (behaves like the main lane), 1 = Liu, 2 = phase 2
@@ -749,6 +762,12 @@ struct Engine {
         active = nullptr;
         on_lane1 = on_lane2 = false;
     }
+    PcCommit* pc = nullptr;          // polynomial-commitment commit phase, created on first use
+    float last_commit_ms = 0;
+    bool use_ipc = false;            // sharded: one-kernel NVLink exchange (k_xchg) instead of NCCL all-gathers
+    uint32_t x_stride = 0;           // entries of one rank's slot in an exchange buffer
+    std::vector<void*> ipc_opened;   // peer mappings to close
+    void setup_ipc_exchange(uint32_t max_rec);
     bool direct_v = false;   // whole-proof: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
     cudaEvent_t ev_eval = nullptr;
     uint32_t region_u_lane1 = 0;
@@ -852,6 +871,10 @@ struct Engine {
         for (auto e : ev_chunk) if (e) cudaEventDestroy(e);
         if (ev_copy_go) cudaEventDestroy(ev_copy_go);
         if (ev_eval) cudaEventDestroy(ev_eval);
+        if (pc) pc_destroy(pc);
+        for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
+        for (XchgLane* X : {&x, &lane1.x, &lane2.x, &lane0b.x, &lane1b.x, &lane2b.x})
+            if (X->base) cudaFree(X->base);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (lane1.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane1.comm);
         if (lane2.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(lane2.comm);
@@ -894,7 +917,7 @@ struct Engine {
 
     void build(const Circuit& circ, int dev, int world_, int rank_, const uint8_t* nccl_id);
     void load_inputs(const uint64_t* host, size_t cnt, bool from_host);
-    void load_inputs_chunked(const uint64_t* host, size_t cnt);
+    void load_inputs_chunked(const uint64_t* host, size_t cnt, bool local = false);
     static constexpr int IN_CHUNKS = 4;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_chunk[IN_CHUNKS] = {nullptr, nullptr, nullptr, nullptr}, ev_copy_go = nullptr;
@@ -902,7 +925,7 @@ struct Engine {
     int pending_chunks = 0;
     void evaluate();
     void run_eq(uint32_t first, uint32_t count);
-    void run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out);
+    void run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out, bool local_only = false);
     void do_vres();
     void do_input_mle();
     void do_init_phase1(int i);
@@ -918,7 +941,7 @@ struct Engine {
     // verifier: O(#gates) sums on the device, protocol checks on the host
     void verify_prepare(int i);
     int verify(const F* tr, int* fail_code, int* fail_layer);
-    DBuf<F> d_vf_partial, d_vf_out;
+    DBuf<F> d_vf_partial, d_vf_out, d_vf_gather;
     static constexpr uint32_t VF_GX = 64;
     DBuf<ChainDesc> d_chains;
     DBuf<ChainSeg> d_chain_segs;
@@ -1328,7 +1351,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     }
     two_lanes = !getenv("VP_ONE_LANE");
     three_lanes = two_lanes && !getenv("VP_TWO_LANES");
-    six_lanes = three_lanes && world == 1 && !getenv("VP_THREE_LANES");
+    // sharded contexts exchange through NVLink-mapped buffers (k_xchg) unless VP_NCCL_EXCHANGE is set or the IPC set-up
+    // fails on some rank; the second set of lanes needs no NCCL communicators then
+    const bool want_ipc = world > 1 && !getenv("VP_NCCL_EXCHANGE");
+    six_lanes = three_lanes && (world == 1 || want_ipc) && !getenv("VP_THREE_LANES");
     d_rowpart.alloc(max_partial);
     auto alloc_lane = [&](LaneRes& R, int role, size_t eqo) {   // role: 0 phase 1, 1 Liu, 2 phase 2
         uint32_t c0 = 4, c1 = 4;
@@ -1381,8 +1407,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         NcclId id;
         memcpy(id.internal, nccl_id, 128);
         NCK(g_nccl.CommInitRank(&comm, world, id, rank));
+        if (want_ipc) setup_ipc_exchange(std::max<uint32_t>(max_rec, 1));
+        if (!use_ipc) six_lanes = false;
     }
-    if (two_lanes && world > 1) {
+    if (two_lanes && world > 1 && !use_ipc) {
         // lane 1 issues its own all-gathers concurrently with lane 0: it needs its own communicator. Rank 0 draws a
         // second unique id and broadcasts it over the first communicator.
         DBuf<unsigned char> d_id;
@@ -1434,6 +1462,74 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     CK(cudaStreamSynchronize(stream));
 }
 
+// Exchange buffers of every lane, mapped into every rank (CUDA IPC over the box's NVLink fabric). Collective: the
+// handles travel through one NCCL all-gather on the main communicator, and the ranks agree on the outcome.
+void Engine::setup_ipc_exchange(uint32_t max_rec) {
+    std::vector<XchgLane*> X{&x};
+    if (two_lanes) X.push_back(&lane1.x);
+    if (three_lanes) X.push_back(&lane2.x);
+    if (six_lanes) { X.push_back(&lane0b.x); X.push_back(&lane1b.x); X.push_back(&lane2b.x); }
+    const size_t nl = X.size();
+    x_stride = align4(max_rec);
+    const size_t entries = 16 + 2 * (size_t)world * x_stride;
+    const size_t n_sc = 3 * 32 + 1 + (size_t)n + 8;
+    bool ok = true;
+    std::string why;
+    std::vector<cudaIpcMemHandle_t> mine(nl);
+    for (size_t i = 0; i < nl && ok; ++i) {
+        if (cudaMalloc(&X[i]->base, entries * sizeof(F)) != cudaSuccess) { ok = false; why = "cudaMalloc"; X[i]->base = nullptr; break; }
+        CK(cudaMemsetAsync(X[i]->base, 0, entries * sizeof(F), stream));
+        X[i]->d_sc.alloc(n_sc);
+        CK(cudaMemsetAsync(X[i]->d_sc.p, 0, n_sc * sizeof(F), stream));
+        X[i]->ticket.alloc(4);
+        CK(cudaMemsetAsync(X[i]->ticket.p, 0, 4 * sizeof(unsigned int), stream));
+        X[i]->seq = 0;
+        if (cudaIpcGetMemHandle(&mine[i], X[i]->base) != cudaSuccess) { ok = false; why = "cudaIpcGetMemHandle"; }
+    }
+    cudaGetLastError();
+    CK(cudaStreamSynchronize(stream));
+    // all-gather the handles (64 bytes each)
+    const size_t hb = sizeof(cudaIpcMemHandle_t), per = nl * hb + 8;   // + this rank's "ok so far"
+    DBuf<unsigned char> d_mine, d_all;
+    d_mine.alloc(per);
+    d_all.alloc(per * world);
+    std::vector<unsigned char> h_mine(per, 0), h_all(per * world, 0);
+    memcpy(h_mine.data(), mine.data(), nl * hb);
+    h_mine[nl * hb] = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(d_mine.p, h_mine.data(), per, cudaMemcpyHostToDevice, stream));
+    NCK(g_nccl.AllGather(d_mine.p, d_all.p, per, /*ncclUint8*/ 1, comm, stream));
+    CK(cudaMemcpyAsync(h_all.data(), d_all.p, per * world, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int q = 0; q < world; ++q) ok = ok && h_all[(size_t)q * per + nl * hb] == 1;
+    if (ok)
+        for (int q = 0; q < world && ok; ++q)
+            for (size_t i = 0; i < nl && ok; ++i) {
+                if (q == rank) { X[i]->peer[q] = X[i]->base; continue; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, h_all.data() + (size_t)q * per + i * hb, hb);
+                void* ptr = nullptr;
+                const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { ok = false; why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); break; }
+                ipc_opened.push_back(ptr);
+                X[i]->peer[q] = (F*)ptr;
+            }
+    // second agreement: did every rank map every peer?
+    h_mine[0] = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(d_mine.p, h_mine.data(), 8, cudaMemcpyHostToDevice, stream));
+    NCK(g_nccl.AllGather(d_mine.p, d_all.p, 8, /*ncclUint8*/ 1, comm, stream));
+    CK(cudaMemcpyAsync(h_all.data(), d_all.p, (size_t)8 * world, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int q = 0; q < world; ++q) ok = ok && h_all[(size_t)q * 8] == 1;
+    use_ipc = ok;
+    if (!ok) {
+        if (rank == 0 || !why.empty())
+            fprintf(stderr, "virgo_b200[rank %d]: NVLink exchange unavailable (%s), using NCCL all-gathers\n", rank, why.empty() ? "a peer failed" : why.c_str());
+        if (pc) pc_destroy(pc);
+        for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
+        ipc_opened.clear();
+    }
+}
+
 // ------------------------------------------------------------------ steps
 void Engine::load_inputs(const uint64_t* host, size_t cnt, bool from_host) {
     if (cnt != C.layer_size(0)) throw CudaError{"vp_set_inputs: wrong number of inputs"};
@@ -1449,8 +1545,11 @@ void Engine::load_inputs(const uint64_t* host, size_t cnt, bool from_host) {
 // vp_prove with host buffers: the upload is cut into IN_CHUNKS instance ranges on a copy stream, and evaluate() walks
 // the same ranges, each behind its chunk's event, so that all but the first chunk's copy overlaps evaluation
 // (the upload of 59 MB is 1.1 ms of the C3 end-to-end step; evaluate is 0.8 ms).
-void Engine::load_inputs_chunked(const uint64_t* host, size_t cnt) {
-    if (cnt != C.layer_size(0)) throw CudaError{"vp_prove: wrong number of inputs"};
+void Engine::load_inputs_chunked(const uint64_t* host, size_t cnt, bool local) {
+    if (local) {   // `host` holds only the instances [k_lo, k_hi) this rank uploads (vp_input_range)
+        if (cnt != (size_t)(k_hi - k_lo) * C.layers[0].size) throw CudaError{"vp_prove_local: wrong number of inputs for this rank's instance range"};
+        host -= (size_t)k_lo * C.layers[0].size;
+    } else if (cnt != C.layer_size(0)) throw CudaError{"vp_prove: wrong number of inputs"};
     if (!copy_stream) {
         CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         for (auto& e : ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1508,13 +1607,13 @@ void Engine::run_eq(uint32_t first, uint32_t count) {
 
 // <X, eq(r,.)> over the replicated layer of template size S. Sharded: every rank sums its own instance slice, the
 // partial sums meet in one 16-byte-per-rank all-gather.
-void Engine::run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out) {
+void Engine::run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out, bool local_only) {
     const uint32_t begin = ko_lo * S, end = ko_hi * S;
-    F* dst = world > 1 ? d_send.p : out;
+    F* dst = (world > 1 && !local_only) ? d_send.p : out;
     k_dot_eq<<<grid_for(std::max<uint32_t>(end - begin, 1), cap_dot), 256, 0, stream>>>(X, begin, end, eq, dst, d_partials.p,
                                                                                        d_counter.p);
     ++launches;
-    if (world > 1) {
+    if (world > 1 && !local_only) {
         NCK(g_nccl.AllGather(d_send.p, d_recv.p, 2, /*ncclUint64*/ 5, comm, stream));
         k_sum_ranks<<<1, 32, 0, stream>>>(d_recv.p, (uint32_t)world, 1, out);
         ++launches;
@@ -1556,8 +1655,9 @@ void Engine::do_init_phase1(int i) {
             bufM[0].p + D.ph1.tab_off[0], bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, D.ph1.maps[0], direct_v ? 0 : 1, k0, k1);
         ++launches;
     }
-    // per output: V read + 3 table writes; per gate: one gathered operand
-    prof_end(h, (double)tot * (direct_v ? 32.0 : 64.0) + (double)D.S * K * 16.0);
+    // per output this rank holds: V read + 3 table writes; per gate it visits: one gathered operand
+    const double rows1 = D.ph1.sharded ? (double)(D.ph1.row_hi[0] - D.ph1.row_lo[0]) : (double)tot;
+    prof_end(h, rows1 * (direct_v ? 32.0 : 64.0) + (double)D.S * (k1 - k0) * 16.0);
     ++launches;
     have_equ = false;
 }
@@ -1597,7 +1697,9 @@ void Engine::do_init_phase2(int i) {
                 kk1);
             ++launches;
         }
-        prof_end(h, (double)D.p2_out_entries * 64.0 + (double)D.p2_gates * K * 16.0);
+        double rows2 = D.p2_out_entries;   // table entries this rank holds
+        if (D.ph2.sharded) { rows2 = 0; for (size_t t = 0; t < D.ph2.row_hi.size(); ++t) rows2 += (double)(D.ph2.row_hi[t] - D.ph2.row_lo[t]); }
+        prof_end(h, rows2 * 64.0 + (double)D.p2_gates * (kk1 - kk0) * 16.0);
         ++launches;
     }
     // unary gates: their sum starts the phase's add_term (see k_phase2_unary); each rank sums its instance slice
@@ -1762,6 +1864,51 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
         else launch_phase_kernel(P.planB, ci, 0, at_init, scal(SC_ADD_TERM), d_claims.p, d_tr.p + tr_rounds, keep);
         return;
     }
+    const F* v_local_x = (v_first && P.maps.size() == 1 && P.tab_off[0] == 0) ? v_first + P.maps[0].lo : nullptr;
+    if (v_first && !v_local_x) throw CudaError{"direct V: unexpected table layout"};
+    if (use_ipc) {
+        // stage A leaves its partial scalars in the lane's scalar buffer (zero between phases); ONE kernel pushes the
+        // record to every rank over NVLink, waits for theirs and merges; stage B as below
+        F* sc = x.d_sc.p;
+        launch_dfs_kernel(P.ppA, ci, 0, at_init, sc + P.n_poly, sc + P.n_poly + 1, sc, nullptr, has_a, values_real ? DFS_VREAL : DFS_PLAIN, v_local_x);
+        XchgArgs a;
+        memset(&a, 0, sizeof a);
+        for (int q = 0; q < world; ++q) a.peer[q] = x.peer[q];
+        a.world = (uint32_t)world;
+        a.me = (uint32_t)rank;
+        a.seq = ++x.seq;
+        a.slot_stride = x_stride;
+        a.buf_off[0] = 16;
+        a.buf_off[1] = 16 + (uint32_t)world * x_stride;
+        a.rec_len = P.rec_len;
+        a.fo = d_fo.p + P.fo_begin;
+        a.n_fo = P.n_fo;
+        const int fb = P.ppA.fin_buf;
+        a.V = bufV[fb].p; a.M = bufM[fb].p; a.A = bufA[fb].p;
+        a.has_a = has_a ? 1 : 0;
+        a.sc = sc;
+        a.sc_base = P.sc_base;
+        a.n_sc = P.n_poly + 1 + P.n_claims;
+        a.ticket = x.ticket.p;
+        a.mg.recv = nullptr;
+        a.mg.rec_len = P.rec_len;
+        a.mg.G = (uint32_t)world;
+        a.mg.tabs = d_mt.p + P.mt_begin;
+        a.mg.n_tabs = P.n_mt;
+        a.mg.sc_base = P.sc_base;
+        a.mg.n_poly = P.n_poly;
+        a.mg.n_claims = P.n_claims;
+        a.mg.outV = bufV[0].p; a.mg.outM = bufM[0].p; a.mg.outA = bufA[0].p;
+        a.mg.out_poly = d_tr.p + tr_rounds;
+        a.mg.add_term = scal(SC_ADD_TERM);
+        a.mg.claims = d_claims.p;
+        const int grid = (int)std::max<uint32_t>(2, std::min<uint32_t>(cdiv(P.rec_len, 512), 32));
+        k_xchg<<<grid, 256, 0, stream>>>(a);
+        ++launches;
+        launch_dfs_kernel(P.ppB, ci, (uint32_t)P.m, scal(SC_ADD_TERM), scal(SC_ADD_TERM), d_claims.p,
+                          d_tr.p + tr_rounds + 3u * (uint32_t)P.m, keep, has_a, DFS_PLAIN);
+        return;
+    }
     F* rec = d_send.p;
     F* sc = rec + P.sc_base;
     CK(cudaMemsetAsync(sc, 0, (size_t)(P.n_poly + 1 + P.n_claims) * sizeof(F), stream));
@@ -1872,7 +2019,8 @@ void Engine::verify_prepare(int i) {
 // vp_prove. Returns 1 (accept) or 0 with the failing check: 1 phase-1 round, 2 phase-2 round, 3 final value of the
 // layer, 4 Liu round, 5 Liu final, 6 input layer -- the codes of the CPU oracle's verifier (tests compare them).
 int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
-    if (world > 1) throw CudaError{"vp_verify needs an unsharded context"};
+    // Sharded context: a collective call -- every rank passes the same transcript, sums the gates of its own slice of
+    // the instances (ko_lo .. ko_hi), and the partial sums of all ranks meet in ONE all-gather before the host checks.
     if (!inputs_loaded) throw CudaError{"vp_verify: inputs not loaded"};
     if (h_chal.size() < n_chal) throw CudaError{"vp_verify: challenges not set"};
     if (active) throw CudaError{"vp_verify: lanes not joined"};
@@ -1888,10 +2036,11 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
     if (d_vf_out.n < out_total) d_vf_out.alloc(out_total);
     if (d_vf_partial.n < (size_t)max_b * VF_GX * 2) d_vf_partial.alloc((size_t)max_b * VF_GX * 2);
     {   // circuitValue[0] from the resident inputs (the verifier does not evaluate the circuit)
-        const uint32_t tot0 = (uint32_t)C.layer_size(0);
-        k_load_inputs<<<cdiv(std::max<uint32_t>(tot0, 1), 256), 256, 0, stream>>>(d_inputs.p, val[0].p, 0, tot0);
+        const uint32_t S0 = (uint32_t)C.layers[0].size, b0 = k_lo * S0, e0 = k_hi * S0;   // the inputs this rank holds
+        k_load_inputs<<<cdiv(std::max<uint32_t>(e0 - b0, 1), 256), 256, 0, stream>>>(d_inputs.p, val[0].p, b0, e0);
         ++launches;
     }
+    CK(cudaMemsetAsync(d_vf_out.p, 0, (size_t)out_total * sizeof(F), stream));
     for (int i = n - 1; i >= 1; --i) {
         LayerDev& D = L[i];
         const uint32_t S_pre = (uint32_t)C.layers[i - 1].size, nb = (uint32_t)D.vf_key.size();
@@ -1903,7 +2052,7 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
             k_verify_sums<<<dim3(VF_GX, nb), 256, 0, stream>>>(D.vf_buckets.p, D.vf_gates.p, D.vf_assert.p, D.c.p, S_pre, D.S, K,
                                                               eqtab(0, C.bit_length(i)), eqtab(1, pb),
                                                               eqtab(6 + (uint32_t)n, std::max(m, 0)), d_chal.p + D.ci_assert,
-                                                              d_vf_partial.p);
+                                                              d_vf_partial.p, ko_lo, ko_hi);
             k_verify_reduce<<<nb, 64, 0, stream>>>(d_vf_partial.p, VF_GX, d_vf_out.p + D.vf_out);
             launches += 2;
         }
@@ -1911,12 +2060,18 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
         run_eq(D.eqb_rl, 2);                 // eq(r_liu, .)
         run_eq(D.eqb_liu, D.n_eqb_liu);      // sig[j - pre] * eq(r_v[j], .)
         k_verify_gr<<<dim3(VF_GX, D.n_vf_liu), 256, 0, stream>>>(D.vf_liu.p, D.liu_eqtabs.p, eqtab(3 + (uint32_t)n, pb),
-                                                                  eqtab(7 + (uint32_t)n, pb), S_pre, K, d_vf_partial.p);
+                                                                  eqtab(7 + (uint32_t)n, pb), S_pre, K, d_vf_partial.p, ko_lo, ko_hi);
         k_verify_reduce<<<D.n_vf_liu, 64, 0, stream>>>(d_vf_partial.p, VF_GX, d_vf_out.p + D.vf_out + 2 * nb);
         launches += 2;
     }
     run_eq(eqb_in, 2);
-    run_dot_eq(val[0].p, (uint32_t)C.layers[0].size, eqtab(2, C.bit_length(0)), d_vf_out.p + out_total - 2);
+    run_dot_eq(val[0].p, (uint32_t)C.layers[0].size, eqtab(2, C.bit_length(0)), d_vf_out.p + out_total - 2, /*local_only=*/true);
+    if (world > 1) {
+        if (d_vf_gather.n < (size_t)out_total * world) d_vf_gather.alloc((size_t)out_total * world);
+        NCK(g_nccl.AllGather(d_vf_out.p, d_vf_gather.p, (size_t)out_total * 2, /*ncclUint64*/ 5, comm, stream));
+        k_sum_ranks_vec<<<cdiv(out_total, 256), 256, 0, stream>>>(d_vf_gather.p, (uint32_t)world, out_total, d_vf_out.p);
+        ++launches;
+    }
     std::vector<F> out(out_total);
     CK(cudaMemcpyAsync(out.data(), d_vf_out.p, (size_t)out_total * sizeof(F), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -2092,6 +2247,9 @@ extern "C" const char* vp_version(void) { return "virgo-plus_b200 0.1 (sm_100a)"
     catch (const CudaError& e) { return fail(VP_ERR_CUDA, "%s", e.msg.c_str()); } \
     catch (const std::bad_alloc&) { return fail(VP_ERR_NOMEM, "out of host memory"); } \
     catch (unsigned int flag) { return fail(VP_ERR_ASSERT, "assert gate violated in layer %u", flag - 1); } \
+    catch (const std::invalid_argument& e) { return fail(VP_ERR_ARG, "%s", e.what()); } \
+    catch (const std::length_error& e) { return fail(VP_ERR_CIRCUIT, "%s", e.what()); } \
+    catch (const std::runtime_error& e) { return fail(VP_ERR_CUDA, "%s", e.what()); } \
     catch (const std::exception& e) { return fail(VP_ERR_ARG, "%s", e.what()); }
 
 // ------------------------------------------------------------------ C ABI: circuit
@@ -2682,8 +2840,8 @@ extern "C" int vp_set_challenges(vp_ctx* ctx, const vp_F* challenges, size_t n) 
     return VP_OK;
     API_END
 }
-extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
-                        size_t n_challenges, vp_F* transcript, size_t transcript_cap) {
+static int prove_impl(vp_ctx* ctx, int host_io, bool local_inputs, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
+                      size_t n_challenges, vp_F* transcript, size_t transcript_cap) {
     if (!ctx) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN
     Engine& e = ctx->e;
@@ -2697,7 +2855,7 @@ extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t
     CK(cudaEventRecord(e.ev0, e.stream));
     if (host_io) {
         e.set_chal(0, challenges, n_challenges);
-        e.load_inputs_chunked(inputs, n_inputs);   // copies overlap evaluate chunk by chunk
+        e.load_inputs_chunked(inputs, n_inputs, local_inputs);   // copies overlap evaluate chunk by chunk
     }
     e.prove_all();
     if (host_io) CK(cudaMemcpyAsync(transcript, e.d_tr.p, e.n_tr * sizeof(F), cudaMemcpyDeviceToHost, e.stream));
@@ -2712,6 +2870,81 @@ extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t
         e.proof_size += (uint64_t)(2 * pb + (m != -1 ? m : 0)) * 3 * sizeof(F) + sizeof(F);
         if (m != -1) e.proof_size += (uint64_t)i * sizeof(F);
     }
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_prove(vp_ctx* ctx, int host_io, const uint64_t* inputs, size_t n_inputs, const vp_F* challenges,
+                        size_t n_challenges, vp_F* transcript, size_t transcript_cap) {
+    return prove_impl(ctx, host_io, false, inputs, n_inputs, challenges, n_challenges, transcript, transcript_cap);
+}
+extern "C" int vp_input_range(const vp_ctx* ctx, uint64_t* first_instance, uint64_t* end_instance) {
+    if (!ctx || !first_instance || !end_instance) return fail(VP_ERR_ARG, "null argument");
+    *first_instance = ctx->e.k_lo;
+    *end_instance = ctx->e.k_hi;
+    return VP_OK;
+}
+extern "C" int vp_prove_local(vp_ctx* ctx, const uint64_t* local_inputs, size_t n_local, const vp_F* challenges, size_t n_challenges,
+                              vp_F* transcript, size_t transcript_cap) {
+    return prove_impl(ctx, 1, true, local_inputs, n_local, challenges, n_challenges, transcript, transcript_cap);
+}
+// ------------------------------------------------------------------ C ABI: polynomial commitment, commit phase (N1)
+static bool mask_all_zero(const vp_F* mask, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (mask[i].re | mask[i].im) return false;
+    return true;
+}
+extern "C" int vp_commit_private(vp_ctx* ctx, const vp_F* mask, size_t n_mask, uint8_t root[32]) {
+    if (!ctx || !root || (n_mask && !mask)) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    if (e.world > 1) return fail(VP_ERR_ARG, "vp_commit_private needs an unsharded context");
+    if (!e.inputs_loaded) return fail(VP_ERR_ARG, "vp_commit_private: inputs not loaded");
+    if (!mask_all_zero(mask, n_mask)) return fail(VP_ERR_ARG, "vp_commit_private: only the GKR prover's zero mask is supported (prover.cpp:524-530)");
+    const int bl = e.C.bit_length(0);
+    if (bl < 6) return fail(VP_ERR_ARG, "vp_commit_private: the input layer needs at least 2^6 padded entries (64 slices)");
+    if (!e.pc) e.pc = pc_create(e.device, bl);
+    if (!e.evaluated) {   // circuitValue[0] from the resident inputs (what prover::evaluate leaves in layer 0)
+        const uint32_t tot0 = (uint32_t)e.C.layer_size(0);
+        k_load_inputs<<<cdiv(std::max<uint32_t>(tot0, 1), 256), 256, 0, e.stream>>>(e.d_inputs.p, e.val[0].p, 0, tot0);
+        ++e.launches;
+    }
+    e.last_commit_ms = pc_commit(e.pc, e.val[0].p, e.C.layer_size(0), e.stream, root);
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_commit_export(vp_ctx* ctx, vp_F* l_eval, uint8_t* leaf_hash, uint8_t* tree) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_commit_export before vp_commit_private");
+    pc_export(e.pc, e.stream, reinterpret_cast<F*>(l_eval), leaf_hash, tree);
+    return VP_OK;
+    API_END
+}
+extern "C" uint64_t vp_commit_slice_size(const vp_ctx* ctx) { return (ctx && ctx->e.pc) ? pc_slice_size(ctx->e.pc) : 0; }
+extern "C" float vp_last_commit_ms(const vp_ctx* ctx) { return ctx ? ctx->e.last_commit_ms : 0.f; }
+// Stand-alone form on a host array (any field elements, e.g. test vectors): array[0..n) zero-padded to 2^log_len.
+extern "C" int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t root[32], vp_F* l_eval, uint8_t* leaf_hash,
+                            uint8_t* tree, float* device_ms) {
+    if (!array || !root) return fail(VP_ERR_ARG, "null argument");
+    if (log_len < 6 || log_len > 30 || n > ((size_t)1 << log_len)) return fail(VP_ERR_ARG, "vp_pc_commit: log_len in [6, 30], n <= 2^log_len");
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw CudaError{std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(ce)};
+    for (size_t i = 0; i < n; ++i)
+        if (array[i].re >= P || array[i].im >= P) return fail(VP_ERR_ARG, "vp_pc_commit: element %zu is not canonical", i);
+    CK(cudaSetDevice(device));
+    struct Guard { PcCommit* p = nullptr; ~Guard() { if (p) pc_destroy(p); } } g;
+    g.p = pc_create(device, log_len);
+    DBuf<F> d;
+    d.alloc(std::max<size_t>(n, 1));
+    CK(cudaMemcpy(d.p, array, n * sizeof(F), cudaMemcpyHostToDevice));
+    const float ms = pc_commit(g.p, d.p, n, 0, root);
+    if (device_ms) *device_ms = ms;
+    pc_export(g.p, 0, reinterpret_cast<F*>(l_eval), leaf_hash, tree);
     return VP_OK;
     API_END
 }

@@ -1732,6 +1732,105 @@ __global__ void k_shard_merge(MergeArgs p) {
     }
 }
 
+// ------------------------------------------------------------------ the same hand-over in ONE kernel over NVLink
+// (sharded contexts, default): every rank's exchange buffer is mapped into every other rank of the box (CUDA IPC). The
+// kernel (a) stores this rank's record -- the level-m value of each of its blocks, its partial round polynomials, partial
+// add_term and locally collapsed claims -- straight into slot `me` of EVERY rank's buffer (peer stores through
+// NVSwitch, 16 bytes per thread, coalesced), (b) the last block to finish raises this rank's flag on every peer
+// (release at system scope), (c) waits until all ranks' flags for this exchange are up and (d) builds the stage-B
+// tables and sums the partial scalars from the local buffer -- what memset + k_fold_only + ncclAllGather +
+// k_shard_merge did in four stream operations and one NCCL launch. Flags carry the exchange's sequence number
+// (monotonic per lane, the ranks run the same sequence of phases), buffers are double buffered by its parity: a rank
+// can be at most one exchange ahead of a peer that is still reading (it needs that peer's next flag to go further).
+struct XchgArgs {
+    F* peer[8];               // base of every rank's exchange buffer as mapped here (peer[me]: the local one)
+    uint32_t world, me, seq;  // this exchange's sequence number (>= 1)
+    uint32_t slot_stride;     // entries between two ranks' slots
+    uint32_t buf_off[2];      // entry offsets of the two parity buffers inside an exchange buffer
+    uint32_t rec_len;
+    const FoldOnlyDesc* fo;   // this rank's distributed tables after the local rounds (one value per block)
+    uint32_t n_fo;
+    const F *V, *M, *A;       // stage-A final buffers
+    uint32_t has_a;
+    F* sc;                    // this rank's partial scalars (written by the stage-A kernel), zeroed again here
+    uint32_t sc_base, n_sc;
+    unsigned int* ticket;     // zero at launch, left zero
+    MergeArgs mg;             // recv is filled in by the kernel
+};
+VP_D void st_f_sys(F* p, const F& v) {   // peer memory: plain 128-bit store, ordered by the release below
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.re), "l"(v.im) : "memory");
+}
+__global__ void __launch_bounds__(256) k_xchg(XchgArgs p) {
+    __shared__ bool s_last;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const uint32_t par = p.seq & 1u;
+    const size_t slot = (size_t)p.buf_off[par] + (size_t)p.me * p.slot_stride;
+    // ---- (a) push: one pass over the record, every element stored to all ranks
+    for (uint32_t t = 0; t < p.n_fo; ++t) {
+        const FoldOnlyDesc d = p.fo[t];
+        for (uint32_t i = tid; i < 3 * d.cnt; i += stride) {
+            const uint32_t which = i / d.cnt, b = i - which * d.cnt;
+            F v = f_zero();
+            if (b < d.in_live && b < d.n_blocks) {
+                const F* src = which == 0 ? p.V : which == 1 ? p.M : p.A;
+                if (which < 2 || p.has_a) v = f_strict(src[d.in_off + b]);
+            }
+            for (uint32_t q = 0; q < p.world; ++q) st_f_sys(p.peer[q] + slot + d.out_base + i, v);
+        }
+    }
+    for (uint32_t i = tid; i < p.n_sc; i += stride) {
+        const F v = p.sc[i];
+        for (uint32_t q = 0; q < p.world; ++q) st_f_sys(p.peer[q] + slot + p.sc_base + i, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        // ---- (b) every block's stores are done (each fenced before its ticket): raise the flags, clear the scalars
+        __threadfence_system();
+        if (threadIdx.x < p.world) {
+            unsigned int* flag = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x]) + p.me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.seq) : "memory");
+        }
+        for (uint32_t i = threadIdx.x; i < p.n_sc; i += blockDim.x) p.sc[i] = f_zero();
+        if (threadIdx.x == 0) *p.ticket = 0;
+    }
+    // ---- (c) wait for every rank's record of this exchange
+    if (threadIdx.x < p.world) {
+        const unsigned int* flag = reinterpret_cast<const unsigned int*>(p.peer[p.me]) + threadIdx.x;
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while ((int)(v - p.seq) < 0);
+        __threadfence_system();
+    }
+    __syncthreads();
+    // ---- (d) merge from the local buffer (written by the peers: bypass L1)
+    const F* recv = p.peer[p.me] + p.buf_off[par];
+    const MergeArgs& m = p.mg;
+    for (uint32_t t = 0; t < m.n_tabs; ++t) {
+        const MergeTab T = m.tabs[t];
+        for (uint32_t beta = tid; beta < T.n_blocks; beta += stride) {
+            uint32_t sl = 0;
+            while (sl + 1 < m.G && beta >= T.sb[sl + 1]) ++sl;
+            const uint32_t owner = T.rev ? m.G - 1 - sl : sl, q = beta - T.sb[sl];
+            const F* rec = recv + (size_t)owner * p.slot_stride + T.rec_base;
+            st_f(m.outV + T.out_off + beta, ld_f_cg(rec + q));
+            st_f(m.outM + T.out_off + beta, ld_f_cg(rec + T.cnt + q));
+            st_f(m.outA + T.out_off + beta, ld_f_cg(rec + 2 * T.cnt + q));
+        }
+    }
+    const uint32_t n_sc = m.n_poly + 1 + m.n_claims;
+    for (uint32_t i = tid; i < n_sc; i += stride) {
+        F s = f_zero();
+        for (uint32_t g = 0; g < m.G; ++g) s = f_add(s, ld_f_cg(recv + (size_t)g * p.slot_stride + m.sc_base + i));
+        if (i < m.n_poly) st_f(m.out_poly + i, s);
+        else if (i == m.n_poly) st_f(m.add_term, s);
+        else st_f(m.claims + (i - m.n_poly - 1), s);
+    }
+}
+
 // ------------------------------------------------------------------ K8 / K9: MLE evaluation = dot with eq
 // prover.cpp:99-129 (Vres) and :532-540 (inner_prod against eq(r_liu,.), verifier.cpp:368-369).
 __global__ void __launch_bounds__(256)
@@ -1762,6 +1861,14 @@ k_dot(const F* __restrict__ X, const F* __restrict__ Y, uint32_t n, F* __restric
     if (grid_sum<1>(v, smem, partials, counter) && threadIdx.x == 0) st_f(out, v[0]);
 }
 
+// out[i] = sum over the G ranks of recv[g * n + i] (sharded vp_verify: partial sums of every rank)
+__global__ void k_sum_ranks_vec(const F* __restrict__ recv, uint32_t G, uint32_t n, F* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F s = f_zero();
+    for (uint32_t g = 0; g < G; ++g) s = f_add(s, recv[(size_t)g * n + i]);
+    st_f(out + i, s);
+}
 // sum of one field element per rank (sharded Vres / input MLE)
 __global__ void k_sum_ranks(const F* __restrict__ recv, uint32_t G, uint32_t stride, F* __restrict__ out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1790,13 +1897,13 @@ struct VfBucket {
 __global__ void __launch_bounds__(256)
 k_verify_sums(const VfBucket* __restrict__ buckets, const VfGate* __restrict__ gates, const uint8_t* __restrict__ is_assert,
               const F* __restrict__ cst, uint32_t S_pre, uint32_t S_cur, uint32_t K, EqTab eqg, EqTab equ, EqTab eqv,
-              const F* __restrict__ assert_r, F* __restrict__ partial) {
+              const F* __restrict__ assert_r, F* __restrict__ partial, uint32_t k_begin, uint32_t k_end) {
     __shared__ F smem[2 * 32];
     const VfBucket B = buckets[blockIdx.y];
-    const uint64_t total = (uint64_t)B.cnt * K;
+    const uint64_t total = (uint64_t)B.cnt * (k_end - k_begin);   // sharded: this rank's slice of the instances
     F acc[2] = {f_zero(), f_zero()};
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(w / B.cnt), j = (uint32_t)(w - (uint64_t)k * B.cnt);
+        const uint32_t kq = (uint32_t)(w / B.cnt), j = (uint32_t)(w - (uint64_t)kq * B.cnt), k = k_begin + kq;
         const VfGate G = gates[B.begin + j];
         F bg = eq_at(eqg, k * S_cur + G.g0);
         if (is_assert && is_assert[G.g0]) bg = f_mul(bg, *assert_r);
@@ -1834,12 +1941,13 @@ struct VfLiuSeg {
 };
 __global__ void __launch_bounds__(256)
 k_verify_gr(const VfLiuSeg* __restrict__ segs, const EqTab* __restrict__ eqs, EqTab eq_g0, EqTab eq_rl, uint32_t S_pre, uint32_t K,
-            F* __restrict__ partial) {
+            F* __restrict__ partial, uint32_t k_begin, uint32_t k_end) {
     __shared__ F smem[2 * 32];
     const VfLiuSeg Sg = segs[blockIdx.y];
-    const uint64_t total = (uint64_t)Sg.D * K;
+    // sharded: this rank's slice [k_begin, k_end) of the instances; a subset segment runs in reverse instance order
+    const uint64_t w_lo = (uint64_t)Sg.D * (blockIdx.y == 0 ? k_begin : K - k_end), total = (uint64_t)Sg.D * (blockIdx.y == 0 ? k_end : K - k_begin);
     F acc[2] = {f_zero(), f_zero()};
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t w = w_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
         if (blockIdx.y == 0) acc[0] = f_add(acc[0], f_mul(eq_at(eq_g0, (uint32_t)w), eq_at(eq_rl, (uint32_t)w)));
         else {
             const uint32_t kk = (uint32_t)(w / Sg.D), g0 = (uint32_t)(w - (uint64_t)kk * Sg.D), k = K - 1 - kk;

@@ -1,0 +1,403 @@
+// Commit phase of Virgo's polynomial commitment on the device -- see pc_commit.h for what it replaces.
+//
+// What commit_private_array computes (poly_commit.h:41-124, constants.h: 2^6 slices, code rate 2^-5):
+//   the array of 2^b values is cut into 64 slices of n = 2^(b-6) consecutive values; every slice is interpolated
+//   (inverse FFT of size n) and re-evaluated on the 32x larger domain (FFT of size N = 32 n) -> l_eval[s][0..N);
+//   a 65th slice holds the mask polynomial (the GKR prover passes a single zero: all zeros);
+//   leaf i (i < N/2) = SHA3 chain over the 65 slices of  H( l_eval[s][i] | l_eval[s][i + N/2] | previous )  (fri.cpp:97-126);
+//   an array-heap Merkle tree over the N/2 leaves with H(left | right) (merkle_tree.cpp:7-51); the root is the commitment.
+//
+// How it is laid out here:
+//   * ONE table of the N powers of the N-th root of unity (k_pc_twiddles: product of the precomputed 2^b-th powers
+//     over the set bits of the exponent); every other twiddle (n-th roots, inverse roots, coset shifts) is an index
+//     into it.
+//   * The size-N evaluation of a degree < n polynomial is 32 size-n transforms on the cosets of the n-th roots:
+//     l_eval[s][32 k + c] = NTT_n( coef_i * w_N^(c i) )[k]   (1/32 of the butterflies of a zero-padded size-N FFT).
+//   * inverse transform = decimation in frequency (natural in, bit-reversed out), forward = decimation in time
+//     (bit-reversed in, natural out): no permutation pass. Up to 2^11 points of a transform are processed in shared
+//     memory (11 stages per pass); longer transforms add one global pass per extra stage.
+//   * SHA3-256 of a 64-byte block is one Keccak-f[1600] permutation (rate 136 bytes); one thread per leaf walks the
+//     65-slice chain with coalesced 16-byte loads, one thread per tree node hashes a level.
+// All arithmetic is the canonical F_{p^2} arithmetic of field.cuh: exact, hence bit-identical to the reference's
+// packed-AVX FFT whatever the butterfly order.
+#include "pc_commit.h"
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace vp {
+
+#define PCK(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + " failed: " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static constexpr int PC_LOG_SLICES = 6, PC_SLICES = 64, PC_LOG_RATE = 5, PC_COSETS = 32;
+static constexpr int PC_SMEM_LOG = 11;   // points of one transform held in shared memory (32 KB)
+
+VP_D F pc_ld(const F* p) {
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+    return F{t.x, t.y};
+}
+VP_D void pc_st(F* p, const F& v) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v.re, v.im); }
+
+struct PcPow {
+    F sq[32];   // sq[b] = w_N^(2^b)
+};
+// tw[t] = w_N^t  (fieldElement::getRootOfUnity, fieldElement.cpp:237-249, gives w_N; L_group of fri.cpp:62-67 is this table)
+__global__ void k_pc_twiddles(F* __restrict__ tw, uint32_t N, PcPow pw) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    F r = f_one();
+    for (uint32_t b = 0; (t >> b) != 0; ++b)
+        if ((t >> b) & 1u) r = f_mul(r, pw.sq[b]);
+    pc_st(tw + t, r);
+}
+
+// the committed array, zero-padded to 2^log_len
+__global__ void k_pc_pad(const F* __restrict__ src, size_t n_valid, F* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        pc_st(dst + i, i < n_valid ? pc_ld(src + i) : f_zero());
+}
+
+// ---- inverse transform (RS_polynomial.cpp:155-220): DIF with the inverse n-th root, natural in, bit-reversed out.
+// One global stage over `batch` transforms of size n stored back to back: stage s pairs p and p + half, half = n >> (s+1).
+__global__ void k_pc_dif_stage(F* __restrict__ a, uint32_t log_n, uint32_t s, size_t total_pairs, const F* __restrict__ tw, uint32_t log_N) {
+    const uint32_t lh = log_n - s - 1, half = 1u << lh, N = 1u << log_N;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_pairs; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = w >> (log_n - 1);                       // transform
+        const uint32_t q = (uint32_t)(w & ((1u << (log_n - 1)) - 1));
+        const uint32_t j = q & (half - 1), p = ((q >> lh) << (lh + 1)) | j;
+        F* x = a + (t << log_n);
+        const F u = pc_ld(x + p), v = pc_ld(x + p + half);
+        const uint32_t e = j << s;                               // exponent of w_n^-1
+        pc_st(x + p, f_add(u, v));
+        pc_st(x + p + half, f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << PC_LOG_RATE)) & (N - 1)))));
+    }
+}
+// The last min(log_n, 11) DIF stages of every transform in shared memory, then the scaling by 1/n (inv_n = n^(p-2)).
+// One block per chunk of m = 2^log_m points (a chunk never straddles two transforms).
+__global__ void __launch_bounds__(512) k_pc_intt_smem(F* __restrict__ a, uint32_t log_n, uint32_t log_m, const F* __restrict__ tw, uint32_t log_N,
+                                                       F inv_n) {
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    F* sh = reinterpret_cast<F*>(pc_smem);
+    const uint32_t m = 1u << log_m, N = 1u << log_N;
+    F* x = a + ((size_t)blockIdx.x << log_m);
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sh[i] = pc_ld(x + i);
+    __syncthreads();
+    for (uint32_t s = log_n - log_m; s < log_n; ++s) {           // global stage index: half = n >> (s+1) < m
+        const uint32_t lh = log_n - s - 1, half = 1u << lh;
+        for (uint32_t q = threadIdx.x; q < m / 2; q += blockDim.x) {
+            const uint32_t j = q & (half - 1), p = ((q >> lh) << (lh + 1)) | j;
+            const F u = sh[p], v = sh[p + half];
+            const uint32_t e = j << s;
+            sh[p] = f_add(u, v);
+            sh[p + half] = f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << PC_LOG_RATE)) & (N - 1))));
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) pc_st(x + i, f_mul(sh[i], inv_n));
+}
+
+// ---- forward transform on coset c (RS_polynomial.cpp:26-153 evaluates the same polynomial on all N points):
+// DIT, bit-reversed in (what the inverse transform left), natural out.
+// First min(log_n, 11) stages in shared memory. coef: [64][n] bit-reversed coefficients. One block per
+// (chunk, coset, slice). If direct != 0 (log_n <= 11) the result goes straight to l_eval[s][32 k + c], else to the work
+// buffer work[(s * 32 + c) * n + p].
+__global__ void __launch_bounds__(512) k_pc_ntt_smem(const F* __restrict__ coef, uint32_t log_n, uint32_t log_m, const F* __restrict__ tw,
+                                                      uint32_t log_N, F* __restrict__ out, int direct) {
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    F* sh = reinterpret_cast<F*>(pc_smem);
+    const uint32_t m = 1u << log_m, n = 1u << log_n, N = 1u << log_N;
+    const uint32_t chunk = blockIdx.x, c = blockIdx.y, sl = blockIdx.z, base = chunk << log_m;
+    const F* x = coef + ((size_t)sl << log_n) + base;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const uint32_t p = base + i, ci = log_n ? __brev(p) >> (32 - log_n) : 0u;   // coefficient index held at position p
+        const F v = pc_ld(x + i);
+        sh[i] = (c == 0 || log_n == 0) ? v : f_mul(v, pc_ld(tw + (((uint64_t)c * ci) & (N - 1))));   // coef_i * w_N^(c i)
+    }
+    __syncthreads();
+    for (uint32_t s = 0; s < log_m; ++s) {
+        const uint32_t half = 1u << s;
+        for (uint32_t q = threadIdx.x; q < m / 2; q += blockDim.x) {
+            const uint32_t j = q & (half - 1), p = ((q >> s) << (s + 1)) | j;
+            const F u = sh[p], v = f_mul(sh[p + half], pc_ld(tw + ((size_t)j << (log_N - s - 1))));   // w_n^(j n / 2^(s+1))
+            sh[p] = f_add(u, v);
+            sh[p + half] = f_sub(u, v);
+        }
+        __syncthreads();
+    }
+    if (direct) {
+        F* o = out + ((size_t)sl << log_N);
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) pc_st(o + (((size_t)(base + i)) << PC_LOG_RATE) + c, sh[i]);
+    } else {
+        F* o = out + ((((size_t)sl << PC_LOG_RATE) + c) << log_n) + base;
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) pc_st(o + i, sh[i]);
+    }
+    (void)n;
+}
+// One global DIT stage s >= 11 over the work buffer ([64 * 32] transforms of size n); the last stage (s == log_n - 1)
+// writes to l_eval[s][32 k + c] instead.
+__global__ void k_pc_dit_stage(F* __restrict__ work, uint32_t log_n, uint32_t s, size_t total_pairs, const F* __restrict__ tw, uint32_t log_N,
+                               F* __restrict__ l_eval, int last) {
+    const uint32_t half = 1u << s;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_pairs; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = w >> (log_n - 1);                       // transform = slice * 32 + coset
+        const uint32_t q = (uint32_t)(w & ((1u << (log_n - 1)) - 1));
+        const uint32_t j = q & (half - 1), p = ((q >> s) << (s + 1)) | j;
+        F* x = work + (t << log_n);
+        const F u = pc_ld(x + p), v = f_mul(pc_ld(x + p + half), pc_ld(tw + ((size_t)j << (log_N - s - 1))));
+        const F r0 = f_add(u, v), r1 = f_sub(u, v);
+        if (last) {
+            const size_t sl = t >> PC_LOG_RATE, c = t & (PC_COSETS - 1);
+            F* o = l_eval + (sl << log_N) + c;
+            pc_st(o + ((size_t)p << PC_LOG_RATE), r0);
+            pc_st(o + ((size_t)(p + half) << PC_LOG_RATE), r1);
+        } else {
+            pc_st(x + p, r0);
+            pc_st(x + p + half, r1);
+        }
+    }
+}
+
+// ---- SHA3-256 of a 64-byte block (my_hhash.h:27-33 -> XKCP SHA3_256; FIPS 202): one Keccak-f[1600] permutation
+__constant__ uint64_t PC_KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
+    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
+    0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
+    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+VP_D uint64_t pc_rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+// msg: 8 words in, digest: words 0..3 out
+VP_D void pc_sha3_64(const uint64_t (&msg)[8], uint64_t (&dig)[4]) {
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) a[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = msg[i];
+    a[8] = 0x06ULL;                      // domain suffix + first pad bit right after the 64 message bytes
+    a[16] = 0x8000000000000000ULL;       // last pad bit in the last byte of the 136-byte rate
+#pragma unroll 1
+    for (int round = 0; round < 24; ++round) {
+        uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20], c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21],
+                 c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22], c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23],
+                 c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
+        const uint64_t d0 = c4 ^ pc_rotl(c1, 1), d1 = c0 ^ pc_rotl(c2, 1), d2 = c1 ^ pc_rotl(c3, 1), d3 = c2 ^ pc_rotl(c4, 1),
+                       d4 = c3 ^ pc_rotl(c0, 1);
+#pragma unroll
+        for (int j = 0; j < 25; j += 5) { a[j] ^= d0; a[j + 1] ^= d1; a[j + 2] ^= d2; a[j + 3] ^= d3; a[j + 4] ^= d4; }
+        // rho + pi
+        uint64_t b[25];
+        b[0] = a[0];
+        b[10] = pc_rotl(a[1], 1);   b[7] = pc_rotl(a[10], 3);   b[11] = pc_rotl(a[7], 6);   b[17] = pc_rotl(a[11], 10);
+        b[18] = pc_rotl(a[17], 15); b[3] = pc_rotl(a[18], 21);  b[5] = pc_rotl(a[3], 28);   b[16] = pc_rotl(a[5], 36);
+        b[8] = pc_rotl(a[16], 45);  b[21] = pc_rotl(a[8], 55);  b[24] = pc_rotl(a[21], 2);  b[4] = pc_rotl(a[24], 14);
+        b[15] = pc_rotl(a[4], 27);  b[23] = pc_rotl(a[15], 41); b[19] = pc_rotl(a[23], 56); b[13] = pc_rotl(a[19], 8);
+        b[12] = pc_rotl(a[13], 25); b[2] = pc_rotl(a[12], 43);  b[20] = pc_rotl(a[2], 62);  b[14] = pc_rotl(a[20], 18);
+        b[22] = pc_rotl(a[14], 39); b[9] = pc_rotl(a[22], 61);  b[6] = pc_rotl(a[9], 20);   b[1] = pc_rotl(a[6], 44);
+        // chi
+#pragma unroll
+        for (int j = 0; j < 25; j += 5) {
+            a[j] = b[j] ^ (~b[j + 1] & b[j + 2]);
+            a[j + 1] = b[j + 1] ^ (~b[j + 2] & b[j + 3]);
+            a[j + 2] = b[j + 2] ^ (~b[j + 3] & b[j + 4]);
+            a[j + 3] = b[j + 3] ^ (~b[j + 4] & b[j]);
+            a[j + 4] = b[j + 4] ^ (~b[j] & b[j + 1]);
+        }
+        a[0] ^= PC_KECCAK_RC[round];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dig[i] = a[i];
+}
+
+// fri.cpp:97-126: leaf i = chain over the slices; slice 64 (the mask) is all zero for the GKR prover's zero mask
+__global__ void __launch_bounds__(128) k_pc_leaf_hash(const F* __restrict__ l_eval, uint32_t log_N, uint64_t* __restrict__ leaf, int mask_is_zero) {
+    const uint32_t half = 1u << (log_N - 1);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint64_t h[4] = {0, 0, 0, 0};
+    for (int s = 0; s <= PC_SLICES; ++s) {
+        uint64_t msg[8];
+        if (s == PC_SLICES && mask_is_zero) { msg[0] = msg[1] = msg[2] = msg[3] = 0; }
+        else {
+            const F x = pc_ld(l_eval + ((size_t)s << log_N) + i), y = pc_ld(l_eval + ((size_t)s << log_N) + i + half);
+            msg[0] = x.re; msg[1] = x.im; msg[2] = y.re; msg[3] = y.im;
+        }
+        msg[4] = h[0]; msg[5] = h[1]; msg[6] = h[2]; msg[7] = h[3];
+        pc_sha3_64(msg, h);
+    }
+    uint64_t* o = leaf + (size_t)i * 4;
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+}
+// merkle_tree.cpp:39-50: one level of the array heap: node lvl + i = H(node 2(lvl + i) | node 2(lvl + i) + 1)
+__global__ void __launch_bounds__(128) k_pc_merkle_level(uint64_t* __restrict__ tree, uint32_t lvl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lvl) return;
+    const uint64_t* c = tree + (size_t)(2 * (lvl + i)) * 4;
+    uint64_t msg[8], h[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) msg[k] = c[k];
+    pc_sha3_64(msg, h);
+    uint64_t* o = tree + (size_t)(lvl + i) * 4;
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+}
+// the top of the tree (levels of <= 128 nodes) in one block
+__global__ void __launch_bounds__(128) k_pc_merkle_top(uint64_t* __restrict__ tree, uint32_t first_lvl) {
+    for (uint32_t lvl = first_lvl; lvl >= 1; lvl >>= 1) {
+        const uint32_t i = threadIdx.x;
+        if (i < lvl) {
+            const uint64_t* c = tree + (size_t)(2 * (lvl + i)) * 4;
+            uint64_t msg[8], h[4];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) msg[k] = c[k];
+            pc_sha3_64(msg, h);
+            uint64_t* o = tree + (size_t)(lvl + i) * 4;
+            o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ driver
+struct PcCommit {
+    int device = 0, log_len = 0, log_n = 0, log_N = 0;
+    size_t n = 0, N = 0;
+    F *tw = nullptr, *coef = nullptr, *work = nullptr, *l_eval = nullptr;
+    uint64_t* tree = nullptr;        // N/2 * 2 nodes of 32 bytes; leaves at [N/2, N)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool tw_ready = false;
+    uint64_t launches = 0;
+    F inv_n;
+};
+
+static F host_pow(F x, unsigned __int128 e) {
+    F r = f_one();
+    while (e) {
+        if (e & 1) r = f_mul(r, x);
+        x = f_mul(x, x);
+        e >>= 1;
+    }
+    return r;
+}
+
+PcCommit* pc_create(int device, int log_len) {
+    if (log_len < PC_LOG_SLICES || log_len > 30) throw std::runtime_error("polynomial commitment: log_len must be in [6, 30]");
+    PcCommit* p = new PcCommit();
+    try {
+        p->device = device;
+        p->log_len = log_len;
+        p->log_n = log_len - PC_LOG_SLICES;
+        p->log_N = p->log_n + PC_LOG_RATE;
+        p->n = (size_t)1 << p->log_n;
+        p->N = (size_t)1 << p->log_N;
+        PCK(cudaSetDevice(device));
+        PCK(cudaMalloc(&p->tw, p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->coef, (PC_SLICES * p->n) * sizeof(F)));
+        if (p->log_n > PC_SMEM_LOG) PCK(cudaMalloc(&p->work, (size_t)PC_SLICES * PC_COSETS * p->n * sizeof(F)));
+        PCK(cudaMalloc(&p->l_eval, (size_t)(PC_SLICES + 1) * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->tree, p->N * 32));
+        PCK(cudaEventCreate(&p->e0));
+        PCK(cudaEventCreate(&p->e1));
+        const F nn{(u64)p->n, 0};
+        p->inv_n = host_pow(nn, (unsigned __int128)P - 2);   // RS_polynomial.cpp:211
+        PCK(cudaFuncSetAttribute(k_pc_intt_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << PC_SMEM_LOG)));
+        PCK(cudaFuncSetAttribute(k_pc_ntt_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << PC_SMEM_LOG)));
+    } catch (...) {
+        pc_destroy(p);
+        throw;
+    }
+    return p;
+}
+void pc_destroy(PcCommit* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->tw); cudaFree(p->coef); cudaFree(p->work); cudaFree(p->l_eval); cudaFree(p->tree);
+    if (p->e0) cudaEventDestroy(p->e0);
+    if (p->e1) cudaEventDestroy(p->e1);
+    delete p;
+}
+size_t pc_slice_size(const PcCommit* p) { return p->N; }
+uint64_t pc_launches(const PcCommit* p) { return p->launches; }
+
+static inline unsigned pc_grid(size_t work, unsigned threads, unsigned cap = 148 * 16) {
+    return (unsigned)std::max<size_t>(1, std::min<size_t>((work + threads - 1) / threads, cap));
+}
+
+float pc_commit(PcCommit* p, const F* d_array, size_t n_valid, cudaStream_t st, uint8_t root[32]) {
+    PCK(cudaSetDevice(p->device));
+    const uint32_t log_n = (uint32_t)p->log_n, log_N = (uint32_t)p->log_N;
+    const uint32_t log_m = std::min<uint32_t>(log_n, PC_SMEM_LOG);
+    const size_t total = (size_t)PC_SLICES << log_n;
+    if (n_valid > total) throw std::runtime_error("polynomial commitment: array longer than 2^log_len");
+    PCK(cudaEventRecord(p->e0, st));
+    if (!p->tw_ready) {   // w_N = the order-2^62 element of fieldElement.cpp:240-241 squared 62 - log_N times
+        F w{2147483648ULL, 1033321771269002680ULL};
+        for (int i = 0; i < 62 - p->log_N; ++i) w = f_mul(w, w);
+        PcPow pw;
+        for (int b = 0; b < 32; ++b) { pw.sq[b] = w; w = f_mul(w, w); }
+        k_pc_twiddles<<<pc_grid(p->N, 256, 1u << 30), 256, 0, st>>>(p->tw, (uint32_t)p->N, pw);
+        ++p->launches;
+        p->tw_ready = true;
+    }
+    k_pc_pad<<<pc_grid(total, 256), 256, 0, st>>>(d_array, n_valid, p->coef, total);
+    ++p->launches;
+    // inverse transforms of the 64 slices
+    if (log_n >= 1) {
+        for (uint32_t s = 0; s + log_m < log_n; ++s) {
+            k_pc_dif_stage<<<pc_grid(total / 2, 256), 256, 0, st>>>(p->coef, log_n, s, total / 2, p->tw, log_N);
+            ++p->launches;
+        }
+    }
+    {
+        const unsigned threads = (unsigned)std::max<size_t>(32, std::min<size_t>(512, ((size_t)1 << log_m) / 2));
+        k_pc_intt_smem<<<(unsigned)(total >> log_m), threads, sizeof(F) << log_m, st>>>(p->coef, log_n, log_m, p->tw, log_N, p->inv_n);
+        ++p->launches;
+        // forward transforms on the 32 cosets
+        const bool direct = log_n <= PC_SMEM_LOG;
+        dim3 grid((unsigned)(1u << (log_n - log_m)), PC_COSETS, PC_SLICES);
+        k_pc_ntt_smem<<<grid, threads, sizeof(F) << log_m, st>>>(p->coef, log_n, log_m, p->tw, log_N, direct ? p->l_eval : p->work, direct ? 1 : 0);
+        ++p->launches;
+        if (!direct) {
+            const size_t pairs = ((size_t)PC_SLICES * PC_COSETS << log_n) / 2;
+            for (uint32_t s = log_m; s < log_n; ++s) {
+                k_pc_dit_stage<<<pc_grid(pairs, 256), 256, 0, st>>>(p->work, log_n, s, pairs, p->tw, log_N, p->l_eval, s == log_n - 1 ? 1 : 0);
+                ++p->launches;
+            }
+        }
+    }
+    PCK(cudaMemsetAsync(p->l_eval + ((size_t)PC_SLICES << log_N), 0, p->N * sizeof(F), st));   // the zero mask's codeword
+    // leaves + tree
+    const uint32_t half = (uint32_t)(p->N / 2);
+    PCK(cudaMemsetAsync(p->tree, 0, 64, st));   // nodes 0 and 1 (node 1 is overwritten unless there is a single leaf... then it IS the leaf)
+    k_pc_leaf_hash<<<(half + 127) / 128, 128, 0, st>>>(p->l_eval, log_N, p->tree + (size_t)half * 4, 1);
+    ++p->launches;
+    uint32_t lvl = half / 2;
+    for (; lvl > 128; lvl >>= 1) {
+        k_pc_merkle_level<<<(lvl + 127) / 128, 128, 0, st>>>(p->tree, lvl);
+        ++p->launches;
+    }
+    if (lvl >= 1) {
+        k_pc_merkle_top<<<1, 128, 0, st>>>(p->tree, lvl);
+        ++p->launches;
+    }
+    PCK(cudaEventRecord(p->e1, st));
+    PCK(cudaGetLastError());
+    PCK(cudaMemcpyAsync(root, p->tree + 4, 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    float ms = 0;
+    PCK(cudaEventElapsedTime(&ms, p->e0, p->e1));
+    return ms;
+}
+
+void pc_export(PcCommit* p, cudaStream_t st, F* l_eval, uint8_t* leaf_hash, uint8_t* tree) {
+    PCK(cudaSetDevice(p->device));
+    if (l_eval) PCK(cudaMemcpyAsync(l_eval, p->l_eval, (size_t)(PC_SLICES + 1) * p->N * sizeof(F), cudaMemcpyDeviceToHost, st));
+    if (leaf_hash) PCK(cudaMemcpyAsync(leaf_hash, p->tree + (p->N / 2) * 4, (p->N / 2) * 32, cudaMemcpyDeviceToHost, st));
+    if (tree) PCK(cudaMemcpyAsync(tree, p->tree, p->N * 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+}
+
+}  // namespace vp

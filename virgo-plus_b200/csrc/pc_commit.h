@@ -1,0 +1,31 @@
+// Commit phase of Virgo's polynomial commitment on the device: internal C++ interface between
+// pc_commit.cu (kernels + driver) and engine.cu (the context-level C ABI entry points).
+// Replaces, for the GKR prover's use of it (prover.cpp:524-530: one zero mask element):
+//   poly_commit_prover::commit_private_array   lib/virgo/src/poly_commit.h:41-124
+//   vpd_prover_init / fri::request_init_commit lib/virgo/src/vpd_prover.cpp:9-14, fri.cpp:36-139
+//   merkle_tree_prover::create_tree            lib/virgo/src/merkle_tree.cpp:7-51
+//   my_hhash (SHA3-256 of 64-byte blocks)      lib/virgo/src/my_hhash.h:27-33
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "field.cuh"
+
+namespace vp {
+
+struct PcCommit;   // device buffers of one commitment (codeword array, leaf hashes, Merkle tree)
+
+// log_len: the committed array has 2^log_len entries (>= 6: 64 slices). Throws std::runtime_error on CUDA failure.
+PcCommit* pc_create(int device, int log_len);
+void pc_destroy(PcCommit* p);
+// d_array: n_valid field elements on the device (the rest of the 2^log_len entries are zero). Runs on `stream`,
+// leaves the Merkle root in root[32] (host) after synchronising the stream. Returns the device time in ms.
+float pc_commit(PcCommit* p, const F* d_array, size_t n_valid, cudaStream_t stream, uint8_t root[32]);
+size_t pc_slice_size(const PcCommit* p);
+// copies to the host (any pointer may be null): l_eval [65 * slice_size], leaf hashes [slice_size / 2 * 32 B],
+// Merkle tree [slice_size * 32 B] as the array heap of merkle_tree.cpp (node 1 = root, node 0 unused = zero)
+void pc_export(PcCommit* p, cudaStream_t stream, F* l_eval, uint8_t* leaf_hash, uint8_t* tree);
+uint64_t pc_launches(const PcCommit* p);
+
+}  // namespace vp

@@ -15,5 +15,7 @@ else:
     K = int(sys.argv[2])
     with lzma.open(os.path.join(ROOT, "tests/golden/SHA256_64.pws.xz")) as f:
         c = B.Circuit.from_pws_text(f.read()).replicate(K)
-    p = B.Prover(c); p.set_challenges(c.draw_challenges()); p.prove(); p.prove()
+    p = B.Prover(c); p.set_challenges(c.draw_challenges())
+    if len(sys.argv) > 3: p.set_lanes(int(sys.argv[3]))   # 1: like bench.py's instrumented pass (a launch has the GPU to itself)
+    p.prove(); p.prove()
     print("ms", p.last_prove_ms)

@@ -1435,6 +1435,28 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
     constexpr int NV = FIRST == DFS_NEED_B ? 5 : 4;   // a1, c1, a2, c2 and (stand-alone, first pass) p1(1) = sum m1*v1 + a1
     const bool coord = blockIdx.x == 0;
     const uint32_t n_workers = gridDim.x - 1;
+    constexpr uint32_t WPB = DFS_THREADS / 32;
+    // Which workers take part in which pass. A pass uses workers 1..active(work) (see below); `active` is NOT monotone in
+    // the work (the share per warp is rounded to 32 items: 2100 items on 8 workers -> 6 of them, 2048 items -> all 8), so a
+    // worker may idle in one pass and be needed again later. s_alive[ps] = the largest `active` of this and all later
+    // passes: workers 1..s_alive[ps] arrive at pass ps's barrier (working or not), the others have left for good.
+    __shared__ uint32_t s_alive[34];
+    if (threadIdx.x == 0) {
+        uint32_t mx = 0;
+        s_alive[p.n_passes < 33 ? p.n_passes : 33] = 0;
+        for (int q = (int)p.n_passes - 1; q >= 0; --q) {
+            const uint32_t work = p.passes[q].work;
+            uint32_t a = 0;
+            if (work > DFS_CHUNK && n_workers != 0) {
+                const uint32_t per_warp = (work + n_workers * WPB - 1) / (n_workers * WPB);
+                const uint32_t sh = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
+                a = min(n_workers, (work + sh * WPB - 1) / (sh * WPB));
+            }
+            mx = max(mx, a);
+            s_alive[q] = mx;
+        }
+    }
+    __syncthreads();
     F at = p.at_init ? *p.at_init : f_zero();
     uint32_t j = 1;       // local round of the pass's first round (= 1 + 2 * ps: every pass but the last has two rounds)
     unsigned int target = 0;
@@ -1446,7 +1468,6 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         // pass that one sweep of the workers can cover is spread as thinly as possible: every warp gets ONE share of
         // `share` items (a multiple of 32, at most DFS_WCHUNK), on as many workers as that takes. Larger passes hand out
         // DFS_WCHUNK-item chunks from an atomic counter.
-        constexpr uint32_t WPB = DFS_THREADS / 32;
         const bool solo = R.work <= DFS_CHUNK || n_workers == 0;       // block 0 alone
         uint32_t share = DFS_WCHUNK, active = 0;
         if (!solo) {
@@ -1455,14 +1476,16 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             active = min(n_workers, (R.work + share * WPB - 1) / (share * WPB));   // worker blocks 1..active
         }
         const bool is_static = solo ? R.work <= DFS_CHUNK : (uint64_t)active * share * WPB >= R.work;
-        if (!coord && blockIdx.x > active) return;                     // work only shrinks: never needed again
+        const uint32_t alive = s_alive[ps];
+        if (!coord && blockIdx.x > alive) return;                      // not needed in this or any later pass
+        const bool idle = !coord && blockIdx.x > active;               // needed again later: only keeps the barrier count
         const uint32_t ib = R.in_buf, ob = ib ^ 1;
         const uint32_t g1 = p.round_base + j;                          // global round of the pass's first round
         const bool scale1 = g1 >= 2;
         const PassCol* cols = p.cols + R.col_begin;
         F* part = p.partials + (size_t)(ps & 1) * gridDim.x * 6;
         F v[NV];
-        if (!coord || solo) {
+        if ((!coord && !idle) || (coord && solo)) {
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < R.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[R.tab_begin + i].work_end;
             __syncthreads();
@@ -1507,19 +1530,13 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
             at = dfs_collapse(at, cols, R.n_cols, 0, p.bufV[ib], p.bufM[ib], p.bufA[ib], scale1, scale1 ? p.chal[g1 - 2] : f_zero(),
                               p.claims, HAS_A);
         if (!solo) {
-            if (!coord && threadIdx.x == 0) {
+            if (!coord && !idle && threadIdx.x == 0) {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) st_f(part + (size_t)blockIdx.x * 6 + k, v[k]);
             }
             pass_arrive(p.bar);
-            target += active + 1;
-            if (!coord) {   // does this worker have work in the next pass? (it needs the barrier only then)
-                const uint32_t next_work = ps + 1 < p.n_passes ? p.passes[ps + 1].work : 0;
-                if (next_work <= DFS_CHUNK) return;
-                const uint32_t npw = (next_work + n_workers * WPB - 1) / (n_workers * WPB);
-                const uint32_t nshare = min(DFS_WCHUNK, (npw + 31u) & ~31u);
-                if (blockIdx.x > min(n_workers, (next_work + nshare * WPB - 1) / (nshare * WPB))) return;
-            }
+            target += alive + 1;                                        // workers 1..alive and the coordinator
+            if (!coord && blockIdx.x > s_alive[ps + 1]) return;         // no later pass needs this worker: no need to wait
             pass_wait(p.bar, target);
             VP_DBG_T(2);
             if (coord) {

@@ -2,6 +2,7 @@
 // /root/reference/src/prover.cpp (line ranges cited per method).
 #include "prover.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -138,14 +139,77 @@ double prover::proveTime() const { return vp_prove_seconds(ctx); }
 double prover::proofSize() const { return (double)vp_proof_size_bytes(ctx) / 1024.0; }
 
 #ifdef USE_VIRGO
-// prover.cpp:524-530: the polynomial commitment stays the reference's CPU library (out of scope,
-// SURVEY 8f N1); it is handed the input layer copied back from the device.
+// prover.cpp:524-530 -> poly_commit_prover::commit_private_array (lib/virgo/src/poly_commit.h:41-124). The heavy part --
+// 64 inverse FFTs, the 32x Reed-Solomon extension, 65 SHA3 evaluations per leaf and the Merkle tree -- runs on the
+// device (vp_commit_private). The reference's OPENING phase (commit_public_array, the FRI rounds, the verifier's
+// Merkle checks) stays its own CPU code and reads process-global arrays that commit_private_array and
+// fri::request_init_commit (fri.cpp:36-139) leave behind: those are allocated here exactly as there and filled from the
+// device results. VP_CPU_COMMIT=1 keeps the reference's CPU commit instead (A/B timing).
+namespace virgo {
+extern int witness_merkle_size[2];   // fri.cpp:22 (not declared in fri.h)
+}
 virgo::__hhash_digest prover::commit_private() {
+    using namespace virgo;
     std::vector<F> mask(1, F_ZERO);
     const int bl = C.circuit[0].bitLength;
-    input_values.assign(1ULL << bl, F_ZERO);
-    ck(vp_get_values(ctx, 0, mf(input_values.data()), C.circuit[0].size), "vp_get_values");
-    return poly_prover.commit_private_array(input_values.data(), bl, mask);
+    if (getenv("VP_CPU_COMMIT") || bl < 6) {
+        input_values.assign(1ULL << bl, F_ZERO);
+        ck(vp_get_values(ctx, 0, mf(input_values.data()), C.circuit[0].size), "vp_get_values");
+        return poly_prover.commit_private_array(input_values.data(), bl, mask);
+    }
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    __hhash_digest root;
+    ck(vp_commit_private(ctx, cf(mask.data()), mask.size(), reinterpret_cast<uint8_t *>(&root)), "vp_commit_private");
+    // ---- poly_commit.h:45-67: slicing parameters, the (padded) mask
+    poly_commit::pre_prepare_executed = true;
+    poly_commit::slice_count = (1 << log_slice_number) + 1;
+    poly_commit::slice_size = 1 << (bl + rs_code_rate - log_slice_number);
+    poly_commit::slice_real_ele_cnt = poly_commit::slice_size >> rs_code_rate;
+    poly_commit::l_eval_len = poly_commit::slice_count * poly_commit::slice_size;
+    poly_commit::l_eval = new fieldElement[poly_commit::l_eval_len];
+    poly_commit::mask_position_gap = poly_commit::slice_size;          // one mask element: the largest power of two <= slice_size / 1
+    poly_prover.all_pri_mask = mask;                                   // mask_size_after_padding == 1
+    poly_commit::all_pri_msk_arr = new fieldElement[1];
+    poly_commit::all_pri_msk_arr[0] = mask[0];
+    init_scratch_pad(poly_commit::slice_size);                         // poly_commit.h:74: FFT scratch of the opening phase
+    const int slice_size = poly_commit::slice_size, half = slice_size / 2;
+    // ---- fri.cpp:36-139 (request_init_commit, oracle 0): bookkeeping + arrays
+    const int lw = bl + rs_code_rate - log_slice_number;               // log_current_witness_size_per_slice
+    fri::__fri_timer = 0;
+    fri::current_step_no = 0;
+    fri::log_current_witness_size_per_slice = lw;
+    fri::witness_bit_length_per_slice = bl - log_slice_number;
+    fri::L_group = new fieldElement[1 << lw];
+    {
+        const fieldElement rou = fieldElement::getRootOfUnity(lw);
+        fri::L_group[0] = fieldElement(1);
+        for (int i = 1; i < (1 << lw); ++i) fri::L_group[i] = fri::L_group[i - 1] * rou;
+    }
+    fri::leaf_hash[0] = new __hhash_digest[half];
+    fri::witness_merkle[0] = (__hhash_digest *)malloc((size_t)half * 2 * sizeof(__hhash_digest));   // merkle_tree.cpp:17
+    merkle_tree::size_after_padding = half;
+    ck(vp_commit_export(ctx, mf(poly_commit::l_eval), reinterpret_cast<uint8_t *>(fri::leaf_hash[0]),
+                        reinterpret_cast<uint8_t *>(fri::witness_merkle[0])),
+       "vp_commit_export");
+    fri::witness_rs_codeword_interleaved[0] = new fieldElement[1 << (bl + rs_code_rate)];
+    const int log_leaf_size = log_slice_number + 1;
+    for (int i = 0; i < slice_number; ++i) {                           // fri.cpp:69-96
+        fri::witness_rs_codeword_before_arrange[0][i] = &poly_commit::l_eval[i * slice_size];
+        fri::witness_rs_mapping[0][i] = new int[1 << lw];
+        const fieldElement *src = fri::witness_rs_codeword_before_arrange[0][i];
+        for (int j = 0; j < half; ++j) {
+            const int at = (j << log_leaf_size) | (i << 1);
+            fri::witness_rs_mapping[0][i][j] = at;
+            fri::witness_rs_mapping[0][i][j + half] = at;
+            fri::witness_rs_codeword_interleaved[0][at] = src[j];
+            fri::witness_rs_codeword_interleaved[0][at | 1] = src[j + half];
+        }
+    }
+    witness_merkle_size[0] = half;
+    fri::visited_init[0] = new bool[1 << lw]();
+    fri::visited_witness[0] = new bool[1 << (bl + rs_code_rate)]();
+    poly_prover.total_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    return root;
 }
 
 // prover.cpp:532-540

@@ -1202,20 +1202,24 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             std::vector<uint8_t> tyv;
             std::vector<P2Table> ptabs;
             ItemPlan ip;
+            // the binary gates of the layer by source layer, in gate order (one pass; a circuit with operands from any
+            // earlier layer has up to i tables here)
+            std::vector<std::vector<uint32_t>> by_src(i);
+            for (uint32_t g = 0; g < S; ++g)
+                if (is_binary(T.ty[g])) by_src[T.l[g]].push_back(g);
             for (size_t t = 0; t < order.size(); ++t) {
                 const int l = order[t];
                 const uint32_t Dsz = (uint32_t)T.dadSize[l];
                 std::vector<uint32_t> cnt(Dsz + 1, 0);
-                for (uint32_t g = 0; g < S; ++g)
-                    if (T.l[g] == l && is_binary(T.ty[g])) ++cnt[T.lv[g] + 1];
+                for (uint32_t g : by_src[l]) ++cnt[T.lv[g] + 1];
                 for (uint32_t x = 0; x < Dsz; ++x) cnt[x + 1] += cnt[x];
                 const uint32_t base = (uint32_t)g0.size();
                 g0.resize(base + cnt[Dsz]);
                 u0.resize(base + cnt[Dsz]);
                 tyv.resize(base + cnt[Dsz]);
                 std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1);
-                for (uint32_t g = 0; g < S; ++g)
-                    if (T.l[g] == l && is_binary(T.ty[g])) {
+                for (uint32_t g : by_src[l])
+                    {
                         uint32_t p = base + pos[T.lv[g]]++;
                         g0[p] = g;
                         u0[p] = T.u[g];
@@ -1980,7 +1984,15 @@ void Engine::verify_prepare(int i) {
         else continue;
         keyed.push_back({key, g});
     }
-    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    {   // stable counting sort by key (keys < 4 + 7 * layers): a comparison sort of 2^20 gates x 64 layers took seconds
+        const uint32_t n_keys = 4u + 7u * (uint32_t)n;
+        std::vector<uint32_t> start(n_keys + 1, 0);
+        for (const auto& kg : keyed) ++start[kg.first + 1];
+        for (uint32_t k = 0; k < n_keys; ++k) start[k + 1] += start[k];
+        std::vector<std::pair<uint32_t, uint32_t>> sorted(keyed.size());
+        for (const auto& kg : keyed) sorted[start[kg.first]++] = kg;
+        keyed.swap(sorted);
+    }
     std::vector<VfGate> gates(keyed.size());
     std::vector<VfBucket> buckets;
     D.vf_key.clear();

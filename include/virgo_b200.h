@@ -124,6 +124,12 @@ int vp_shard_describe(const vp_circuit* c, int world, int rank, int layer, int p
 int vp_shard_eval_ranges(const vp_circuit* c, int world, int rank, uint32_t* lo, uint32_t* hi);
 int vp_shard_map_index(uint32_t lo, uint32_t hi, uint32_t idx, uint32_t* local);
 
+/* SHARDED CONTEXTS and the method-by-method API. Every entry point below except vp_get_values also works on a sharded
+ * context, as a COLLECTIVE call: all ranks call it in the same order with the same arguments and all get the same
+ * results (like the reference's single prover, whose messages every rank's verifier copy sees). A round of a sharded
+ * phase folds the rank's own table rows and exchanges 48 bytes per rank (the partial round polynomial, partial add_term
+ * included); after the local rounds the remaining <= 2^10 values per table are gathered once and the last rounds run
+ * replicated (src/prover.cpp:436-455 per round). */
 /* Upload the witness inputs (instances * layer_size(0) values < p); default: the circuit's own. */
 int vp_set_inputs(vp_ctx* ctx, const uint64_t* inputs, size_t n);
 /* prover::evaluate (prover.cpp:27-91) + the assert check of the constructor (:16-24). */

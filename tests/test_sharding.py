@@ -171,3 +171,26 @@ def test_sharded_proof_matches_oracle_on_2_gpus():
                         "127.0.0.1", "--master-port", "29655", os.path.join(ROOT, "tests", "dist_gpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_dropin_program_on_2_gpus(tmp_path, sha_pws_text):
+    """the reference's UNMODIFIED main + verifier, two copies of the program (VP_WORLD=2, one per GPU) sharing one sharded
+    prover through the drop-in class: both must print `Verification pass` and the reference's proof size"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    exe = os.path.join(ROOT, "oracle", "_ref", "virgo_plus_run_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/virgo_plus_run_b200 not built")
+    pws = tmp_path / "SHA256_64.pws"
+    pws.write_bytes(sha_pws_text)
+    idf = str(tmp_path / "nccl_id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, VP_WORLD="2", VP_RANK=str(r), VP_NCCL_ID_FILE=idf)
+        procs.append(subprocess.Popen([exe, str(pws)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert "Verification pass" in err, err[-2000:]
+        assert "proof size = 22.437500 kb" in out, out

@@ -232,6 +232,7 @@ struct PhasePlan {
     std::vector<uint32_t> row_lo, row_hi;  // live table entries [row_lo, row_hi) this rank holds (global indices)
     std::vector<uint8_t> present;
     uint32_t fo_begin = 0, n_fo = 0, mt_begin = 0, n_mt = 0;
+    uint32_t foi_begin = 0;            // the same hand-over descriptors for the one-round-per-launch plans (a fold pending)
     uint32_t rec_len = 0, sc_base = 0, n_poly = 0, n_claims = 0;
     uint32_t cap0 = 0, cap1 = 0;
     double bytes_total() const { return ppA.bytes + ppB.bytes; }
@@ -366,12 +367,35 @@ static PhasePlan make_phase(const std::vector<PhaseTabG>& T, int rounds, const s
     }
     P.n_fo = (uint32_t)dist.size();
     P.n_mt = (uint32_t)dist.size();
+    // the method-by-method entry points (vp_round) run the same stages with one round per launch: stage A = planA on
+    // the local tables (after m rounds every block holds TWO stored values with the fold by r_m pending), stage B =
+    // planB on the gathered tables
+    P.planA = build_plan(tabsA, m, {}, A);
+    P.planB = build_plan(tabsB, rounds - m, finB, A);
+    for (const FinDesc& f : collapsed_fins) {
+        A.fins.push_back(f);
+        ++P.planB.n_fin;
+    }
+    for (uint32_t o : empty_fin_out) {
+        A.fins.push_back(FinDesc{0, 0, -1, o});
+        ++P.planB.n_fin;
+    }
+    P.foi_begin = (uint32_t)A.fo.size();
+    {
+        uint32_t b2 = 0;
+        for (size_t q = 0; q < dist.size(); ++q) {
+            const Dist& d = dist[q];
+            const uint32_t ia = idxA[d.t];
+            A.fo.push_back(FoldOnlyDesc{P.planA.end_off[ia], P.planA.end_live[ia], d.local_blocks, b2, d.cnt, 1});
+            b2 += 3 * d.cnt;
+        }
+    }
     P.sc_base = base;
     P.n_poly = 3u * (uint32_t)m;
     P.n_claims = (uint32_t)n_claims;
     P.rec_len = base + P.n_poly + 1 + P.n_claims;
-    P.cap0 = std::max(P.ppA.cap0, P.ppB.cap0);
-    P.cap1 = std::max(P.ppA.cap1, P.ppB.cap1);
+    P.cap0 = std::max({P.ppA.cap0, P.ppB.cap0, P.planA.cap0, P.planB.cap0});
+    P.cap1 = std::max({P.ppA.cap1, P.ppB.cap1, P.planA.cap1, P.planB.cap1});
     return P;
 }
 
@@ -566,10 +590,14 @@ static void sort_items_by_length(std::vector<RowItem>& items) {
     const char* e = getenv("VP_ITEM_SORT_WINDOW");
     const size_t window = e ? (size_t)atoi(e) : 8192;
     if (window < 2) return;
-    for (size_t b = 0; b < items.size(); b += window) {
+    std::vector<RowItem> tmp(std::min(items.size(), window));
+    for (size_t b = 0; b < items.size(); b += window) {   // stable counting sort by length (0..255), longest first
         const size_t end = std::min(items.size(), b + window);
-        std::stable_sort(items.begin() + b, items.begin() + end,
-                         [](const RowItem& x, const RowItem& y) { return (x.cnt_slot & 0xff) > (y.cnt_slot & 0xff); });
+        size_t start[257] = {0};
+        for (size_t i = b; i < end; ++i) ++start[256 - (items[i].cnt_slot & 0xff)];   // bucket k+1 holds length 255-k
+        for (int k = 0; k < 256; ++k) start[k + 1] += start[k];
+        for (size_t i = b; i < end; ++i) tmp[start[255 - (items[i].cnt_slot & 0xff)]++] = items[i];
+        std::copy(tmp.begin(), tmp.begin() + (end - b), items.begin() + b);
     }
 }
 
@@ -901,7 +929,7 @@ struct Engine {
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
     int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
-    bool old_p2 = false, getenv_no_hs = false;
+    bool old_p2 = false, getenv_no_hs = false, liu_old = false;
     DBuf<F> d_hs;   // phase-2 init: products of the second-half eq factors, K * ng * nu entries (k_p2_hs)
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: phase-1 init uses the one-real-product-per-gate kernel
@@ -930,7 +958,8 @@ struct Engine {
     void do_input_mle();
     void do_init_phase1(int i);
     void do_init_phase2(int i);
-    void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init);
+    void do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init, bool continues = false, F* poly_out = nullptr);
+    void sharded_round(const PhasePlan& PP, int phase, int j, uint32_t ci, uint32_t tr, const F* at_init);
     void do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep);
     void do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* keep, const F* at_init, bool has_a = true,
                   const F* v_first = nullptr);
@@ -1021,6 +1050,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             if ((T.ty[g] == T_ADDC || T.ty[g] == T_MULC) && T.c[g].im != 0) values_real = false;
     lane_init = values_real && !getenv("VP_NO_LANE_INIT");
     old_p2 = getenv("VP_OLD_P2") != nullptr;
+    liu_old = getenv("VP_LIU_OLD") != nullptr;
     getenv_no_hs = getenv("VP_NO_HS") != nullptr;
     d_hs.alloc((size_t)K * 64);   // development knob: the five-products-per-gate phase-2 init
     {
@@ -1301,10 +1331,19 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
                 const size_t window = ev ? (size_t)atoi(ev) : 8192;
                 std::vector<uint32_t> perm(S_pre);
                 for (uint32_t x = 0; x < S_pre; ++x) perm[x] = x;
-                if (window >= 2 && world == 1)
-                    for (size_t b = 0; b < S_pre; b += window)
-                        std::stable_sort(perm.begin() + b, perm.begin() + std::min<size_t>(S_pre, b + window),
-                                         [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; });
+                if (window >= 2 && world == 1) {   // stable counting sort by the number of scattered terms, most first
+                    std::vector<uint32_t> tmp(std::min<size_t>(S_pre, window)), start;
+                    for (size_t b = 0; b < S_pre; b += window) {
+                        const size_t end = std::min<size_t>(S_pre, b + window);
+                        uint32_t mx = 0;
+                        for (size_t x = b; x < end; ++x) mx = std::max(mx, off[x + 1] - off[x]);
+                        start.assign((size_t)mx + 2, 0);
+                        for (size_t x = b; x < end; ++x) ++start[mx - (off[x + 1] - off[x]) + 1];
+                        for (uint32_t k = 0; k <= mx; ++k) start[k + 1] += start[k];
+                        for (size_t x = b; x < end; ++x) tmp[start[mx - (off[x + 1] - off[x])]++] = (uint32_t)x;
+                        std::copy(tmp.begin(), tmp.begin() + (end - b), perm.begin() + b);
+                    }
+                }
                 D.liu_perm.upload(perm, stream);
             }
             // lane 1's copy of beta_u is only used by Liu: bake s[0] in. Its descriptors sit right before the Liu tables'
@@ -1732,6 +1771,13 @@ void Engine::do_init_liu(int i, bool write_a) {
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
+    if (world == 1 && K >= 8 && !liu_old) {   // template-major: one thread per template entry, a chunk of instances each
+        const uint32_t k_chunk = 8;
+        dim3 grid(cdiv(S_pre, 256), cdiv(K, k_chunk));
+        k_init_liu_tm<<<grid, 256, 0, stream>>>(D.liu_off.p, D.liu_perm.p, D.liu_ent.p, eq_off ? D.liu_eqtabs_b.p : D.liu_eqtabs.p, S_pre, K, k_chunk,
+                                               eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p, bufV[0].p + D.ph3.tab_off[0],
+                                               bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1);
+    } else
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
         D.liu_off.p, world == 1 ? D.liu_perm.p : nullptr, D.liu_ent.p, eq_off ? D.liu_eqtabs_b.p : D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,
         bufV[0].p + D.ph3.tab_off[0], bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], D.ph3.maps[0], n_local,
@@ -1741,7 +1787,9 @@ void Engine::do_init_liu(int i, bool write_a) {
 }
 
 // round j (1-based) of plan P; ci_prev = challenge index of the previous round's challenge (j >= 2)
-void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init) {
+// continues: round 1 of the PLAN is not round 1 of the phase (stage B of a sharded phase): add_term carries over and is
+// scaled by (1 - previous challenge) although no fold is pending. poly_out: where the polynomial goes (default: transcript).
+void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init, bool continues, F* poly_out) {
     const RoundPlan& R = P.r[j - 1];
     RoundArgs a;
     const int ib = R.in_buf, ob = ib ^ 1;
@@ -1754,11 +1802,11 @@ void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t t
     a.prev_r = d_chal.p + ci_prev;
     a.add_term = scal(SC_ADD_TERM);
     a.claims = d_claims.p;
-    a.out_poly = d_tr.p + tr_out;
+    a.out_poly = poly_out ? poly_out : d_tr.p + tr_out;
     a.partials = d_partials.p;
     a.counter = d_counter.p;
-    a.first_round = j == 1;
-    a.reset_add_term = j == 1;
+    a.first_round = j == 1 && !continues;
+    a.reset_add_term = j == 1 && !continues;
     a.at_init = at_init;
     const int grid = grid_for(R.work, R.fold ? cap_round : cap_round1);
     size_t h = prof_begin(R.fold ? KC_ROUND_FOLD : KC_ROUND_FIRST);
@@ -1766,6 +1814,60 @@ void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t t
     else k_round<false><<<grid, 256, 0, stream>>>(a);
     prof_end(h, R.bytes);
     ++launches;
+}
+
+// Round j (1-based) of a SHARDED phase through the method-by-method API (collective: every rank makes the same call).
+// Rounds 1..m fold this rank's table rows (planA): the partial round polynomials -- which carry the rank's partial
+// add_term -- meet in one 48-byte-per-rank all-gather and are summed (the per-round exchange of an
+// interactive sharded prover). Before round m + 1 the blocks' two stored values are folded with r_m and gathered
+// together with the partial add_term and the locally collapsed claims (k_fold_only + all-gather + k_shard_merge); the
+// remaining rounds run replicated on every rank (planB), so no further communication is needed.
+void Engine::sharded_round(const PhasePlan& PP, int phase, int j, uint32_t ci, uint32_t tr, const F* at_init) {
+    (void)phase;
+    if (j == 1) CK(cudaMemsetAsync(d_claims.p, 0, ((size_t)n + 1) * sizeof(F), stream));   // partial claims are summed over the ranks
+    if (j <= PP.m) {
+        F* part = d_send.p;   // 3 F
+        do_round(PP.planA, j, ci + (uint32_t)std::max(0, j - 2), 0, at_init, false, part);
+        NCK(g_nccl.AllGather(part, d_recv.p, 6, /*ncclUint64*/ 5, comm, stream));
+        k_sum_ranks_vec<<<1, 32, 0, stream>>>(d_recv.p, (uint32_t)world, 3, d_tr.p + tr);
+        ++launches;
+        return;
+    }
+    if (j == PP.m + 1) {
+        F* rec = d_send.p;
+        const uint32_t n_sc = 1 + PP.n_claims, sc0 = PP.sc_base + PP.n_poly;   // record: table regions, (unused polynomials), add_term, claims
+        CK(cudaMemsetAsync(rec, 0, (size_t)PP.rec_len * sizeof(F), stream));
+        if (PP.n_fo) {
+            const FoldOnlyDesc& f0 = arena.fo[PP.foi_begin];
+            dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>(cdiv(f0.cnt, 128), 64)), PP.n_fo);
+            const int fb = PP.planA.fin_buf;
+            k_fold_only<<<grid, 128, 0, stream>>>(d_fo.p + PP.foi_begin, (int)PP.n_fo, bufV[fb].p, bufM[fb].p, bufA[fb].p,
+                                                 d_chal.p + ci + (uint32_t)(PP.m - 1), rec);
+            ++launches;
+        }
+        CK(cudaMemcpyAsync(rec + sc0, scal(SC_ADD_TERM), sizeof(F), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(rec + sc0 + 1, d_claims.p, (size_t)PP.n_claims * sizeof(F), cudaMemcpyDeviceToDevice, stream));
+        NCK(g_nccl.AllGather(rec, d_recv.p, (size_t)PP.rec_len * 2, /*ncclUint64*/ 5, comm, stream));
+        MergeArgs ma;
+        ma.recv = d_recv.p;
+        ma.rec_len = PP.rec_len;
+        ma.G = (uint32_t)world;
+        ma.tabs = d_mt.p + PP.mt_begin;
+        ma.n_tabs = PP.n_mt;
+        ma.sc_base = sc0;          // no polynomials in this record: scalar 0 is add_term, then the claims
+        ma.n_poly = 0;
+        ma.n_claims = PP.n_claims;
+        ma.outV = bufV[0].p; ma.outM = bufM[0].p; ma.outA = bufA[0].p;
+        ma.out_poly = d_send.p;    // unused (n_poly == 0)
+        ma.add_term = scal(SC_ADD_TERM);
+        ma.claims = d_claims.p;
+        (void)n_sc;
+        k_shard_merge<<<8, 256, 0, stream>>>(ma);
+        ++launches;
+        do_round(PP.planB, 1, ci + (uint32_t)(PP.m - 1), tr, nullptr, /*continues=*/true);
+        return;
+    }
+    do_round(PP.planB, j - PP.m, ci + (uint32_t)(j - 2), tr, nullptr);
 }
 
 void Engine::do_finalize(const SumcheckPlan& P, uint32_t ci_last, F* keep) {
@@ -2621,7 +2723,6 @@ extern "C" int vp_evaluate(vp_ctx* ctx) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     e.evaluate();
     ctx->e.check_assert_flag();
     return VP_OK;
@@ -2632,7 +2733,7 @@ extern "C" int vp_get_values(vp_ctx* ctx, int layer, vp_F* out, size_t n) {
     API_BEGIN
     Engine& e = ctx->e;
     cudaSetDevice(e.device);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
+    if (e.world > 1) return fail(VP_ERR_ARG, "vp_get_values: a rank of a sharded context only holds the values of its own instance range");
     if (n > e.C.layer_size(layer)) return fail(VP_ERR_ARG, "n exceeds the layer size");
     CK(cudaMemcpyAsync(out, e.val[layer].p, n * sizeof(F), cudaMemcpyDeviceToHost, e.stream));
     CK(cudaStreamSynchronize(e.stream));
@@ -2644,7 +2745,6 @@ extern "C" int vp_vres(vp_ctx* ctx, const vp_F* r, int n, vp_F* out) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (!e.evaluated) return fail(VP_ERR_ARG, "vp_vres before vp_evaluate");
     if (n != e.C.bit_length(e.n - 1)) return fail(VP_ERR_ARG, "vp_vres: n must be the output layer's bit length");
     if (n) e.set_chal(e.ci_out, r, (size_t)n);
@@ -2658,7 +2758,6 @@ extern "C" int vp_sumcheck_init_all(vp_ctx* ctx, const vp_F* r_last, int n) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n != e.C.bit_length(e.n - 1)) return fail(VP_ERR_ARG, "sumcheck_init_all: wrong n");
     if (n) e.set_chal(e.ci_out, r_last, (size_t)n);
     e.cur_layer = e.n;
@@ -2670,7 +2769,6 @@ extern "C" int vp_sumcheck_init_all(vp_ctx* ctx, const vp_F* r_last, int n) {
 extern "C" int vp_sumcheck_init(vp_ctx* ctx) {
     if (!ctx) return fail(VP_ERR_ARG, "null argument");
     Engine& e = ctx->e;
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer <= 1) return fail(VP_ERR_ARG, "sumcheck_init below layer 1");
     --e.cur_layer;
     e.phase = 0;
@@ -2681,7 +2779,6 @@ extern "C" int vp_init_phase1(vp_ctx* ctx, const vp_F* assert_random) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_phase1 outside a layer");
     e.set_chal(e.L[e.cur_layer].ci_assert, assert_random);
     e.do_init_phase1(e.cur_layer);
@@ -2696,7 +2793,6 @@ extern "C" int vp_init_phase2(vp_ctx* ctx) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_phase2 outside a layer");
     if (e.L[e.cur_layer].max_dad_bl == -1) return fail(VP_ERR_ARG, "layer %d has no phase 2", e.cur_layer);
     e.do_init_phase2(e.cur_layer);
@@ -2711,7 +2807,6 @@ extern "C" int vp_init_liu(vp_ctx* ctx, const vp_F* sig, int n) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (e.cur_layer < 1 || e.cur_layer >= e.n) return fail(VP_ERR_ARG, "init_liu outside a layer");
     const int need = e.n - e.cur_layer + 1;
     if (n < need) return fail(VP_ERR_ARG, "init_liu: need %d sigma values, got %d", need, n);
@@ -2727,25 +2822,26 @@ static uint32_t phase_ci(Engine& e, int phase) {
     LayerDev& D = e.L[e.cur_layer];
     return phase == 1 ? D.ci_ru : phase == 2 ? D.ci_rv : D.ci_rliu;
 }
-static const SumcheckPlan& phase_plan(Engine& e, int phase) {
+static const PhasePlan& phase_plan(Engine& e, int phase) {
     LayerDev& D = e.L[e.cur_layer];
-    return phase == 1 ? D.ph1.planB : phase == 2 ? D.ph2.planB : D.ph3.planB;
+    return phase == 1 ? D.ph1 : phase == 2 ? D.ph2 : D.ph3;
 }
 extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_F out_abc[3]) {
     if (!ctx || !previous_random || !out_abc) return fail(VP_ERR_ARG, "null argument");
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (phase < 1 || phase > 3 || phase != e.phase) return fail(VP_ERR_ARG, "vp_round: phase %d not initialised", phase);
     LayerDev& D = e.L[e.cur_layer];
-    const SumcheckPlan& P = phase_plan(e, phase);
-    if (e.round >= P.rounds) return fail(VP_ERR_ARG, "vp_round: all %d rounds already done", P.rounds);
+    const PhasePlan& PP = phase_plan(e, phase);
+    if (e.round >= PP.rounds) return fail(VP_ERR_ARG, "vp_round: all %d rounds already done", PP.rounds);
     const uint32_t ci = phase_ci(e, phase);
     if (e.round >= 1) e.set_chal(ci + (uint32_t)(e.round - 1), previous_random);  // r_arr.at(round-1) = prev (prover.cpp:441)
     ++e.round;
     const uint32_t tr = (phase == 1 ? D.tr_p1 : phase == 2 ? D.tr_p2 : D.tr_liu) + 3u * (uint32_t)(e.round - 1);
-    e.do_round(P, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, phase == 2 ? e.scal(Engine::SC_UNARY) : nullptr);
+    const F* at_init = phase == 2 ? e.scal(Engine::SC_UNARY) : nullptr;
+    if (PP.sharded) e.sharded_round(PP, phase, e.round, ci, tr, at_init);
+    else e.do_round(PP.planB, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, at_init);
     e.get_tr(tr, out_abc, 3);
     e.proof_size += 3 * sizeof(F);
     return VP_OK;
@@ -2754,14 +2850,14 @@ extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_
 static int finalize_common(vp_ctx* ctx, int phase, const vp_F* prev, vp_F* out, int n_out) {
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (phase != e.phase) return fail(VP_ERR_ARG, "finalize: phase %d not initialised", phase);
     LayerDev& D = e.L[e.cur_layer];
-    const SumcheckPlan& P = phase_plan(e, phase);
-    if (e.round != P.rounds) return fail(VP_ERR_ARG, "finalize after %d of %d rounds", e.round, P.rounds);
+    const PhasePlan& PP = phase_plan(e, phase);
+    if (e.round != PP.rounds) return fail(VP_ERR_ARG, "finalize after %d of %d rounds", e.round, PP.rounds);
     const uint32_t ci = phase_ci(e, phase);
     if (e.round >= 1) e.set_chal(ci + (uint32_t)(e.round - 1), prev);
-    e.do_finalize(P, ci + (uint32_t)std::max(0, P.rounds - 1), phase == 1 ? e.scal(Engine::SC_VU) : nullptr);
+    // a sharded phase ends in its replicated stage B: every rank holds the same claims
+    e.do_finalize(PP.planB, ci + (uint32_t)std::max(0, PP.rounds - 1), phase == 1 ? e.scal(Engine::SC_VU) : nullptr);
     const uint32_t tr = phase == 1 ? D.tr_claim_u : phase == 2 ? D.tr_claims_v : D.tr_claim_liu;
     e.get_tr(tr, out, (size_t)n_out);
     e.phase = 0;
@@ -2796,13 +2892,21 @@ extern "C" int vp_inner_prod(vp_ctx* ctx, const vp_F* pub, size_t n, vp_F* out) 
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n > e.C.layer_size(0)) return fail(VP_ERR_ARG, "inner_prod: n exceeds the input layer");
     if (e.d_pub.n < n) e.d_pub.alloc(n);
     CK(cudaMemcpyAsync(e.d_pub.p, pub, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
-    k_dot<<<e.grid_for((uint32_t)n, e.cap_dot), 256, 0, e.stream>>>(e.val[0].p, e.d_pub.p, (uint32_t)n, e.d_tr.p + e.tr_input,
-                                                           e.d_partials.p, e.d_counter.p);
-    ++e.launches;
+    if (e.world == 1) {
+        k_dot<<<e.grid_for((uint32_t)n, e.cap_dot), 256, 0, e.stream>>>(e.val[0].p, e.d_pub.p, (uint32_t)n, e.d_tr.p + e.tr_input,
+                                                               e.d_partials.p, e.d_counter.p);
+        ++e.launches;
+    } else {   // every rank sums its own slice of the instances, one 16-byte-per-rank all-gather (collective call)
+        const size_t S0 = e.C.layers[0].size, b = std::min(n, (size_t)e.ko_lo * S0), en = std::min(n, (size_t)e.ko_hi * S0);
+        k_dot<<<e.grid_for((uint32_t)std::max<size_t>(en - b, 1), e.cap_dot), 256, 0, e.stream>>>(e.val[0].p + b, e.d_pub.p + b, (uint32_t)(en - b),
+                                                                                              e.d_send.p, e.d_partials.p, e.d_counter.p);
+        NCK(g_nccl.AllGather(e.d_send.p, e.d_recv.p, 2, /*ncclUint64*/ 5, e.comm, e.stream));
+        k_sum_ranks<<<1, 32, 0, e.stream>>>(e.d_recv.p, (uint32_t)e.world, 1, e.d_tr.p + e.tr_input);
+        e.launches += 3;
+    }
     e.get_tr(e.tr_input, out);
     return VP_OK;
     API_END
@@ -2830,7 +2934,6 @@ extern "C" int vp_input_mle(vp_ctx* ctx, const vp_F* r, int n, vp_F* out) {
     API_BEGIN
     Engine& e = ctx->e;
     ScopedTimer t(e);
-    if (e.world > 1) return fail(VP_ERR_ARG, "%s: a sharded context only supports vp_prove / vp_verify (whole proof); the method-by-method entry points need one GPU", __func__);
     if (n != e.C.bit_length(0)) return fail(VP_ERR_ARG, "input_mle: n must be the input layer's bit length");
     if (n) e.set_chal(e.L[1].ci_rliu, r, (size_t)n);
     e.do_input_mle();

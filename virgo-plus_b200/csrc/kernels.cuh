@@ -729,6 +729,43 @@ k_init_liu(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, 
     }
 }
 
+// Template-major form of K5 for unsharded contexts: a thread owns ONE template entry u0 (visited in length-sorted order)
+// and walks a chunk of the data-parallel instances, so everything that only depends on the template -- the CSR bounds,
+// the scattered terms' (table, slot, subset size), the tables' descriptors -- is read once per thread instead of once
+// per (entry, instance), the instance index needs no division, and two instances are in flight per iteration
+// (independent reduction chains). Lanes of a warp still hold neighbouring entries of the same instance: the table
+// stores and the eq lookups stay as coalesced as in k_init_liu.
+__global__ void __launch_bounds__(256)
+k_init_liu_tm(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
+              uint32_t S_pre, uint32_t K, uint32_t k_chunk, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
+              F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, int write_a, int equ_scaled, int write_v) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= S_pre) return;
+    const uint32_t u0 = perm ? perm[x] : x;
+    const uint32_t eb = off[u0], n_terms = off[u0 + 1] - eb;
+    const uint32_t k0 = blockIdx.y * k_chunk, k1 = min(K, k0 + k_chunk);
+    const F s0 = *s0_ptr;
+    // the first two scattered terms live in registers (most entries have at most two)
+    LiuEntry E0{0, 0, 0}, E1{0, 0, 0};
+    EqTab T0 = equ, T1 = equ;
+    if (n_terms >= 1) { E0 = ent[eb]; T0 = eqs[E0.eq_id]; }
+    if (n_terms >= 2) { E1 = ent[eb + 1]; T1 = eqs[E1.eq_id]; }
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t u = k * S_pre + u0, kk = K - 1 - k;
+        F M = eq_at_weak(equ, u);
+        if (!equ_scaled) M = f_mul(M, s0);
+        if (n_terms >= 1) M = eq_at_acc_w(T0, kk * E0.D + E0.slot0, M);
+        if (n_terms >= 2) M = eq_at_acc_w(T1, kk * E1.D + E1.slot0, M);
+        for (uint32_t q = 2; q < n_terms; ++q) {
+            const LiuEntry E = ent[eb + q];
+            M = eq_at_acc_w(eqs[E.eq_id], kk * E.D + E.slot0, M);
+        }
+        if (write_v) st_f(tV + u, ld_f(Vpre + u));
+        st_f(tM + u, f_strict(M));
+        if (write_a) st_f(tA + u, f_zero());
+    }
+}
+
 // ------------------------------------------------------------------ K6: fused fold + round polynomial
 // prover.cpp:436-492 (sumcheckUpdate / sumcheckUpdateEach).
 struct TabDesc {        // a table that is still >= one pair in this round

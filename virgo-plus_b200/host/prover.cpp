@@ -2,9 +2,12 @@
 // /root/reference/src/prover.cpp (line ranges cited per method).
 #include "prover.h"
 
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "virgo_b200.h"
 
@@ -23,7 +26,7 @@ inline vp_F *mf(F *p) { return reinterpret_cast<vp_F *>(p); }
 }  // namespace
 
 // prover.cpp:14-25: evaluate, then fail if an assert gate is non-zero.
-prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr), sumcheckLayerId(0) {
+prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr), sumcheckLayerId(0), world(1) {
     const int n = C.size;
     std::vector<uint64_t> layer_size(n), u, v, lv, dad_size((size_t)n * n, 0), dad_id;
     std::vector<uint8_t> ty, is_assert;
@@ -51,8 +54,37 @@ prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr),
     ck(vp_circuit_from_arrays(n, layer_size.data(), ty.data(), l.data(), u.data(), v.data(), lv.data(), cst.data(),
                               is_assert.data(), dad_size.data(), dad_id.data(), &circ),
        "vp_circuit_from_arrays");
-    const char *dev = getenv("VP_DEVICE");
-    ck(vp_create(circ, dev ? atoi(dev) : 0, &ctx), "vp_create");
+    // One GPU: VP_DEVICE (default 0). Several GPUs of one box: start VP_WORLD copies of the program, one per GPU, with
+    // VP_RANK = 0 .. VP_WORLD-1 (and VP_NCCL_ID_FILE = a path all of them can reach): the copies run the same verifier
+    // (its challenges are deterministic), every prover call is a collective of the sharded engine.
+    const char *dev = getenv("VP_DEVICE"), *w = getenv("VP_WORLD");
+    world = w ? atoi(w) : 1;
+    if (world > 1) {
+        const char *r = getenv("VP_RANK"), *idf = getenv("VP_NCCL_ID_FILE");
+        if (!r || !idf) { fprintf(stderr, "virgo_b200 prover: VP_WORLD needs VP_RANK and VP_NCCL_ID_FILE\n"); exit(EXIT_FAILURE); }
+        const int rank = atoi(r);
+        uint8_t id[128];
+        if (rank == 0) {   // publish the NCCL id: write to a temporary name, then rename (readers never see a partial file)
+            ck(vp_nccl_unique_id(id), "vp_nccl_unique_id");
+            const std::string tmp = std::string(idf) + ".tmp";
+            FILE *f = fopen(tmp.c_str(), "wb");
+            if (!f || fwrite(id, 1, 128, f) != 128) { fprintf(stderr, "virgo_b200 prover: cannot write %s\n", tmp.c_str()); exit(EXIT_FAILURE); }
+            fclose(f);
+            rename(tmp.c_str(), idf);
+        } else {
+            for (int tries = 0;; ++tries) {
+                FILE *f = fopen(idf, "rb");
+                if (f) {
+                    const size_t got = fread(id, 1, 128, f);
+                    fclose(f);
+                    if (got == 128) break;
+                }
+                if (tries > 3000) { fprintf(stderr, "virgo_b200 prover: no NCCL id in %s\n", idf); exit(EXIT_FAILURE); }
+                usleep(10000);
+            }
+        }
+        ck(vp_create_sharded(circ, dev ? atoi(dev) : rank, rank, world, id, &ctx), "vp_create_sharded");
+    } else ck(vp_create(circ, dev ? atoi(dev) : 0, &ctx), "vp_create");
     evaluate();
 }
 
@@ -152,9 +184,9 @@ virgo::__hhash_digest prover::commit_private() {
     using namespace virgo;
     std::vector<F> mask(1, F_ZERO);
     const int bl = C.circuit[0].bitLength;
-    if (getenv("VP_CPU_COMMIT") || bl < 6) {
+    if (getenv("VP_CPU_COMMIT") || bl < 6 || world > 1) {   // (the device commit needs the whole input layer on one GPU)
         input_values.assign(1ULL << bl, F_ZERO);
-        ck(vp_get_values(ctx, 0, mf(input_values.data()), C.circuit[0].size), "vp_get_values");
+        for (u64 g = 0; g < C.circuit[0].size; ++g) input_values[g] = F((long long)C.circuit[0].gates[g].u);   // prover.cpp:30-36
         return poly_prover.commit_private_array(input_values.data(), bl, mask);
     }
     const auto t0 = std::chrono::high_resolution_clock::now();

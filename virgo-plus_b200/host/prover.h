@@ -60,5 +60,6 @@ private:
     vp_circuit *circ;
     vp_ctx *ctx;
     int sumcheckLayerId;
+    int world;                    // GPUs this prover is sharded over (VP_WORLD copies of the program, one per GPU)
     std::vector<F> input_values;  // host copy of circuitValue[0], zero-padded to 2^bitLength (for the PC)
 };

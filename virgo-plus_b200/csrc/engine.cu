@@ -929,7 +929,7 @@ struct Engine {
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
     int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
-    bool old_p2 = false, getenv_no_hs = false, liu_old = false;
+    bool old_p2 = false, getenv_no_hs = false, liu_old = false, p1_old = false;
     DBuf<F> d_hs;   // phase-2 init: products of the second-half eq factors, K * ng * nu entries (k_p2_hs)
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: phase-1 init uses the one-real-product-per-gate kernel
@@ -1004,7 +1004,16 @@ struct Engine {
 
 // ------------------------------------------------------------------ build: upload wiring, CSRs, plans
 void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const uint8_t* nccl_id) {
+    const bool timing = getenv("VP_CREATE_TIMING") != nullptr;   // development aid: where vp_create spends its host time
+    auto t_prev = std::chrono::steady_clock::now();
+    double t_acc[8] = {0};
+    auto lap = [&](int k) {
+        const auto now = std::chrono::steady_clock::now();
+        t_acc[k] += std::chrono::duration<double>(now - t_prev).count();
+        t_prev = now;
+    };
     C = circ;
+    lap(0);
     device = dev;
     world = world_;
     rank = rank_;
@@ -1051,6 +1060,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     lane_init = values_real && !getenv("VP_NO_LANE_INIT");
     old_p2 = getenv("VP_OLD_P2") != nullptr;
     liu_old = getenv("VP_LIU_OLD") != nullptr;
+    p1_old = getenv("VP_P1_OLD") != nullptr;
     getenv_no_hs = getenv("VP_NO_HS") != nullptr;
     d_hs.alloc((size_t)K * 64);   // development knob: the five-products-per-gate phase-2 init
     {
@@ -1163,6 +1173,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.G = GateArrays{D.ty.p, D.l.p, D.u.p, D.v.p, D.c.p};
             CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
         }
+        lap(1);
         // phase-1 CSR by u0
         {
             std::vector<uint32_t> off(S_pre + 1, 0), g0(S), v0(S), tyl(S);
@@ -1188,6 +1199,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.p1_tyl.upload(tyl, stream);
             CK(cudaStreamSynchronize(stream));
         }
+        lap(2);
         const int pb = C.bit_length(i - 1);
         // plans for phase 1 and Liu: one table over layer i-1
         {
@@ -1209,6 +1221,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         add_eq_build(6 + (uint32_t)n, D.ci_rv, std::max(D.max_dad_bl, 0), -1);
         D.eqb_rl = (uint32_t)eq_descs.size();
         add_eq_build(7 + (uint32_t)n, D.ci_rliu, pb, -1);
+        lap(3);
         // phase 2
         if (D.max_dad_bl != -1) {
             const int m = D.max_dad_bl;
@@ -1303,6 +1316,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.un_ty.upload(ut, stream);
             CK(cudaStreamSynchronize(stream));
         }
+        lap(4);
         // Liu CSR: all (j >= i, slot0) with dadId_j[i-1][slot0] = u0
         {
             const int pre = i - 1;
@@ -1365,6 +1379,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             D.liu_eqtabs_b.upload(tabs, stream);
             CK(cudaStreamSynchronize(stream));
         }
+        lap(5);
     }
     eqb_in = (uint32_t)eq_descs.size();
     add_eq_build(2, L[1].ci_rliu, C.bit_length(0), -1);
@@ -1503,6 +1518,10 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     CK(cudaStreamSynchronize(stream));
     load_inputs(C.inputs.data(), C.inputs.size(), true);
     CK(cudaStreamSynchronize(stream));
+    lap(6);
+    if (timing)
+        fprintf(stderr, "vp_create: copy %.2f s, gate arrays %.2f, phase-1 CSR %.2f, plans %.2f, phase-2 CSR %.2f, Liu CSR %.2f, buffers/lanes/comm %.2f\n",
+                t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4], t_acc[5], t_acc[6]);
 }
 
 // Exchange buffers of every lane, mapped into every rank (CUDA IPC over the box's NVLink fabric). Collective: the
@@ -1682,7 +1701,13 @@ void Engine::do_init_phase1(int i) {
     const uint32_t k0 = D.ph1.sharded ? D.p1_k0 : 0, k1 = D.ph1.sharded ? D.p1_k1 : K;
     const uint64_t work = (uint64_t)D.p1_items.n * (k1 - k0);
     size_t h = prof_begin(KC_INIT1);
-    if (lane_init && work < 0xffffffffull && n <= 64)
+    if (lane_init && world == 1 && K >= 8 && n <= 64 && !p1_old) {   // template-major: an item of the template x 4 instances per thread
+        dim3 grid(cdiv((uint32_t)D.p1_items.n, 256), cdiv(K, 4));
+        k_init_phase1_real_tm<4><<<grid, 256, 0, stream>>>(
+            D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
+            d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
+            bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, direct_v ? 0 : 1, (uint32_t)i);
+    } else if (lane_init && work < 0xffffffffull && n <= 64)
         k_init_phase1_real<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1il), 256, 0, stream>>>(
             D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
             d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
@@ -1949,7 +1974,10 @@ void Engine::launch_dfs_kernel(const PassPlan& P, uint32_t ci, uint32_t round_ba
     // this one is down to its small passes
     // three lanes: two of the three block slots of an SM, so that the other lanes' kernels (gather-latency bound inits,
     // another phase's passes) are co-resident with a compute-bound pass (measured: C3 13.3 -> 12.9 ms)
-    uint32_t cap = three_lanes ? (uint32_t)std::max(2, 2 * cap_dfs / 3) : two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
+    // six lanes: 1.25 blocks per SM per pass kernel (of three slots) -- measured on C3: 444 blocks 11.33 ms, 296 10.95, 222 10.65,
+    // 185 10.78, 148 10.75, 111 11.02, 74 11.7; the 65 x 2^20 random circuit prefers 148 (profiles/r2b_dfs_grid_sweep.txt)
+    uint32_t cap = six_lanes ? (uint32_t)std::max(2, std::min(cap_dfs, 5 * n_sm / 4))
+                 : three_lanes ? (uint32_t)std::max(2, 2 * cap_dfs / 3) : two_lanes ? (uint32_t)std::max(1, cap_dfs - 8) : (uint32_t)cap_dfs;
     if (dfs_grid_override) cap = std::max<uint32_t>(2, std::min<uint32_t>((uint32_t)dfs_grid_override, (uint32_t)cap_dfs));
     // block 0 coordinates, blocks 1.. work; a phase that fits one block runs on block 0 alone
     const int grid = P.max_work <= DFS_CHUNK ? 1 : (int)std::min<uint32_t>(cdiv(P.max_work, DFS_CHUNK) + 1, std::max<uint32_t>(cap, 2));

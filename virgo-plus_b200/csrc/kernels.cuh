@@ -444,6 +444,91 @@ k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 cs
     }
 }
 
+// Template-major form of k_init_phase1_real for unsharded contexts with K >= KC instances: a thread owns one work item
+// of the TEMPLATE and a chunk of KC consecutive instances. The CSR words of an entry (gate id, type, source layer,
+// operand index, constant) are read and decoded once for the KC instances, whose loads (gathered operand + two eq
+// half-table entries each) are all address-computable at once and whose product chains are independent: 3 KC loads in
+// flight per entry instead of a dependent CSR -> pointer -> operand chain per (entry, instance). Lanes of a warp hold
+// neighbouring items of the same instances, so gathers and stores coalesce as before.
+template <int KC>
+__global__ void __launch_bounds__(256, 2)
+k_init_phase1_real_tm(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
+                      EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
+                      const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
+                      F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, int write_v, uint32_t n_src) {
+    __shared__ const u64* s_vals[64];
+    __shared__ uint32_t s_sizes[64];
+    for (uint32_t i = threadIdx.x; i < min(n_src, 64u); i += blockDim.x) { s_vals[i] = reinterpret_cast<const u64*>(vals[i]); s_sizes[i] = sizes[i]; }
+    __syncthreads();
+    const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const uint32_t k0 = blockIdx.y * KC, nk = min((uint32_t)KC, K - k0);
+    const RowItem I = items[it];
+    u64 Mre[KC], Mim[KC], Are[KC], Aim[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) { Mre[j] = Mim[j] = Are[j] = Aim[j] = 0; }
+    const uint32_t e1 = I.e_begin + (I.cnt_slot & 0xff);
+    for (uint32_t e = I.e_begin; e < e1; ++e) {
+        const uint32_t g0 = csr.g0[e], tyl = csr.tyl[e], v0 = csr.v0[e];
+        const int l = (int)(tyl >> 8) - 1;
+        const uint32_t ty = tyl & 0x7f, lc = l >= 0 ? (uint32_t)l : 0u;
+        const bool is_as = (tyl & TY_ASSERT_BIT) != 0, has_v = l >= 0, is_const = ty == T_ADDC || ty == T_MULC;
+        const u64* vb = s_vals[lc] + 2 * (size_t)v0;
+        const size_t vstride = 2 * (size_t)s_sizes[lc];
+        const u64 xc = is_const ? cst[g0].re : 0;
+        ulonglong2 ha[KC], hb[KC];
+        u64 Vv[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+            const uint32_t k = k0 + (j < (int)nk ? j : 0), idx = k * S_cur + g0;
+            ha[j] = __ldg(reinterpret_cast<const ulonglong2*>(eqg.f + (idx & eqg.mask)));
+            hb[j] = __ldg(reinterpret_cast<const ulonglong2*>(eqg.s + (idx >> eqg.fh)));
+            Vv[j] = has_v ? __ldg(vb + (size_t)k * vstride) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+            F beta = f_mul_w(F{ha[j].x, ha[j].y}, F{hb[j].x, hb[j].y});
+            if (is_as) beta = f_mul(beta, *assert_r);
+            const u64 x = is_const ? xc : Vv[j];
+            F Pp = f_zero();
+            if (ty != T_COPY && ty != T_NOT) Pp = f_mad_real_w(f_zero(), beta, x);
+            const F nP = F{P - Pp.re, P - Pp.im}, nB = F{P - beta.re, P - beta.im};
+            u64 are = 0, aim = 0, mre = 0, mim = 0;
+            switch (ty) {   // prover.cpp:229-272 (same table as k_init_phase1_real)
+                case T_ADD: case T_ADDC: are = Pp.re; aim = Pp.im; mre = beta.re; mim = beta.im; break;
+                case T_SUB: are = nP.re; aim = nP.im; mre = beta.re; mim = beta.im; break;
+                case T_ANTISUB: are = Pp.re; aim = Pp.im; mre = nB.re; mim = nB.im; break;
+                case T_MUL: case T_MULC: mre = Pp.re; mim = Pp.im; break;
+                case T_NAAB: are = Pp.re; aim = Pp.im; mre = nP.re; mim = nP.im; break;
+                case T_ANTINAAB: mre = beta.re + nP.re; mim = beta.im + nP.im; break;
+                case T_COPY: mre = beta.re; mim = beta.im; break;
+                case T_NOT: are = beta.re; aim = beta.im; mre = nB.re; mim = nB.im; break;
+                case T_XOR: are = Pp.re; aim = Pp.im; mre = beta.re + 2 * nP.re; mim = beta.im + 2 * nP.im; break;
+                default: break;
+            }
+            Are[j] = fp_fold(Are[j] + are); Aim[j] = fp_fold(Aim[j] + aim);
+            Mre[j] = fp_fold(Mre[j] + mre); Mim[j] = fp_fold(Mim[j] + mim);   // <= p + 7
+        }
+    }
+    const uint32_t slot = I.cnt_slot >> 8;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+        if (j >= (int)nk) break;
+        const uint32_t k = k0 + j;
+        const F Mr = F{fp_canon(Mre[j]), fp_canon(Mim[j])}, Ar = F{fp_canon(Are[j]), fp_canon(Aim[j])};
+        if (slot == 0) {
+            const uint32_t loc = k * S_pre + I.row;
+            if (write_v) st_f(tV + loc, ld_f(Vpre + loc));
+            st_f(tM + loc, Mr);
+            st_f(tA + loc, Ar);
+        } else {
+            F* dst = partial + 2 * ((size_t)k * n_slots + (slot - 1));
+            st_f(dst, Mr);
+            st_f(dst + 1, Ar);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_combine_phase1(const LongRow* __restrict__ rows, uint32_t n_rows, uint32_t S_pre, uint32_t K, const F* __restrict__ Vpre,
                  F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, const F* __restrict__ partial, uint32_t n_slots,
@@ -1477,21 +1562,26 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
     // the work (the share per warp is rounded to 32 items: 2100 items on 8 workers -> 6 of them, 2048 items -> all 8), so a
     // worker may idle in one pass and be needed again later. s_alive[ps] = the largest `active` of this and all later
     // passes: workers 1..s_alive[ps] arrive at pass ps's barrier (working or not), the others have left for good.
-    __shared__ uint32_t s_alive[34];
-    if (threadIdx.x == 0) {
-        uint32_t mx = 0;
-        s_alive[p.n_passes < 33 ? p.n_passes : 33] = 0;
-        for (int q = (int)p.n_passes - 1; q >= 0; --q) {
+    __shared__ uint32_t s_alive[34], s_active[34], s_share[34];
+    if (threadIdx.x < 34) {   // (one load per pass, in parallel: this sits in front of the first pass of every launch)
+        const uint32_t q = threadIdx.x;
+        uint32_t a = 0, sh = DFS_WCHUNK;
+        if (q < p.n_passes) {
             const uint32_t work = p.passes[q].work;
-            uint32_t a = 0;
             if (work > DFS_CHUNK && n_workers != 0) {
                 const uint32_t per_warp = (work + n_workers * WPB - 1) / (n_workers * WPB);
-                const uint32_t sh = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
+                sh = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
                 a = min(n_workers, (work + sh * WPB - 1) / (sh * WPB));
             }
-            mx = max(mx, a);
-            s_alive[q] = mx;
         }
+        s_alive[q] = a;
+        s_active[q] = a;
+        s_share[q] = sh;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t mx = 0;
+        for (int q = 33; q >= 0; --q) { mx = max(mx, s_alive[q]); s_alive[q] = mx; }
     }
     __syncthreads();
     F at = p.at_init ? *p.at_init : f_zero();
@@ -1506,12 +1596,9 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         // `share` items (a multiple of 32, at most DFS_WCHUNK), on as many workers as that takes. Larger passes hand out
         // DFS_WCHUNK-item chunks from an atomic counter.
         const bool solo = R.work <= DFS_CHUNK || n_workers == 0;       // block 0 alone
-        uint32_t share = DFS_WCHUNK, active = 0;
-        if (!solo) {
-            const uint32_t per_warp = (R.work + n_workers * WPB - 1) / (n_workers * WPB);
-            share = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
-            active = min(n_workers, (R.work + share * WPB - 1) / (share * WPB));   // worker blocks 1..active
-        }
+        // share = roundup32(ceil(work / (workers * warps))) capped at DFS_WCHUNK, active = ceil(work / (share * warps))
+        // worker blocks 1..active (tabulated per pass at the top of the kernel)
+        const uint32_t share = s_share[ps], active = s_active[ps];
         const bool is_static = solo ? R.work <= DFS_CHUNK : (uint64_t)active * share * WPB >= R.work;
         const uint32_t alive = s_alive[ps];
         if (!coord && blockIdx.x > alive) return;                      // not needed in this or any later pass

@@ -203,6 +203,20 @@ float vp_last_commit_ms(const vp_ctx* ctx);   /* device time of the last vp_comm
 int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t root[32], vp_F* l_eval, uint8_t* leaf_hash,
                  uint8_t* tree, float* device_ms);
 
+/* ------------------------------------------------------------------ Fiat-Shamir mode
+ * The reference ships a hash-based challenge source, transcriptCache (lib/virgo/src/transcriptCache.hpp:14-50: a byte
+ * pool hashed with SHA3-256 per challenge, challenge = first two digest words mod p), but never calls it. This mode uses
+ * exactly that class, fed with seed[32] and then every prover message (16 bytes {u64 real, u64 img} each) in emission
+ * order; a round's challenge is drawn right after the round's polynomial was stored (order: host/fiat_shamir.h). Only the
+ * one-round-per-launch path applies (a challenge depends on the previous message). vp_prove_fs uses the resident inputs
+ * and returns the transcript and, optionally, the challenges it drew (usual layout, unused slots zero);
+ * vp_fs_challenges recomputes them from a transcript alone; vp_verify_fs = vp_fs_challenges + vp_verify (fail_code 7:
+ * a non-canonical transcript element). Not parity-bound to the reference (it has no such mode); pinned against the
+ * oracle's restatement of transcriptCache. */
+int vp_prove_fs(vp_ctx* ctx, const uint8_t seed[32], vp_F* transcript, size_t transcript_cap, vp_F* challenges, size_t challenges_cap);
+int vp_fs_challenges(const vp_circuit* c, const uint8_t seed[32], const vp_F* transcript, size_t n, vp_F* challenges, size_t cap);
+int vp_verify_fs(vp_ctx* ctx, const uint8_t seed[32], const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer);
+
 /* Self-test of the device-only arithmetic paths of csrc/field.cuh (inline-PTX carry chains, mul.wide / mad.wide):
    runs one routine on n caller-provided operand triples and returns the results, so that tests can feed edge values
    (0, 1, p-1, p, limb boundaries) and compare with big-integer arithmetic.  op: 0 weak fold a + c*(b-a); 1 the same for

@@ -726,6 +726,10 @@ void ogkr_evaluate(const ogkr_circuit* c, ofe* values) {
 /* ------------------------------------------------------------------ verifier
  * verifier.cpp:50-61 (betaInit*), :63-113 (predicatePhase1/2), :115-132 (getFinalValue),
  * :134-189 (verify), :191-337 (verifyPhase1/2/Liu). Messages come from a transcript. */
+static const ofe* g_ch_replay = NULL; /* if set: the verifier's draws replay this challenge array (its layout IS the draw order) */
+static size_t g_ch_pos = 0;
+static ofe verifier_draw(void) { return g_ch_replay ? g_ch_replay[g_ch_pos++] : ogkr_random_field(); }
+
 int ogkr_verify(const ogkr_circuit* c, unsigned seed, const ofe* tr, int* fail_code, int* fail_layer) {
     int n = c->n_layers, mbl = max_bl(c);
     int mdb_all = -1;
@@ -755,15 +759,15 @@ int ogkr_verify(const ogkr_circuit* c, unsigned seed, const ofe* tr, int* fail_c
 
     ogkr_seed(seed);
     int out_bl = layer_bl(c, n - 1);
-    for (int i = 0; i < out_bl; ++i) r_liu[i] = ogkr_random_field();
+    for (int i = 0; i < out_bl; ++i) r_liu[i] = verifier_draw();
     ofe previousSum = tr[ti++]; /* Vres */
     for (int i = n - 1; i >= 1; --i) {
         u64 cur_size = c->layer_size[i], off = c->gate_off[i];
         int pb = layer_bl(c, i - 1), m = max_dad_bl(c, i);
         /* ---- verifyPhase1 */
-        for (int k = 0; k < mbl; ++k) r_u[k] = ogkr_random_field();
+        for (int k = 0; k < mbl; ++k) r_u[k] = verifier_draw();
         ofe prev = F_ZERO;
-        ofe assert_random = ogkr_random_field();
+        ofe assert_random = verifier_draw();
         for (int j = 0; j < pb; ++j) {
             quad q = {tr[ti], tr[ti + 1], tr[ti + 2]};
             ti += 3;
@@ -803,7 +807,7 @@ int ogkr_verify(const ogkr_circuit* c, unsigned seed, const ofe* tr, int* fail_c
             for (int k = 0; k < n; ++k) coeff_r[t][k] = F_ZERO;
         /* ---- verifyPhase2 */
         if (m != -1) {
-            for (int k = 0; k < m; ++k) r_v[i][k] = ogkr_random_field();
+            for (int k = 0; k < m; ++k) r_v[i][k] = verifier_draw();
             prev = F_ZERO;
             for (int j = 0; j < m; ++j) {
                 quad q = {tr[ti], tr[ti + 1], tr[ti + 2]};
@@ -858,8 +862,8 @@ int ogkr_verify(const ogkr_circuit* c, unsigned seed, const ofe* tr, int* fail_c
         /* ---- verifyLiu */
         {
             int pre = i - 1;
-            for (int k = 0; k < n; ++k) sig[k] = ogkr_random_field();
-            for (int k = 0; k < mbl; ++k) r_liu[k] = ogkr_random_field();
+            for (int k = 0; k < n; ++k) sig[k] = verifier_draw();
+            for (int k = 0; k < mbl; ++k) r_liu[k] = verifier_draw();
             previousSum = ofe_mul(sig[0], claim_u);
             for (int j = i; j < n; ++j)
                 if (dad_bl(c, j, pre) >= 0)
@@ -913,6 +917,158 @@ done:
  * sumcheckUpdateEach (prover.cpp:457-492) on one table triple with total == totalSize == 2^log_n,
  * add_term == 0; the trailing three values are Vmult/addV/mult [0].eval(r_last) as Finalize would
  * compute them (prover.cpp:497). */
+
+/* ------------------------------------------------------------------ Fiat-Shamir mode
+ * transcriptCache restated (lib/virgo/src/transcriptCache.hpp:14-50): store() appends bytes, random() hashes the pool
+ * with SHA3-256, the digest becomes the pool, challenge = (word0 mod p, word1 mod p). The reference never calls it;
+ * the order of stores and draws used here is the one documented in virgo-plus_b200/host/fiat_shamir.h (a round's
+ * challenge is drawn after the round's polynomial). Parity: UNPINNED against the reference (no call sites there);
+ * the hash is pinned by the FIPS 202 known answers. */
+void opc_sha3_256(const unsigned char* msg, size_t len, unsigned char out[32]);
+typedef struct { unsigned char* pool; size_t len, cap; } fs_cache;
+static void fs_store(fs_cache* f, const void* in, size_t n) {
+    if (f->len + n > f->cap) { f->cap = 2 * (f->len + n) + 64; f->pool = (unsigned char*)realloc(f->pool, f->cap); }
+    memcpy(f->pool + f->len, in, n);
+    f->len += n;
+}
+static void fs_store_fe(fs_cache* f, ofe x) { fs_store(f, &x, sizeof x); }
+static ofe fs_random(fs_cache* f) {
+    unsigned char out[32];
+    opc_sha3_256(f->pool, f->len, out);
+    memcpy(f->pool, out, 32);
+    f->len = 32;
+    u64 re, im;
+    memcpy(&re, out, 8);
+    memcpy(&im, out + 8, 8);
+    ofe r = {re % PRIME, im % PRIME};
+    return r;
+}
+
+/* challenges of an FS transcript from the messages alone, usual layout (unused slots zero) */
+void ogkr_fs_challenges(const ogkr_circuit* c, const unsigned char seed[32], const ofe* tr, ofe* ch) {
+    int n = c->n_layers, mbl = max_bl(c);
+    size_t nc = ogkr_challenge_count(c), ci = 0, ti = 0;
+    memset(ch, 0, nc * sizeof(ofe));
+    fs_cache f = {NULL, 0, 0};
+    fs_store(&f, seed, 32);
+    for (int k = 0; k < layer_bl(c, n - 1); ++k) ch[ci++] = fs_random(&f);
+    fs_store_fe(&f, tr[ti++]);
+    for (int i = n - 1; i >= 1; --i) {
+        int pb = layer_bl(c, i - 1), m = max_dad_bl(c, i);
+        size_t ci_ru = ci, ci_assert = ci_ru + (size_t)mbl, ci_rv = ci_assert + 1, ci_sig = ci_rv + (m != -1 ? (size_t)m : 0), ci_rliu = ci_sig + (size_t)n;
+        ch[ci_assert] = fs_random(&f);
+        for (int j = 0; j < pb; ++j) { for (int q = 0; q < 3; ++q) fs_store_fe(&f, tr[ti++]); ch[ci_ru + (size_t)j] = fs_random(&f); }
+        fs_store_fe(&f, tr[ti++]);
+        if (m != -1) {
+            for (int j = 0; j < m; ++j) { for (int q = 0; q < 3; ++q) fs_store_fe(&f, tr[ti++]); ch[ci_rv + (size_t)j] = fs_random(&f); }
+            for (int l = 0; l < i; ++l) fs_store_fe(&f, tr[ti++]);
+        }
+        for (int k = 0; k < n; ++k) ch[ci_sig + (size_t)k] = fs_random(&f);
+        for (int j = 0; j < pb; ++j) { for (int q = 0; q < 3; ++q) fs_store_fe(&f, tr[ti++]); ch[ci_rliu + (size_t)j] = fs_random(&f); }
+        fs_store_fe(&f, tr[ti++]);
+        ci = ci_rliu + (size_t)mbl;
+    }
+    free(f.pool);
+}
+
+/* the prover of ogkr_prove driven by the FS challenge source; ch_out (may be NULL): usual layout, unused slots zero */
+int ogkr_prove_fs(const ogkr_circuit* c, const unsigned char seed[32], ofe* tr, ofe* ch_out) {
+    prover_t P;
+    memset(&P, 0, sizeof P);
+    P.C = c;
+    int n = c->n_layers, mbl = max_bl(c);
+    size_t ti = 0, nc = ogkr_challenge_count(c), ci = 0;
+    ofe* ch = (ofe*)calloc(nc + 1, sizeof(ofe));
+    prover_evaluate(&P);
+    if (prover_check_asserts(&P)) { prover_free(&P); free(ch); return -1; }
+    prover_init(&P);
+    fs_cache f = {NULL, 0, 0};
+    fs_store(&f, seed, 32);
+    ofe* sig = (ofe*)calloc((size_t)n, sizeof(ofe));
+    ofe* r_liu = (ofe*)calloc((size_t)mbl + 1, sizeof(ofe));
+    ofe* claims = (ofe*)calloc((size_t)n, sizeof(ofe));
+    int out_bl = layer_bl(c, n - 1);
+    for (int k = 0; k < out_bl; ++k) { r_liu[k] = fs_random(&f); ch[ci++] = r_liu[k]; }
+    tr[ti] = prover_vres(&P, r_liu, out_bl);
+    fs_store_fe(&f, tr[ti++]);
+    prover_init_all(&P, r_liu);
+    int rc = 0;
+    for (int i = n - 1; i >= 1 && rc == 0; --i) {
+        int pb = layer_bl(c, i - 1), m = max_dad_bl(c, i);
+        size_t ci_ru = ci, ci_assert = ci_ru + (size_t)mbl, ci_rv = ci_assert + 1, ci_sig = ci_rv + (m != -1 ? (size_t)m : 0), ci_rliu = ci_sig + (size_t)n;
+        prover_layer_init(&P);
+        ofe assert_random = fs_random(&f);
+        ch[ci_assert] = assert_random;
+        rc = prover_init_phase1(&P, assert_random);
+        if (rc) break;
+        ofe prev = F_ZERO;
+        for (int j = 0; j < pb; ++j) {
+            quad q = prover_update(&P, prev, P.r_u, 1);
+            tr[ti] = q.a; tr[ti + 1] = q.b; tr[ti + 2] = q.c;
+            for (int k = 0; k < 3; ++k) fs_store_fe(&f, tr[ti + k]);
+            ti += 3;
+            prev = fs_random(&f);
+            ch[ci_ru + (size_t)j] = prev;
+        }
+        tr[ti] = prover_finalize1(&P, prev);
+        fs_store_fe(&f, tr[ti++]);
+        if (m != -1) {
+            prover_init_phase2(&P);
+            prev = F_ZERO;
+            for (int j = 0; j < m; ++j) {
+                quad q = prover_update(&P, prev, P.r_v[i], i);
+                tr[ti] = q.a; tr[ti + 1] = q.b; tr[ti + 2] = q.c;
+                for (int k = 0; k < 3; ++k) fs_store_fe(&f, tr[ti + k]);
+                ti += 3;
+                prev = fs_random(&f);
+                ch[ci_rv + (size_t)j] = prev;
+            }
+            prover_finalize2(&P, prev, claims);
+            for (int l = 0; l < i; ++l) { tr[ti] = claims[l]; fs_store_fe(&f, tr[ti++]); }
+        }
+        for (int k = 0; k < n; ++k) { sig[k] = fs_random(&f); ch[ci_sig + (size_t)k] = sig[k]; }
+        prover_init_liu(&P, sig);
+        prev = F_ZERO;
+        memset(r_liu, 0, ((size_t)mbl + 1) * sizeof(ofe));
+        for (int j = 0; j < pb; ++j) {
+            quad q = prover_update(&P, prev, P.r_liu, 1);
+            tr[ti] = q.a; tr[ti + 1] = q.b; tr[ti + 2] = q.c;
+            for (int k = 0; k < 3; ++k) fs_store_fe(&f, tr[ti + k]);
+            ti += 3;
+            prev = fs_random(&f);
+            ch[ci_rliu + (size_t)j] = prev;
+            r_liu[j] = prev;
+        }
+        tr[ti] = prover_finalize_liu(&P, prev);
+        fs_store_fe(&f, tr[ti++]);
+        ci = ci_rliu + (size_t)mbl;
+    }
+    if (rc == 0) {
+        int b0 = layer_bl(c, 0);
+        ofe* eq = (ofe*)calloc(1ULL << b0, sizeof(ofe));
+        ogkr_beta_table(eq, b0, r_liu, F_ONE);
+        tr[ti++] = prover_inner_prod(P.value[0], eq, c->layer_size[0]);
+        free(eq);
+    }
+    if (ch_out) memcpy(ch_out, ch, nc * sizeof(ofe));
+    free(ch); free(sig); free(r_liu); free(claims); free(f.pool);
+    prover_free(&P);
+    return rc;
+}
+
+/* verify an FS transcript: recompute the challenges from the messages, then the checks of ogkr_verify */
+int ogkr_verify_fs(const ogkr_circuit* c, const unsigned char seed[32], const ofe* tr, int* fail_code, int* fail_layer) {
+    size_t nc = ogkr_challenge_count(c);
+    ofe* ch = (ofe*)calloc(nc + 1, sizeof(ofe));
+    ogkr_fs_challenges(c, seed, tr, ch);
+    g_ch_replay = ch;
+    g_ch_pos = 0;
+    int ok = ogkr_verify(c, 0, tr, fail_code, fail_layer);
+    g_ch_replay = NULL;
+    free(ch);
+    return ok;
+}
+
 void ogkr_sumcheck_tables(const ofe* V, const ofe* add, const ofe* mult, int log_n, const ofe* r, ofe* out) {
     u64 total = 1ULL << log_n;
     lin* tv = (lin*)malloc(total * sizeof(lin));

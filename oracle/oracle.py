@@ -103,6 +103,35 @@ class OracleCircuit:
         ok = lib().ogkr_verify(self.ref, seed, _p(tr), C.byref(code), C.byref(layer))
         return bool(ok), code.value, layer.value
 
+    # ---- Fiat-Shamir mode (transcriptCache restated; order of virgo-plus_b200/host/fiat_shamir.h)
+    def prove_fs(self, seed32):
+        """-> (transcript, challenges in the usual layout)"""
+        L = lib()
+        L.ogkr_prove_fs.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+        tr = np.zeros(self.transcript_len, F_DTYPE)
+        ch = np.zeros(self.challenge_count, F_DTYPE)
+        rc = L.ogkr_prove_fs(self.ref, bytes(seed32), _p(tr), _p(ch))
+        if rc != 0:
+            raise RuntimeError("oracle: assert gate violated")
+        return tr, ch
+
+    def fs_challenges(self, seed32, transcript):
+        L = lib()
+        L.ogkr_fs_challenges.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+        L.ogkr_fs_challenges.restype = None
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        ch = np.zeros(self.challenge_count, F_DTYPE)
+        L.ogkr_fs_challenges(self.ref, bytes(seed32), _p(tr), _p(ch))
+        return ch
+
+    def verify_fs(self, seed32, transcript):
+        L = lib()
+        L.ogkr_verify_fs.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        code, layer = C.c_int(), C.c_int()
+        ok = L.ogkr_verify_fs(self.ref, bytes(seed32), _p(tr), C.byref(code), C.byref(layer))
+        return bool(ok), code.value, layer.value
+
     def evaluate(self):
         n = int(self.flat["layer_size"].sum())
         out = np.zeros(n, F_DTYPE)

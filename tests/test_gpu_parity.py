@@ -649,3 +649,25 @@ def test_commit_private_through_the_context(B, O, sha_circuit):
         with pytest.raises(B.VpError):
             p.commit_private(mask=B.fe_array([(1, 0)]))  # only the GKR prover's zero mask
         p.close()
+
+
+# ------------------------------------------------------------------ Fiat-Shamir mode
+def test_fiat_shamir_mode_matches_oracle(B, O, sha_circuit):
+    """vp_prove_fs: challenges hashed from the transcript (transcriptCache restated) -- transcript and challenges equal
+    the oracle's FS prover; both verifiers accept it and reject a tampered or re-seeded one"""
+    seed = bytes((7 * i + 1) % 256 for i in range(32))
+    for circ, flat in ((B.Circuit.random(5, 6, 3), None), (sha_circuit, None), (_all_types_circuit(B, 11, with_assert=True).replicate(9), "expand")):
+        f = circ.expand() if flat else circ
+        oc = O.OracleCircuit(f.flat())
+        want_tr, want_ch = oc.prove_fs(seed)
+        p = B.Prover(circ)
+        tr, ch = p.prove_fs(seed)
+        _assert_same(ch, want_ch, "FS challenges")
+        _assert_same(tr, want_tr, "FS transcript")
+        assert oc.verify_fs(seed, tr) == (True, 0, 0)
+        assert p.verify_fs(seed, tr) == (True, 0, 0)
+        bad = tr.copy()
+        bad[5]["im"] = (int(bad[5]["im"]) + 1) % B.P
+        assert not p.verify_fs(seed, bad)[0] and not oc.verify_fs(seed, bad)[0]
+        assert not p.verify_fs(bytes(32), tr)[0]
+        p.close()

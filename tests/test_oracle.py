@@ -301,3 +301,33 @@ def test_pc_oracle_matches_live_reference_when_available(B, O):
         a["im"] = rng.integers(0, B.P, 1 << b, dtype=np.uint64)
         r, o = O.ref_pc_commit(a, b), O.pc_commit_private(a, b)
         assert r["root"] == o["root"] and (r["l_eval"] == o["l_eval"]).all() and (r["leaf_hash"] == o["leaf_hash"]).all()
+
+
+# ------------------------------------------------------------------ Fiat-Shamir mode (N4): transcriptCache restated
+def test_fiat_shamir_oracle_and_host_challenges(B, O, sha_circuit):
+    """the oracle's FS prover/verifier agree with each other, the product's host-side vp_fs_challenges recomputes the same
+    challenges from the transcript alone, and the first draws match transcriptCache::random by hand"""
+    seed = bytes(range(32))
+    # transcriptCache::random (transcriptCache.hpp:40-46) by hand for the first two draws
+    d1 = hashlib.sha3_256(seed).digest()
+    d2 = hashlib.sha3_256(d1).digest()
+    P = B.P
+    for circ in (B.Circuit.random(4, 4, 9), sha_circuit):
+        oc = O.OracleCircuit(circ.flat())
+        tr, ch = oc.prove_fs(seed)
+        assert (int(ch[0]["re"]), int(ch[0]["im"])) == (int.from_bytes(d1[:8], "little") % P, int.from_bytes(d1[8:16], "little") % P)
+        if circ.bit_length(circ.n_layers - 1) >= 2:
+            assert (int(ch[1]["re"]), int(ch[1]["im"])) == (int.from_bytes(d2[:8], "little") % P, int.from_bytes(d2[8:16], "little") % P)
+        assert oc.verify_fs(seed, tr) == (True, 0, 0)
+        ch2 = oc.fs_challenges(seed, tr)
+        assert (ch2 == ch).all()
+        ch3 = circ.fs_challenges(seed, tr)                     # product, host only
+        assert (ch3["re"] == ch["re"]).all() and (ch3["im"] == ch["im"]).all()
+        bad = tr.copy()
+        k = len(bad) // 2
+        bad[k]["re"] = (int(bad[k]["re"]) + 1) % P
+        assert not oc.verify_fs(seed, bad)[0]                  # every later challenge changes with the message
+        assert not oc.verify_fs(bytes(32), tr)[0]              # another seed: other challenges
+        # the FS transcript differs from the interactive one (other challenges), same length
+        tr_i, _, _ = oc.prove()
+        assert len(tr_i) == len(tr) and (tr_i["re"] != tr["re"]).any()

@@ -111,6 +111,9 @@ def _declare(L):
     L.vp_last_commit_ms.argtypes = [vp]
     L.vp_last_commit_ms.restype = C.c_float
     L.vp_pc_commit.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.vp_prove_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
+    L.vp_fs_challenges.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
+    L.vp_verify_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.vp_get_transcript.argtypes = [vp, vp, C.c_size_t]
     L.vp_last_prove_ms.argtypes = [vp]
     L.vp_last_prove_ms.restype = C.c_float
@@ -311,6 +314,13 @@ class Circuit:
         buf = np.zeros(n.value, np.uint8)
         _ck(lib().vp_transcript_text(self.h, _ptr(tr), _ptr(ch), _ptr(buf), len(buf), C.byref(n)))
         return buf.tobytes().decode()
+
+    def fs_challenges(self, seed32, transcript):
+        """the challenges of a Fiat-Shamir transcript, recomputed from the messages (host only)"""
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        ch = np.zeros(self.challenge_count, F_DTYPE)
+        _ck(lib().vp_fs_challenges(self.h, bytes(seed32), _ptr(tr), len(tr), _ptr(ch), len(ch)))
+        return ch
 
     def flat(self):
         """Flat arrays of this circuit (instances must be 1), concatenated over layers (used by tests)."""
@@ -538,6 +548,19 @@ class Prover:
     @property
     def last_commit_ms(self):
         return float(lib().vp_last_commit_ms(self.h))
+
+    def prove_fs(self, seed32):
+        """Fiat-Shamir mode: (transcript, challenges) with every challenge hashed from the messages before it"""
+        tr = np.zeros(self.circuit.transcript_len, F_DTYPE)
+        ch = np.zeros(self.circuit.challenge_count, F_DTYPE)
+        _ck(lib().vp_prove_fs(self.h, bytes(seed32), _ptr(tr), len(tr), _ptr(ch), len(ch)))
+        return tr, ch
+
+    def verify_fs(self, seed32, transcript):
+        tr = np.ascontiguousarray(transcript, dtype=F_DTYPE)
+        a, c, l = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(lib().vp_verify_fs(self.h, bytes(seed32), _ptr(tr), len(tr), C.byref(a), C.byref(c), C.byref(l)))
+        return bool(a.value), c.value, l.value
 
     def input_range(self):
         """instances [first, end) whose witness this rank uploads (everything on an unsharded context)"""

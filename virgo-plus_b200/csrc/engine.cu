@@ -20,6 +20,7 @@
 #include "../../include/virgo_b200.h"
 #include "../host/circuit_model.h"
 #include "../host/proof_io.h"
+#include "../host/fiat_shamir.h"
 #include "kernels.cuh"
 #include "pc_commit.h"
 
@@ -981,6 +982,7 @@ struct Engine {
     uint32_t tail_work = 512;
     bool use_phase_kernel = true;
     void prove_all();
+    void prove_fs(const uint8_t seed[32], F* tr_out, F* ch_out);
     std::vector<F> h_chal;   // host copy of the challenges: the pass kernel gets their limbs through its parameters
     void set_chal(uint32_t idx, const vp_F* v, size_t cnt = 1) {
         // the limb arithmetic needs canonical challenges (split31 would silently drop the top bits of anything else)
@@ -2375,6 +2377,108 @@ void Engine::prove_all() {
     CK(cudaGetLastError());
 }
 
+// Fiat-Shamir mode: the whole proof through the one-round-per-launch path, every challenge drawn from
+// the transcript cache right after the message it has to depend on (order: host/fiat_shamir.h). The two-rounds-per-pass
+// kernel cannot be used here: it needs the challenges of a phase before the phase starts.
+void Engine::prove_fs(const uint8_t seed[32], F* tr_out, F* ch_out) {
+    leave();
+    FsCache fs;
+    fs.store(seed, 32);
+    std::vector<F> ch(n_chal, f_zero());
+    auto draw_to = [&](uint32_t idx) {
+        ch[idx] = fs.random();
+        const vp_F v{ch[idx].re, ch[idx].im};
+        set_chal(idx, &v);
+    };
+    auto fetch = [&](uint32_t idx, size_t cnt) {
+        get_tr(idx, reinterpret_cast<vp_F*>(tr_out + idx), cnt);
+        for (size_t k = 0; k < cnt; ++k) fs.store(tr_out[idx + k]);
+    };
+    {   // unused challenge slots are zero on the device as well
+        CK(cudaMemsetAsync(d_chal.p, 0, (n_chal + 1) * sizeof(F), stream));
+        h_chal.assign(n_chal, f_zero());
+    }
+    evaluate();
+    check_assert_flag();
+    for (int k = 0; k < C.bit_length(n - 1); ++k) draw_to(ci_out + (uint32_t)k);
+    do_vres();
+    fetch(tr_vres, 1);
+    auto run_phase = [&](int i, int phase, const PhasePlan& PP, uint32_t ci, uint32_t tr, const F* at_init) {
+        (void)i;
+        for (int j = 1; j <= PP.rounds; ++j) {
+            const uint32_t t = tr + 3u * (uint32_t)(j - 1);
+            if (PP.sharded) sharded_round(PP, phase, j, ci, t, at_init);
+            else do_round(PP.planB, j, ci + (uint32_t)std::max(0, j - 2), t, at_init);
+            fetch(t, 3);
+            draw_to(ci + (uint32_t)(j - 1));
+        }
+    };
+    for (int i = n - 1; i >= 1; --i) {
+        LayerDev& D = L[i];
+        const int m = D.max_dad_bl;
+        cur_layer = i;
+        draw_to(D.ci_assert);
+        do_init_phase1(i);
+        run_phase(i, 1, D.ph1, D.ci_ru, D.tr_p1, nullptr);
+        do_finalize(D.ph1.planB, D.ci_ru + (uint32_t)std::max(0, D.ph1.rounds - 1), scal(SC_VU));
+        fetch(D.tr_claim_u, 1);
+        if (m != -1) {
+            do_init_phase2(i);
+            run_phase(i, 2, D.ph2, D.ci_rv, D.tr_p2, scal(SC_UNARY));
+            do_finalize(D.ph2.planB, D.ci_rv + (uint32_t)std::max(0, D.ph2.rounds - 1), nullptr);
+            fetch(D.tr_claims_v, (size_t)i);
+        }
+        for (int k = 0; k < n; ++k) draw_to(D.ci_sig + (uint32_t)k);
+        do_init_liu(i, true);
+        run_phase(i, 3, D.ph3, D.ci_rliu, D.tr_liu, nullptr);
+        do_finalize(D.ph3.planB, D.ci_rliu + (uint32_t)std::max(0, D.ph3.rounds - 1), nullptr);
+        fetch(D.tr_claim_liu, 1);
+    }
+    do_input_mle();
+    fetch(tr_input, 1);
+    if (ch_out) memcpy(ch_out, ch.data(), n_chal * sizeof(F));
+    proof_size = 0;
+    for (int i = n - 1; i >= 1; --i) {
+        const int pb = C.bit_length(i - 1), m = L[i].max_dad_bl;
+        proof_size += (uint64_t)(2 * pb + (m != -1 ? m : 0)) * 3 * sizeof(F) + sizeof(F);
+        if (m != -1) proof_size += (uint64_t)i * sizeof(F);
+    }
+}
+
+// The challenges of a Fiat-Shamir transcript, recomputed from the messages alone (what a verifier does first), in the
+// usual challenge layout (vp_draw_challenges order; unused slots zero).
+static void fs_challenges(const Circuit& C, const uint8_t seed[32], const F* tr, F* ch, size_t n_chal) {
+    const int n = C.n_layers(), mbl = C.max_bit_length();
+    FsCache fs;
+    fs.store(seed, 32);
+    for (size_t k = 0; k < n_chal; ++k) ch[k] = f_zero();
+    size_t ci = 0, ti = 0;
+    for (int k = 0; k < C.bit_length(n - 1); ++k) ch[ci++] = fs.random();
+    fs.store(tr[ti++]);
+    auto rounds = [&](int cnt, size_t ci0) {
+        for (int j = 0; j < cnt; ++j) {
+            for (int q = 0; q < 3; ++q) fs.store(tr[ti++]);
+            ch[ci0 + (size_t)j] = fs.random();
+        }
+    };
+    for (int i = n - 1; i >= 1; --i) {
+        const int pb = C.bit_length(i - 1), m = C.max_dad_bit_length(i);
+        const size_t ci_ru = ci, ci_assert = ci_ru + (size_t)mbl, ci_rv = ci_assert + 1, ci_sig = ci_rv + (m != -1 ? (size_t)m : 0),
+                     ci_rliu = ci_sig + (size_t)n;
+        ch[ci_assert] = fs.random();
+        rounds(pb, ci_ru);
+        fs.store(tr[ti++]);
+        if (m != -1) {
+            rounds(m, ci_rv);
+            for (int l = 0; l < i; ++l) fs.store(tr[ti++]);
+        }
+        for (int k = 0; k < n; ++k) ch[ci_sig + (size_t)k] = fs.random();
+        rounds(pb, ci_rliu);
+        fs.store(tr[ti++]);
+        ci = ci_rliu + (size_t)mbl;
+    }
+}
+
 struct vp_ctx {
     Engine e;
 };
@@ -3088,6 +3192,52 @@ extern "C" int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len
     const float ms = pc_commit(g.p, d.p, n, 0, root);
     if (device_ms) *device_ms = ms;
     pc_export(g.p, 0, reinterpret_cast<F*>(l_eval), leaf_hash, tree);
+    return VP_OK;
+    API_END
+}
+// ------------------------------------------------------------------ C ABI: Fiat-Shamir mode (N4)
+extern "C" int vp_prove_fs(vp_ctx* ctx, const uint8_t seed[32], vp_F* transcript, size_t transcript_cap, vp_F* challenges, size_t challenges_cap) {
+    if (!ctx || !seed || !transcript) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    ScopedTimer t(e);
+    if (transcript_cap < e.n_tr) return fail(VP_ERR_ARG, "transcript buffer too small (%zu < %zu)", transcript_cap, e.n_tr);
+    if (challenges && challenges_cap < e.n_chal) return fail(VP_ERR_ARG, "challenge buffer too small (%zu < %zu)", challenges_cap, e.n_chal);
+    if (!e.inputs_loaded) return fail(VP_ERR_ARG, "vp_prove_fs: inputs not loaded");
+    const uint64_t l0 = e.launches;
+    CK(cudaEventRecord(e.ev0, e.stream));
+    e.prove_fs(seed, reinterpret_cast<F*>(transcript), reinterpret_cast<F*>(challenges));
+    CK(cudaEventRecord(e.ev1, e.stream));
+    CK(cudaStreamSynchronize(e.stream));
+    CK(cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1));
+    e.last_launches = e.launches - l0;
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_fs_challenges(const vp_circuit* c, const uint8_t seed[32], const vp_F* transcript, size_t n, vp_F* challenges, size_t cap) {
+    if (!c || !seed || !transcript || !challenges) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    if (n != vp_transcript_len(c)) return fail(VP_ERR_ARG, "expected a transcript of %zu field elements, got %zu", vp_transcript_len(c), n);
+    const size_t nc = vp_challenge_count(c);
+    if (cap < nc) return fail(VP_ERR_ARG, "challenge buffer too small (%zu < %zu)", cap, nc);
+    for (size_t i = 0; i < n; ++i)
+        if (transcript[i].re >= P || transcript[i].im >= P) return fail(VP_ERR_ARG, "transcript element %zu is not canonical", i);
+    fs_challenges(c->c, seed, reinterpret_cast<const F*>(transcript), reinterpret_cast<F*>(challenges), nc);
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_verify_fs(vp_ctx* ctx, const uint8_t seed[32], const vp_F* transcript, size_t n, int* accept, int* fail_code, int* fail_layer) {
+    if (!ctx || !seed || !transcript || !accept) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    if (n != e.n_tr) return fail(VP_ERR_ARG, "expected a transcript of %zu field elements, got %zu", e.n_tr, n);
+    for (size_t i = 0; i < n; ++i)
+        if (transcript[i].re >= P || transcript[i].im >= P) { *accept = 0; if (fail_code) *fail_code = 7; if (fail_layer) *fail_layer = 0; return VP_OK; }
+    std::vector<F> ch(e.n_chal);
+    fs_challenges(e.C, seed, reinterpret_cast<const F*>(transcript), ch.data(), e.n_chal);
+    e.set_chal(0, reinterpret_cast<const vp_F*>(ch.data()), e.n_chal);
+    *accept = e.verify(reinterpret_cast<const F*>(transcript), fail_code, fail_layer);
     return VP_OK;
     API_END
 }

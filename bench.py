@@ -119,6 +119,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)   # before any pinned allocation: first touch places the pages
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = entry.binding()
@@ -200,7 +201,7 @@ def run_ours(args):
                         f"configs[4] family at N>1), {gates} gates per GPU, one full GKR proof per step",
             "instances_per_gpu": inst, "gates_per_gpu": gates, "rounds": None,
             "l2": "tables + values are several GB per proof, far larger than the 126 MB L2 (no flush needed)",
-            "lanes": lanes,
+            "lanes": lanes, "host_numa_node": numa,
             "parallelism": "1 GPU" if world == 1 else f"one proof sharded over {world} GPUs: every sumcheck table cut into contiguous block "
                            f"ranges by index (= contiguous instance slices), local rounds without communication, one exchange per "
                            f"sumcheck phase, each rank evaluates and uploads only its own instance slice",
@@ -235,9 +236,13 @@ def run_ours(args):
                                            "integer-pipe latency, see DESIGN.md and profiles/",
                             "alg_bytes_per_launch": rf["bytes"] / rf["launches"],
                             "note": "launch durations come from the instrumented pass, which runs the phases on ONE stream "
-                                    "(vp_set_lanes(1)); `value` is the un-instrumented pass with the lanes overlapped (six streams on one GPU, three per rank when sharded), so the "
+                                    "(vp_set_lanes(1)); `value` is the un-instrumented pass with the six lanes overlapped, so the "
                                     "per-class times add up to more than the step. `traffic` = DRAM bytes read + written per launch "
-                                    "(ncu, profiles/r1_dfs_traffic.json), averaged over the 42 launches of one proof like `achieved`"}
+                                    "(ncu, profiles/r2_dfs_counters.json), averaged over the 42 launches of one proof like `achieved`. "
+                                    "`frac` is the SURVEY 8(d) algorithmic-byte figure the contract asks for; the kernel is NOT HBM bound: "
+                                    "`dram_frac` = its real DRAM traffic over the measured HBM peak, `int_pipe.frac` = issued warp "
+                                    "instructions per clock per SM over the limit of its own instruction mix (4 issue slots, ALU pipe and "
+                                    "FMA-heavy pipe 2 / clk / SM each), `bound` names the larger of the two"}
         add_binding_roofline(line["roofline"], ctr, rf["ms"] * 1e-3 / rf["launches"], peak, clocks)
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),
                                   "launches_per_step": v["launches"] // args.steps} for k, v in prof.items() if v["launches"]}
@@ -250,6 +255,7 @@ def run_ours(args):
     del prover
     if not args.no_extras:
         if world == 1:
+            line["pc_commit"] = run_pc_commit(B, tmpl)
             line["sumcheck_c2"] = run_c2(B, peak)
             line["single_proof_c1"] = run_c1(B, tmpl)
             line["dropin"] = run_dropin(B, tmpl, circ, inst)
@@ -263,6 +269,31 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         emit(line)
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank's host thread on the CPU socket its GPU hangs off (sysfs numa_node of the GPU's PCI function), so that
+    the pinned witness buffers are first-touched there and host->device copies do not cross the socket interconnect. With one
+    process per GPU started by torchrun nothing else places the ranks. Returns the node, or None if it cannot be determined."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 class Env:
@@ -418,6 +449,32 @@ def run_c5(env, B, tmpl, args):
            "ms_per_proof": ms, "gates_per_s": circ.total_gates / (ms * 1e-3), "n_gpus": env.world, "vp_create_ms": create_ms,
            "parity": env.parity(p, circ, np_tr.copy(), inp, ch, "sha256_64_x%d" % circ.instances, single_gpu_check=True)}
     p.close()
+    return out
+
+
+def run_pc_commit(B, tmpl):
+    """SURVEY 8(f) N1: prover::commit_private (the polynomial commitment's commit phase) on the device, for the input layer
+    of SHA256_64 and of SHA256_64 x 16, beside what the reference's own commit_private_array took on one host core
+    (tests/golden/pc_commit.json, recorded with oracle/_ref/ref_pc_commit) and with the Merkle roots compared"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "pc_commit.json")) as f:
+            golden = json.load(f)
+    except Exception:
+        golden = {}
+    out = {}
+    for name, circ in (("sha256_64", tmpl), ("sha256_64_x16", tmpl.replicate(16))):
+        p = B.Prover(circ)
+        root = p.commit_private()
+        ms = []
+        for _ in range(5):
+            p.commit_private()
+            ms.append(p.last_commit_ms)
+        g = golden.get(name, {})
+        out[name] = {"inputs": int(circ.num_inputs), "log_len": int(circ.bit_length(0)), "device_ms": statistics.median(ms),
+                     "root": root.hex(), "root_equals_reference": (root.hex() == g.get("root")) if g else None,
+                     "reference_cpu_seconds": g.get("reference_commit_seconds")}
+        p.close()
+    out["what"] = "64 inverse NTTs + 2048 coset NTTs over F_p^2, 65 SHA3-256 per Merkle leaf, array-heap Merkle tree (vp_commit_private)"
     return out
 
 

@@ -241,6 +241,9 @@ virgo::__hhash_digest prover::commit_private() {
     fri::visited_init[0] = new bool[1 << lw]();
     fri::visited_witness[0] = new bool[1 << (bl + rs_code_rate)]();
     poly_prover.total_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    if (getenv("VP_TIMING"))
+        fprintf(stderr, "virgo_b200 prover: commit_private %.3f ms (device commit %.3f ms, the rest: copies + the reference's bookkeeping arrays)\n",
+                poly_prover.total_time * 1e3, (double)vp_last_commit_ms(ctx));
     return root;
 }
 

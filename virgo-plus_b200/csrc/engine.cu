@@ -899,6 +899,7 @@ struct Engine {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto e : ev_chunk) if (e) cudaEventDestroy(e);
         if (ev_copy_go) cudaEventDestroy(ev_copy_go);
+        if (ev_extra) cudaEventDestroy(ev_extra);
         if (ev_eval) cudaEventDestroy(ev_eval);
         if (pc) pc_destroy(pc);
         for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
@@ -952,6 +953,13 @@ struct Engine {
     cudaEvent_t ev_chunk[IN_CHUNKS] = {nullptr, nullptr, nullptr, nullptr}, ev_copy_go = nullptr;
     uint32_t chunk_lo[IN_CHUNKS] = {0}, chunk_hi[IN_CHUNKS] = {0};
     int pending_chunks = 0;
+    // Sharded contexts: the inputs a rank needs beyond [core_lo, core_hi) -- the instances whose higher layers it
+    // evaluates -- are only read as layer-0 values (the V gathers of phase-2 tables sourced from the input layer and a
+    // block's worth of rows of layer 1's tables). With host buffers they are uploaded AFTER the core range on the copy
+    // stream and turned into circuitValue[0] there; only the kernels that may read them wait for ev_extra.
+    uint32_t core_lo = 0, core_hi = 0;
+    cudaEvent_t ev_extra = nullptr;
+    bool extras_pending = false;
     void evaluate();
     void run_eq(uint32_t first, uint32_t count);
     void run_dot_eq(const F* X, uint32_t S, EqTab eq, F* out, bool local_only = false);
@@ -1401,6 +1409,8 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         }
         k_lo = ev_lo[0];   // the inputs this rank uploads
         k_hi = std::min(ev_hi[0], K);
+        core_lo = n > 1 ? std::max(k_lo, std::min(ev_lo[1], k_hi)) : k_lo;   // instances whose layers >= 1 this rank evaluates
+        core_hi = n > 1 ? std::min(k_hi, std::max(ev_hi[1], core_lo)) : k_hi;
     }
 
     for (int b = 0; b < 2; ++b) {
@@ -1619,18 +1629,31 @@ void Engine::load_inputs_chunked(const uint64_t* host, size_t cnt, bool local) {
         for (auto& e : ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_copy_go, cudaEventDisableTiming));
     }
-    const uint32_t span = k_hi - k_lo;
+    if (!ev_extra) CK(cudaEventCreateWithFlags(&ev_extra, cudaEventDisableTiming));
+    const uint32_t span = core_hi - core_lo;
     const int nc = span >= 64 ? IN_CHUNKS : 1;
     CK(cudaEventRecord(ev_copy_go, stream));              // after everything queued so far (the previous proof read d_inputs)
     CK(cudaStreamWaitEvent(copy_stream, ev_copy_go, 0));
     const size_t S0 = C.layers[0].size;
     for (int c = 0; c < nc; ++c) {
-        chunk_lo[c] = k_lo + (uint32_t)((uint64_t)span * c / nc);
-        chunk_hi[c] = k_lo + (uint32_t)((uint64_t)span * (c + 1) / nc);
+        chunk_lo[c] = core_lo + (uint32_t)((uint64_t)span * c / nc);
+        chunk_hi[c] = core_lo + (uint32_t)((uint64_t)span * (c + 1) / nc);
         const size_t b = (size_t)chunk_lo[c] * S0, e = (size_t)chunk_hi[c] * S0;
         if (e > b) CK(cudaMemcpyAsync(d_inputs.p + b, host + b, (e - b) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
         CK(cudaEventRecord(ev_chunk[c], copy_stream));
     }
+    // the extra layer-0 instances left and right of the core range: copy + convert on the copy stream, off the critical path
+    extras_pending = false;
+    const uint32_t ex[2][2] = {{k_lo, core_lo}, {core_hi, k_hi}};
+    for (int q = 0; q < 2; ++q) {
+        const size_t b = (size_t)ex[q][0] * S0, e = (size_t)ex[q][1] * S0;
+        if (e <= b) continue;
+        CK(cudaMemcpyAsync(d_inputs.p + b, host + b, (e - b) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+        k_load_inputs<<<cdiv((uint32_t)(e - b), 256), 256, 0, copy_stream>>>(d_inputs.p, val[0].p, (uint32_t)b, (uint32_t)e);
+        ++launches;
+        extras_pending = true;
+    }
+    if (extras_pending) CK(cudaEventRecord(ev_extra, copy_stream));
     pending_chunks = nc;
     inputs_loaded = true;
     evaluated = false;
@@ -2322,11 +2345,23 @@ void Engine::prove_all() {
         if (lane6)
             for (LaneRes* R : {&lane0b, &lane1b, &lane2b}) CK(cudaStreamWaitEvent(R->stream, ev_eval, 0));
     }
+    const bool extras = extras_pending;
+    extras_pending = false;
+    if (extras) {   // phase 2 gathers V from any lower layer, also from the extra layer-0 instances: its lanes wait at once
+        if (lane3) CK(cudaStreamWaitEvent(lane2.stream, ev_extra, 0));
+        if (lane6) CK(cudaStreamWaitEvent(lane2b.stream, ev_extra, 0));
+        if (!lane3) CK(cudaStreamWaitEvent(stream, ev_extra, 0));
+    }
     do_vres();
     for (int i = n - 1; i >= 1; --i) {
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
         const bool odd = lane6 && ((n - 1 - i) & 1);   // six lanes: every other layer on the second set of lanes
+        if (extras && i == 1) {   // layer 1's own tables run over layer 0: a block's worth of rows may lie outside the core range
+            CK(cudaStreamWaitEvent(stream, ev_extra, 0));
+            if (lane) CK(cudaStreamWaitEvent(lane1.stream, ev_extra, 0));
+            if (lane6) { CK(cudaStreamWaitEvent(lane0b.stream, ev_extra, 0)); CK(cudaStreamWaitEvent(lane1b.stream, ev_extra, 0)); }
+        }
         // ---- phase 1
         if (odd) enter(lane0b, 0);
         do_init_phase1(i);

@@ -1184,6 +1184,18 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
         }
         lap(1);
+        const int pb = C.bit_length(i - 1);
+        // plans for phase 1 and Liu: one table over layer i-1
+        {
+            D.ph1 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_u}}, pb, {}, world, rank, n, arena);
+            D.ph3 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_liu}}, pb, {}, world, rank, n, arena);
+            cap0 = std::max(cap0, std::max(D.ph1.cap0, D.ph3.cap0));
+            cap1 = std::max(cap1, std::max(D.ph1.cap1, D.ph3.cap1));
+            max_rec = std::max(max_rec, std::max(D.ph1.rec_len, D.ph3.rec_len));
+        }
+        // A circuit that is ONE instance has no instance ranges to deal out: a rank of a sharded context keeps only the
+        // work items (and long rows) of the table rows it owns, so the init kernels are owner-computes here as well.
+        const bool own_rows_only = world > 1 && K == 1;
         // phase-1 CSR by u0
         {
             std::vector<uint32_t> off(S_pre + 1, 0), g0(S), v0(S), tyl(S);
@@ -1199,6 +1211,12 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             }
             ItemPlan ip;
             add_rows(ip, off, 0);
+            if (own_rows_only && D.ph1.sharded) {
+                const ShardMap sm = D.ph1.maps[0];
+                auto mine = [&](uint32_t row) { return row >= sm.lo && row < sm.hi; };
+                ip.items.erase(std::remove_if(ip.items.begin(), ip.items.end(), [&](const RowItem& x) { return !mine(x.row); }), ip.items.end());
+                ip.longs.erase(std::remove_if(ip.longs.begin(), ip.longs.end(), [&](const LongRow& x) { return !mine(x.row); }), ip.longs.end());
+            }
             sort_items_by_length(ip.items);
             D.p1_items.upload(ip.items, stream);
             D.p1_long.upload(ip.longs, stream);
@@ -1210,15 +1228,6 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
             CK(cudaStreamSynchronize(stream));
         }
         lap(2);
-        const int pb = C.bit_length(i - 1);
-        // plans for phase 1 and Liu: one table over layer i-1
-        {
-            D.ph1 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_u}}, pb, {}, world, rank, n, arena);
-            D.ph3 = make_phase({PhaseTabG{pb, (uint32_t)C.layer_size(i - 1), -1, D.tr_claim_liu}}, pb, {}, world, rank, n, arena);
-            cap0 = std::max(cap0, std::max(D.ph1.cap0, D.ph3.cap0));
-            cap1 = std::max(cap1, std::max(D.ph1.cap1, D.ph3.cap1));
-            max_rec = std::max(max_rec, std::max(D.ph1.rec_len, D.ph3.rec_len));
-        }
         D.eqb_g = (uint32_t)eq_descs.size();
         add_eq_build(0, D.ci_g, C.bit_length(i), -1);
         D.eqb_u = (uint32_t)eq_descs.size();
@@ -1293,6 +1302,11 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
                 for (uint32_t x = 0; x < Dsz; ++x) dad_all.push_back(T.dadId[l][x]);
                 add_rows(ip, off, (uint32_t)ptabs.size());
                 ptabs.push_back(pt);
+            }
+            if (own_rows_only && D.ph2.sharded) {
+                auto mine = [&](uint32_t tab, uint32_t row) { return D.ph2.present[tab] && row >= D.ph2.maps[tab].lo && row < D.ph2.maps[tab].hi; };
+                ip.items.erase(std::remove_if(ip.items.begin(), ip.items.end(), [&](const RowItem& x) { return !mine(x.tab, x.row); }), ip.items.end());
+                ip.longs.erase(std::remove_if(ip.longs.begin(), ip.longs.end(), [&](const LongRow& x) { return !mine(x.tab, x.row); }), ip.longs.end());
             }
             sort_items_by_length(ip.items);
             D.p2_items.upload(ip.items, stream);

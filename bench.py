@@ -244,6 +244,7 @@ def run_ours(args):
                                     "instructions per clock per SM over the limit of its own instruction mix (4 issue slots, ALU pipe and "
                                     "FMA-heavy pipe 2 / clk / SM each), `bound` names the larger of the two"}
         add_binding_roofline(line["roofline"], ctr, rf["ms"] * 1e-3 / rf["launches"], peak, clocks)
+        add_step_int_frac(line["roofline"], inst, world, ms_resident, clocks)
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),
                                   "launches_per_step": v["launches"] // args.steps} for k, v in prof.items() if v["launches"]}
 
@@ -526,6 +527,22 @@ def dfs_counters(inst, world):
         return d if d.get("instances") == inst and world == 1 else {}
     except Exception:
         return {}
+
+
+def add_step_int_frac(rf, inst, world, ms_step, clocks):
+    """How busy the integer pipes are over the WHOLE step (six lanes overlapped): warp instructions of one proof (ncu launch
+    list of the same command, profiles/r2_step_counters.json) over what the pipes could issue in the measured step time."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_step_counters.json")) as f:
+            c = json.load(f)
+        if c.get("instances") != inst or world != 1 or not clocks.get("sm_mhz"):
+            return
+        ipc = c["warp_insts_per_proof"] / (ms_step * 1e-3 * clocks["sm_mhz"] * 1e6 * c.get("n_sm", 148))
+        rf["step_int_pipe"] = {"warp_insts_per_step": c["warp_insts_per_proof"], "achieved_warp_inst_per_clk_per_sm": ipc,
+                               "peak_for_this_mix": c["mix_limited_ipc_per_sm"], "frac": ipc / c["mix_limited_ipc_per_sm"],
+                               "what": "all kernels of one proof over the un-instrumented step time"}
+    except Exception:
+        pass
 
 
 def add_binding_roofline(rf, ctr, avg_launch_s, hbm_peak_gbs, clocks):

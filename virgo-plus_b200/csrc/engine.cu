@@ -931,7 +931,7 @@ struct Engine {
     int n_sm = 148;
     int cap_p1il = 0, cap_p2v2 = 0;
     int dfs_grid_override = 0;   // VP_DFS_GRID: development knob
-    bool old_p2 = false, getenv_no_hs = false, liu_old = false, p1_old = false;
+    bool old_p2 = false, getenv_no_hs = false, liu_old = false, p1_old = false, layer_order_by_size = true;
     DBuf<F> d_hs;   // phase-2 init: products of the second-half eq factors, K * ng * nu entries (k_p2_hs)
     bool values_real = true;   // no gate constant has an imaginary part: every circuit value is in the base field
     bool lane_init = false;    // base-field values: phase-1 init uses the one-real-product-per-gate kernel
@@ -1071,6 +1071,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     old_p2 = getenv("VP_OLD_P2") != nullptr;
     liu_old = getenv("VP_LIU_OLD") != nullptr;
     p1_old = getenv("VP_P1_OLD") != nullptr;
+    layer_order_by_size = getenv("VP_LAYERS_TOP_DOWN") == nullptr;
     getenv_no_hs = getenv("VP_NO_HS") != nullptr;
     d_hs.alloc((size_t)K * 64);   // development knob: the five-products-per-gate phase-2 init
     {
@@ -2367,10 +2368,37 @@ void Engine::prove_all() {
         if (!lane3) CK(cudaStreamWaitEvent(stream, ev_extra, 0));
     }
     do_vres();
-    for (int i = n - 1; i >= 1; --i) {
+    // Order of the layers. All phases of a proof are independent once the challenges are known (only phase 2 of a layer
+    // waits for phase 1 of the same layer), so the two lane sets need not walk the layers top-down: the layers are sorted by
+    // size, dealt out alternately, and set A walks its share from the largest down while set B walks its share from the
+    // smallest up -- at any time one large, throughput-bound layer is in flight next to a small, latency-bound one that
+    // hides under it (top-down, the eight small top layers of SHA256 ran against each other with the GPU mostly idle).
+    std::vector<std::pair<int, bool>> seq;   // (layer, on the second lane set)
+    if (lane6 && layer_order_by_size) {
+        std::vector<int> by_size;
+        for (int i = 1; i < n; ++i) by_size.push_back(i);
+        std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) {
+            return (double)C.layer_size(a - 1) * 2 + L[a].p2_out_entries > (double)C.layer_size(b - 1) * 2 + L[b].p2_out_entries;
+        });
+        std::vector<int> sa, sb;
+        for (size_t k = 0; k < by_size.size(); ++k) (k & 1 ? sb : sa).push_back(by_size[k]);
+        std::reverse(sb.begin(), sb.end());
+        if (extras)   // layer 1 waits for the extra input instances: last in its set
+            for (std::vector<int>* v : {&sa, &sb}) {
+                auto it = std::find(v->begin(), v->end(), 1);
+                if (it != v->end()) { v->erase(it); v->push_back(1); }
+            }
+        for (size_t k = 0; k < std::max(sa.size(), sb.size()); ++k) {
+            if (k < sa.size()) seq.push_back({sa[k], false});
+            if (k < sb.size()) seq.push_back({sb[k], true});
+        }
+    } else
+        for (int i = n - 1; i >= 1; --i) seq.push_back({i, lane6 && ((n - 1 - i) & 1)});   // every other layer on the second set of lanes
+    for (const auto& lo : seq) {
+        const int i = lo.first;
         LayerDev& D = L[i];
         const int pb = C.bit_length(i - 1), m = D.max_dad_bl;
-        const bool odd = lane6 && ((n - 1 - i) & 1);   // six lanes: every other layer on the second set of lanes
+        const bool odd = lo.second;
         if (extras && i == 1) {   // layer 1's own tables run over layer 0: a block's worth of rows may lie outside the core range
             CK(cudaStreamWaitEvent(stream, ev_extra, 0));
             if (lane) CK(cudaStreamWaitEvent(lane1.stream, ev_extra, 0));

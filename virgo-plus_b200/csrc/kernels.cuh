@@ -1373,6 +1373,13 @@ VP_D void dfs_pair(PassAcc& s, PassAccB* sb, const F& v0, const F& v1, const F& 
 #endif
 static constexpr uint32_t DFS_WCHUNK = 128;   // items per warp chunk
 static constexpr uint32_t DFS_CHUNK = (VP_DFS_THREADS / 32) * DFS_WCHUNK;    // items a block covers in one sweep (sizing of grids / worker counts)
+#ifndef VP_DFS_SOLO
+#define VP_DFS_SOLO 128
+#endif
+#ifndef VP_DFS_SOLO_THIN
+#define VP_DFS_SOLO_THIN 1
+#endif
+static constexpr uint32_t DFS_SOLO = VP_DFS_SOLO;   // a pass of at most this many items runs on block 0 alone (no grid barrier)
 static constexpr uint32_t DFS_STAGE_F = 3 * 128;              // F slots per stage: 3 tables x 32 quads
 static constexpr uint32_t DFS_WARP_SMEM_F = 2 * DFS_STAGE_F;  // two stages per warp
 
@@ -1568,10 +1575,14 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         uint32_t a = 0, sh = DFS_WCHUNK;
         if (q < p.n_passes) {
             const uint32_t work = p.passes[q].work;
-            if (work > DFS_CHUNK && n_workers != 0) {
+            if (work > DFS_SOLO && n_workers != 0) {
                 const uint32_t per_warp = (work + n_workers * WPB - 1) / (n_workers * WPB);
                 sh = min(DFS_WCHUNK, (per_warp + 31u) & ~31u);
                 a = min(n_workers, (work + sh * WPB - 1) / (sh * WPB));
+            } else if (work <= DFS_CHUNK && VP_DFS_SOLO_THIN) {
+                // block 0 alone: spread the items over its warps as thinly as possible as well (an item is a ~4.5 us
+                // dependent chain: 128 items on one warp are four of them back to back, on four warps one)
+                sh = min(DFS_WCHUNK, max(32u, ((work + WPB - 1) / WPB + 31u) & ~31u));
             }
         }
         s_alive[q] = a;
@@ -1595,7 +1606,7 @@ __global__ void __launch_bounds__(VP_DFS_THREADS, VP_DFS_MINB) k_phase_dfs(DfsAr
         // pass that one sweep of the workers can cover is spread as thinly as possible: every warp gets ONE share of
         // `share` items (a multiple of 32, at most DFS_WCHUNK), on as many workers as that takes. Larger passes hand out
         // DFS_WCHUNK-item chunks from an atomic counter.
-        const bool solo = R.work <= DFS_CHUNK || n_workers == 0;       // block 0 alone
+        const bool solo = R.work <= DFS_SOLO || n_workers == 0;        // block 0 alone
         // share = roundup32(ceil(work / (workers * warps))) capped at DFS_WCHUNK, active = ceil(work / (share * warps))
         // worker blocks 1..active (tabulated per pass at the top of the kernel)
         const uint32_t share = s_share[ps], active = s_active[ps];

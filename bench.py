@@ -463,7 +463,7 @@ def run_pc_commit(B, tmpl):
     except Exception:
         golden = {}
     out = {}
-    for name, circ in (("sha256_64", tmpl), ("sha256_64_x16", tmpl.replicate(16))):
+    for name, circ in (("sha256_64", tmpl), ("sha256_64_x16", tmpl.replicate(16)), ("sha256_64_x1024", tmpl.replicate(1024))):
         p = B.Prover(circ)
         root = p.commit_private()
         ms = []

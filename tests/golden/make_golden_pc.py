@@ -6,6 +6,7 @@ codeword array l_eval, of the leaf hashes and of the Merkle tree (nodes 1..) it 
 
   sha256_64        the input layer of data/SHA256_64.pws (7226 values, padded to 2^13): what prover::commit_private commits
   sha256_64_x16    16 instances (115616 values, 2^17)
+  sha256_64_x1024  the C3 benchmark circuit's input layer (7.4 M values, 2^23; 135 s in the reference; `--full`)
   random_<b>_<s>   2^b random F_p^2 elements, numpy default_rng(s); b = 10 has all-zero slices (the reference short-cuts them)
 b = 8 is left out on purpose: the reference's 4-point inverse FFT runs zero iterations of its unrolled stage
 (RS_polynomial.cpp:100) and returns uninitialised memory.
@@ -30,8 +31,8 @@ def case_array(B, O, name):
     if name.startswith("sha256_64"):
         with lzma.open(os.path.join(HERE, "SHA256_64.pws.xz"), "rb") as f:
             c = B.Circuit.from_pws_text(f.read())
-        if name.endswith("_x16"):
-            c = c.replicate(16)
+        if "_x" in name:
+            c = c.replicate(int(name.split("_x")[1]))
         a = np.zeros(c.num_inputs, O.F_DTYPE)
         a["re"] = c.inputs()
         return a, c.bit_length(0)
@@ -58,8 +59,9 @@ def digest_of(r):
 
 def main():
     B, O = entry.binding(), entry.oracle()
-    out = {}
-    for name in CASES:
+    path = os.path.join(HERE, "pc_commit.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    for name in CASES + (["sha256_64_x1024"] if "--full" in sys.argv else []):
         a, b = case_array(B, O, name)
         r = O.ref_pc_commit(a, b)
         out[name] = dict(digest_of(r), log_len=b, n=int(len(a)), reference_commit_seconds=r["seconds"])

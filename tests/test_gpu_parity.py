@@ -671,3 +671,18 @@ def test_fiat_shamir_mode_matches_oracle(B, O, sha_circuit):
         assert not p.verify_fs(seed, bad)[0] and not oc.verify_fs(seed, bad)[0]
         assert not p.verify_fs(bytes(32), tr)[0]
         p.close()
+
+
+def test_pc_commit_c3_size_matches_reference(B, O):
+    """the commit phase at the C3 benchmark size (input layer of SHA256_64 x 1024: 7.4 M values, 2^23 padded, slices of 2^17
+    points: six global NTT stages on top of the shared-memory ones) against what the reference produced in 135 s"""
+    import hashlib
+    mk, golden = _pc_tools()
+    if "sha256_64_x1024" not in golden:
+        pytest.skip("no full-size commitment in pc_commit.json")
+    a, b = mk.case_array(B, O, "sha256_64_x1024")
+    got = B.pc_commit(a, b, want_l_eval=False)
+    g = golden["sha256_64_x1024"]
+    assert got["root"].hex() == g["root"]
+    assert hashlib.sha256(got["leaf_hash"].tobytes()).hexdigest() == g["leaf_sha256"]
+    assert hashlib.sha256(got["tree"][32:].tobytes()).hexdigest() == g["tree_sha256"]

@@ -365,12 +365,12 @@ def selftest_field(op, a, b, c, device=0):
     return out
 
 
-def pc_commit(array, log_len, device=0, want_arrays=True):
+def pc_commit(array, log_len, device=0, want_arrays=True, want_l_eval=True):
     """commit phase of the polynomial commitment on a host array (vp_pc_commit) -> dict(root, l_eval, leaf_hash, tree, ms)"""
     a = np.ascontiguousarray(array, dtype=F_DTYPE)
     ss = 1 << (log_len - 1)
     root = np.zeros(32, np.uint8)
-    l_eval = np.zeros(65 * ss, F_DTYPE) if want_arrays else None
+    l_eval = np.zeros(65 * ss, F_DTYPE) if want_arrays and want_l_eval else None
     leaf = np.zeros(ss // 2 * 32, np.uint8) if want_arrays else None
     tree = np.zeros(ss * 32, np.uint8) if want_arrays else None
     ms = C.c_float()

@@ -1381,7 +1381,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
                 const size_t window = ev ? (size_t)atoi(ev) : 8192;
                 std::vector<uint32_t> perm(S_pre);
                 for (uint32_t x = 0; x < S_pre; ++x) perm[x] = x;
-                if (window >= 2 && world == 1) {   // stable counting sort by the number of scattered terms, most first
+                if (window >= 2) {   // stable counting sort by the number of scattered terms, most first
                     std::vector<uint32_t> tmp(std::min<size_t>(S_pre, window)), start;
                     for (size_t b = 0; b < S_pre; b += window) {
                         const size_t end = std::min<size_t>(S_pre, b + window);
@@ -1784,12 +1784,12 @@ void Engine::do_init_phase1(int i) {
     const uint32_t k0 = D.ph1.sharded ? D.p1_k0 : 0, k1 = D.ph1.sharded ? D.p1_k1 : K;
     const uint64_t work = (uint64_t)D.p1_items.n * (k1 - k0);
     size_t h = prof_begin(KC_INIT1);
-    if (lane_init && world == 1 && K >= 8 && n <= 64 && !p1_old) {   // template-major: an item of the template x 4 instances per thread
-        dim3 grid(cdiv((uint32_t)D.p1_items.n, 256), cdiv(K, 4));
+    if (lane_init && K >= 8 && k1 - k0 >= 4 && n <= 64 && !p1_old) {   // template-major: an item of the template x 4 instances per thread
+        dim3 grid(cdiv(std::max<uint32_t>((uint32_t)D.p1_items.n, 1), 256), cdiv(k1 - k0, 4));
         k_init_phase1_real_tm<4><<<grid, 256, 0, stream>>>(
             D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
             d_valptr.p, d_sizes.p, D.c.p, val[i - 1].p, bufV[0].p + D.ph1.tab_off[0], bufM[0].p + D.ph1.tab_off[0],
-            bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, direct_v ? 0 : 1, (uint32_t)i);
+            bufA[0].p + D.ph1.tab_off[0], d_rowpart.p, D.p1_nslots, direct_v ? 0 : 1, (uint32_t)i, D.ph1.maps[0], k0, k1);
     } else if (lane_init && work < 0xffffffffull && n <= 64)
         k_init_phase1_real<<<grid_for((uint32_t)std::min<uint64_t>(work, 0xffffffffu), cap_p1il), 256, 0, stream>>>(
             D.p1_items.p, (uint32_t)D.p1_items.n, csr, S_pre, D.S, K, eqtab(0, C.bit_length(i)), d_chal.p + D.ci_assert,
@@ -1879,12 +1879,19 @@ void Engine::do_init_liu(int i, bool write_a) {
     const uint32_t tot = (uint32_t)C.layer_size(i - 1);
     size_t h = prof_begin(KC_INIT_LIU);
     const uint32_t n_local = D.ph3.sharded ? D.ph3.local_len[0] : tot;
-    if (world == 1 && K >= 8 && !liu_old) {   // template-major: one thread per template entry, a chunk of instances each
+    // the instances this rank's rows of the table touch (all of them on an unsharded context)
+    uint32_t lk0 = 0, lk1 = K;
+    if (D.ph3.sharded) {
+        lk0 = lk1 = 0;
+        if (D.ph3.row_hi[0] > D.ph3.row_lo[0]) { lk0 = D.ph3.row_lo[0] / S_pre; lk1 = std::min(K, (D.ph3.row_hi[0] - 1) / S_pre + 1); }
+    }
+    if (K >= 8 && lk1 - lk0 >= 8 && !liu_old) {   // template-major: one thread per template entry, a chunk of instances each
         const uint32_t k_chunk = 8;
-        dim3 grid(cdiv(S_pre, 256), cdiv(K, k_chunk));
+        dim3 grid(cdiv(S_pre, 256), cdiv(lk1 - lk0, k_chunk));
         k_init_liu_tm<<<grid, 256, 0, stream>>>(D.liu_off.p, D.liu_perm.p, D.liu_ent.p, eq_off ? D.liu_eqtabs_b.p : D.liu_eqtabs.p, S_pre, K, k_chunk,
                                                eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p, bufV[0].p + D.ph3.tab_off[0],
-                                               bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1);
+                                               bufM[0].p + D.ph3.tab_off[0], bufA[0].p + D.ph3.tab_off[0], write_a ? 1 : 0, on_lane1 ? 1 : 0, direct_v ? 0 : 1,
+                                               D.ph3.maps[0], lk0, lk1);
     } else
     k_init_liu<<<grid_for(std::max<uint32_t>(n_local, 1), cap_liu), 256, 0, stream>>>(
         D.liu_off.p, world == 1 ? D.liu_perm.p : nullptr, D.liu_ent.p, eq_off ? D.liu_eqtabs_b.p : D.liu_eqtabs.p, S_pre, K, eqtab(reg_u, C.bit_length(i - 1)), d_chal.p + D.ci_sig, val[i - 1].p,

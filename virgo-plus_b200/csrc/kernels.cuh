@@ -444,7 +444,7 @@ k_init_phase1_real(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 cs
     }
 }
 
-// Template-major form of k_init_phase1_real for unsharded contexts with K >= KC instances: a thread owns one work item
+// Template-major form of k_init_phase1_real for K >= KC instances: a thread owns one work item
 // of the TEMPLATE and a chunk of KC consecutive instances. The CSR words of an entry (gate id, type, source layer,
 // operand index, constant) are read and decoded once for the KC instances, whose loads (gathered operand + two eq
 // half-table entries each) are all address-computable at once and whose product chains are independent: 3 KC loads in
@@ -455,14 +455,16 @@ __global__ void __launch_bounds__(256, 2)
 k_init_phase1_real_tm(const RowItem* __restrict__ items, uint32_t n_items, CsrP1 csr, uint32_t S_pre, uint32_t S_cur, uint32_t K,
                       EqTab eqg, const F* __restrict__ assert_r, F* const* __restrict__ vals, const uint32_t* __restrict__ sizes,
                       const F* __restrict__ cst, const F* __restrict__ Vpre, F* __restrict__ tV, F* __restrict__ tM,
-                      F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, int write_v, uint32_t n_src) {
+                      F* __restrict__ tA, F* __restrict__ partial, uint32_t n_slots, int write_v, uint32_t n_src, ShardMap sm,
+                      uint32_t k_begin, uint32_t k_end) {
+    (void)K;
     __shared__ const u64* s_vals[64];
     __shared__ uint32_t s_sizes[64];
     for (uint32_t i = threadIdx.x; i < min(n_src, 64u); i += blockDim.x) { s_vals[i] = reinterpret_cast<const u64*>(vals[i]); s_sizes[i] = sizes[i]; }
     __syncthreads();
     const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
-    const uint32_t k0 = blockIdx.y * KC, nk = min((uint32_t)KC, K - k0);
+    const uint32_t k0 = k_begin + blockIdx.y * KC, nk = min((uint32_t)KC, k_end - k0);   // sharded: the rank's instance range
     const RowItem I = items[it];
     u64 Mre[KC], Mim[KC], Are[KC], Aim[KC];
 #pragma unroll
@@ -516,9 +518,10 @@ k_init_phase1_real_tm(const RowItem* __restrict__ items, uint32_t n_items, CsrP1
         if (j >= (int)nk) break;
         const uint32_t k = k0 + j;
         const F Mr = F{fp_canon(Mre[j]), fp_canon(Mim[j])}, Ar = F{fp_canon(Are[j]), fp_canon(Aim[j])};
+        uint32_t loc;
+        if (!shard_local(sm, k * S_pre + I.row, loc)) continue;   // (sharded) another rank owns this table entry
         if (slot == 0) {
-            const uint32_t loc = k * S_pre + I.row;
-            if (write_v) st_f(tV + loc, ld_f(Vpre + loc));
+            if (write_v) st_f(tV + loc, ld_f(Vpre + k * S_pre + I.row));
             st_f(tM + loc, Mr);
             st_f(tA + loc, Ar);
         } else {
@@ -814,7 +817,7 @@ k_init_liu(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, 
     }
 }
 
-// Template-major form of K5 for unsharded contexts: a thread owns ONE template entry u0 (visited in length-sorted order)
+// Template-major form of K5: a thread owns ONE template entry u0 (visited in length-sorted order)
 // and walks a chunk of the data-parallel instances, so everything that only depends on the template -- the CSR bounds,
 // the scattered terms' (table, slot, subset size), the tables' descriptors -- is read once per thread instead of once
 // per (entry, instance), the instance index needs no division, and two instances are in flight per iteration
@@ -823,12 +826,13 @@ k_init_liu(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, 
 __global__ void __launch_bounds__(256)
 k_init_liu_tm(const uint32_t* __restrict__ off, const uint32_t* __restrict__ perm, const LiuEntry* __restrict__ ent, const EqTab* __restrict__ eqs,
               uint32_t S_pre, uint32_t K, uint32_t k_chunk, EqTab equ, const F* __restrict__ s0_ptr, const F* __restrict__ Vpre,
-              F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, int write_a, int equ_scaled, int write_v) {
+              F* __restrict__ tV, F* __restrict__ tM, F* __restrict__ tA, int write_a, int equ_scaled, int write_v, ShardMap sm,
+              uint32_t k_begin, uint32_t k_end) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= S_pre) return;
     const uint32_t u0 = perm ? perm[x] : x;
     const uint32_t eb = off[u0], n_terms = off[u0 + 1] - eb;
-    const uint32_t k0 = blockIdx.y * k_chunk, k1 = min(K, k0 + k_chunk);
+    const uint32_t k0 = k_begin + blockIdx.y * k_chunk, k1 = min(k_end, k0 + k_chunk);   // sharded: the instances the rank's rows touch
     const F s0 = *s0_ptr;
     // the first two scattered terms live in registers (most entries have at most two)
     LiuEntry E0{0, 0, 0}, E1{0, 0, 0};
@@ -837,6 +841,8 @@ k_init_liu_tm(const uint32_t* __restrict__ off, const uint32_t* __restrict__ per
     if (n_terms >= 2) { E1 = ent[eb + 1]; T1 = eqs[E1.eq_id]; }
     for (uint32_t k = k0; k < k1; ++k) {
         const uint32_t u = k * S_pre + u0, kk = K - 1 - k;
+        uint32_t loc;
+        if (!shard_local(sm, u, loc)) continue;   // (sharded) a row of another rank
         F M = eq_at_weak(equ, u);
         if (!equ_scaled) M = f_mul(M, s0);
         if (n_terms >= 1) M = eq_at_acc_w(T0, kk * E0.D + E0.slot0, M);
@@ -845,9 +851,9 @@ k_init_liu_tm(const uint32_t* __restrict__ off, const uint32_t* __restrict__ per
             const LiuEntry E = ent[eb + q];
             M = eq_at_acc_w(eqs[E.eq_id], kk * E.D + E.slot0, M);
         }
-        if (write_v) st_f(tV + u, ld_f(Vpre + u));
-        st_f(tM + u, f_strict(M));
-        if (write_a) st_f(tA + u, f_zero());
+        if (write_v) st_f(tV + loc, ld_f(Vpre + u));
+        st_f(tM + loc, f_strict(M));
+        if (write_a) st_f(tA + loc, f_zero());
     }
 }
 

@@ -67,6 +67,39 @@ def main():
         ok_all &= same and same2 and same3 and vok and same4
         p.close()
         dist.barrier()
+    # A batch large enough for the ranks to differ in what they upload (250 instances per rank: on 4 GPUs only some ranks
+    # need input instances beyond the range they evaluate): every way of proving it == the same circuit on ONE GPU
+    import hashlib
+    K = 250 * world
+    circ = sha.replicate(K)
+    inp, ch = circ.inputs(), circ.draw_challenges()
+    sha_h = lambda tr: hashlib.sha256(np.ascontiguousarray(tr).tobytes()).hexdigest()
+    ref = [None]
+    if rank == 0:
+        os.environ["VP_ONE_LANE"] = "1"
+        p1 = B.Prover(circ, device=local)
+        ref[0] = sha_h(p1.prove(inputs=inp, challenges=ch))
+        p1.close()
+        del os.environ["VP_ONE_LANE"]
+    dist.broadcast_object_list(ref, 0)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.from_numpy(B.nccl_unique_id()))
+    dist.broadcast(idt, 0)
+    p = B.Prover(circ, device=local, rank=rank, world=world, nccl_id=idt.cpu().numpy())
+    p.set_inputs(inp); p.set_challenges(ch)
+    p.prove()
+    got = [sha_h(p.transcript())]
+    lo, hi = p.input_range(); s0 = circ.num_inputs // K
+    got.append(sha_h(p.prove_local(inp[lo * s0:hi * s0], ch)))
+    got.append(sha_h(p.prove(inputs=inp, challenges=ch)))
+    p.prove()
+    got.append(sha_h(p.transcript()))
+    big_ok = all(h == ref[0] for h in got)
+    print(f"[rank {rank}/{world}] sha256_64 x {K} vs the single-GPU proof: resident / local / host-io / resident {[h == ref[0] for h in got]}", flush=True)
+    ok_all &= big_ok
+    p.close()
+    dist.barrier()
     t = torch.tensor([1 if ok_all else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -799,6 +799,7 @@ struct Engine {
     bool use_ipc = false;            // sharded: one-kernel NVLink exchange (k_xchg) instead of NCCL all-gathers
     uint32_t x_stride = 0;           // entries of one rank's slot in an exchange buffer
     std::vector<void*> ipc_opened;   // peer mappings to close
+    DBuf<unsigned int> d_xerr;       // set by k_xchg when the ranks exchange records of different phases
     void setup_ipc_exchange(uint32_t max_rec);
     bool direct_v = false;   // whole-proof: phase 1 / Liu read V from circuitValue[i-1] instead of a copy
     cudaEvent_t ev_eval = nullptr;
@@ -1008,9 +1009,14 @@ struct Engine {
         CK(cudaStreamSynchronize(stream));
     }
     void check_assert_flag() {
-        unsigned int flag = 0;
+        unsigned int flag = 0, xerr = 0;
         CK(cudaMemcpyAsync(&flag, d_counter.p + 1, sizeof flag, cudaMemcpyDeviceToHost, stream));
+        if (d_xerr.p) CK(cudaMemcpyAsync(&xerr, d_xerr.p, sizeof xerr, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (xerr) {
+            CK(cudaMemsetAsync(d_xerr.p, 0, sizeof(unsigned int), stream));
+            throw CudaError{"sharded exchange: the ranks are not walking the same sequence of phases (same vp_set_lanes / same calls on every rank?)"};
+        }
         if (flag) throw flag;
     }
 };
@@ -1469,6 +1475,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
         k_hi = std::min(ev_hi[0], K);
         core_lo = n > 1 ? std::max(k_lo, std::min(ev_lo[1], k_hi)) : k_lo;   // instances whose layers >= 1 this rank evaluates
         core_hi = n > 1 ? std::min(k_hi, std::max(ev_hi[1], core_lo)) : k_hi;
+        if (getenv("VP_NO_EXTRAS")) { core_lo = k_lo; core_hi = k_hi; }
     }
 
     for (int b = 0; b < 2; ++b) {
@@ -1602,7 +1609,7 @@ void Engine::setup_ipc_exchange(uint32_t max_rec) {
     if (three_lanes) X.push_back(&lane2.x);
     if (six_lanes) { X.push_back(&lane0b.x); X.push_back(&lane1b.x); X.push_back(&lane2b.x); }
     const size_t nl = X.size();
-    x_stride = align4(max_rec);
+    x_stride = align4(max_rec + 1);   // + the record's tag
     const size_t entries = 16 + 2 * (size_t)world * x_stride;
     const size_t n_sc = 3 * 32 + 1 + (size_t)n + 8;
     bool ok = true;
@@ -1653,6 +1660,8 @@ void Engine::setup_ipc_exchange(uint32_t max_rec) {
     CK(cudaStreamSynchronize(stream));
     for (int q = 0; q < world; ++q) ok = ok && h_all[(size_t)q * 8] == 1;
     use_ipc = ok;
+    d_xerr.alloc(1);
+    CK(cudaMemsetAsync(d_xerr.p, 0, sizeof(unsigned int), stream));
     if (!ok) {
         if (rank == 0 || !why.empty())
             fprintf(stderr, "virgo_b200[rank %d]: NVLink exchange unavailable (%s), using NCCL all-gathers\n", rank, why.empty() ? "a peer failed" : why.c_str());
@@ -2114,6 +2123,8 @@ void Engine::do_phase(const PhasePlan& P, uint32_t ci, uint32_t tr_rounds, F* ke
         a.sc_base = P.sc_base;
         a.n_sc = P.n_poly + 1 + P.n_claims;
         a.ticket = x.ticket.p;
+        a.tag = tr_rounds;
+        a.err = d_xerr.p;
         a.mg.recv = nullptr;
         a.mg.rec_len = P.rec_len;
         a.mg.G = (uint32_t)world;
@@ -2433,7 +2444,11 @@ void Engine::prove_all() {
         std::vector<int> sa, sb;
         for (size_t k = 0; k < by_size.size(); ++k) (k & 1 ? sb : sa).push_back(by_size[k]);
         std::reverse(sb.begin(), sb.end());
-        if (extras)   // layer 1 waits for the extra input instances: last in its set
+        // Sharded: layer 1 may have to wait for the extra input instances, so it goes last in its set -- on EVERY rank and in
+        // every call, whether this rank has extras or not: the ranks must walk the same sequence of phases per lane (the
+        // NVLink exchange pairs the k-th exchange of a lane on one rank with the k-th on the others). Deciding this per rank
+        // paired records of different phases on 4 GPUs, where only some ranks have extras (caught by bench.py's parity check).
+        if (world > 1)
             for (std::vector<int>* v : {&sa, &sb}) {
                 auto it = std::find(v->begin(), v->end(), 1);
                 if (it != v->end()) { v->erase(it); v->push_back(1); }

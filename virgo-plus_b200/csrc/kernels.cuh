@@ -1913,6 +1913,8 @@ struct XchgArgs {
     F* sc;                    // this rank's partial scalars (written by the stage-A kernel), zeroed again here
     uint32_t sc_base, n_sc;
     unsigned int* ticket;     // zero at launch, left zero
+    uint32_t tag;             // identifies the phase (its transcript offset): every rank must be exchanging the same phase
+    unsigned int* err;        // set to 1 if a peer's record carries another tag / sequence number
     MergeArgs mg;             // recv is filled in by the kernel
 };
 VP_D void st_f_sys(F* p, const F& v) {   // peer memory: plain 128-bit store, ordered by the release below
@@ -1940,6 +1942,8 @@ __global__ void __launch_bounds__(256) k_xchg(XchgArgs p) {
         const F v = p.sc[i];
         for (uint32_t q = 0; q < p.world; ++q) st_f_sys(p.peer[q] + slot + p.sc_base + i, v);
     }
+    if (tid == 0)   // what this record belongs to (checked by every receiver)
+        for (uint32_t q = 0; q < p.world; ++q) st_f_sys(p.peer[q] + slot + p.rec_len, F{p.tag, p.seq});
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
@@ -1966,6 +1970,10 @@ __global__ void __launch_bounds__(256) k_xchg(XchgArgs p) {
     __syncthreads();
     // ---- (d) merge from the local buffer (written by the peers: bypass L1)
     const F* recv = p.peer[p.me] + p.buf_off[par];
+    if (tid < p.world) {   // the ranks must walk the same sequence of phases per lane: a record of another phase is an error
+        const F t = ld_f_cg(recv + (size_t)tid * p.slot_stride + p.rec_len);
+        if (t.re != p.tag || t.im != p.seq) atomicExch(p.err, 1u);
+    }
     const MergeArgs& m = p.mg;
     for (uint32_t t = 0; t < m.n_tabs; ++t) {
         const MergeTab T = m.tabs[t];

@@ -199,9 +199,21 @@ int vp_commit_private(vp_ctx* ctx, const vp_F* mask, size_t n_mask, uint8_t root
 int vp_commit_export(vp_ctx* ctx, vp_F* l_eval, uint8_t* leaf_hash, uint8_t* tree);
 uint64_t vp_commit_slice_size(const vp_ctx* ctx);
 float vp_last_commit_ms(const vp_ctx* ctx);   /* device time of the last vp_commit_private */
+/* prover::commit_public (prover.cpp:542-546) -> commit_public_array (poly_commit.h:126-349) after vp_commit_private: pub =
+ * the public array (the verifier's eq table over r_liu, verifier.cpp:367-381; n <= 2^bitLength(0) canonical elements), mask
+ * = the public mask (one zero: others return VP_ERR_ARG). Encodes pub like the private array, gets the 2n coefficients
+ * of l*q per slice from its values on the 2n-th roots, extends the quotient h (l q = g + (x^n - 1) h) to all points, builds
+ * the virtual oracle (g - const) n / x and all_sum[65], and commits to h_eval_arr (second Merkle tree): root_h.
+ * vp_commit_public_export: h_eval_arr [65 * slice_size], virtual_oracle_witness [64 * slice_size] (interleaved like
+ * fri::virtual_oracle_witness), leaf hashes and tree of the second commitment (any pointer may be NULL).
+ * Not reproduced: bitLength(0) == 7 (the reference's 4-point inverse FFT, see above). */
+int vp_commit_public(vp_ctx* ctx, const vp_F* pub, size_t n, const vp_F* mask, size_t n_mask, uint8_t root_h[32], vp_F all_sum[65]);
+int vp_commit_public_export(vp_ctx* ctx, vp_F* h_eval, vp_F* vow, uint8_t* leaf_hash, uint8_t* tree);
 /* The same on a host array of n canonical field elements, zero-padded to 2^log_len (6 <= log_len <= 30). */
 int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t root[32], vp_F* l_eval, uint8_t* leaf_hash,
                  uint8_t* tree, float* device_ms);
+int vp_pc_commit_public(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, uint8_t root_l[32],
+                        uint8_t root_h[32], vp_F all_sum[65], vp_F* h_eval, vp_F* vow, float* device_ms);
 
 /* ------------------------------------------------------------------ Fiat-Shamir mode
  * The reference ships a hash-based challenge source, transcriptCache (lib/virgo/src/transcriptCache.hpp:14-50: a byte

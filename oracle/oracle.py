@@ -245,7 +245,42 @@ def pc_commit_private(array, log_len, mask=None, want_arrays=True):
     return dict(root=root.tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss)
 
 
+def pc_commit_public(array, pub, log_len):
+    """poly_commit_prover::commit_public_array restated (poly_commit.h:126-349, zero masks) -> dict(root_h, all_sum, h_eval, vow)"""
+    L = lib()
+    L.opc_commit_public.restype = C.c_long
+    L.opc_commit_public.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    a = np.zeros(1 << log_len, F_DTYPE); a[:len(array)] = array
+    q = np.zeros(1 << log_len, F_DTYPE); q[:len(pub)] = pub
+    N = 1 << (log_len - 1)
+    root = np.zeros(32, np.uint8)
+    all_sum, h_eval, vow = np.zeros(65, F_DTYPE), np.zeros(65 * N, F_DTYPE), np.zeros(64 * N, F_DTYPE)
+    rc = L.opc_commit_public(_p(a), _p(q), log_len, _p(all_sum), _p(h_eval), _p(vow), _p(root))
+    assert rc == N, rc
+    return dict(root_h=root.tobytes(), all_sum=all_sum, h_eval=h_eval, vow=vow, slice_size=N)
+
+
 REF_PC = os.path.join(REF_DIR, "ref_pc_commit")
+
+
+def ref_pc_commit_public(array, pub, log_len):
+    """the UNMODIFIED reference commit_private_array + commit_public_array -> dict(root_h, all_sum, h_eval, vow, vow_msk, seconds)"""
+    import tempfile
+    a = np.zeros(1 << log_len, F_DTYPE); a[:len(array)] = array
+    q = np.zeros(1 << log_len, F_DTYPE); q[:len(pub)] = pub
+    N = 1 << (log_len - 1)
+    with tempfile.TemporaryDirectory() as td:
+        fa, fq, fo, fo2 = (os.path.join(td, x) for x in ("a.bin", "q.bin", "o.bin", "o2.bin"))
+        a.tofile(fa); q.tofile(fq)
+        r = subprocess.run([REF_PC, str(log_len), fa, fo, fq, fo2], capture_output=True, text=True, check=True)
+        raw = np.fromfile(fo2, dtype=np.uint8)
+    o = 32
+    all_sum = raw[o:o + 65 * 16].view(F_DTYPE); o += 65 * 16
+    h_eval = raw[o:o + 65 * N * 16].view(F_DTYPE); o += 65 * N * 16
+    vow = raw[o:o + 64 * N * 16].view(F_DTYPE); o += 64 * N * 16
+    vow_msk = raw[o:o + N * 16].view(F_DTYPE)
+    return dict(root_h=raw[:32].tobytes(), all_sum=all_sum, h_eval=h_eval, vow=vow, vow_msk=vow_msk, slice_size=N,
+                seconds=float(r.stdout.split("commit_public_seconds")[1]))
 
 
 def ref_pc_commit(array, log_len):

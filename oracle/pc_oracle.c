@@ -212,3 +212,86 @@ long opc_commit_private(const ofe* array, int log_len, const ofe* mask, int n_ma
     free(l_eval); free(tmp); free(m); free(leaf); free(tree);
     return slice_size;
 }
+
+/* ------------------------------------------------------------------ commit_public_array
+ * poly_commit.h:126-349 for the GKR use of it (verifier.cpp:367-383: public array = the eq table over r_liu, ONE zero
+ * public mask, private mask one zero) + fri::request_init_commit(.., 1) (fri.cpp:36-139) on h_eval_arr.
+ *   q_eval: the public array encoded like the private one (per-slice inverse FFT + 32x extension), mask slice zero;
+ *   per slice: the 2n evaluations of l*q on the 2n-th roots (every 16th codeword position) -> 2n coefficients; the upper n
+ *   are h (l*q = g + (x^n - 1) h), evaluated on all N points -> h_eval; all_sum = n (lq_0 + h_0);
+ *   virtual_oracle_witness[(j mod N/2) << 7 | slice << 1 | (j >= N/2)] = (l q - (x^n - 1) h - (lq_0 + h_0)) * n * x^-1, x = w_N^j.
+ * With zero masks the 65th slice of everything is zero.
+ * Outputs (any may be NULL): all_sum [65], h_eval [65 N], vow [64 N], root_h [32]. Returns N, or -1. */
+long opc_commit_public(const ofe* array, const ofe* pub, int log_len, ofe* all_sum_out, ofe* h_eval_out, ofe* vow_out,
+                       unsigned char root_out[32]) {
+    const int LOG_SLICE = 6, RATE = 5, SLICES = 1 << LOG_SLICE;
+    if (log_len < LOG_SLICE) return -1;
+    const int slice_count = SLICES + 1;
+    const int N = 1 << (log_len + RATE - LOG_SLICE), n = N >> RATE, half = N / 2;
+    int lg_n = 0, lg_N = 0, lg_2n = 0;
+    while ((1 << lg_n) < n) ++lg_n;
+    while ((1 << lg_N) < N) ++lg_N;
+    while ((1 << lg_2n) < 2 * n) ++lg_2n;
+    ofe* l_eval = (ofe*)calloc((size_t)slice_count * N, sizeof(ofe));
+    ofe* q_eval = (ofe*)calloc((size_t)slice_count * N, sizeof(ofe));
+    ofe* h_eval = (ofe*)calloc((size_t)slice_count * N, sizeof(ofe));
+    ofe* vow = (ofe*)calloc((size_t)SLICES * N, sizeof(ofe));
+    ofe* tmp = (ofe*)calloc((size_t)2 * n, sizeof(ofe));
+    ofe* lq = (ofe*)calloc((size_t)2 * n, sizeof(ofe));
+    ofe all_sum[65];
+    for (int i = 0; i < SLICES; ++i) {
+        ifft(array + (size_t)i * n, n, opc_root_of_unity(lg_n), tmp);
+        fft(tmp, n, N, opc_root_of_unity(lg_N), l_eval + (size_t)i * N);
+        ifft(pub + (size_t)i * n, n, opc_root_of_unity(lg_n), tmp);
+        fft(tmp, n, N, opc_root_of_unity(lg_N), q_eval + (size_t)i * N);
+    }
+    const ofe rou = opc_root_of_unity(lg_N);
+    ofe inv_rou = ONE;   /* rou^(N-1) */
+    {
+        ofe t = rou;
+        for (int b = 0; b < lg_N; ++b) { inv_rou = ofe_mul(inv_rou, t); t = ofe_mul(t, t); }
+    }
+    const ofe rou_n = f_pow(rou, (unsigned __int128)n);
+    const ofe n_fe = {(u64)n, 0};
+    for (int i = 0; i < SLICES; ++i) {
+        const int step = N / (2 * n);
+        for (int j = 0; j < 2 * n; ++j) lq[j] = ofe_mul(l_eval[(size_t)i * N + (size_t)j * step], q_eval[(size_t)i * N + (size_t)j * step]);
+        ifft(lq, 2 * n, opc_root_of_unity(lg_2n), tmp);          /* tmp = lq_coef */
+        fft(tmp + n, n, N, rou, h_eval + (size_t)i * N);            /* h_coef = upper half */
+        const ofe c0 = ofe_add(tmp[0], tmp[n]);
+        all_sum[i] = ofe_mul(c0, n_fe);
+        const ofe const_sum = ofe_sub(ZERO, c0);
+        ofe inv_x = n_fe, x_n = ONE;
+        for (int j = 0; j < N; ++j) {
+            const ofe lqv = ofe_mul(l_eval[(size_t)i * N + j], q_eval[(size_t)i * N + j]);
+            const ofe g = ofe_sub(lqv, ofe_mul(ofe_sub(x_n, ONE), h_eval[(size_t)i * N + j]));
+            const ofe v = ofe_mul(ofe_add(g, const_sum), inv_x);
+            if (j < half) vow[((size_t)j << (LOG_SLICE + 1)) | ((size_t)i << 1)] = v;
+            else vow[((size_t)(j - half) << (LOG_SLICE + 1)) | ((size_t)i << 1) | 1] = v;
+            inv_x = ofe_mul(inv_x, inv_rou);
+            x_n = ofe_mul(x_n, rou_n);
+        }
+    }
+    all_sum[SLICES] = ZERO;
+    /* Merkle commitment of h_eval_arr (same leaf chain and tree as for l_eval) */
+    unsigned char* tree = (unsigned char*)calloc((size_t)N, 32);
+    for (int i = 0; i < half; ++i) {
+        unsigned char h[32], data[64];
+        memset(h, 0, 32);
+        for (int s2 = 0; s2 < slice_count; ++s2) {
+            memcpy(data, &h_eval[(size_t)s2 * N + i], 16);
+            memcpy(data + 16, &h_eval[(size_t)s2 * N + i + half], 16);
+            memcpy(data + 32, h, 32);
+            hhash64(data, h);
+        }
+        memcpy(tree + (size_t)(half + i) * 32, h, 32);
+    }
+    for (int lvl = half / 2; lvl >= 1; lvl /= 2)
+        for (int i = 0; i < lvl; ++i) hhash64(tree + (size_t)(2 * (lvl + i)) * 32, tree + (size_t)(lvl + i) * 32);
+    if (root_out) memcpy(root_out, tree + 32, 32);
+    if (all_sum_out) memcpy(all_sum_out, all_sum, sizeof all_sum);
+    if (h_eval_out) memcpy(h_eval_out, h_eval, (size_t)slice_count * N * sizeof(ofe));
+    if (vow_out) memcpy(vow_out, vow, (size_t)SLICES * N * sizeof(ofe));
+    free(l_eval); free(q_eval); free(h_eval); free(vow); free(tmp); free(lq); free(tree);
+    return N;
+}

@@ -1,10 +1,14 @@
 // TEST INFRASTRUCTURE ONLY (oracle/_ref build): runs the UNMODIFIED reference poly_commit_prover::commit_private_array
 // (lib/virgo/src/poly_commit.h:41-124 -> vpd_prover.cpp:9-14 -> fri.cpp:36-139 -> merkle_tree.cpp:7-51, SHA3 from the
 // reference's prebuilt libXKCP.a) on an array read from a file and dumps what it produced:
-//   usage: ref_pc_commit <log_len> <array.bin> <out.bin>
+//   usage: ref_pc_commit <log_len> <array.bin> <out.bin> [<public.bin> <out2.bin>]
 //   array.bin: 2^log_len field elements {u64 real, u64 img};  the mask is the GKR prover's: one zero (prover.cpp:524-530)
 //   out.bin  : root[32] | l_eval[65 * slice_size * 16] | leaf_hash[slice_size/2 * 32] | merkle tree[slice_size * 32]
 // and prints the commit time the reference accounts for itself (poly_prover.total_time).
+// With public.bin (2^log_len elements: the verifier's eq table in the real program, verifier.cpp:367-381) it goes on with
+// commit_public_array (poly_commit.h:126-349; public mask = one zero, target sum = <array, public>) and dumps
+//   out2.bin : root_h[32] | all_sum[65 * 16] | h_eval_arr[65 * slice_size * 16] | virtual_oracle_witness[64 * slice_size * 16]
+//              | virtual_oracle_witness_msk[slice_size * 16]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -35,5 +39,25 @@ int main(int argc, char **argv) {
     fwrite(fri::witness_merkle[0], 32, slice_size, f);
     fclose(f);
     printf("slice_size %zu commit_seconds %.6f\n", slice_size, p.total_time);
+    if (argc >= 6) {
+        std::vector<fieldElement> pub(n);
+        f = fopen(argv[4], "rb");
+        if (!f || fread(pub.data(), sizeof(fieldElement), n, f) != n) return 5;
+        fclose(f);
+        fieldElement target = fieldElement::zero();
+        for (size_t i = 0; i < n; ++i) target = target + arr[i] * pub[i];
+        std::vector<fieldElement> pub_mask(1, fieldElement::zero()), all_sum(poly_commit::slice_count);
+        const double t_before = p.total_time;
+        __hhash_digest root_h = p.commit_public_array(pub_mask, pub.data(), log_len, target, all_sum.data());
+        f = fopen(argv[5], "wb");
+        if (!f) return 6;
+        fwrite(&root_h, 32, 1, f);
+        fwrite(all_sum.data(), sizeof(fieldElement), all_sum.size(), f);
+        fwrite(poly_commit::h_eval_arr, sizeof(fieldElement), (size_t)poly_commit::slice_count * slice_size, f);
+        fwrite(fri::virtual_oracle_witness, sizeof(fieldElement), (size_t)(poly_commit::slice_count - 1) * slice_size, f);
+        fwrite(fri::virtual_oracle_witness_msk, sizeof(fieldElement), slice_size, f);
+        fclose(f);
+        printf("commit_public_seconds %.6f\n", p.total_time - t_before);
+    }
     return 0;
 }

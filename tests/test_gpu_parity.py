@@ -686,3 +686,41 @@ def test_pc_commit_c3_size_matches_reference(B, O):
     assert got["root"].hex() == g["root"]
     assert hashlib.sha256(got["leaf_hash"].tobytes()).hexdigest() == g["leaf_sha256"]
     assert hashlib.sha256(got["tree"][32:].tobytes()).hexdigest() == g["tree_sha256"]
+
+
+@pytest.mark.parametrize("name", ["random_6_1", "random_9_3", "random_10_4", "random_12_6", "sha256_64"])
+def test_pc_commit_public_matches_reference_golden(B, O, name):
+    """device commit_public (public array encoded, l*q coefficients, quotient h extended, virtual oracle, second Merkle
+    commitment) == what the reference's commit_public_array produced"""
+    import importlib.util
+    import json
+    import os
+    import helpers as H
+    spec = importlib.util.spec_from_file_location("make_golden_pc_public", os.path.join(H.GOLDEN, "make_golden_pc_public.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    with open(os.path.join(H.GOLDEN, "pc_commit_public.json")) as f:
+        g = json.load(f)[name]
+    a, q, b = mk.case_arrays(B, O, name)
+    got = B.pc_commit_public(a, q, b)
+    d = mk.digest_of(got)
+    if d["h_eval_sha256"] != g["h_eval_sha256"] or d["vow_sha256"] != g["vow_sha256"]:
+        want = O.pc_commit_public(a, q, b)
+        _assert_same(got["all_sum"], want["all_sum"], "all_sum")
+        _assert_same(got["h_eval"], want["h_eval"], "h_eval")
+        _assert_same(got["vow"], want["vow"], "virtual oracle")
+    for k in ("root_h", "all_sum_sha256", "h_eval_sha256", "vow_sha256"):
+        assert d[k] == g[k], k
+
+
+def test_pc_commit_public_long_transforms_vs_oracle(B, O):
+    """2^18 inputs: slices of 2^12 points, l*q transforms of 2^13 (global stages in both directions)"""
+    rng = np.random.default_rng(31)
+    b = 18
+    a, q = _rand_fe(B, rng, (1 << b) - 5), _rand_fe(B, rng, 1 << b)
+    got = B.pc_commit_public(a, q, b)
+    want = O.pc_commit_public(a, q, b)
+    _assert_same(got["all_sum"], want["all_sum"], "all_sum")
+    _assert_same(got["h_eval"], want["h_eval"], "h_eval")
+    _assert_same(got["vow"], want["vow"], "virtual oracle")
+    assert got["root_h"] == want["root_h"]

@@ -331,3 +331,19 @@ def test_fiat_shamir_oracle_and_host_challenges(B, O, sha_circuit):
         # the FS transcript differs from the interactive one (other challenges), same length
         tr_i, _, _ = oc.prove()
         assert len(tr_i) == len(tr) and (tr_i["re"] != tr["re"]).any()
+
+
+@pytest.mark.parametrize("name", ["random_6_1", "random_9_3", "random_10_4", "random_12_6", "sha256_64"])
+def test_pc_oracle_matches_reference_commit_public(B, O, name):
+    """pc_oracle.c's commit_public == the reference's commit_public_array: root of the second commitment, all_sum, h_eval_arr,
+    virtual oracle (golden: make_golden_pc_public.py)"""
+    import json
+    spec = importlib.util.spec_from_file_location("make_golden_pc_public", os.path.join(H.GOLDEN, "make_golden_pc_public.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    with open(os.path.join(H.GOLDEN, "pc_commit_public.json")) as f:
+        g = json.load(f)[name]
+    a, q, b = mk.case_arrays(B, O, name)
+    got = mk.digest_of(O.pc_commit_public(a, q, b))
+    for k in ("root_h", "all_sum_sha256", "h_eval_sha256", "vow_sha256", "slice_size"):
+        assert got[k] == g[k], k

@@ -111,6 +111,9 @@ def _declare(L):
     L.vp_last_commit_ms.argtypes = [vp]
     L.vp_last_commit_ms.restype = C.c_float
     L.vp_pc_commit.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.vp_pc_commit_public.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.vp_commit_public.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp]
+    L.vp_commit_public_export.argtypes = [vp, vp, vp, vp, vp]
     L.vp_prove_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
     L.vp_fs_challenges.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
     L.vp_verify_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -378,6 +381,21 @@ def pc_commit(array, log_len, device=0, want_arrays=True, want_l_eval=True):
     return dict(root=root.tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss, ms=ms.value)
 
 
+def pc_commit_public(array, pub, log_len, device=0, want_arrays=True):
+    """commit_private_array + commit_public_array on host arrays -> dict(root_l, root_h, all_sum, h_eval, vow, ms)"""
+    a = np.ascontiguousarray(array, dtype=F_DTYPE)
+    q = np.ascontiguousarray(pub, dtype=F_DTYPE)
+    N = 1 << (log_len - 1)
+    root_l, root_h = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+    all_sum = np.zeros(65, F_DTYPE)
+    h_eval = np.zeros(65 * N, F_DTYPE) if want_arrays else None
+    vow = np.zeros(64 * N, F_DTYPE) if want_arrays else None
+    ms = C.c_float()
+    _ck(lib().vp_pc_commit_public(device, _ptr(a), len(a), _ptr(q), len(q), log_len, _ptr(root_l), _ptr(root_h), _ptr(all_sum), _ptr(h_eval),
+                                  _ptr(vow), C.byref(ms)))
+    return dict(root_l=root_l.tobytes(), root_h=root_h.tobytes(), all_sum=all_sum, h_eval=h_eval, vow=vow, slice_size=N, ms=ms.value)
+
+
 def shard_describe(circuit, world, rank, layer, phase):
     out = np.zeros(10 * 256, np.uint32)
     n = C.c_size_t()
@@ -538,6 +556,14 @@ class Prover:
         root = np.zeros(32, np.uint8)
         _ck(lib().vp_commit_private(self.h, _ptr(m), len(m), _ptr(root)))
         return root.tobytes()
+
+    def commit_public(self, pub, mask=None):
+        """prover::commit_public's commitment part on the device -> (root_h, all_sum[65])"""
+        q = np.ascontiguousarray(pub, dtype=F_DTYPE)
+        m = np.zeros(1, F_DTYPE) if mask is None else np.ascontiguousarray(mask, dtype=F_DTYPE)
+        root, all_sum = np.zeros(32, np.uint8), np.zeros(65, F_DTYPE)
+        _ck(lib().vp_commit_public(self.h, _ptr(q), len(q), _ptr(m), len(m), _ptr(root), _ptr(all_sum)))
+        return root.tobytes(), all_sum
 
     def commit_export(self):
         ss = int(lib().vp_commit_slice_size(self.h))

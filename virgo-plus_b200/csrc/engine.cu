@@ -3311,6 +3311,32 @@ extern "C" int vp_commit_export(vp_ctx* ctx, vp_F* l_eval, uint8_t* leaf_hash, u
     return VP_OK;
     API_END
 }
+// prover::commit_public (prover.cpp:542-546) -> commit_public_array (poly_commit.h:126-349), zero masks
+extern "C" int vp_commit_public(vp_ctx* ctx, const vp_F* pub, size_t n, const vp_F* mask, size_t n_mask, uint8_t root_h[32], vp_F all_sum[65]) {
+    if (!ctx || !pub || !root_h || !all_sum || (n_mask && !mask)) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    cudaSetDevice(e.device);
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_commit_public before vp_commit_private");
+    if (!mask_all_zero(mask, n_mask)) return fail(VP_ERR_ARG, "vp_commit_public: only the zero public mask of verifier.cpp:376 is supported");
+    if (n > ((size_t)1 << e.C.bit_length(0))) return fail(VP_ERR_ARG, "vp_commit_public: public array longer than the padded input layer");
+    for (size_t i = 0; i < n; ++i)
+        if (pub[i].re >= P || pub[i].im >= P) return fail(VP_ERR_ARG, "vp_commit_public: element %zu is not canonical", i);
+    if (e.d_pub.n < n) e.d_pub.alloc(n);
+    CK(cudaMemcpyAsync(e.d_pub.p, pub, n * sizeof(F), cudaMemcpyHostToDevice, e.stream));
+    e.last_commit_ms = pc_commit_public(e.pc, e.d_pub.p, n, e.stream, root_h, reinterpret_cast<F*>(all_sum));
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_commit_public_export(vp_ctx* ctx, vp_F* h_eval, vp_F* vow, uint8_t* leaf_hash, uint8_t* tree) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_commit_public_export before vp_commit_public");
+    pc_export_public(e.pc, e.stream, reinterpret_cast<F*>(h_eval), reinterpret_cast<F*>(vow), leaf_hash, tree);
+    return VP_OK;
+    API_END
+}
 extern "C" uint64_t vp_commit_slice_size(const vp_ctx* ctx) { return (ctx && ctx->e.pc) ? pc_slice_size(ctx->e.pc) : 0; }
 extern "C" float vp_last_commit_ms(const vp_ctx* ctx) { return ctx ? ctx->e.last_commit_ms : 0.f; }
 // Stand-alone form on a host array (any field elements, e.g. test vectors): array[0..n) zero-padded to 2^log_len.
@@ -3334,6 +3360,35 @@ extern "C" int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len
     const float ms = pc_commit(g.p, d.p, n, 0, root);
     if (device_ms) *device_ms = ms;
     pc_export(g.p, 0, reinterpret_cast<F*>(l_eval), leaf_hash, tree);
+    return VP_OK;
+    API_END
+}
+// Both phases on host arrays: commit_private_array on `array`, then commit_public_array with the public array `pub`.
+extern "C" int vp_pc_commit_public(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, uint8_t root_l[32],
+                                   uint8_t root_h[32], vp_F all_sum[65], vp_F* h_eval, vp_F* vow, float* device_ms) {
+    if (!array || !pub || !root_l || !root_h || !all_sum) return fail(VP_ERR_ARG, "null argument");
+    if (log_len < 6 || log_len > 30 || n > ((size_t)1 << log_len) || n_pub > ((size_t)1 << log_len)) return fail(VP_ERR_ARG, "vp_pc_commit_public: log_len in [6, 30], n <= 2^log_len");
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw CudaError{std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(ce)};
+    for (size_t i = 0; i < n; ++i)
+        if (array[i].re >= P || array[i].im >= P) return fail(VP_ERR_ARG, "vp_pc_commit_public: array element %zu is not canonical", i);
+    for (size_t i = 0; i < n_pub; ++i)
+        if (pub[i].re >= P || pub[i].im >= P) return fail(VP_ERR_ARG, "vp_pc_commit_public: public element %zu is not canonical", i);
+    CK(cudaSetDevice(device));
+    struct Guard { PcCommit* p = nullptr; ~Guard() { if (p) pc_destroy(p); } } g;
+    g.p = pc_create(device, log_len);
+    DBuf<F> d, dq;
+    d.alloc(std::max<size_t>(n, 1));
+    dq.alloc(std::max<size_t>(n_pub, 1));
+    CK(cudaMemcpy(d.p, array, n * sizeof(F), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dq.p, pub, n_pub * sizeof(F), cudaMemcpyHostToDevice));
+    pc_commit(g.p, d.p, n, 0, root_l);
+    const float ms = pc_commit_public(g.p, dq.p, n_pub, 0, root_h, reinterpret_cast<F*>(all_sum));
+    if (device_ms) *device_ms = ms;
+    pc_export_public(g.p, 0, reinterpret_cast<F*>(h_eval), reinterpret_cast<F*>(vow), nullptr, nullptr);
     return VP_OK;
     API_END
 }

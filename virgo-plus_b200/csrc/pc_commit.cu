@@ -65,7 +65,8 @@ __global__ void k_pc_pad(const F* __restrict__ src, size_t n_valid, F* __restric
 
 // ---- inverse transform (RS_polynomial.cpp:155-220): DIF with the inverse n-th root, natural in, bit-reversed out.
 // One global stage over `batch` transforms of size n stored back to back: stage s pairs p and p + half, half = n >> (s+1).
-__global__ void k_pc_dif_stage(F* __restrict__ a, uint32_t log_n, uint32_t s, size_t total_pairs, const F* __restrict__ tw, uint32_t log_N) {
+__global__ void k_pc_dif_stage(F* __restrict__ a, uint32_t log_n, uint32_t s, size_t total_pairs, const F* __restrict__ tw, uint32_t log_N,
+                               uint32_t tw_shift /* log2(N / transform size): w_size = w_N^(2^tw_shift) */) {
     const uint32_t lh = log_n - s - 1, half = 1u << lh, N = 1u << log_N;
     for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_pairs; w += (size_t)gridDim.x * blockDim.x) {
         const size_t t = w >> (log_n - 1);                       // transform
@@ -75,13 +76,13 @@ __global__ void k_pc_dif_stage(F* __restrict__ a, uint32_t log_n, uint32_t s, si
         const F u = pc_ld(x + p), v = pc_ld(x + p + half);
         const uint32_t e = j << s;                               // exponent of w_n^-1
         pc_st(x + p, f_add(u, v));
-        pc_st(x + p + half, f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << PC_LOG_RATE)) & (N - 1)))));
+        pc_st(x + p + half, f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << tw_shift)) & (N - 1)))));
     }
 }
 // The last min(log_n, 11) DIF stages of every transform in shared memory, then the scaling by 1/n (inv_n = n^(p-2)).
 // One block per chunk of m = 2^log_m points (a chunk never straddles two transforms).
 __global__ void __launch_bounds__(512) k_pc_intt_smem(F* __restrict__ a, uint32_t log_n, uint32_t log_m, const F* __restrict__ tw, uint32_t log_N,
-                                                       F inv_n) {
+                                                       F inv_n, uint32_t tw_shift) {
     extern __shared__ __align__(16) unsigned char pc_smem[];
     F* sh = reinterpret_cast<F*>(pc_smem);
     const uint32_t m = 1u << log_m, N = 1u << log_N;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(512) k_pc_intt_smem(F* __restrict__ a, uint32_
             const F u = sh[p], v = sh[p + half];
             const uint32_t e = j << s;
             sh[p] = f_add(u, v);
-            sh[p + half] = f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << PC_LOG_RATE)) & (N - 1))));
+            sh[p + half] = f_mul(f_sub(u, v), pc_ld(tw + ((N - (e << tw_shift)) & (N - 1))));
         }
         __syncthreads();
     }
@@ -107,16 +108,19 @@ __global__ void __launch_bounds__(512) k_pc_intt_smem(F* __restrict__ a, uint32_
 // First min(log_n, 11) stages in shared memory. coef: [64][n] bit-reversed coefficients. One block per
 // (chunk, coset, slice). If direct != 0 (log_n <= 11) the result goes straight to l_eval[s][32 k + c], else to the work
 // buffer work[(s * 32 + c) * n + p].
+// Coefficient i of slice sl sits at coef[sl * slice_stride + i * in_stride + in_off] (private / public array: stride 1;
+// the quotient h of commit_public: the odd positions of the bit-reversed 2n coefficients of l*q).
 __global__ void __launch_bounds__(512) k_pc_ntt_smem(const F* __restrict__ coef, uint32_t log_n, uint32_t log_m, const F* __restrict__ tw,
-                                                      uint32_t log_N, F* __restrict__ out, int direct) {
+                                                      uint32_t log_N, F* __restrict__ out, int direct, size_t slice_stride, uint32_t in_stride,
+                                                      uint32_t in_off) {
     extern __shared__ __align__(16) unsigned char pc_smem[];
     F* sh = reinterpret_cast<F*>(pc_smem);
     const uint32_t m = 1u << log_m, n = 1u << log_n, N = 1u << log_N;
     const uint32_t chunk = blockIdx.x, c = blockIdx.y, sl = blockIdx.z, base = chunk << log_m;
-    const F* x = coef + ((size_t)sl << log_n) + base;
+    const F* x = coef + (size_t)sl * slice_stride + (size_t)base * in_stride + in_off;
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         const uint32_t p = base + i, ci = log_n ? __brev(p) >> (32 - log_n) : 0u;   // coefficient index held at position p
-        const F v = pc_ld(x + i);
+        const F v = pc_ld(x + (size_t)i * in_stride);
         sh[i] = (c == 0 || log_n == 0) ? v : f_mul(v, pc_ld(tw + (((uint64_t)c * ci) & (N - 1))));   // coef_i * w_N^(c i)
     }
     __syncthreads();
@@ -160,6 +164,39 @@ __global__ void k_pc_dit_stage(F* __restrict__ work, uint32_t log_n, uint32_t s,
             pc_st(x + p, r0);
             pc_st(x + p + half, r1);
         }
+    }
+}
+
+// ---- commit_public_array (poly_commit.h:126-349): products of the two codewords on the 2n-th roots, the quotient
+// polynomial's oracle values
+// lq[s][j] = l_eval[s][16 j] * q_eval[s][16 j], j < 2n  (the 2n evaluations of l*q that determine it: degree < 2n - 1)
+__global__ void k_pc_lq(const F* __restrict__ l_eval, const F* __restrict__ q_eval, uint32_t log_n, uint32_t log_N, F* __restrict__ lq, size_t total) {
+    const uint32_t step_log = log_N - log_n - 1;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t sl = w >> (log_n + 1), j = w & (((size_t)1 << (log_n + 1)) - 1);
+        const size_t at = (sl << log_N) + (j << step_log);
+        pc_st(lq + w, f_mul(pc_ld(l_eval + at), pc_ld(q_eval + at)));
+    }
+}
+// lqc: bit-reversed coefficients of l*q per slice (2n each): coefficient 0 at position 0, coefficient n (= h_0) at position 1.
+// all_sum[s] = n (lq_0 + h_0) (poly_commit.h:330); per point x = w_N^j:
+//   vow[(j mod N/2) << 7 | s << 1 | (j >= N/2)] = (l q - (x^n - 1) h - (lq_0 + h_0)) * n * x^-1        (:303-323)
+__global__ void k_pc_vow(const F* __restrict__ l_eval, const F* __restrict__ q_eval, const F* __restrict__ h_eval, const F* __restrict__ lqc,
+                         const F* __restrict__ tw, uint32_t log_n, uint32_t log_N, F* __restrict__ vow, F* __restrict__ all_sum, size_t total) {
+    const uint32_t N = 1u << log_N, n = 1u << log_n, half = N >> 1;
+    const F n_fe{(u64)n, 0};
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t sl = (uint32_t)(w >> log_N), j = (uint32_t)(w & (N - 1));
+        const F* c = lqc + ((size_t)sl << (log_n + 1));
+        const F c0 = f_add(pc_ld(c), pc_ld(c + 1));
+        if (j == 0) pc_st(all_sum + sl, f_mul(c0, n_fe));
+        const F x_n = pc_ld(tw + (((size_t)j << log_n) & (N - 1)));                    // (w_N^n)^j
+        const F inv_x = f_mul(n_fe, pc_ld(tw + ((N - j) & (N - 1))));                    // n * w_N^-j
+        const F lqv = f_mul(pc_ld(l_eval + w), pc_ld(q_eval + w));
+        const F g = f_sub(lqv, f_mul(f_sub(x_n, f_one()), pc_ld(h_eval + w)));
+        const F v = f_mul(f_sub(g, c0), inv_x);
+        const size_t at = j < half ? (((size_t)j << (PC_LOG_SLICES + 1)) | ((size_t)sl << 1)) : (((size_t)(j - half) << (PC_LOG_SLICES + 1)) | ((size_t)sl << 1) | 1);
+        pc_st(vow + at, v);
     }
 }
 
@@ -267,6 +304,11 @@ struct PcCommit {
     size_t n = 0, N = 0;
     F *tw = nullptr, *coef = nullptr, *work = nullptr, *l_eval = nullptr;
     uint64_t* tree = nullptr;        // N/2 * 2 nodes of 32 bytes; leaves at [N/2, N)
+    // commit_public (allocated on first use): the public array's codewords, l*q coefficients, h's codewords, the
+    // virtual oracle, the second tree, all_sum
+    F *q_eval = nullptr, *lqc = nullptr, *h_eval = nullptr, *vow = nullptr, *all_sum = nullptr;
+    uint64_t* tree_h = nullptr;
+    F inv_2n;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool tw_ready = false;
     uint64_t launches = 0;
@@ -303,6 +345,7 @@ PcCommit* pc_create(int device, int log_len) {
         PCK(cudaEventCreate(&p->e1));
         const F nn{(u64)p->n, 0};
         p->inv_n = host_pow(nn, (unsigned __int128)P - 2);   // RS_polynomial.cpp:211
+        p->inv_2n = host_pow(F{(u64)(2 * p->n), 0}, (unsigned __int128)P - 2);
         PCK(cudaFuncSetAttribute(k_pc_intt_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << PC_SMEM_LOG)));
         PCK(cudaFuncSetAttribute(k_pc_ntt_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(F) << PC_SMEM_LOG)));
     } catch (...) {
@@ -315,6 +358,7 @@ void pc_destroy(PcCommit* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->tw); cudaFree(p->coef); cudaFree(p->work); cudaFree(p->l_eval); cudaFree(p->tree);
+    cudaFree(p->q_eval); cudaFree(p->lqc); cudaFree(p->h_eval); cudaFree(p->vow); cudaFree(p->all_sum); cudaFree(p->tree_h);
     if (p->e0) cudaEventDestroy(p->e0);
     if (p->e1) cudaEventDestroy(p->e1);
     delete p;
@@ -326,63 +370,78 @@ static inline unsigned pc_grid(size_t work, unsigned threads, unsigned cap = 148
     return (unsigned)std::max<size_t>(1, std::min<size_t>((work + threads - 1) / threads, cap));
 }
 
-float pc_commit(PcCommit* p, const F* d_array, size_t n_valid, cudaStream_t st, uint8_t root[32]) {
-    PCK(cudaSetDevice(p->device));
-    const uint32_t log_n = (uint32_t)p->log_n, log_N = (uint32_t)p->log_N;
-    const uint32_t log_m = std::min<uint32_t>(log_n, PC_SMEM_LOG);
-    const size_t total = (size_t)PC_SLICES << log_n;
-    if (n_valid > total) throw std::runtime_error("polynomial commitment: array longer than 2^log_len");
-    PCK(cudaEventRecord(p->e0, st));
-    if (!p->tw_ready) {   // w_N = the order-2^62 element of fieldElement.cpp:240-241 squared 62 - log_N times
-        F w{2147483648ULL, 1033321771269002680ULL};
-        for (int i = 0; i < 62 - p->log_N; ++i) w = f_mul(w, w);
-        PcPow pw;
-        for (int b = 0; b < 32; ++b) { pw.sq[b] = w; w = f_mul(w, w); }
-        k_pc_twiddles<<<pc_grid(p->N, 256, 1u << 30), 256, 0, st>>>(p->tw, (uint32_t)p->N, pw);
-        ++p->launches;
-        p->tw_ready = true;
-    }
-    k_pc_pad<<<pc_grid(total, 256), 256, 0, st>>>(d_array, n_valid, p->coef, total);
+// twiddles (once), then: zero-padded copy -> 64 inverse transforms -> 32 coset transforms per slice -> eval[0 .. 64 N)
+static void pc_twiddles(PcCommit* p, cudaStream_t st) {
+    if (p->tw_ready) return;   // w_N = the order-2^62 element of fieldElement.cpp:240-241 squared 62 - log_N times
+    F w{2147483648ULL, 1033321771269002680ULL};
+    for (int i = 0; i < 62 - p->log_N; ++i) w = f_mul(w, w);
+    PcPow pw;
+    for (int b = 0; b < 32; ++b) { pw.sq[b] = w; w = f_mul(w, w); }
+    k_pc_twiddles<<<pc_grid(p->N, 256, 1u << 30), 256, 0, st>>>(p->tw, (uint32_t)p->N, pw);
     ++p->launches;
-    // inverse transforms of the 64 slices
-    if (log_n >= 1) {
-        for (uint32_t s = 0; s + log_m < log_n; ++s) {
-            k_pc_dif_stage<<<pc_grid(total / 2, 256), 256, 0, st>>>(p->coef, log_n, s, total / 2, p->tw, log_N);
+    p->tw_ready = true;
+}
+// forward transforms on the 32 cosets of every slice: coefficients (bit-reversed) at src[sl * slice_stride + i * in_stride + in_off]
+static void pc_extend(PcCommit* p, const F* src, size_t slice_stride, uint32_t in_stride, uint32_t in_off, F* eval, cudaStream_t st) {
+    const uint32_t log_n = (uint32_t)p->log_n, log_N = (uint32_t)p->log_N, log_m = std::min<uint32_t>(log_n, PC_SMEM_LOG);
+    const unsigned threads = (unsigned)std::max<size_t>(32, std::min<size_t>(512, ((size_t)1 << log_m) / 2));
+    const bool direct = log_n <= PC_SMEM_LOG;
+    dim3 grid((unsigned)(1u << (log_n - log_m)), PC_COSETS, PC_SLICES);
+    k_pc_ntt_smem<<<grid, threads, sizeof(F) << log_m, st>>>(src, log_n, log_m, p->tw, log_N, direct ? eval : p->work, direct ? 1 : 0, slice_stride,
+                                                            in_stride, in_off);
+    ++p->launches;
+    if (!direct) {
+        const size_t pairs = ((size_t)PC_SLICES * PC_COSETS << log_n) / 2;
+        for (uint32_t s = log_m; s < log_n; ++s) {
+            k_pc_dit_stage<<<pc_grid(pairs, 256), 256, 0, st>>>(p->work, log_n, s, pairs, p->tw, log_N, eval, s == log_n - 1 ? 1 : 0);
             ++p->launches;
         }
     }
-    {
-        const unsigned threads = (unsigned)std::max<size_t>(32, std::min<size_t>(512, ((size_t)1 << log_m) / 2));
-        k_pc_intt_smem<<<(unsigned)(total >> log_m), threads, sizeof(F) << log_m, st>>>(p->coef, log_n, log_m, p->tw, log_N, p->inv_n);
+}
+// `count` inverse transforms of size 2^log_t stored back to back in buf (in place; natural in, bit-reversed out, scaled)
+static void pc_inverse(PcCommit* p, F* buf, uint32_t log_t, size_t count, F inv, cudaStream_t st) {
+    const uint32_t log_N = (uint32_t)p->log_N, log_m = std::min<uint32_t>(log_t, PC_SMEM_LOG), tw_shift = log_N - log_t;
+    const size_t total = count << log_t;
+    for (uint32_t s = 0; s + log_m < log_t; ++s) {
+        k_pc_dif_stage<<<pc_grid(total / 2, 256), 256, 0, st>>>(buf, log_t, s, total / 2, p->tw, log_N, tw_shift);
         ++p->launches;
-        // forward transforms on the 32 cosets
-        const bool direct = log_n <= PC_SMEM_LOG;
-        dim3 grid((unsigned)(1u << (log_n - log_m)), PC_COSETS, PC_SLICES);
-        k_pc_ntt_smem<<<grid, threads, sizeof(F) << log_m, st>>>(p->coef, log_n, log_m, p->tw, log_N, direct ? p->l_eval : p->work, direct ? 1 : 0);
-        ++p->launches;
-        if (!direct) {
-            const size_t pairs = ((size_t)PC_SLICES * PC_COSETS << log_n) / 2;
-            for (uint32_t s = log_m; s < log_n; ++s) {
-                k_pc_dit_stage<<<pc_grid(pairs, 256), 256, 0, st>>>(p->work, log_n, s, pairs, p->tw, log_N, p->l_eval, s == log_n - 1 ? 1 : 0);
-                ++p->launches;
-            }
-        }
     }
-    PCK(cudaMemsetAsync(p->l_eval + ((size_t)PC_SLICES << log_N), 0, p->N * sizeof(F), st));   // the zero mask's codeword
-    // leaves + tree
+    const unsigned threads = (unsigned)std::max<size_t>(32, std::min<size_t>(512, ((size_t)1 << log_m) / 2));
+    k_pc_intt_smem<<<(unsigned)(total >> log_m), threads, sizeof(F) << log_m, st>>>(buf, log_t, log_m, p->tw, log_N, inv, tw_shift);
+    ++p->launches;
+}
+static void pc_encode(PcCommit* p, const F* d_array, size_t n_valid, F* eval, cudaStream_t st) {
+    const size_t total = (size_t)PC_SLICES << p->log_n;
+    if (n_valid > total) throw std::runtime_error("polynomial commitment: array longer than 2^log_len");
+    pc_twiddles(p, st);
+    k_pc_pad<<<pc_grid(total, 256), 256, 0, st>>>(d_array, n_valid, p->coef, total);
+    ++p->launches;
+    pc_inverse(p, p->coef, (uint32_t)p->log_n, PC_SLICES, p->inv_n, st);
+    pc_extend(p, p->coef, p->n, 1, 0, eval, st);
+    PCK(cudaMemsetAsync(eval + ((size_t)PC_SLICES << p->log_N), 0, p->N * sizeof(F), st));   // the zero mask's codeword
+}
+// leaves + tree over eval[65][N] (mask slice zero) -> tree (array heap), root to the host
+static void pc_merkle(PcCommit* p, const F* eval, uint64_t* tree, cudaStream_t st) {
     const uint32_t half = (uint32_t)(p->N / 2);
-    PCK(cudaMemsetAsync(p->tree, 0, 64, st));   // nodes 0 and 1 (node 1 is overwritten unless there is a single leaf... then it IS the leaf)
-    k_pc_leaf_hash<<<(half + 127) / 128, 128, 0, st>>>(p->l_eval, log_N, p->tree + (size_t)half * 4, 1);
+    PCK(cudaMemsetAsync(tree, 0, 64, st));   // nodes 0 and 1 (node 1 is overwritten: there are always >= 16 leaves)
+    k_pc_leaf_hash<<<(half + 127) / 128, 128, 0, st>>>(eval, (uint32_t)p->log_N, tree + (size_t)half * 4, 1);
     ++p->launches;
     uint32_t lvl = half / 2;
     for (; lvl > 128; lvl >>= 1) {
-        k_pc_merkle_level<<<(lvl + 127) / 128, 128, 0, st>>>(p->tree, lvl);
+        k_pc_merkle_level<<<(lvl + 127) / 128, 128, 0, st>>>(tree, lvl);
         ++p->launches;
     }
     if (lvl >= 1) {
-        k_pc_merkle_top<<<1, 128, 0, st>>>(p->tree, lvl);
+        k_pc_merkle_top<<<1, 128, 0, st>>>(tree, lvl);
         ++p->launches;
     }
+}
+
+float pc_commit(PcCommit* p, const F* d_array, size_t n_valid, cudaStream_t st, uint8_t root[32]) {
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaEventRecord(p->e0, st));
+    pc_encode(p, d_array, n_valid, p->l_eval, st);
+    pc_merkle(p, p->l_eval, p->tree, st);
     PCK(cudaEventRecord(p->e1, st));
     PCK(cudaGetLastError());
     PCK(cudaMemcpyAsync(root, p->tree + 4, 32, cudaMemcpyDeviceToHost, st));
@@ -390,6 +449,53 @@ float pc_commit(PcCommit* p, const F* d_array, size_t n_valid, cudaStream_t st, 
     float ms = 0;
     PCK(cudaEventElapsedTime(&ms, p->e0, p->e1));
     return ms;
+}
+
+// commit_public_array (poly_commit.h:126-349) for zero masks, after pc_commit on the same object (needs l_eval):
+// q_eval = the public array encoded like the private one; per slice the 2n coefficients of l*q from its values on the
+// 2n-th roots; h = the upper n coefficients, extended to all N points; the virtual oracle and all_sum; the Merkle
+// commitment of h_eval_arr (fri::request_init_commit(.., 1)).
+float pc_commit_public(PcCommit* p, const F* d_pub, size_t n_valid, cudaStream_t st, uint8_t root_h[32], F all_sum_host[65]) {
+    PCK(cudaSetDevice(p->device));
+    const uint32_t log_n = (uint32_t)p->log_n, log_N = (uint32_t)p->log_N;
+    if (!p->q_eval) {
+        PCK(cudaMalloc(&p->q_eval, (size_t)(PC_SLICES + 1) * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->h_eval, (size_t)(PC_SLICES + 1) * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->vow, (size_t)PC_SLICES * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->lqc, (size_t)PC_SLICES * 2 * p->n * sizeof(F)));
+        PCK(cudaMalloc(&p->all_sum, (PC_SLICES + 1) * sizeof(F)));
+        PCK(cudaMalloc(&p->tree_h, p->N * 32));
+    }
+    PCK(cudaEventRecord(p->e0, st));
+    pc_encode(p, d_pub, n_valid, p->q_eval, st);
+    const size_t n_lq = (size_t)PC_SLICES << (log_n + 1), n_pts = (size_t)PC_SLICES << log_N;
+    k_pc_lq<<<pc_grid(n_lq, 256), 256, 0, st>>>(p->l_eval, p->q_eval, log_n, log_N, p->lqc, n_lq);
+    ++p->launches;
+    pc_inverse(p, p->lqc, log_n + 1, PC_SLICES, p->inv_2n, st);
+    // h's coefficient j (natural) is coefficient n + j of l*q = position (bitrev(j) << 1) | 1 of the bit-reversed output
+    pc_extend(p, p->lqc, 2 * p->n, 2, 1, p->h_eval, st);
+    PCK(cudaMemsetAsync(p->h_eval + ((size_t)PC_SLICES << log_N), 0, p->N * sizeof(F), st));
+    PCK(cudaMemsetAsync(p->all_sum, 0, (PC_SLICES + 1) * sizeof(F), st));
+    k_pc_vow<<<pc_grid(n_pts, 256), 256, 0, st>>>(p->l_eval, p->q_eval, p->h_eval, p->lqc, p->tw, log_n, log_N, p->vow, p->all_sum, n_pts);
+    ++p->launches;
+    pc_merkle(p, p->h_eval, p->tree_h, st);
+    PCK(cudaEventRecord(p->e1, st));
+    PCK(cudaGetLastError());
+    PCK(cudaMemcpyAsync(root_h, p->tree_h + 4, 32, cudaMemcpyDeviceToHost, st));
+    if (all_sum_host) PCK(cudaMemcpyAsync(all_sum_host, p->all_sum, (PC_SLICES + 1) * sizeof(F), cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    float ms = 0;
+    PCK(cudaEventElapsedTime(&ms, p->e0, p->e1));
+    return ms;
+}
+void pc_export_public(PcCommit* p, cudaStream_t st, F* h_eval, F* vow, uint8_t* leaf_hash, uint8_t* tree) {
+    PCK(cudaSetDevice(p->device));
+    if (!p->q_eval) throw std::runtime_error("polynomial commitment: export before commit_public");
+    if (h_eval) PCK(cudaMemcpyAsync(h_eval, p->h_eval, (size_t)(PC_SLICES + 1) * p->N * sizeof(F), cudaMemcpyDeviceToHost, st));
+    if (vow) PCK(cudaMemcpyAsync(vow, p->vow, (size_t)PC_SLICES * p->N * sizeof(F), cudaMemcpyDeviceToHost, st));
+    if (leaf_hash) PCK(cudaMemcpyAsync(leaf_hash, p->tree_h + (p->N / 2) * 4, (p->N / 2) * 32, cudaMemcpyDeviceToHost, st));
+    if (tree) PCK(cudaMemcpyAsync(tree, p->tree_h, p->N * 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
 }
 
 void pc_export(PcCommit* p, cudaStream_t st, F* l_eval, uint8_t* leaf_hash, uint8_t* tree) {

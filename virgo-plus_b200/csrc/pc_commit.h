@@ -26,6 +26,11 @@ size_t pc_slice_size(const PcCommit* p);
 // copies to the host (any pointer may be null): l_eval [65 * slice_size], leaf hashes [slice_size / 2 * 32 B],
 // Merkle tree [slice_size * 32 B] as the array heap of merkle_tree.cpp (node 1 = root, node 0 unused = zero)
 void pc_export(PcCommit* p, cudaStream_t stream, F* l_eval, uint8_t* leaf_hash, uint8_t* tree);
+// commit_public_array (lib/virgo/src/poly_commit.h:126-349, zero masks) on the object pc_commit ran on: d_pub = the
+// public array (n_valid elements on the device, zero-padded). Leaves the root of the second commitment (h) in root_h and
+// all_sum[65] on the host. pc_export_public: h_eval_arr [65 N], virtual oracle [64 N], leaf hashes, tree of h.
+float pc_commit_public(PcCommit* p, const F* d_pub, size_t n_valid, cudaStream_t stream, uint8_t root_h[32], F all_sum_host[65]);
+void pc_export_public(PcCommit* p, cudaStream_t stream, F* h_eval, F* vow, uint8_t* leaf_hash, uint8_t* tree);
 uint64_t pc_launches(const PcCommit* p);
 
 }  // namespace vp

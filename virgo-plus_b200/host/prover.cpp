@@ -26,7 +26,7 @@ inline vp_F *mf(F *p) { return reinterpret_cast<vp_F *>(p); }
 }  // namespace
 
 // prover.cpp:14-25: evaluate, then fail if an assert gate is non-zero.
-prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr), sumcheckLayerId(0), world(1) {
+prover::prover(const layeredCircuit &cir) : C(cir), circ(nullptr), ctx(nullptr), sumcheckLayerId(0), world(1), gpu_commit(false) {
     const int n = C.size;
     std::vector<uint64_t> layer_size(n), u, v, lv, dad_size((size_t)n * n, 0), dad_id;
     std::vector<uint8_t> ty, is_assert;
@@ -189,6 +189,7 @@ virgo::__hhash_digest prover::commit_private() {
         for (u64 g = 0; g < C.circuit[0].size; ++g) input_values[g] = F((long long)C.circuit[0].gates[g].u);   // prover.cpp:30-36
         return poly_prover.commit_private_array(input_values.data(), bl, mask);
     }
+    gpu_commit = true;
     const auto t0 = std::chrono::high_resolution_clock::now();
     __hhash_digest root;
     ck(vp_commit_private(ctx, cf(mask.data()), mask.size(), reinterpret_cast<uint8_t *>(&root)), "vp_commit_private");
@@ -254,10 +255,78 @@ F prover::inner_prod(const vector<F> &a, const vector<F> &b, u64 l) {
     return out;
 }
 
-// prover.cpp:542-546
+// prover.cpp:542-546 -> commit_public_array (lib/virgo/src/poly_commit.h:126-349). The inner product, the encoding of the
+// public array, the 2n-point products / inverse FFT / quotient extension per slice, the virtual oracle and the second
+// Merkle commitment run on the device (vp_inner_prod, vp_commit_public); as in commit_private, the process-global arrays
+// the reference's FRI rounds and verifier read afterwards are allocated and indexed exactly as there and filled from the
+// device results (poly_commit.h:131-136,202,303-330; fri.cpp:36-139 for oracle 1).
 virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum, std::vector<F> &mask,
                                             vector<F> &all_sum) {
+    using namespace virgo;
     ck(vp_inner_prod(ctx, cf(pub.data()), C.circuit[0].size, mf(&inner_product_sum)), "vp_inner_prod");
-    return poly_prover.commit_public_array(mask, pub.data(), C.circuit[0].bitLength, inner_product_sum, all_sum.data());
+    const int bl = C.circuit[0].bitLength;
+    bool zero_mask = true;
+    for (const F &m : mask) zero_mask = zero_mask && m == F_ZERO;
+    if (!gpu_commit || !zero_mask)
+        return poly_prover.commit_public_array(mask, pub.data(), bl, inner_product_sum, all_sum.data());
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    __hhash_digest root_h;
+    std::vector<vp_F> sums(slice_number + 1);
+    ck(vp_commit_public(ctx, cf(pub.data()), pub.size(), cf(mask.data()), mask.size(), reinterpret_cast<uint8_t *>(&root_h), sums.data()),
+       "vp_commit_public");
+    const int slice_size = poly_commit::slice_size, slice_count = poly_commit::slice_count, half = slice_size / 2;
+    for (int i = 0; i < slice_count; ++i) all_sum[i] = F((long long)sums[i].re, (long long)sums[i].im);
+    // ---- poly_commit.h:131-136,202: arrays of the virtual oracle and of h
+    fri::virtual_oracle_witness = new fieldElement[slice_size * slice_count];
+    fri::virtual_oracle_witness_msk = new fieldElement[slice_size]();
+    fri::virtual_oracle_witness_msk_mapping = new int[slice_size];
+    fri::virtual_oracle_witness_mapping = new int[slice_size * slice_count];
+    poly_commit::q_eval_len = poly_commit::l_eval_len;
+    poly_commit::q_eval = new fieldElement[1];                       // (only read inside commit_public_array itself)
+    while (mask.size() < (size_t)(slice_size / poly_commit::mask_position_gap)) mask.push_back(F_ZERO);   // :139-140
+    poly_commit::all_pub_msk_arr = new fieldElement[mask.size()]();
+    poly_commit::h_eval_arr = new fieldElement[slice_count * slice_size];
+    fri::leaf_hash[1] = new __hhash_digest[half];
+    fri::witness_merkle[1] = (__hhash_digest *)malloc((size_t)half * 2 * sizeof(__hhash_digest));
+    ck(vp_commit_public_export(ctx, mf(poly_commit::h_eval_arr), mf(fri::virtual_oracle_witness), reinterpret_cast<uint8_t *>(fri::leaf_hash[1]),
+                               reinterpret_cast<uint8_t *>(fri::witness_merkle[1])),
+       "vp_commit_public_export");
+    const int log_leaf_size = log_slice_number + 1;
+    for (int j = 0; j < slice_size; ++j)                              // :258-266 (mask slice: values zero)
+        fri::virtual_oracle_witness_msk_mapping[j] = (j < half ? j : j - half) << 1;
+    for (int i = 0; i < slice_number; ++i)                            // :310-321
+        for (int j = 0; j < slice_size; ++j) {
+            const int jj = j < half ? j : j - half;
+            fri::virtual_oracle_witness_mapping[jj << log_slice_number | i] = jj << log_leaf_size | (i << 1) | 0;
+        }
+    // ---- fri.cpp:36-139 (request_init_commit, oracle 1)
+    const int lw = bl + rs_code_rate - log_slice_number;
+    fri::__fri_timer = 0;
+    fri::current_step_no = 0;
+    fri::log_current_witness_size_per_slice = lw;
+    fri::witness_bit_length_per_slice = bl - log_slice_number;
+    merkle_tree::size_after_padding = half;
+    fri::witness_rs_codeword_interleaved[1] = new fieldElement[1 << (bl + rs_code_rate)];
+    for (int i = 0; i < slice_number; ++i) {
+        fri::witness_rs_codeword_before_arrange[1][i] = &poly_commit::h_eval_arr[i * slice_size];
+        fri::witness_rs_mapping[1][i] = new int[1 << lw];
+        const fieldElement *src = fri::witness_rs_codeword_before_arrange[1][i];
+        for (int j = 0; j < half; ++j) {
+            const int at = (j << log_leaf_size) | (i << 1);
+            fri::witness_rs_mapping[1][i][j] = at;
+            fri::witness_rs_mapping[1][i][j + half] = at;
+            fri::witness_rs_codeword_interleaved[1][at] = src[j];
+            fri::witness_rs_codeword_interleaved[1][at | 1] = src[j + half];
+        }
+    }
+    witness_merkle_size[1] = half;
+    fri::visited_init[1] = new bool[1 << lw]();
+    fri::visited_witness[1] = new bool[1 << (bl + rs_code_rate)]();
+    const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    poly_prover.total_time += dt;
+    if (getenv("VP_TIMING"))
+        fprintf(stderr, "virgo_b200 prover: commit_public %.3f ms (device %.3f ms, the rest: copies + the reference's bookkeeping arrays)\n",
+                dt * 1e3, (double)vp_last_commit_ms(ctx));
+    return root_h;
 }
 #endif

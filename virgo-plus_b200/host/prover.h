@@ -61,5 +61,6 @@ private:
     vp_ctx *ctx;
     int sumcheckLayerId;
     int world;                    // GPUs this prover is sharded over (VP_WORLD copies of the program, one per GPU)
+    bool gpu_commit;              // commit_private ran on the device: commit_public does too
     std::vector<F> input_values;  // host copy of circuitValue[0], zero-padded to 2^bitLength (for the PC)
 };

@@ -215,6 +215,23 @@ int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t r
 int vp_pc_commit_public(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, uint8_t root_l[32],
                         uint8_t root_h[32], vp_F all_sum[65], vp_F* h_eval, vp_F* vow, float* device_ms);
 
+/* FRI commit phase (fri::commit_phase_step, lib/virgo/src/fri.cpp:289-418, as poly_commit_prover::commit_phase drives it,
+ * vpd_verifier.cpp:43-73) on the virtual oracle vp_commit_public left on the device. One step per fold challenge: every
+ * slice's codeword f on the M-th roots becomes g(x^2) = (f(x) + f(-x))/2 + r (f(x) - f(-x))/(2x) on the M/2-th roots, the
+ * M/4 leaves (one pair of opposite points of all 64 slices + the zero mask pair each) are hashed and the level's tree
+ * built; roots[k] = the root after step k. vp_fri_steps(ctx) = bitLength(0) - 6 steps leave 32 points per slice (the
+ * reference stops there). vp_fri_export_level: level lvl's codewords in the layout of fri::cpd.rs_codeword[lvl]
+ * (64 * (slice_size >> (lvl+1)) elements) and its tree (array heap, (slice_size >> (lvl+1)) nodes of 32 bytes); any pointer
+ * may be NULL. vp_fri_restart: back to step 0 on the same virtual oracle. Challenges must be canonical. */
+int vp_fri_commit_steps(vp_ctx* ctx, const vp_F* randomness, int n_steps, uint8_t* roots /* n_steps * 32 */);
+int vp_fri_steps(const vp_ctx* ctx);
+int vp_fri_restart(vp_ctx* ctx);
+int vp_fri_export_level(vp_ctx* ctx, int lvl, vp_F* rs_codeword, uint8_t* merkle);
+/* Stand-alone: both commitments of host arrays (as vp_pc_commit_public), then n_steps <= log_len - 6 FRI steps.
+ * codes / trees (may be NULL): the levels back to back. 7 <= log_len <= 30. */
+int vp_pc_fri(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, const vp_F* randomness, int n_steps,
+              uint8_t root_l[32], uint8_t root_h[32], uint8_t* roots, vp_F* codes, uint8_t* trees, float* device_ms);
+
 /* ------------------------------------------------------------------ Fiat-Shamir mode
  * The reference ships a hash-based challenge source, transcriptCache (lib/virgo/src/transcriptCache.hpp:14-50: a byte
  * pool hashed with SHA3-256 per challenge, challenge = first two digest words mod p), but never calls it. This mode uses

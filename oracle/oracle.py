@@ -260,7 +260,57 @@ def pc_commit_public(array, pub, log_len):
     return dict(root_h=root.tobytes(), all_sum=all_sum, h_eval=h_eval, vow=vow, slice_size=N)
 
 
+def pc_fri_commit_phase(vow, log_N, randomness):
+    """fri::commit_phase_step restated (fri.cpp:289-418), one step per element of `randomness`, from the virtual oracle
+    -> dict(roots [steps] bytes, codes [per level np array], trees [per level bytes])"""
+    L = lib()
+    L.opc_fri_commit_phase.restype = C.c_long
+    L.opc_fri_commit_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    N, steps = 1 << log_N, len(randomness)
+    v = np.ascontiguousarray(vow, F_DTYPE)
+    assert len(v) == 64 * N
+    r = np.ascontiguousarray(randomness, F_DTYPE)
+    sizes = [N >> (l + 1) for l in range(steps)]
+    roots = np.zeros(32 * steps, np.uint8)
+    codes = np.zeros(64 * sum(sizes), F_DTYPE)
+    trees = np.zeros(32 * sum(sizes), np.uint8)
+    rc = L.opc_fri_commit_phase(_p(v), log_N, _p(r), steps, _p(roots), _p(codes), _p(trees))
+    assert rc == steps, rc
+    out, o = dict(roots=[roots[32 * l:32 * l + 32].tobytes() for l in range(steps)], codes=[], trees=[]), 0
+    for m in sizes:
+        out["codes"].append(codes[64 * o:64 * (o + m)])
+        out["trees"].append(trees[32 * o:32 * (o + m)].tobytes())
+        o += m
+    return out
+
+
 REF_PC = os.path.join(REF_DIR, "ref_pc_commit")
+
+
+def ref_pc_fri(array, pub, log_len, randomness):
+    """the UNMODIFIED reference: commit_private_array, commit_public_array, then fri::commit_phase_step per element of
+    `randomness` (log_len - 6 of them) -> dict(root_l, root_h, roots, codes, trees, seconds)"""
+    import tempfile
+    a = np.zeros(1 << log_len, F_DTYPE); a[:len(array)] = array
+    q = np.zeros(1 << log_len, F_DTYPE); q[:len(pub)] = pub
+    r = np.ascontiguousarray(randomness, F_DTYPE)
+    steps, N = log_len - 6, 1 << (log_len - 1)
+    assert len(r) == steps
+    with tempfile.TemporaryDirectory() as td:
+        fa, fq, fo, fo2, fr, fo3 = (os.path.join(td, x) for x in ("a.bin", "q.bin", "o.bin", "o2.bin", "r.bin", "o3.bin"))
+        a.tofile(fa); q.tofile(fq); r.tofile(fr)
+        pr = subprocess.run([REF_PC, str(log_len), fa, fo, fq, fo2, fr, fo3], capture_output=True, text=True, check=True)
+        root_l = np.fromfile(fo, dtype=np.uint8, count=32).tobytes()
+        root_h = np.fromfile(fo2, dtype=np.uint8, count=32).tobytes()
+        raw = np.fromfile(fo3, dtype=np.uint8)
+    out = dict(root_l=root_l, root_h=root_h, roots=[raw[32 * l:32 * l + 32].tobytes() for l in range(steps)], codes=[], trees=[],
+               seconds=float(pr.stdout.split("fri_commit_seconds")[1]))
+    o = 32 * steps
+    for l in range(steps):
+        m = N >> (l + 1)
+        out["codes"].append(raw[o:o + 64 * m * 16].view(F_DTYPE)); o += 64 * m * 16
+        out["trees"].append(raw[o:o + m * 32].tobytes()); o += m * 32
+    return out
 
 
 def ref_pc_commit_public(array, pub, log_len):

@@ -295,3 +295,68 @@ long opc_commit_public(const ofe* array, const ofe* pub, int log_len, ofe* all_s
     free(l_eval); free(q_eval); free(h_eval); free(vow); free(tmp); free(lq); free(tree);
     return N;
 }
+
+/* ------------------------------------------------------------------ FRI commit phase
+ * fri::commit_phase_step (fri.cpp:289-418) as poly_commit_prover::commit_phase drives it (vpd_verifier.cpp:43-73: one step
+ * per randomness until 32 points per slice are left), starting from the virtual oracle of commit_public_array, with the
+ * zero mask codeword of the GKR use (rs_codeword_msk stays zero).
+ * A level holds, per slice j, a codeword f_j of M points on the M-th roots, stored as pairs of opposite points:
+ *   f_j[k] at  (k mod M/2) << 7 | j << 1 | (k >= M/2)          (virtual_oracle_witness_mapping / rs_codeword_mapping)
+ * one step: g_j[i] = ( f_j[i] + f_j[i + M/2]  +  r w_M^-i ( f_j[i] - f_j[i + M/2] ) ) / 2,  i < M/2   (:316-337; pos == i always:
+ * (M/2 + i)/2 >= i for i < M/2), stored the same way with M/2 for M (:339-357); leaf i < M/4 = the SHA3 chain over the
+ * 64 pairs of leaf i and then the (zero) mask pair (:383-404); array-heap tree over the M/4 leaves (:405).
+ *   vow: 64 N elements; randomness: n_steps elements, n_steps <= log_N - 5.
+ * Outputs (any may be NULL): roots [n_steps * 32]; codes: the levels back to back, level l = 64 * (N >> (l+1)) elements;
+ * trees: level l = (N >> (l+1)) * 32 bytes (node 0 zero, node 1 the root). Returns the number of steps done, or -1. */
+long opc_fri_commit_phase(const ofe* vow, int log_N, const ofe* randomness, int n_steps, unsigned char* roots_out, ofe* codes_out,
+                          unsigned char* trees_out) {
+    const int LOG_SLICE = 6, RATE = 5, SLICES = 1 << LOG_SLICE;
+    if (log_N < RATE || n_steps < 0 || n_steps > log_N - RATE) return -1;
+    const size_t N = (size_t)1 << log_N;
+    const ofe two = {2, 0};
+    const ofe inv2 = f_pow(two, (unsigned __int128)2305843009213693951ULL - 2);
+    ofe* prev = (ofe*)malloc((size_t)SLICES * N * sizeof(ofe));
+    memcpy(prev, vow, (size_t)SLICES * N * sizeof(ofe));
+    size_t code_off = 0, tree_off = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const size_t M = N >> s, half = M / 2, quarter = M / 4;
+        const ofe r = randomness[s];
+        const ofe w = opc_root_of_unity(log_N - s);
+        const ofe w_inv = f_pow(w, (unsigned __int128)(M - 1));
+        ofe* cur = (ofe*)malloc((size_t)SLICES * half * sizeof(ofe));
+        ofe inv_mu = ONE;   /* w_M^-i */
+        for (size_t i = 0; i < half; ++i) {
+            const ofe rm = ofe_mul(inv_mu, r);
+            for (int j = 0; j < SLICES; ++j) {
+                const ofe a = prev[(i << (LOG_SLICE + 1)) | ((size_t)j << 1)], b = prev[(i << (LOG_SLICE + 1)) | ((size_t)j << 1) | 1];
+                const ofe v = ofe_mul(inv2, ofe_add(ofe_add(a, b), ofe_mul(rm, ofe_sub(a, b))));
+                cur[((i % quarter) << (LOG_SLICE + 1)) | ((size_t)j << 1) | (i >= quarter)] = v;
+            }
+            inv_mu = ofe_mul(inv_mu, w_inv);
+        }
+        unsigned char* tree = (unsigned char*)calloc(half, 32);
+        for (size_t i = 0; i < quarter; ++i) {
+            unsigned char h[32], data[64];
+            memset(h, 0, 32);
+            for (int j = 0; j <= SLICES; ++j) {
+                if (j < SLICES) memcpy(data, &cur[(i << (LOG_SLICE + 1)) | ((size_t)j << 1)], 32);
+                else memset(data, 0, 32);   /* rs_codeword_msk: zero */
+                memcpy(data + 32, h, 32);
+                hhash64(data, h);
+            }
+            memcpy(tree + (quarter + i) * 32, h, 32);
+        }
+        for (size_t lvl = quarter / 2; lvl >= 1; lvl /= 2)
+            for (size_t i = 0; i < lvl; ++i) hhash64(tree + (2 * (lvl + i)) * 32, tree + (lvl + i) * 32);
+        if (roots_out) memcpy(roots_out + (size_t)s * 32, tree + 32, 32);
+        if (codes_out) memcpy(codes_out + code_off, cur, (size_t)SLICES * half * sizeof(ofe));
+        if (trees_out) memcpy(trees_out + tree_off, tree, half * 32);
+        code_off += (size_t)SLICES * half;
+        tree_off += half * 32;
+        free(tree);
+        free(prev);
+        prev = cur;
+    }
+    free(prev);
+    return n_steps;
+}

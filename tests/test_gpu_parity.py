@@ -724,3 +724,87 @@ def test_pc_commit_public_long_transforms_vs_oracle(B, O):
     _assert_same(got["h_eval"], want["h_eval"], "h_eval")
     _assert_same(got["vow"], want["vow"], "virtual oracle")
     assert got["root_h"] == want["root_h"]
+
+
+def _fri_tools():
+    import importlib.util
+    import json
+    import os
+    import helpers as H
+    spec = importlib.util.spec_from_file_location("make_golden_pc_fri", os.path.join(H.GOLDEN, "make_golden_pc_fri.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    with open(os.path.join(H.GOLDEN, "pc_fri.json")) as f:
+        return mk, json.load(f)
+
+
+@pytest.mark.parametrize("name", ["random_9_3", "random_10_4", "random_12_6", "sha256_64", "random_16_9"])
+def test_pc_fri_commit_phase_matches_reference_golden(B, O, name):
+    """device FRI commit phase (fold, leaf chains, tree per level) == what the reference's fri::commit_phase_step produced
+    from its own virtual oracle: every level's root, all codewords, all trees"""
+    mk, golden = _fri_tools()
+    g = golden[name]
+    a, q, b, r = mk.case_inputs(B, O, name)
+    got = B.pc_fri(a, q, b, r)
+    assert got["root_l"].hex() == g["root_l"] and got["root_h"].hex() == g["root_h"]
+    d = mk.digest_of(got["roots"], got["codes"], got["trees"])
+    if d["codes_sha256"] != g["codes_sha256"] and b <= 13:
+        want = O.pc_fri_commit_phase(O.pc_commit_public(a, q, b)["vow"], b - 1, r)
+        for l, (x, y) in enumerate(zip(got["codes"], want["codes"])):
+            _assert_same(x, y, "codewords of level %d" % l)
+    for k in ("roots", "codes_sha256", "trees_sha256", "final_sha256"):
+        assert d[k] == g[k], k
+
+
+def test_pc_fri_on_context_stepwise_and_restart(B, O, sha_circuit):
+    """the context path the drop-in prover uses: commit_private, commit_public, then the steps one by one == all at once ==
+    the oracle; exported levels equal the oracle's; too many steps / steps before commit_public are refused"""
+    rng = np.random.default_rng(12)
+    c = sha_circuit
+    b = c.bit_length(0)
+    p = B.Prover(c)
+    p.evaluate()
+    with pytest.raises(B.VpError):
+        p.fri_commit_steps(_rand_fe(B, rng, 1))              # no commitment yet
+    p.commit_private()
+    with pytest.raises(B.VpError):
+        p.fri_commit_steps(_rand_fe(B, rng, 1))              # no virtual oracle yet
+    q = O.beta_table(_rand_fe(B, rng, b))
+    root_h, _ = p.commit_public(q)
+    r = _rand_fe(B, rng, b - 6)
+    assert p.fri_steps == b - 6
+    one_by_one = [p.fri_commit_steps(r[k:k + 1])[0] for k in range(len(r))]
+    with pytest.raises(B.VpError):
+        p.fri_commit_steps(r[:1])                             # finished: 32 points per slice left
+    p.fri_restart()
+    at_once = p.fri_commit_steps(r)
+    assert one_by_one == at_once
+    a = np.zeros(c.num_inputs, B.F_DTYPE)
+    a["re"] = c.inputs()
+    pub = O.pc_commit_public(a, q, b)
+    assert pub["root_h"] == root_h
+    want = O.pc_fri_commit_phase(pub["vow"], b - 1, r)
+    assert at_once == want["roots"]
+    for lvl in (0, len(r) - 1):
+        code, tree = p.fri_export_level(lvl)
+        _assert_same(code, want["codes"][lvl], "level %d" % lvl)
+        assert tree[32:] == want["trees"][lvl][32:]
+    bad = r.copy()
+    bad[0]["re"] = (1 << 61) - 1
+    p.fri_restart()
+    with pytest.raises(B.VpError):
+        p.fri_commit_steps(bad)                               # not canonical
+    p.close()
+
+
+def test_pc_fri_full_size_roots_equal_reference(B, O):
+    """BASELINE size: the 7.4 M inputs of SHA256_64 x 1024 (2^23 padded): every FRI level's root and the final codewords
+    equal the reference's (golden made by make_golden_pc_fri.py --full)"""
+    mk, golden = _fri_tools()
+    if "sha256_64_x1024" not in golden:
+        pytest.skip("no full-size case in pc_fri.json")
+    g = golden["sha256_64_x1024"]
+    a, q, b, r = mk.case_inputs(B, O, "sha256_64_x1024")
+    got = B.pc_fri(a, q, b, r, want_arrays=False)
+    assert got["root_l"].hex() == g["root_l"] and got["root_h"].hex() == g["root_h"]
+    assert [x.hex() for x in got["roots"]] == g["roots"]

@@ -347,3 +347,68 @@ def test_pc_oracle_matches_reference_commit_public(B, O, name):
     got = mk.digest_of(O.pc_commit_public(a, q, b))
     for k in ("root_h", "all_sum_sha256", "h_eval_sha256", "vow_sha256", "slice_size"):
         assert got[k] == g[k], k
+
+
+def _fri_tools():
+    import json
+    spec = importlib.util.spec_from_file_location("make_golden_pc_fri", os.path.join(H.GOLDEN, "make_golden_pc_fri.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    with open(os.path.join(H.GOLDEN, "pc_fri.json")) as f:
+        return mk, json.load(f)
+
+
+@pytest.mark.parametrize("name", ["random_9_3", "random_10_4", "random_12_6", "sha256_64"])
+def test_pc_oracle_matches_reference_fri_commit_phase(B, O, name):
+    """pc_oracle.c's FRI commit phase == the reference's fri::commit_phase_step run on its own virtual oracle: the root of
+    every level, all level codewords and trees (golden: make_golden_pc_fri.py)"""
+    mk, golden = _fri_tools()
+    g = golden[name]
+    a, q, b, r = mk.case_inputs(B, O, name)
+    pub = O.pc_commit_public(a, q, b)
+    assert pub["root_h"].hex() == g["root_h"]
+    got = O.pc_fri_commit_phase(pub["vow"], b - 1, r)
+    d = mk.digest_of(got["roots"], got["codes"], got["trees"])
+    assert len(d["roots"]) == b - 6
+    for k in ("roots", "codes_sha256", "trees_sha256", "final_sha256"):
+        assert d[k] == g[k], k
+
+
+def test_pc_oracle_fri_fold_is_the_even_odd_split(O):
+    """size-independent property of one step, checked with plain Python integers: the codeword of a polynomial f folds to
+    the codeword of f_even + r f_odd on the squared domain (what makes the phase a low-degree test)"""
+    P = (1 << 61) - 1
+    rng = np.random.default_rng(77)
+    log_N, n = 8, 8                                           # 256 points, degree < 8
+    N = 1 << log_N
+    mul = lambda x, y: ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+    add = lambda x, y: ((x[0] + y[0]) % P, (x[1] + y[1]) % P)
+    w = (2147483648, 1033321771269002680)                     # order 2^62 (fieldElement.cpp:240-241)
+    for _ in range(62 - log_N):
+        w = mul(w, w)
+    pw = [(1, 0)]
+    for _ in range(N - 1):
+        pw.append(mul(pw[-1], w))
+    assert mul(pw[-1], w) == (1, 0) and pw[N // 2] == (P - 1, 0)
+    coef = [[(int(rng.integers(0, P)), int(rng.integers(0, P))) for _ in range(n)] for _ in range(64)]
+    r = (int(rng.integers(0, P)), int(rng.integers(0, P)))
+
+    def ev(c, x):
+        acc = (0, 0)
+        for a in reversed(c):
+            acc = add(mul(acc, x), a)
+        return acc
+    vow = np.zeros(64 * N, O.F_DTYPE)
+    for j in range(64):
+        for k in range(N):
+            vow[((k % (N // 2)) << 7) | (j << 1) | (1 if k >= N // 2 else 0)] = ev(coef[j], pw[k])
+    rr = np.zeros(1, O.F_DTYPE)
+    rr[0] = r
+    got = O.pc_fri_commit_phase(vow, log_N, rr)["codes"][0]
+    M = N // 2
+    for j in (0, 17, 63):
+        folded = [add(coef[j][2 * t], mul(r, coef[j][2 * t + 1])) for t in range(n // 2)]
+        for k in (0, 1, 5, M // 2, M - 1):
+            want = ev(folded, pw[(2 * k) % N])
+            at = ((k % (M // 2)) << 7) | (j << 1) | (1 if k >= M // 2 else 0)
+            assert (int(got[at]["re"]), int(got[at]["im"])) == want, (j, k)

@@ -114,6 +114,11 @@ def _declare(L):
     L.vp_pc_commit_public.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_commit_public.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp]
     L.vp_commit_public_export.argtypes = [vp, vp, vp, vp, vp]
+    L.vp_fri_commit_steps.argtypes = [vp, vp, C.c_int, vp]
+    L.vp_fri_steps.argtypes = [vp]
+    L.vp_fri_restart.argtypes = [vp]
+    L.vp_fri_export_level.argtypes = [vp, C.c_int, vp, vp]
+    L.vp_pc_fri.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_prove_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
     L.vp_fs_challenges.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
     L.vp_verify_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -396,6 +401,30 @@ def pc_commit_public(array, pub, log_len, device=0, want_arrays=True):
     return dict(root_l=root_l.tobytes(), root_h=root_h.tobytes(), all_sum=all_sum, h_eval=h_eval, vow=vow, slice_size=N, ms=ms.value)
 
 
+def pc_fri(array, pub, log_len, randomness, device=0, want_arrays=True):
+    """both commitments of host arrays, then one FRI commit step per fold challenge (fri::commit_phase_step)
+    -> dict(root_l, root_h, roots [steps], codes [per level], trees [per level], ms = device time of the steps)"""
+    a = np.ascontiguousarray(array, dtype=F_DTYPE)
+    q = np.ascontiguousarray(pub, dtype=F_DTYPE)
+    r = np.ascontiguousarray(randomness, dtype=F_DTYPE)
+    N, steps = 1 << (log_len - 1), len(r)
+    sizes = [N >> (l + 1) for l in range(steps)]
+    root_l, root_h, roots = np.zeros(32, np.uint8), np.zeros(32, np.uint8), np.zeros(32 * max(steps, 1), np.uint8)
+    codes = np.zeros(64 * sum(sizes), F_DTYPE) if want_arrays else None
+    trees = np.zeros(32 * sum(sizes), np.uint8) if want_arrays else None
+    ms = C.c_float()
+    _ck(lib().vp_pc_fri(device, _ptr(a), len(a), _ptr(q), len(q), log_len, _ptr(r), steps, _ptr(root_l), _ptr(root_h), _ptr(roots), _ptr(codes),
+                        _ptr(trees), C.byref(ms)))
+    out = dict(root_l=root_l.tobytes(), root_h=root_h.tobytes(), roots=[roots[32 * l:32 * l + 32].tobytes() for l in range(steps)], codes=[],
+               trees=[], ms=ms.value)
+    o = 0
+    for m in sizes if want_arrays else []:
+        out["codes"].append(codes[64 * o:64 * (o + m)])
+        out["trees"].append(trees[32 * o:32 * (o + m)].tobytes())
+        o += m
+    return out
+
+
 def shard_describe(circuit, world, rank, layer, phase):
     out = np.zeros(10 * 256, np.uint32)
     n = C.c_size_t()
@@ -564,6 +593,26 @@ class Prover:
         root, all_sum = np.zeros(32, np.uint8), np.zeros(65, F_DTYPE)
         _ck(lib().vp_commit_public(self.h, _ptr(q), len(q), _ptr(m), len(m), _ptr(root), _ptr(all_sum)))
         return root.tobytes(), all_sum
+
+    def fri_commit_steps(self, randomness):
+        """fri::commit_phase_step per fold challenge on the virtual oracle commit_public left on the device -> [root]"""
+        r = np.ascontiguousarray(randomness, dtype=F_DTYPE)
+        roots = np.zeros(32 * max(len(r), 1), np.uint8)
+        _ck(lib().vp_fri_commit_steps(self.h, _ptr(r), len(r), _ptr(roots)))
+        return [roots[32 * l:32 * l + 32].tobytes() for l in range(len(r))]
+
+    @property
+    def fri_steps(self):
+        return int(lib().vp_fri_steps(self.h))
+
+    def fri_restart(self):
+        _ck(lib().vp_fri_restart(self.h))
+
+    def fri_export_level(self, lvl):
+        m = int(lib().vp_commit_slice_size(self.h)) >> (lvl + 1)
+        code, tree = np.zeros(64 * m, F_DTYPE), np.zeros(32 * m, np.uint8)
+        _ck(lib().vp_fri_export_level(self.h, lvl, _ptr(code), _ptr(tree)))
+        return code, tree.tobytes()
 
     def commit_export(self):
         ss = int(lib().vp_commit_slice_size(self.h))

@@ -3392,6 +3392,81 @@ extern "C" int vp_pc_commit_public(int device, const vp_F* array, size_t n, cons
     return VP_OK;
     API_END
 }
+// fri::commit_phase_step (fri.cpp:289-418), n_steps of them from the context's current FRI level (0 right after
+// vp_commit_public): fold every slice's codeword with randomness[k], hash the leaves, build the level's tree.
+extern "C" int vp_fri_commit_steps(vp_ctx* ctx, const vp_F* randomness, int n_steps, uint8_t* roots) {
+    if (!ctx || !randomness || !roots || n_steps < 0) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_fri_commit_steps before vp_commit_public");
+    if (pc_fri_steps_done(e.pc) + n_steps > pc_fri_steps(e.pc))
+        return fail(VP_ERR_ARG, "vp_fri_commit_steps: %d steps asked, %d of %d already done", n_steps, pc_fri_steps_done(e.pc), pc_fri_steps(e.pc));
+    for (int k = 0; k < n_steps; ++k)
+        if (randomness[k].re >= P || randomness[k].im >= P) return fail(VP_ERR_ARG, "vp_fri_commit_steps: challenge %d is not canonical", k);
+    e.last_commit_ms = pc_fri_steps_run(e.pc, reinterpret_cast<const F*>(randomness), n_steps, e.stream, roots);
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_fri_steps(const vp_ctx* ctx) { return (ctx && ctx->e.pc) ? pc_fri_steps(ctx->e.pc) : 0; }
+extern "C" int vp_fri_restart(vp_ctx* ctx) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    if (!ctx->e.pc) return fail(VP_ERR_ARG, "vp_fri_restart before vp_commit_public");
+    pc_fri_restart(ctx->e.pc);
+    return VP_OK;
+    API_END
+}
+extern "C" int vp_fri_export_level(vp_ctx* ctx, int lvl, vp_F* rs_codeword, uint8_t* merkle) {
+    if (!ctx) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_fri_export_level before vp_fri_commit_steps");
+    if (lvl < 0 || lvl >= pc_fri_steps_done(e.pc)) return fail(VP_ERR_ARG, "vp_fri_export_level: level %d not computed (%d done)", lvl, pc_fri_steps_done(e.pc));
+    pc_fri_export(e.pc, e.stream, lvl, reinterpret_cast<F*>(rs_codeword), merkle);
+    return VP_OK;
+    API_END
+}
+// Stand-alone form: both commitments on host arrays, then the whole FRI commit phase with the given fold challenges.
+// codes / trees (may be NULL): the levels back to back (level l: 64 * (slice_size >> (l+1)) elements, (slice_size >> (l+1)) * 32 bytes).
+extern "C" int vp_pc_fri(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, const vp_F* randomness, int n_steps,
+                         uint8_t root_l[32], uint8_t root_h[32], uint8_t* roots, vp_F* codes, uint8_t* trees, float* device_ms) {
+    if (!array || !pub || !root_l || !root_h || !randomness || !roots) return fail(VP_ERR_ARG, "null argument");
+    if (log_len < 7 || log_len > 30 || n > ((size_t)1 << log_len) || n_pub > ((size_t)1 << log_len)) return fail(VP_ERR_ARG, "vp_pc_fri: log_len in [7, 30], n <= 2^log_len");
+    if (n_steps < 0 || n_steps > log_len - 6) return fail(VP_ERR_ARG, "vp_pc_fri: at most log_len - 6 steps");
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw CudaError{std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(ce)};
+    for (size_t i = 0; i < n; ++i)
+        if (array[i].re >= P || array[i].im >= P) return fail(VP_ERR_ARG, "vp_pc_fri: array element %zu is not canonical", i);
+    for (size_t i = 0; i < n_pub; ++i)
+        if (pub[i].re >= P || pub[i].im >= P) return fail(VP_ERR_ARG, "vp_pc_fri: public element %zu is not canonical", i);
+    for (int k = 0; k < n_steps; ++k)
+        if (randomness[k].re >= P || randomness[k].im >= P) return fail(VP_ERR_ARG, "vp_pc_fri: challenge %d is not canonical", k);
+    CK(cudaSetDevice(device));
+    struct Guard { PcCommit* p = nullptr; ~Guard() { if (p) pc_destroy(p); } } g;
+    g.p = pc_create(device, log_len);
+    DBuf<F> d, dq;
+    d.alloc(std::max<size_t>(n, 1));
+    dq.alloc(std::max<size_t>(n_pub, 1));
+    CK(cudaMemcpy(d.p, array, n * sizeof(F), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dq.p, pub, n_pub * sizeof(F), cudaMemcpyHostToDevice));
+    F all_sum[65];
+    pc_commit(g.p, d.p, n, 0, root_l);
+    pc_commit_public(g.p, dq.p, n_pub, 0, root_h, all_sum);
+    const float ms = pc_fri_steps_run(g.p, reinterpret_cast<const F*>(randomness), n_steps, 0, roots);
+    if (device_ms) *device_ms = ms;
+    const size_t N = pc_slice_size(g.p);
+    size_t off = 0;
+    for (int l = 0; l < n_steps; ++l) {
+        const size_t m = N >> (l + 1);
+        pc_fri_export(g.p, 0, l, codes ? reinterpret_cast<F*>(codes) + 64 * off : nullptr, trees ? trees + 32 * off : nullptr);
+        off += m;
+    }
+    return VP_OK;
+    API_END
+}
 // ------------------------------------------------------------------ C ABI: Fiat-Shamir mode (N4)
 extern "C" int vp_prove_fs(vp_ctx* ctx, const uint8_t seed[32], vp_F* transcript, size_t transcript_cap, vp_F* challenges, size_t challenges_cap) {
     if (!ctx || !seed || !transcript) return fail(VP_ERR_ARG, "null argument");

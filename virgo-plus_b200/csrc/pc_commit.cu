@@ -298,6 +298,50 @@ __global__ void __launch_bounds__(128) k_pc_merkle_top(uint64_t* __restrict__ tr
     }
 }
 
+// ---- FRI commit phase (fri.cpp:289-418). A level stores the 64 codewords of M points as pairs of opposite points:
+// point k of slice j at (k mod M/2) << 7 | j << 1 | (k >= M/2), so that leaf i of the level's tree is 2 KB of consecutive
+// memory. One thread folds the two pairs (i, i + M/2) and (i + M/4, i + 3M/4) of one slice into the pair (i, i + M/4) of
+// the next level: g[i] = ((a + b) + r w_M^-i (a - b)) / 2 -- two 32-byte loads, one 32-byte store per thread, a warp covers
+// 1 KB of each of the two source leaves.
+__global__ void k_pc_fri_fold(const F* __restrict__ prev, uint32_t log_M, const F* __restrict__ tw, uint32_t log_N, F r_half, F inv2,
+                              F* __restrict__ out, size_t total) {
+    const uint32_t N = 1u << log_N, quarter = 1u << (log_M - 2), sh = log_N - log_M;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(t >> PC_LOG_SLICES), j = (uint32_t)(t & (PC_SLICES - 1));
+        F v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t k = i + h * quarter;
+            const F* src = prev + (((size_t)k << (PC_LOG_SLICES + 1)) | ((size_t)j << 1));
+            const F a = pc_ld(src), b = pc_ld(src + 1);
+            const F inv_mu = pc_ld(tw + ((N - (k << sh)) & (N - 1)));                  // w_M^-k
+            v[h] = f_add(f_mul(inv2, f_add(a, b)), f_mul(f_mul(r_half, inv_mu), f_sub(a, b)));
+        }
+        F* dst = out + (((size_t)i << (PC_LOG_SLICES + 1)) | ((size_t)j << 1));
+        pc_st(dst, v[0]);
+        pc_st(dst + 1, v[1]);
+    }
+}
+// fri.cpp:383-404: leaf i of a level = chain over the 64 pairs of the leaf, then the (zero) pair of the mask codeword
+__global__ void __launch_bounds__(128) k_pc_fri_leaf_hash(const F* __restrict__ code, uint32_t n_leaves, uint64_t* __restrict__ leaf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(code + ((size_t)i << (PC_LOG_SLICES + 1)));
+    uint64_t h[4] = {0, 0, 0, 0};
+    for (int s = 0; s <= PC_SLICES; ++s) {
+        uint64_t msg[8];
+        if (s == PC_SLICES) { msg[0] = msg[1] = msg[2] = msg[3] = 0; }
+        else {
+            const ulonglong2 x = src[2 * s], y = src[2 * s + 1];
+            msg[0] = x.x; msg[1] = x.y; msg[2] = y.x; msg[3] = y.y;
+        }
+        msg[4] = h[0]; msg[5] = h[1]; msg[6] = h[2]; msg[7] = h[3];
+        pc_sha3_64(msg, h);
+    }
+    uint64_t* o = leaf + (size_t)i * 4;
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+}
+
 // ------------------------------------------------------------------ driver
 struct PcCommit {
     int device = 0, log_len = 0, log_n = 0, log_N = 0;
@@ -308,6 +352,10 @@ struct PcCommit {
     // virtual oracle, the second tree, all_sum
     F *q_eval = nullptr, *lqc = nullptr, *h_eval = nullptr, *vow = nullptr, *all_sum = nullptr;
     uint64_t* tree_h = nullptr;
+    // FRI commit phase: the levels back to back (level l: 64 * (N >> (l+1)) elements, (N >> (l+1)) tree nodes)
+    F* fri_code = nullptr;
+    uint64_t* fri_tree = nullptr;
+    int fri_step = -1;               // next step; -1: no virtual oracle yet
     F inv_2n;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool tw_ready = false;
@@ -359,6 +407,7 @@ void pc_destroy(PcCommit* p) {
     cudaSetDevice(p->device);
     cudaFree(p->tw); cudaFree(p->coef); cudaFree(p->work); cudaFree(p->l_eval); cudaFree(p->tree);
     cudaFree(p->q_eval); cudaFree(p->lqc); cudaFree(p->h_eval); cudaFree(p->vow); cudaFree(p->all_sum); cudaFree(p->tree_h);
+    cudaFree(p->fri_code); cudaFree(p->fri_tree);
     if (p->e0) cudaEventDestroy(p->e0);
     if (p->e1) cudaEventDestroy(p->e1);
     delete p;
@@ -421,12 +470,17 @@ static void pc_encode(PcCommit* p, const F* d_array, size_t n_valid, F* eval, cu
     PCK(cudaMemsetAsync(eval + ((size_t)PC_SLICES << p->log_N), 0, p->N * sizeof(F), st));   // the zero mask's codeword
 }
 // leaves + tree over eval[65][N] (mask slice zero) -> tree (array heap), root to the host
+static void pc_tree_levels(PcCommit* p, uint64_t* tree, uint32_t n_leaves, cudaStream_t st);
 static void pc_merkle(PcCommit* p, const F* eval, uint64_t* tree, cudaStream_t st) {
     const uint32_t half = (uint32_t)(p->N / 2);
     PCK(cudaMemsetAsync(tree, 0, 64, st));   // nodes 0 and 1 (node 1 is overwritten: there are always >= 16 leaves)
     k_pc_leaf_hash<<<(half + 127) / 128, 128, 0, st>>>(eval, (uint32_t)p->log_N, tree + (size_t)half * 4, 1);
     ++p->launches;
-    uint32_t lvl = half / 2;
+    pc_tree_levels(p, tree, half, st);
+}
+// the inner nodes of an array heap whose n_leaves (a power of two >= 2) leaves are in place
+static void pc_tree_levels(PcCommit* p, uint64_t* tree, uint32_t n_leaves, cudaStream_t st) {
+    uint32_t lvl = n_leaves / 2;
     for (; lvl > 128; lvl >>= 1) {
         k_pc_merkle_level<<<(lvl + 127) / 128, 128, 0, st>>>(tree, lvl);
         ++p->launches;
@@ -479,6 +533,7 @@ float pc_commit_public(PcCommit* p, const F* d_pub, size_t n_valid, cudaStream_t
     k_pc_vow<<<pc_grid(n_pts, 256), 256, 0, st>>>(p->l_eval, p->q_eval, p->h_eval, p->lqc, p->tw, log_n, log_N, p->vow, p->all_sum, n_pts);
     ++p->launches;
     pc_merkle(p, p->h_eval, p->tree_h, st);
+    p->fri_step = 0;
     PCK(cudaEventRecord(p->e1, st));
     PCK(cudaGetLastError());
     PCK(cudaMemcpyAsync(root_h, p->tree_h + 4, 32, cudaMemcpyDeviceToHost, st));
@@ -495,6 +550,62 @@ void pc_export_public(PcCommit* p, cudaStream_t st, F* h_eval, F* vow, uint8_t* 
     if (vow) PCK(cudaMemcpyAsync(vow, p->vow, (size_t)PC_SLICES * p->N * sizeof(F), cudaMemcpyDeviceToHost, st));
     if (leaf_hash) PCK(cudaMemcpyAsync(leaf_hash, p->tree_h + (p->N / 2) * 4, (p->N / 2) * 32, cudaMemcpyDeviceToHost, st));
     if (tree) PCK(cudaMemcpyAsync(tree, p->tree_h, p->N * 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+}
+
+// ---- FRI commit phase
+int pc_fri_steps(const PcCommit* p) { return p->log_n; }
+int pc_fri_steps_done(const PcCommit* p) { return p->fri_step < 0 ? 0 : p->fri_step; }
+static inline size_t pc_fri_offset(const PcCommit* p, int lvl) { return p->N - (p->N >> lvl); }   // sum of N >> (l+1), l < lvl
+void pc_fri_restart(PcCommit* p) {
+    if (p->fri_step < 0) throw std::runtime_error("polynomial commitment: FRI commit phase before commit_public");
+    p->fri_step = 0;
+}
+// one fold + leaf hashes + tree on the stream; no synchronisation
+static void pc_fri_step_async(PcCommit* p, F r, cudaStream_t st) {
+    if (p->fri_step < 0) throw std::runtime_error("polynomial commitment: FRI commit phase before commit_public");
+    if (p->fri_step >= p->log_n) throw std::runtime_error("polynomial commitment: the FRI commit phase is finished (32 points per slice left)");
+    if (!p->fri_code) {
+        PCK(cudaMalloc(&p->fri_code, (size_t)PC_SLICES * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->fri_tree, p->N * 32));
+    }
+    const int s = p->fri_step;
+    const uint32_t log_M = (uint32_t)(p->log_N - s);
+    const size_t quarter = ((size_t)1 << log_M) / 4;
+    const F* prev = s == 0 ? p->vow : p->fri_code + PC_SLICES * pc_fri_offset(p, s - 1);
+    F* out = p->fri_code + PC_SLICES * pc_fri_offset(p, s);
+    uint64_t* tree = p->fri_tree + pc_fri_offset(p, s) * 4;
+    const F inv2{(P + 1) / 2, 0};
+    const size_t total = quarter << PC_LOG_SLICES;
+    k_pc_fri_fold<<<pc_grid(total, 256), 256, 0, st>>>(prev, log_M, p->tw, (uint32_t)p->log_N, f_mul(r, inv2), inv2, out, total);
+    ++p->launches;
+    PCK(cudaMemsetAsync(tree, 0, 64, st));
+    k_pc_fri_leaf_hash<<<(unsigned)((quarter + 127) / 128), 128, 0, st>>>(out, (uint32_t)quarter, tree + quarter * 4);
+    ++p->launches;
+    pc_tree_levels(p, tree, (uint32_t)quarter, st);
+    ++p->fri_step;
+}
+// n steps from the current one; roots: n * 32 bytes on the host
+float pc_fri_steps_run(PcCommit* p, const F* r, int n, cudaStream_t st, uint8_t* roots) {
+    PCK(cudaSetDevice(p->device));
+    const int first = p->fri_step;
+    PCK(cudaEventRecord(p->e0, st));
+    for (int k = 0; k < n; ++k) pc_fri_step_async(p, r[k], st);
+    PCK(cudaEventRecord(p->e1, st));
+    PCK(cudaGetLastError());
+    for (int k = 0; k < n; ++k)
+        PCK(cudaMemcpyAsync(roots + (size_t)k * 32, p->fri_tree + pc_fri_offset(p, first + k) * 4 + 4, 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    float ms = 0;
+    PCK(cudaEventElapsedTime(&ms, p->e0, p->e1));
+    return ms;
+}
+void pc_fri_export(PcCommit* p, cudaStream_t st, int lvl, F* code, uint8_t* tree) {
+    PCK(cudaSetDevice(p->device));
+    if (lvl < 0 || lvl >= p->fri_step) throw std::runtime_error("polynomial commitment: FRI level not computed");
+    const size_t m = p->N >> (lvl + 1);
+    if (code) PCK(cudaMemcpyAsync(code, p->fri_code + PC_SLICES * pc_fri_offset(p, lvl), PC_SLICES * m * sizeof(F), cudaMemcpyDeviceToHost, st));
+    if (tree) PCK(cudaMemcpyAsync(tree, p->fri_tree + pc_fri_offset(p, lvl) * 4, m * 32, cudaMemcpyDeviceToHost, st));
     PCK(cudaStreamSynchronize(st));
 }
 

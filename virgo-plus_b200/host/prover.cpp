@@ -179,7 +179,14 @@ double prover::proofSize() const { return (double)vp_proof_size_bytes(ctx) / 102
 // device results. VP_CPU_COMMIT=1 keeps the reference's CPU commit instead (A/B timing).
 namespace virgo {
 extern int witness_merkle_size[2];   // fri.cpp:22 (not declared in fri.h)
+namespace fri {
+// the reference's own CPU step, kept under this name when fri.cpp is compiled with
+// -Dcommit_phase_step=commit_phase_step_reference (oracle/Makefile)
+__hhash_digest commit_phase_step_reference(fieldElement r);
 }
+}
+// the context whose device holds the virtual oracle (set by commit_public): fri::commit_phase_step is a free function
+static vp_ctx *g_fri_ctx = nullptr;
 virgo::__hhash_digest prover::commit_private() {
     using namespace virgo;
     std::vector<F> mask(1, F_ZERO);
@@ -322,6 +329,7 @@ virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum
     witness_merkle_size[1] = half;
     fri::visited_init[1] = new bool[1 << lw]();
     fri::visited_witness[1] = new bool[1 << (bl + rs_code_rate)]();
+    g_fri_ctx = ctx;
     const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     poly_prover.total_time += dt;
     if (getenv("VP_TIMING"))
@@ -329,4 +337,43 @@ virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum
                 dt * 1e3, (double)vp_last_commit_ms(ctx));
     return root_h;
 }
+#ifdef VP_DROPIN_FRI
+// fri::commit_phase_step (lib/virgo/src/fri.cpp:289-418), called once per fold challenge by
+// poly_commit_prover::commit_phase (vpd_verifier.cpp:43-73). The fold of the 64 codewords, the leaf chains and the level's
+// Merkle tree run on the device (vp_fri_commit_steps) on the virtual oracle commit_public left there; the arrays the
+// reference's query phase reads (fri::request_step_commit, fri.cpp:232-287: cpd.rs_codeword / _msk / their mappings,
+// cpd.merkle, visited) are allocated and indexed exactly as there and filled from the device results.
+// When the commitments were made by the reference's CPU code (VP_CPU_COMMIT, non-zero masks) so is this step.
+virgo::__hhash_digest virgo::fri::commit_phase_step(virgo::fieldElement r) {
+    using namespace virgo;
+    if (!g_fri_ctx) return commit_phase_step_reference(r);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    const int lvl = current_step_no, nxt = (1 << log_current_witness_size_per_slice) / 2, half = nxt / 2;
+    const int slice_count = poly_commit::slice_count, log_leaf_size = log_slice_number + 1;
+    __hhash_digest root;
+    ck(vp_fri_commit_steps(g_fri_ctx, cf(&r), 1, reinterpret_cast<uint8_t *>(&root)), "vp_fri_commit_steps");
+    if (cpd.rs_codeword[lvl] == NULL) cpd.rs_codeword[lvl] = new fieldElement[(size_t)nxt * slice_count];          // :290-293
+    if (cpd.rs_codeword_msk[lvl] == NULL) cpd.rs_codeword_msk[lvl] = new fieldElement[nxt];
+    for (int i = 0; i < nxt; ++i) cpd.rs_codeword_msk[lvl][i] = fieldElement(0);                                  // zero mask: :359-386
+    if (cpd.merkle[lvl] == NULL) cpd.merkle[lvl] = (__hhash_digest *)malloc((size_t)half * 2 * sizeof(__hhash_digest));   // merkle_tree.cpp:17
+    ck(vp_fri_export_level(g_fri_ctx, lvl, mf(cpd.rs_codeword[lvl]), reinterpret_cast<uint8_t *>(cpd.merkle[lvl])), "vp_fri_export_level");
+    for (int i = 0; i < nxt; ++i) L_group[i] = L_group[i * 2];                                                   // :338-340
+    cpd.rs_codeword_mapping[lvl] = new int[(size_t)nxt * slice_count];                                            // :343-357
+    for (int i = 0; i < half; ++i)
+        for (int j = 0; j < slice_number; ++j) {
+            const int at = (i << log_leaf_size) | (j << 1);
+            cpd.rs_codeword_mapping[lvl][i << log_slice_number | j] = at;
+            cpd.rs_codeword_mapping[lvl][(i + half) << log_slice_number | j] = at;
+        }
+    cpd.rs_codeword_msk_mapping[lvl] = new int[nxt];                                                              // :374-381
+    for (int i = 0; i < half; ++i) cpd.rs_codeword_msk_mapping[lvl][i] = cpd.rs_codeword_msk_mapping[lvl][i + half] = i << 1;
+    visited[lvl] = new bool[(size_t)nxt * 4 * slice_count]();                                                      // :386-387
+    merkle_tree::size_after_padding = half;
+    cpd.merkle_size[lvl] = half;
+    __fri_timer += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    log_current_witness_size_per_slice--;
+    current_step_no++;
+    return root;
+}
+#endif
 #endif

@@ -181,7 +181,7 @@ namespace virgo {
 extern int witness_merkle_size[2];   // fri.cpp:22 (not declared in fri.h)
 namespace fri {
 // the reference's own CPU step, kept under this name when fri.cpp is compiled with
-// -Dcommit_phase_step=commit_phase_step_reference (oracle/Makefile)
+// -Dcommit_phase_step=commit_phase_step_reference
 __hhash_digest commit_phase_step_reference(fieldElement r);
 }
 }

@@ -453,15 +453,57 @@ def run_c5(env, B, tmpl, args):
     return out
 
 
+_P61 = (1 << 61) - 1
+
+
+def _mulmod61(a, b):
+    """a * b mod 2^61 - 1 on uint64 numpy arrays of canonical values (31-bit limbs: every partial sum stays below 2^64)"""
+    m31, m30 = np.uint64((1 << 31) - 1), np.uint64((1 << 30) - 1)
+    a0, a1, b0, b1 = a & m31, a >> np.uint64(31), b & m31, b >> np.uint64(31)
+    mid = a1 * b0 + a0 * b1
+    t = np.uint64(2) * (a1 * b1) + (mid >> np.uint64(30)) + ((mid & m30) << np.uint64(31)) + a0 * b0
+    pp = np.uint64(_P61)
+    t = (t & pp) + (t >> np.uint64(61))
+    t = (t & pp) + (t >> np.uint64(61))
+    return np.where(t >= pp, t - pp, t)
+
+
+def eq_table(B, r):
+    """initBetaTable(output, n, r, F_ONE) (the public array verifyPoly commits, verifier.cpp:367-383) with numpy:
+    out[k] = prod_i (bit_i(k) ? r_i : 1 - r_i) over F_p[i]/(i^2 + 1)"""
+    pp = np.uint64(_P61)
+    sub = lambda x, y: np.where(x >= y, x - y, x + pp - y)
+    add = lambda x, y: np.where(x + y >= pp, x + y - pp, x + y)
+    re, im = np.ones(1, np.uint64), np.zeros(1, np.uint64)
+    for x in r:
+        xr, xi = np.uint64(x["re"]), np.uint64(x["im"])
+        tr = sub(_mulmod61(re, xr), _mulmod61(im, xi))
+        ti = add(_mulmod61(re, xi), _mulmod61(im, xr))
+        re, im = np.concatenate([sub(re, tr), tr]), np.concatenate([sub(im, ti), ti])
+    out = np.zeros(len(re), B.F_DTYPE)
+    out["re"], out["im"] = re, im
+    return out
+
+
+def _rand_fe(B, seed, n):
+    rng = np.random.default_rng(seed)
+    a = np.zeros(n, B.F_DTYPE)
+    a["re"] = rng.integers(0, _P61, n, dtype=np.uint64)
+    a["im"] = rng.integers(0, _P61, n, dtype=np.uint64)
+    return a
+
+
 def run_pc_commit(B, tmpl):
     """SURVEY 8(f) N1: prover::commit_private (the polynomial commitment's commit phase) on the device, for the input layer
     of SHA256_64 and of SHA256_64 x 16, beside what the reference's own commit_private_array took on one host core
     (tests/golden/pc_commit.json, recorded with oracle/_ref/ref_pc_commit) and with the Merkle roots compared"""
-    try:
-        with open(os.path.join(ROOT, "tests", "golden", "pc_commit.json")) as f:
-            golden = json.load(f)
-    except Exception:
-        golden = {}
+    def load(name):
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+                return json.load(f)
+        except Exception:
+            return {}
+    golden, golden_fri = load("pc_commit.json"), load("pc_fri.json")
     out = {}
     for name, circ in (("sha256_64", tmpl), ("sha256_64_x16", tmpl.replicate(16)), ("sha256_64_x1024", tmpl.replicate(1024))):
         p = B.Prover(circ)
@@ -474,8 +516,26 @@ def run_pc_commit(B, tmpl):
         out[name] = {"inputs": int(circ.num_inputs), "log_len": int(circ.bit_length(0)), "device_ms": statistics.median(ms),
                      "root": root.hex(), "root_equals_reference": (root.hex() == g.get("root")) if g else None,
                      "reference_cpu_seconds": g.get("reference_commit_seconds")}
+        # commit_public_array + the FRI commit phase on the inputs of tests/golden/make_golden_pc_fri.py: the eq table of
+        # the point default_rng(2024) draws, fold challenges from default_rng(2224)
+        b = int(circ.bit_length(0))
+        q, r = eq_table(B, _rand_fe(B, 2024, b)), _rand_fe(B, 2224, b - 6)
+        ms_pub, ms_fri = [], []
+        for _ in range(3):
+            root_h, _ = p.commit_public(q)
+            ms_pub.append(p.last_commit_ms)
+            roots = p.fri_commit_steps(r)
+            ms_fri.append(p.last_commit_ms)
+        gf = golden_fri.get(name, {})
+        out[name].update({"commit_public_device_ms": statistics.median(ms_pub), "fri_commit_phase_device_ms": statistics.median(ms_fri),
+                          "fri_steps": len(r), "root_h_equals_reference": (root_h.hex() == gf.get("root_h")) if gf else None,
+                          "fri_roots_equal_reference": ([x.hex() for x in roots] == gf.get("roots")) if gf else None,
+                          "reference_fri_commit_phase_seconds": gf.get("reference_fri_commit_seconds")})
         p.close()
-    out["what"] = "64 inverse NTTs + 2048 coset NTTs over F_p^2, 65 SHA3-256 per Merkle leaf, array-heap Merkle tree (vp_commit_private)"
+    out["what"] = ("commit_private: 64 inverse NTTs + 2048 coset NTTs over F_p^2, 65 SHA3-256 per Merkle leaf, array-heap Merkle tree "
+                   "(vp_commit_private); commit_public: the same encoding of the public array, per-slice 2n-point products -> quotient h "
+                   "-> its extension, virtual oracle, second tree (vp_commit_public); FRI commit phase: log_len - 6 folds of the 64 "
+                   "codewords with leaf chains and a tree per level (vp_fri_commit_steps)")
     return out
 
 

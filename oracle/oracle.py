@@ -304,7 +304,9 @@ def ref_pc_fri(array, pub, log_len, randomness):
         root_h = np.fromfile(fo2, dtype=np.uint8, count=32).tobytes()
         raw = np.fromfile(fo3, dtype=np.uint8)
     out = dict(root_l=root_l, root_h=root_h, roots=[raw[32 * l:32 * l + 32].tobytes() for l in range(steps)], codes=[], trees=[],
-               seconds=float(pr.stdout.split("fri_commit_seconds")[1]))
+               seconds=float(pr.stdout.split("fri_commit_seconds")[1]),
+               commit_seconds=float(pr.stdout.split("commit_seconds")[1].split()[0]),
+               commit_public_seconds=float(pr.stdout.split("commit_public_seconds")[1].split()[0]))
     o = 32 * steps
     for l in range(steps):
         m = N >> (l + 1)

@@ -53,7 +53,8 @@ def main():
         a, q, b, r = case_inputs(B, O, name)
         ref = O.ref_pc_fri(a, q, b, r)
         out[name] = dict(digest_of(ref["roots"], ref["codes"], ref["trees"]), log_len=b, root_l=ref["root_l"].hex(), root_h=ref["root_h"].hex(),
-                         reference_fri_commit_seconds=ref["seconds"])
+                         reference_fri_commit_seconds=ref["seconds"], reference_commit_seconds=ref["commit_seconds"],
+                         reference_commit_public_seconds=ref["commit_public_seconds"])
         print(name, {k: v for k, v in out[name].items() if k != "roots"})
     with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)

@@ -167,6 +167,45 @@ __global__ void k_pc_dit_stage(F* __restrict__ work, uint32_t log_n, uint32_t s,
     }
 }
 
+// g <= 6 consecutive global DIT stages s0 .. s0+g-1 in ONE pass over the work buffer. Those stages only couple positions that
+// differ in bits s0 .. s0+g-1, so position p = top << (s0+g) | mid << s0 | lo splits every transform into independent 2^g-point
+// columns of stride 2^s0; a block takes 32 neighbouring columns (32 consecutive lo: 512-byte rows) into shared memory
+// (2^g x 32 elements <= 32 KB), runs the g stages there and writes the tile back -- or, in the last group, to
+// l_eval[slice][32 p + coset].
+static constexpr int PC_DIT_GROUP = 6, PC_DIT_COLS_LOG = 5;
+__global__ void __launch_bounds__(256) k_pc_dit_group(F* __restrict__ work, uint32_t log_n, uint32_t s0, uint32_t g, const F* __restrict__ tw,
+                                                       uint32_t log_N, F* __restrict__ l_eval, int last) {
+    __shared__ __align__(16) F sh[(1 << PC_DIT_GROUP) << PC_DIT_COLS_LOG];
+    const uint32_t tiles_log = log_n - g - PC_DIT_COLS_LOG;                     // tiles per transform
+    const size_t t = (size_t)blockIdx.x >> tiles_log;                          // transform = slice * 32 + coset
+    const uint32_t tile = blockIdx.x & ((1u << tiles_log) - 1);
+    const uint32_t lo_bits = s0 - PC_DIT_COLS_LOG;                              // tile = top << lo_bits | (lo >> 5)
+    const uint32_t top = tile >> lo_bits, lo0 = (tile & ((1u << lo_bits) - 1)) << PC_DIT_COLS_LOG;
+    const uint32_t base = (top << (s0 + g)) | lo0, cols = 1u << PC_DIT_COLS_LOG, count = cols << g;
+    F* x = work + (t << log_n);
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) sh[i] = pc_ld(x + (base | ((i >> PC_DIT_COLS_LOG) << s0) | (i & (cols - 1))));
+    __syncthreads();
+    for (uint32_t k = 0; k < g; ++k) {
+        const uint32_t s = s0 + k;
+        for (uint32_t q = threadIdx.x; q < count / 2; q += blockDim.x) {
+            const uint32_t w = q & (cols - 1), mq = q >> PC_DIT_COLS_LOG, jl = mq & ((1u << k) - 1), m0 = ((mq >> k) << (k + 1)) | jl;
+            const uint32_t i0 = (m0 << PC_DIT_COLS_LOG) | w, i1 = i0 + (cols << k);
+            const uint32_t j = (jl << s0) | lo0 | w;                            // p & (2^s - 1)
+            const F u = sh[i0], v = f_mul(sh[i1], pc_ld(tw + ((size_t)j << (log_N - s - 1))));
+            sh[i0] = f_add(u, v);
+            sh[i1] = f_sub(u, v);
+        }
+        __syncthreads();
+    }
+    if (last) {
+        F* o = l_eval + ((t >> PC_LOG_RATE) << log_N) + (t & (PC_COSETS - 1));
+        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
+            pc_st(o + ((size_t)(base | ((i >> PC_DIT_COLS_LOG) << s0) | (i & (cols - 1))) << PC_LOG_RATE), sh[i]);
+    } else {
+        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) pc_st(x + (base | ((i >> PC_DIT_COLS_LOG) << s0) | (i & (cols - 1))), sh[i]);
+    }
+}
+
 // ---- commit_public_array (poly_commit.h:126-349): products of the two codewords on the 2n-th roots, the quotient
 // polynomial's oracle values
 // lq[s][j] = l_eval[s][16 j] * q_eval[s][16 j], j < 2n  (the 2n evaluations of l*q that determine it: degree < 2n - 1)
@@ -181,12 +220,21 @@ __global__ void k_pc_lq(const F* __restrict__ l_eval, const F* __restrict__ q_ev
 // lqc: bit-reversed coefficients of l*q per slice (2n each): coefficient 0 at position 0, coefficient n (= h_0) at position 1.
 // all_sum[s] = n (lq_0 + h_0) (poly_commit.h:330); per point x = w_N^j:
 //   vow[(j mod N/2) << 7 | s << 1 | (j >= N/2)] = (l q - (x^n - 1) h - (lq_0 + h_0)) * n * x^-1        (:303-323)
-__global__ void k_pc_vow(const F* __restrict__ l_eval, const F* __restrict__ q_eval, const F* __restrict__ h_eval, const F* __restrict__ lqc,
-                         const F* __restrict__ tw, uint32_t log_n, uint32_t log_N, F* __restrict__ vow, F* __restrict__ all_sum, size_t total) {
-    const uint32_t N = 1u << log_N, n = 1u << log_n, half = N >> 1;
+// A block produces 16 leaves of the virtual oracle (2048 elements, 32 KB contiguous): it reads, for every slice and both
+// halves, 16 consecutive codeword positions (256-byte segments), and writes the tile through shared memory so that the
+// interleaved output goes out in full lines.
+static constexpr int PC_VOW_LEAVES_LOG = 4;
+__global__ void __launch_bounds__(256) k_pc_vow(const F* __restrict__ l_eval, const F* __restrict__ q_eval, const F* __restrict__ h_eval,
+                                                 const F* __restrict__ lqc, const F* __restrict__ tw, uint32_t log_n, uint32_t log_N,
+                                                 F* __restrict__ vow, F* __restrict__ all_sum) {
+    __shared__ __align__(16) F sh[(2 * PC_SLICES) << PC_VOW_LEAVES_LOG];
+    const uint32_t N = 1u << log_N, n = 1u << log_n, half = N >> 1, leaves = 1u << PC_VOW_LEAVES_LOG;
+    const uint32_t j0 = blockIdx.x << PC_VOW_LEAVES_LOG;
     const F n_fe{(u64)n, 0};
-    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t sl = (uint32_t)(w >> log_N), j = (uint32_t)(w & (N - 1));
+    for (uint32_t i = threadIdx.x; i < (2 * PC_SLICES) << PC_VOW_LEAVES_LOG; i += blockDim.x) {
+        const uint32_t jj = i & (leaves - 1), hf = (i >> PC_VOW_LEAVES_LOG) & 1u, sl = i >> (PC_VOW_LEAVES_LOG + 1);
+        const uint32_t j = j0 + jj + hf * half;
+        const size_t w = ((size_t)sl << log_N) + j;
         const F* c = lqc + ((size_t)sl << (log_n + 1));
         const F c0 = f_add(pc_ld(c), pc_ld(c + 1));
         if (j == 0) pc_st(all_sum + sl, f_mul(c0, n_fe));
@@ -194,10 +242,11 @@ __global__ void k_pc_vow(const F* __restrict__ l_eval, const F* __restrict__ q_e
         const F inv_x = f_mul(n_fe, pc_ld(tw + ((N - j) & (N - 1))));                    // n * w_N^-j
         const F lqv = f_mul(pc_ld(l_eval + w), pc_ld(q_eval + w));
         const F g = f_sub(lqv, f_mul(f_sub(x_n, f_one()), pc_ld(h_eval + w)));
-        const F v = f_mul(f_sub(g, c0), inv_x);
-        const size_t at = j < half ? (((size_t)j << (PC_LOG_SLICES + 1)) | ((size_t)sl << 1)) : (((size_t)(j - half) << (PC_LOG_SLICES + 1)) | ((size_t)sl << 1) | 1);
-        pc_st(vow + at, v);
+        sh[(jj << (PC_LOG_SLICES + 1)) | (sl << 1) | hf] = f_mul(f_sub(g, c0), inv_x);
     }
+    __syncthreads();
+    F* o = vow + ((size_t)j0 << (PC_LOG_SLICES + 1));
+    for (uint32_t i = threadIdx.x; i < (2 * PC_SLICES) << PC_VOW_LEAVES_LOG; i += blockDim.x) pc_st(o + i, sh[i]);
 }
 
 // ---- SHA3-256 of a 64-byte block (my_hhash.h:27-33 -> XKCP SHA3_256; FIPS 202): one Keccak-f[1600] permutation
@@ -341,6 +390,66 @@ __global__ void __launch_bounds__(128) k_pc_fri_leaf_hash(const F* __restrict__ 
     uint64_t* o = leaf + (size_t)i * 4;
     o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
 }
+// The levels lie back to back and a leaf is 128 consecutive elements, so the leaves of ALL levels form one array: global leaf
+// g of level l (local index g - goff(l), goff(l) = N/2 - (N >> (l+1))) starts at code + 128 g. Hashing the levels of several
+// steps in one launch matters for small codewords, where a level's 65-permutation chains are latency-bound.
+__global__ void __launch_bounds__(128) k_pc_fri_leaf_hash_all(const F* __restrict__ code, uint32_t g_begin, uint32_t g_end, uint32_t log_N,
+                                                              uint64_t* __restrict__ tree) {
+    const uint32_t g = g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g_end) return;
+    const uint32_t half_N = 1u << (log_N - 1), d = half_N - g;                    // N >> (l+2) < d <= N >> (l+1)
+    const uint32_t l = log_N - 1 - (32 - __clz(d - 1));                          // ceil(log2 d) = 32 - clz(d - 1)  (d >= 16)
+    const uint32_t leaves = 1u << (log_N - l - 2), goff = half_N - (2u * leaves);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(code + ((size_t)g << (PC_LOG_SLICES + 1)));
+    uint64_t h[4] = {0, 0, 0, 0};
+    for (int s = 0; s <= PC_SLICES; ++s) {
+        uint64_t msg[8];
+        if (s == PC_SLICES) { msg[0] = msg[1] = msg[2] = msg[3] = 0; }
+        else {
+            const ulonglong2 x = src[2 * s], y = src[2 * s + 1];
+            msg[0] = x.x; msg[1] = x.y; msg[2] = y.x; msg[3] = y.y;
+        }
+        msg[4] = h[0]; msg[5] = h[1]; msg[6] = h[2]; msg[7] = h[3];
+        pc_sha3_64(msg, h);
+    }
+    uint64_t* o = tree + ((size_t)2 * goff + leaves + (g - goff)) * 4;            // level l's heap starts at node 2 goff(l)
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+}
+// pass `hgt` of all levels' trees at once: blockIdx.y = level first + y; in level l the nodes [c, 2c), c = leaves_l >> hgt,
+// are hashed from their children if c > 128 (the last <= 128-node part of every tree is k_pc_fri_tree_top_all's)
+__global__ void __launch_bounds__(128) k_pc_fri_tree_pass_all(uint64_t* __restrict__ tree, uint32_t log_N, uint32_t first, uint32_t hgt) {
+    const uint32_t l = first + blockIdx.y;
+    const uint32_t leaves = 1u << (log_N - l - 2), c = leaves >> hgt, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= 128 || i >= c) return;
+    uint64_t* t = tree + ((size_t)(1u << log_N) - ((size_t)(1u << log_N) >> l)) * 4;
+    const uint64_t* ch = t + (size_t)(2 * (c + i)) * 4;
+    uint64_t msg[8], h[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) msg[k] = ch[k];
+    pc_sha3_64(msg, h);
+    uint64_t* o = t + (size_t)(c + i) * 4;
+    o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+}
+// one block per level: node 0 zeroed, then the levels of <= 128 nodes
+__global__ void __launch_bounds__(128) k_pc_fri_tree_top_all(uint64_t* __restrict__ tree, uint32_t log_N, uint32_t first) {
+    const uint32_t l = first + blockIdx.x;
+    const uint32_t leaves = 1u << (log_N - l - 2);
+    uint64_t* t = tree + ((size_t)(1u << log_N) - ((size_t)(1u << log_N) >> l)) * 4;
+    if (threadIdx.x < 4) t[threadIdx.x] = 0;
+    for (uint32_t lvl = min(leaves / 2, 128u); lvl >= 1; lvl >>= 1) {
+        const uint32_t i = threadIdx.x;
+        if (i < lvl) {
+            const uint64_t* c = t + (size_t)(2 * (lvl + i)) * 4;
+            uint64_t msg[8], h[4];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) msg[k] = c[k];
+            pc_sha3_64(msg, h);
+            uint64_t* o = t + (size_t)(lvl + i) * 4;
+            o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+        }
+        __syncthreads();
+    }
+}
 
 // ------------------------------------------------------------------ driver
 struct PcCommit {
@@ -439,11 +548,19 @@ static void pc_extend(PcCommit* p, const F* src, size_t slice_stride, uint32_t i
     k_pc_ntt_smem<<<grid, threads, sizeof(F) << log_m, st>>>(src, log_n, log_m, p->tw, log_N, direct ? eval : p->work, direct ? 1 : 0, slice_stride,
                                                             in_stride, in_off);
     ++p->launches;
-    if (!direct) {
+    if (!direct && getenv("VP_PC_SINGLE_STAGES")) {                 // one pass per stage (kept for A/B timing)
         const size_t pairs = ((size_t)PC_SLICES * PC_COSETS << log_n) / 2;
         for (uint32_t s = log_m; s < log_n; ++s) {
             k_pc_dit_stage<<<pc_grid(pairs, 256), 256, 0, st>>>(p->work, log_n, s, pairs, p->tw, log_N, eval, s == log_n - 1 ? 1 : 0);
             ++p->launches;
+        }
+    } else if (!direct) {
+        for (uint32_t s0 = log_m; s0 < log_n;) {                   // up to 6 stages per pass
+            const uint32_t g = std::min<uint32_t>(PC_DIT_GROUP, log_n - s0);
+            const size_t blocks = ((size_t)PC_SLICES * PC_COSETS) << (log_n - g - PC_DIT_COLS_LOG);
+            k_pc_dit_group<<<(unsigned)blocks, 256, 0, st>>>(p->work, log_n, s0, g, p->tw, log_N, eval, s0 + g == log_n ? 1 : 0);
+            ++p->launches;
+            s0 += g;
         }
     }
 }
@@ -522,7 +639,7 @@ float pc_commit_public(PcCommit* p, const F* d_pub, size_t n_valid, cudaStream_t
     }
     PCK(cudaEventRecord(p->e0, st));
     pc_encode(p, d_pub, n_valid, p->q_eval, st);
-    const size_t n_lq = (size_t)PC_SLICES << (log_n + 1), n_pts = (size_t)PC_SLICES << log_N;
+    const size_t n_lq = (size_t)PC_SLICES << (log_n + 1);
     k_pc_lq<<<pc_grid(n_lq, 256), 256, 0, st>>>(p->l_eval, p->q_eval, log_n, log_N, p->lqc, n_lq);
     ++p->launches;
     pc_inverse(p, p->lqc, log_n + 1, PC_SLICES, p->inv_2n, st);
@@ -530,7 +647,7 @@ float pc_commit_public(PcCommit* p, const F* d_pub, size_t n_valid, cudaStream_t
     pc_extend(p, p->lqc, 2 * p->n, 2, 1, p->h_eval, st);
     PCK(cudaMemsetAsync(p->h_eval + ((size_t)PC_SLICES << log_N), 0, p->N * sizeof(F), st));
     PCK(cudaMemsetAsync(p->all_sum, 0, (PC_SLICES + 1) * sizeof(F), st));
-    k_pc_vow<<<pc_grid(n_pts, 256), 256, 0, st>>>(p->l_eval, p->q_eval, p->h_eval, p->lqc, p->tw, log_n, log_N, p->vow, p->all_sum, n_pts);
+    k_pc_vow<<<(unsigned)((p->N / 2) >> PC_VOW_LEAVES_LOG), 256, 0, st>>>(p->l_eval, p->q_eval, p->h_eval, p->lqc, p->tw, log_n, log_N, p->vow, p->all_sum);
     ++p->launches;
     pc_merkle(p, p->h_eval, p->tree_h, st);
     p->fri_step = 0;
@@ -561,8 +678,8 @@ void pc_fri_restart(PcCommit* p) {
     if (p->fri_step < 0) throw std::runtime_error("polynomial commitment: FRI commit phase before commit_public");
     p->fri_step = 0;
 }
-// one fold + leaf hashes + tree on the stream; no synchronisation
-static void pc_fri_step_async(PcCommit* p, F r, cudaStream_t st) {
+// one fold (+ leaf hashes + tree if with_tree) on the stream; no synchronisation
+static void pc_fri_step_async(PcCommit* p, F r, cudaStream_t st, bool with_tree) {
     if (p->fri_step < 0) throw std::runtime_error("polynomial commitment: FRI commit phase before commit_public");
     if (p->fri_step >= p->log_n) throw std::runtime_error("polynomial commitment: the FRI commit phase is finished (32 points per slice left)");
     if (!p->fri_code) {
@@ -579,18 +696,38 @@ static void pc_fri_step_async(PcCommit* p, F r, cudaStream_t st) {
     const size_t total = quarter << PC_LOG_SLICES;
     k_pc_fri_fold<<<pc_grid(total, 256), 256, 0, st>>>(prev, log_M, p->tw, (uint32_t)p->log_N, f_mul(r, inv2), inv2, out, total);
     ++p->launches;
+    ++p->fri_step;
+    if (!with_tree) return;
     PCK(cudaMemsetAsync(tree, 0, 64, st));
     k_pc_fri_leaf_hash<<<(unsigned)((quarter + 127) / 128), 128, 0, st>>>(out, (uint32_t)quarter, tree + quarter * 4);
     ++p->launches;
     pc_tree_levels(p, tree, (uint32_t)quarter, st);
-    ++p->fri_step;
+}
+// several steps whose challenges are all known: the folds one after the other (each needs only the previous level's
+// codewords), then the leaf chains of ALL new levels in one launch and their trees side by side
+static void pc_fri_steps_batched(PcCommit* p, const F* r, int n, cudaStream_t st) {
+    const int first = p->fri_step;
+    for (int k = 0; k < n; ++k) pc_fri_step_async(p, r[k], st, false);
+    const uint32_t log_N = (uint32_t)p->log_N;
+    const uint32_t g_begin = (uint32_t)(pc_fri_offset(p, first) / 2), g_end = (uint32_t)(pc_fri_offset(p, first + n) / 2);
+    k_pc_fri_leaf_hash_all<<<(g_end - g_begin + 127) / 128, 128, 0, st>>>(p->fri_code, g_begin, g_end, log_N, p->fri_tree);
+    ++p->launches;
+    const uint32_t leaves0 = 1u << (log_N - first - 2);
+    for (uint32_t hgt = 1; (leaves0 >> hgt) > 128; ++hgt) {
+        dim3 grid(((leaves0 >> hgt) + 127) / 128, (unsigned)n);
+        k_pc_fri_tree_pass_all<<<grid, 128, 0, st>>>(p->fri_tree, log_N, (uint32_t)first, hgt);
+        ++p->launches;
+    }
+    k_pc_fri_tree_top_all<<<(unsigned)n, 128, 0, st>>>(p->fri_tree, log_N, (uint32_t)first);
+    ++p->launches;
 }
 // n steps from the current one; roots: n * 32 bytes on the host
 float pc_fri_steps_run(PcCommit* p, const F* r, int n, cudaStream_t st, uint8_t* roots) {
     PCK(cudaSetDevice(p->device));
     const int first = p->fri_step;
     PCK(cudaEventRecord(p->e0, st));
-    for (int k = 0; k < n; ++k) pc_fri_step_async(p, r[k], st);
+    if (n >= 2 && !getenv("VP_FRI_STEPWISE")) pc_fri_steps_batched(p, r, n, st);
+    else for (int k = 0; k < n; ++k) pc_fri_step_async(p, r[k], st, true);
     PCK(cudaEventRecord(p->e1, st));
     PCK(cudaGetLastError());
     for (int k = 0; k < n; ++k)

@@ -232,6 +232,27 @@ int vp_fri_export_level(vp_ctx* ctx, int lvl, vp_F* rs_codeword, uint8_t* merkle
 int vp_pc_fri(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n_pub, int log_len, const vp_F* randomness, int n_steps,
               uint8_t root_l[32], uint8_t root_h[32], uint8_t* roots, vp_F* codes, uint8_t* trees, float* device_ms);
 
+/* ------------------------------------------------------------------ the commitment's inner GKR
+ * fft_circuit_gkr::fft_gkr (lib/virgo/src/fft_circuit_GKR.cpp:833-849), which poly_commit_verifier::verify_poly_commitment
+ * runs once per opening (vpd_verifier.cpp:92): prover and verifier of a layered GKR over a fixed circuit family -- the eq
+ * table of a random point, lg_size inverse-FFT butterfly layers, a scaling, 64 x 2^lg_size products with the powers of 64
+ * random points and their row sums -- walked from the outputs back to the eq table with 2 + 2 lg_size sumchecks. The
+ * reference draws all randomness with fieldElement::random() and none of it depends on a prover message; here the caller
+ * passes it as one array in the reference's draw order:
+ *   r[lg] | x[64] | r_0[lg+10] | r_1[lg+10] | addition layer: r_u[lg+6], r_v[lg+6] | mult layer: r_u[lg], r_v[lg] |
+ *   per butterfly layer (lg of them): r_u[lg], r_v[lg], alpha, beta          (vp_fft_gkr_rnd_count(lg) elements, canonical)
+ * The prover side (circuit evaluation, all sumcheck tables and rounds) runs on the device without a host round trip; the
+ * verifier's claim chain and closed-form wiring predicates run on the host afterwards.
+ * Outputs: proof_size = the reference's `ps` (48 bytes per round + extension_gkr's count), ok = 1 if every verifier check
+ * passed (the reference prints "Error, fft gkr failed" otherwise), verifier_seconds / prover_seconds = its `vt` / `pt`;
+ * optional (NULL to skip): layers = E, F_{lg-1}..F_0, S (2^lg each), P (64 * 2^lg), O (64); polys = 3 elements per round in
+ * protocol order (vp_fft_gkr_poly_count(lg) rounds); claims = the running claim a_0, after the addition / mult /
+ * intermediate layer, after every butterfly layer, then the final alpha, beta (4 + lg + 2 elements). 1 <= lg_size <= 24. */
+size_t vp_fft_gkr_rnd_count(int lg_size);
+size_t vp_fft_gkr_poly_count(int lg_size);
+int vp_fft_gkr(int device, int lg_size, const vp_F* rnd, size_t n_rnd, vp_F* layers, vp_F* polys, size_t polys_cap, vp_F* claims,
+               int* proof_size, int* ok, double* verifier_seconds, double* prover_seconds, float* device_ms);
+
 /* ------------------------------------------------------------------ Fiat-Shamir mode
  * The reference ships a hash-based challenge source, transcriptCache (lib/virgo/src/transcriptCache.hpp:14-50: a byte
  * pool hashed with SHA3-256 per challenge, challenge = first two digest words mod p), but never calls it. This mode uses

@@ -352,3 +352,52 @@ def ref_pc_commit(array, log_len):
     tree = raw[o:o + ss * 32]
     return dict(root=raw[:32].tobytes(), l_eval=l_eval, leaf_hash=leaf, tree=tree, slice_size=ss,
                 seconds=float(r.stdout.split("commit_seconds")[1]))
+
+
+# ------------------------------------------------------------------ the polynomial commitment's inner GKR (fft_circuit_GKR)
+def fft_gkr_rnd_count(lg):
+    return lg + 64 + 2 * (lg + 10) + 2 * (lg + 6) + 2 * lg + lg * (2 * lg + 2)
+
+
+def fft_gkr_poly_count(lg):
+    return (lg + 6) + lg + 2 * lg * lg
+
+
+def fft_gkr(lg, rnd, want_layers=True):
+    """fft_circuit_GKR.cpp restated (fftgkr_oracle.c) -> dict(layers, polys [n, 3], claims, proof_size, ok)"""
+    L = lib()
+    L.ofg_run.restype = C.c_long
+    L.ofg_run.argtypes = [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rnd = np.ascontiguousarray(rnd, F_DTYPE)
+    n = 1 << lg
+    layers = np.zeros((lg + 2) * n + 64 * n + 64, F_DTYPE) if want_layers else None
+    npoly = fft_gkr_poly_count(lg)
+    polys = np.zeros(3 * npoly, F_DTYPE)
+    claims = np.zeros(4 + lg + 2, F_DTYPE)
+    n_polys, ps, ok = C.c_long(), C.c_int(), C.c_int()
+    rc = L.ofg_run(lg, _p(rnd), len(rnd), _p(layers) if want_layers else None, _p(polys), npoly, _p(claims), C.byref(n_polys), C.byref(ps), C.byref(ok))
+    assert rc == fft_gkr_rnd_count(lg), rc
+    assert n_polys.value == npoly, (n_polys.value, npoly)
+    return dict(layers=layers, polys=polys.reshape(npoly, 3), claims=claims, proof_size=ps.value, ok=bool(ok.value))
+
+
+REF_FFTGKR = os.path.join(REF_DIR, "ref_fftgkr")
+
+
+def ref_fft_gkr(lg, seed):
+    """the UNMODIFIED reference fft_circuit_GKR driven stage by stage (oracle/_ref/ref_fftgkr)
+    -> dict(rnd, layers, claims [a_0, add, mult, intermediate, ifft, alpha, beta], proof_size, ok, fft_gkr_ps, seconds)"""
+    import tempfile
+    n = 1 << lg
+    with tempfile.TemporaryDirectory() as td:
+        fo = os.path.join(td, "o.bin")
+        pr = subprocess.run([REF_FFTGKR, str(lg), str(seed), fo], capture_output=True, text=True, check=True)
+        raw = np.fromfile(fo, dtype=np.uint8)
+    n_rnd = int(raw[:8].view(np.uint64)[0]); o = 8
+    rnd = raw[o:o + 16 * n_rnd].view(F_DTYPE); o += 16 * n_rnd
+    nl = (lg + 2) * n + 64 * n + 64
+    layers = raw[o:o + 16 * nl].view(F_DTYPE); o += 16 * nl
+    claims = raw[o:o + 16 * 7].view(F_DTYPE); o += 16 * 7
+    ps, ok, ps2 = (int(x) for x in raw[o:o + 24].view(np.uint64))
+    return dict(rnd=rnd, layers=layers, claims=claims, proof_size=ps, ok=bool(ok), fft_gkr_ps=ps2,
+                seconds=float(pr.stdout.split("prover_seconds")[1].split()[0]))

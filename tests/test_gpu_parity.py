@@ -808,3 +808,48 @@ def test_pc_fri_full_size_roots_equal_reference(B, O):
     got = B.pc_fri(a, q, b, r, want_arrays=False)
     assert got["root_l"].hex() == g["root_l"] and got["root_h"].hex() == g["root_h"]
     assert [x.hex() for x in got["roots"]] == g["roots"]
+
+
+# ------------------------------------------------------------------ the commitment's inner GKR (fft_circuit_GKR)
+@pytest.mark.parametrize("name", ["lg1_seed3", "lg2_seed5", "lg5_seed77", "lg7_seed3396", "lg10_seed11", "lg13_seed2024"])
+def test_fft_gkr_matches_reference_golden_and_oracle(B, O, name):
+    """device fft_gkr: layer values, running claims, proof size, verdict == the reference's (golden); every round polynomial ==
+    the oracle's (which the reference does not expose: pinned through the claim chain, see fftgkr_oracle.c)"""
+    import json
+    import os
+    import helpers as H
+    import test_oracle as T
+    with open(os.path.join(H.GOLDEN, "fft_gkr.json")) as f:
+        g = json.load(f)[name]
+    lg = g["lg"]
+    rnd = O.draw_challenges(O.fft_gkr_rnd_count(lg), seed=g["seed"])
+    assert B.fft_gkr_rnd_count(lg) == len(rnd)
+    got = B.fft_gkr(lg, rnd)
+    T.fft_gkr_check_against_golden(got, g)
+    want = O.fft_gkr(lg, rnd, want_layers=False)
+    _assert_same(got["polys"].reshape(-1), want["polys"].reshape(-1), "round polynomials")
+    _assert_same(got["claims"], want["claims"], "claims")
+
+
+def test_fft_gkr_full_size_matches_reference_golden(B, O):
+    """lg = 17: the inner GKR of a commitment to 2^23 values (BASELINE's 1024-instance circuit); reference: 6.5 s on one core"""
+    import json
+    import os
+    import helpers as H
+    import test_oracle as T
+    with open(os.path.join(H.GOLDEN, "fft_gkr.json")) as f:
+        g = json.load(f)["lg17_seed7"]
+    rnd = O.draw_challenges(O.fft_gkr_rnd_count(17), seed=g["seed"])
+    T.fft_gkr_check_against_golden(B.fft_gkr(17, rnd), g)
+
+
+def test_fft_gkr_argument_checks(B, O):
+    rnd = O.draw_challenges(O.fft_gkr_rnd_count(4), seed=1)
+    with pytest.raises(B.VpError):
+        B.fft_gkr(4, rnd[:-1])                       # one random element short
+    bad = rnd.copy()
+    bad[7]["im"] = (1 << 61) - 1
+    with pytest.raises(B.VpError):
+        B.fft_gkr(4, bad)                            # not canonical
+    with pytest.raises(B.VpError):
+        B.fft_gkr(0, rnd)

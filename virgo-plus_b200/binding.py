@@ -118,6 +118,12 @@ def _declare(L):
     L.vp_fri_steps.argtypes = [vp]
     L.vp_fri_restart.argtypes = [vp]
     L.vp_fri_export_level.argtypes = [vp, C.c_int, vp, vp]
+    L.vp_fft_gkr_rnd_count.argtypes = [C.c_int]
+    L.vp_fft_gkr_rnd_count.restype = C.c_size_t
+    L.vp_fft_gkr_poly_count.argtypes = [C.c_int]
+    L.vp_fft_gkr_poly_count.restype = C.c_size_t
+    L.vp_fft_gkr.argtypes = [C.c_int, C.c_int, vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.vp_pc_fri.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_prove_fs.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
     L.vp_fs_challenges.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp, C.c_size_t]
@@ -423,6 +429,24 @@ def pc_fri(array, pub, log_len, randomness, device=0, want_arrays=True):
         out["trees"].append(trees[32 * o:32 * (o + m)].tobytes())
         o += m
     return out
+
+
+def fft_gkr_rnd_count(lg):
+    return int(lib().vp_fft_gkr_rnd_count(lg))
+
+
+def fft_gkr(lg, rnd, device=0, want_layers=True):
+    """the polynomial commitment's inner GKR (fft_circuit_gkr::fft_gkr) with the randomness handed in
+    -> dict(layers, polys [rounds, 3], claims, proof_size, ok, verifier_seconds, prover_seconds, device_ms)"""
+    r = np.ascontiguousarray(rnd, dtype=F_DTYPE)
+    n, npoly = 1 << lg, int(lib().vp_fft_gkr_poly_count(lg))
+    layers = np.zeros((lg + 2) * n + 64 * n + 64, F_DTYPE) if want_layers else None
+    polys, claims = np.zeros(3 * npoly, F_DTYPE), np.zeros(4 + lg + 2, F_DTYPE)
+    ps, ok, vt, pt, ms = C.c_int(), C.c_int(), C.c_double(), C.c_double(), C.c_float()
+    _ck(lib().vp_fft_gkr(device, lg, _ptr(r), len(r), _ptr(layers), _ptr(polys), npoly, _ptr(claims), C.byref(ps), C.byref(ok), C.byref(vt),
+                         C.byref(pt), C.byref(ms)))
+    return dict(layers=layers, polys=polys.reshape(npoly, 3), claims=claims, proof_size=ps.value, ok=bool(ok.value),
+                verifier_seconds=vt.value, prover_seconds=pt.value, device_ms=ms.value)
 
 
 def shard_describe(circuit, world, rank, layer, phase):

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <mutex>
 #include <thread>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -3639,7 +3640,10 @@ struct vp_sumcheck {
     }
 };
 
-extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
+static int sumcheck_create_impl(int log_n, int device, vp_sumcheck** out, bool with_src);
+extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) { return sumcheck_create_impl(log_n, device, out, true); }
+// with_src = false: no pristine copies of the three tables (the caller fills buf[0] itself before every run)
+static int sumcheck_create_impl(int log_n, int device, vp_sumcheck** out, bool with_src) {
     if (!out || log_n < 1 || log_n > 30) return fail(VP_ERR_ARG, "bad argument");
     API_BEGIN
     int ndev = 0;
@@ -3651,8 +3655,8 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
     s->device = device;
     s->N = 1u << log_n;
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    struct { int multiProcessorCount = 0; } prop;   // (cudaGetDeviceProperties takes milliseconds; one attribute is all that is needed)
+    CK(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, device));
     int occ = 0, occ1 = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_round<true>, 256, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_round<false>, 256, 0));
@@ -3672,7 +3676,8 @@ extern "C" int vp_sumcheck_create(int log_n, int device, vp_sumcheck** out) {
         s->cap_dfs = prop.multiProcessorCount * std::max(1, occd);
         s->max_grid = std::max(s->max_grid, s->cap_dfs);
     }
-    for (int i = 0; i < 3; ++i) s->src[i].alloc(s->N);
+    if (with_src)
+        for (int i = 0; i < 3; ++i) s->src[i].alloc(s->N);
     for (int b = 0; b < 2; ++b) {
         const uint32_t cap = std::max<uint32_t>(4, b == 0 ? std::max(s->plan.cap0, s->pp.cap0) : std::max(s->plan.cap1, s->pp.cap1));
         s->bufV[b].alloc(cap);
@@ -3799,17 +3804,11 @@ extern "C" int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out, float* 
 }
 // Same result as vp_sumcheck_run, all rounds in ONE cooperative launch with two rounds per pass (k_phase_dfs):
 // possible because all challenges r[] are known up front.
-extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, float* device_ms) {
-    if (!s || !r || !out) return fail(VP_ERR_ARG, "null argument");
-    API_BEGIN
-    cudaSetDevice(s->device);
+// (the launches only: tables already in buf[0], challenges r[] on the host; results stay in s->d_out)
+static void sumcheck_fused_async(vp_sumcheck* s, const vp_F* r) {
     cudaStream_t st = s->stream;
     const int n = s->log_n;
     CK(cudaMemcpyAsync(s->d_r.p, r, (size_t)n * sizeof(F), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->bufV[0].p, s->src[0].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(s->bufA[0].p, s->src[1].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(s->bufM[0].p, s->src[2].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
-    CK(cudaEventRecord(s->ev[0], st));
     DfsArgs a;
     for (int b = 0; b < 2; ++b) { a.bufV[b] = s->bufV[b].p; a.bufM[b] = s->bufM[b].p; a.bufA[b] = s->bufA[b].p; }
     a.passes = s->d_pdev.p + s->pp.pass_begin;
@@ -3845,6 +3844,18 @@ extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, f
     const FinDesc fv = s->arena.fins[s->pp.fin_begin];
     const F* fin_tabs[2] = {s->bufA[s->pp.fin_buf].p, s->bufM[s->pp.fin_buf].p};
     for (int k = 0; k < 2; ++k) k_strict_copy<<<1, 32, 0, st>>>(s->d_out.p + 3 * n + 1 + k, fin_tabs[k] + fv.in_off, 1);
+}
+extern "C" int vp_sumcheck_run_fused(vp_sumcheck* s, const vp_F* r, vp_F* out, float* device_ms) {
+    if (!s || !r || !out) return fail(VP_ERR_ARG, "null argument");
+    API_BEGIN
+    cudaSetDevice(s->device);
+    cudaStream_t st = s->stream;
+    const int n = s->log_n;
+    CK(cudaMemcpyAsync(s->bufV[0].p, s->src[0].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->bufA[0].p, s->src[1].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(s->bufM[0].p, s->src[2].p, (size_t)s->N * sizeof(F), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(s->ev[0], st));
+    sumcheck_fused_async(s, r);
     CK(cudaEventRecord(s->ev[1], st));
     CK(cudaMemcpyAsync(out, s->d_out.p, ((size_t)3 * n + 3) * sizeof(F), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -3872,4 +3883,33 @@ extern "C" void vp_sumcheck_destroy(vp_sumcheck* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     delete s;
+}
+
+// ------------------------------------------------------------------ the polynomial commitment's inner GKR
+#include "fft_gkr.cuh"
+extern "C" size_t vp_fft_gkr_rnd_count(int lg_size) { return (lg_size < 1 || lg_size > 24) ? 0 : fg::rnd_count(lg_size); }
+extern "C" size_t vp_fft_gkr_poly_count(int lg_size) { return (lg_size < 1 || lg_size > 24) ? 0 : fg::poly_count(lg_size); }
+// fft_circuit_gkr::fft_gkr (lib/virgo/src/fft_circuit_GKR.cpp:833-849) with the randomness handed in
+extern "C" int vp_fft_gkr(int device, int lg_size, const vp_F* rnd, size_t n_rnd, vp_F* layers, vp_F* polys, size_t polys_cap, vp_F* claims,
+                          int* proof_size, int* ok, double* verifier_seconds, double* prover_seconds, float* device_ms) {
+    if (!rnd || !proof_size || !ok) return fail(VP_ERR_ARG, "null argument");
+    if (lg_size < 1 || lg_size > 24) return fail(VP_ERR_ARG, "vp_fft_gkr: lg_size must be in [1, 24]");
+    if (n_rnd < fg::rnd_count(lg_size)) return fail(VP_ERR_ARG, "vp_fft_gkr: %zu random elements given, %zu needed", n_rnd, fg::rnd_count(lg_size));
+    if (polys && polys_cap < fg::poly_count(lg_size)) return fail(VP_ERR_ARG, "vp_fft_gkr: polynomial buffer too small (%zu < %zu)", polys_cap, fg::poly_count(lg_size));
+    for (size_t i = 0; i < fg::rnd_count(lg_size); ++i)
+        if (rnd[i].re >= P || rnd[i].im >= P) return fail(VP_ERR_ARG, "vp_fft_gkr: random element %zu is not canonical", i);
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw CudaError{std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(ce)};
+    const fg::Result r = fg::run(device, lg_size, reinterpret_cast<const F*>(rnd), reinterpret_cast<F*>(layers), reinterpret_cast<F*>(polys),
+                                 reinterpret_cast<F*>(claims));
+    *proof_size = r.proof_size;
+    *ok = r.ok;
+    if (verifier_seconds) *verifier_seconds = r.verifier_seconds;
+    if (prover_seconds) *prover_seconds = r.prover_seconds;
+    if (device_ms) *device_ms = r.device_ms;
+    return VP_OK;
+    API_END
 }

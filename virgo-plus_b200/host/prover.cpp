@@ -184,9 +184,15 @@ namespace fri {
 // -Dcommit_phase_step=commit_phase_step_reference
 __hhash_digest commit_phase_step_reference(fieldElement r);
 }
+namespace fft_circuit_gkr {
+int fft_gkr(int lg_size, double &vt, int &ps, double &pt);             // fft_circuit_GKR.h:4
+int fft_gkr_reference(int lg_size, double &vt, int &ps, double &pt);   // the reference's own, renamed the same way
 }
-// the context whose device holds the virtual oracle (set by commit_public): fri::commit_phase_step is a free function
+}
+// the context whose device holds the virtual oracle (set by commit_public): fri::commit_phase_step and
+// fft_circuit_gkr::fft_gkr are free functions
 static vp_ctx *g_fri_ctx = nullptr;
+static int g_device = 0;
 virgo::__hhash_digest prover::commit_private() {
     using namespace virgo;
     std::vector<F> mask(1, F_ZERO);
@@ -330,6 +336,7 @@ virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum
     fri::visited_init[1] = new bool[1 << lw]();
     fri::visited_witness[1] = new bool[1 << (bl + rs_code_rate)]();
     g_fri_ctx = ctx;
+    g_device = getenv("VP_DEVICE") ? atoi(getenv("VP_DEVICE")) : 0;   // (the device commit is single-GPU: same choice as in the constructor)
     const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     poly_prover.total_time += dt;
     if (getenv("VP_TIMING"))
@@ -374,6 +381,24 @@ virgo::__hhash_digest virgo::fri::commit_phase_step(virgo::fieldElement r) {
     log_current_witness_size_per_slice--;
     current_step_no++;
     return root;
+}
+
+// fft_circuit_gkr::fft_gkr (lib/virgo/src/fft_circuit_GKR.cpp:833-849), called once per opening by
+// poly_commit_verifier::verify_poly_commitment (vpd_verifier.cpp:92). The reference draws every random value of this inner
+// GKR with fieldElement::random() and none depends on a prover message: they are drawn here, in the reference's order and
+// number (so the verifier's later draws see the same stream), and the whole protocol runs in vp_fft_gkr.
+int virgo::fft_circuit_gkr::fft_gkr(int lg_size, double &vt, int &ps, double &pt) {
+    using namespace virgo;
+    if (!g_fri_ctx || lg_size < 1 || lg_size > 24) return fft_gkr_reference(lg_size, vt, ps, pt);
+    const size_t n_rnd = vp_fft_gkr_rnd_count(lg_size);
+    std::vector<fieldElement> rnd(n_rnd);
+    for (auto &x : rnd) x = fieldElement::random();
+    int ok = 0;
+    ps = 0;
+    ck(vp_fft_gkr(g_device, lg_size, cf(rnd.data()), n_rnd, nullptr, nullptr, 0, nullptr, &ps, &ok, &vt, &pt, nullptr), "vp_fft_gkr");
+    if (!ok) fprintf(stderr, "Error, fft gkr failed\n");   // :843-844
+    if (getenv("VP_TIMING")) fprintf(stderr, "virgo_b200 prover: fft_gkr(%d) %.3f ms\n", lg_size, pt * 1e3);
+    return 0;
 }
 #endif
 #endif

@@ -257,6 +257,7 @@ def run_ours(args):
     if not args.no_extras:
         if world == 1:
             line["pc_commit"] = run_pc_commit(B, tmpl)
+            line["fft_gkr"] = run_fft_gkr(B)
             line["sumcheck_c2"] = run_c2(B, peak)
             line["single_proof_c1"] = run_c1(B, tmpl)
             line["dropin"] = run_dropin(B, tmpl, circ, inst)
@@ -536,6 +537,38 @@ def run_pc_commit(B, tmpl):
                    "(vp_commit_private); commit_public: the same encoding of the public array, per-slice 2n-point products -> quotient h "
                    "-> its extension, virtual oracle, second tree (vp_commit_public); FRI commit phase: log_len - 6 folds of the 64 "
                    "codewords with leaf chains and a tree per level (vp_fri_commit_steps)")
+    return out
+
+
+def run_fft_gkr(B):
+    """SURVEY 8(f) N4: the commitment's inner GKR (fft_circuit_gkr::fft_gkr, once per opening) on the device, on the randomness
+    stream of tests/golden/fft_gkr.json (glibc random() after srand(seed)): its running claims, proof size and verdict are
+    compared with what the UNMODIFIED reference functions produced on the same stream; reference seconds from that file."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fft_gkr.json")) as f:
+            golden = json.load(f)
+    except Exception:
+        golden = {}
+    out = {}
+    for name in ("lg7_seed3396", "lg13_seed2024", "lg17_seed7"):
+        g = golden.get(name)
+        if not g:
+            continue
+        lg = g["lg"]
+        rnd = B.draw_field(B.fft_gkr_rnd_count(lg), g["seed"])
+        first = B.fft_gkr(lg, rnd, want_layers=False)
+        runs = [B.fft_gkr(lg, rnd, want_layers=False) for _ in range(5)]
+        r = runs[-1]
+        fe_hex = lambda x: "%016x%016x" % (int(x["re"]), int(x["im"]))
+        claims = [fe_hex(r["claims"][i]) for i in (0, 1, 2, 3, 3 + lg, 4 + lg, 5 + lg)]
+        out[name] = {"lg_size": lg, "commitment_entries": 1 << (lg + 6), "device_ms": statistics.median(x["device_ms"] for x in runs),
+                     "wall_ms": statistics.median(x["prover_seconds"] for x in runs) * 1e3, "first_call_wall_ms": first["prover_seconds"] * 1e3,
+                     "verifier_ms": r["verifier_seconds"] * 1e3, "ok": r["ok"], "proof_size": r["proof_size"],
+                     "claims_and_proof_size_equal_reference": claims == g["claims"] and r["proof_size"] == g["proof_size"],
+                     "reference_cpu_seconds": g["reference_prover_seconds"]}
+    out["what"] = ("eq table, lg inverse-FFT butterfly layers, 64 x 2^lg products and their sums evaluated on the device; 2 + 2 lg sumchecks "
+                   "(one pass-kernel launch each) without a host round trip; the verifier's closed forms on the host (vp_fft_gkr). "
+                   "first_call_wall_ms includes creating the two cached sumcheck objects")
     return out
 
 

@@ -91,6 +91,8 @@ int vp_circuit_set_inputs(vp_circuit* c, const uint64_t* in /* num_inputs, each 
  * random() after srand(seed) (fieldElement.cpp:106-124); seed 3396 reproduces F::init(). */
 size_t vp_challenge_count(const vp_circuit* c);
 int vp_draw_challenges(const vp_circuit* c, unsigned seed, vp_F* out /* vp_challenge_count */);
+/* The same generator as a plain stream: the first n values of fieldElement::random() after srand(seed). */
+int vp_draw_field(unsigned seed, size_t n, vp_F* out);
 /* Prover messages: Vres; per layer top..1: bl(i-1) x (a,b,c), claim_u, [maxDad(i) x (a,b,c), claims_v[0..i)],
  * bl(i-1) x (a,b,c), claim_liu; finally the input-layer MLE. */
 size_t vp_transcript_len(const vp_circuit* c);

@@ -68,6 +68,7 @@ def _declare(L):
     L.vp_challenge_count.argtypes = [vp]
     L.vp_challenge_count.restype = C.c_size_t
     L.vp_draw_challenges.argtypes = [vp, C.c_uint, vp]
+    L.vp_draw_field.argtypes = [C.c_uint, C.c_size_t, vp]
     L.vp_transcript_len.argtypes = [vp]
     L.vp_transcript_len.restype = C.c_size_t
     L.vp_transcript_to_gkrproof.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -428,6 +429,13 @@ def pc_fri(array, pub, log_len, randomness, device=0, want_arrays=True):
         out["codes"].append(codes[64 * o:64 * (o + m)])
         out["trees"].append(trees[32 * o:32 * (o + m)].tobytes())
         o += m
+    return out
+
+
+def draw_field(n, seed=3396):
+    """the first n values of fieldElement::random() after srand(seed)"""
+    out = np.zeros(n, F_DTYPE)
+    _ck(lib().vp_draw_field(seed, n, _ptr(out)))
     return out
 
 

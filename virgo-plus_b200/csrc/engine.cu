@@ -2828,6 +2828,16 @@ extern "C" int vp_draw_challenges(const vp_circuit* c, unsigned seed, vp_F* out)
     }
     return VP_OK;
 }
+// n values of fieldElement::random() (fieldElement.cpp:119-124, 362-367) after srand(seed), as a plain stream
+extern "C" int vp_draw_field(unsigned seed, size_t n, vp_F* out) {
+    if (!out && n) return fail(VP_ERR_ARG, "null argument");
+    GlibcRandom rng(seed);
+    for (size_t i = 0; i < n; ++i) {
+        const F x = rng.field();
+        out[i] = vp_F{x.re, x.im};
+    }
+    return VP_OK;
+}
 extern "C" size_t vp_transcript_len(const vp_circuit* c) {
     if (!c) return 0;
     const Circuit& C = c->c;

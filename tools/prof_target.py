@@ -1,4 +1,5 @@
 """Short workloads for ncu captures: `c2` = one 2^24 sumcheck, `gkr K` = one proof of SHA256_64 x K,
+`fftgkr LG` = the commitment's inner GKR,
 `pc LOG_LEN` = both commitments + the FRI commit phase of a random 2^LOG_LEN-entry array."""
 import lzma, os, sys
 import numpy as np
@@ -12,6 +13,12 @@ if sys.argv[1] == "c2":
     r = np.zeros(log_n, B.F_DTYPE); r["re"] = np.arange(1, log_n + 1) * 1234567891; r["im"] = 77
     s.run(r); s.run(r)
     if len(sys.argv) > 3: s.run(r, fused=True); s.run(r, fused=True)
+elif sys.argv[1] == "fftgkr":
+    lg = int(sys.argv[2])
+    rnd = B.draw_field(B.fft_gkr_rnd_count(lg), 9)
+    B.fft_gkr(lg, rnd, want_layers=False)
+    out = B.fft_gkr(lg, rnd, want_layers=False)
+    print("fft_gkr ms", out["device_ms"], out["ok"])
 elif sys.argv[1] == "pc":
     b = int(sys.argv[2])
     rng = np.random.default_rng(1)

@@ -20,3 +20,10 @@ if True:
     g2 = B.pc_fri(a, q, b, r, want_arrays=False)
     assert g2["roots"] == g["roots"]
     print("sanitize target pc ok")
+# the commitment's inner GKR: circuit kernels, table fills (incl. the device-side v_u feed), fused sumchecks on two streams
+for lg in (1, 4, 9):
+    rnd = B.draw_field(B.fft_gkr_rnd_count(lg), 5 + lg)
+    g = B.fft_gkr(lg, rnd)
+    w = O.fft_gkr(lg, rnd)
+    assert g["ok"] and (g["polys"] == w["polys"]).all() and (g["layers"] == w["layers"]).all() and g["proof_size"] == w["proof_size"]
+print("sanitize target fft_gkr ok")

@@ -576,7 +576,8 @@ def run_dropin(B, tmpl, circ, inst):
     """What the reference program sees. (1) oracle/_ref/virgo_plus_run_b200 = the reference's UNMODIFIED main.cpp + verifier.cpp +
     polynomial commitment linked against the drop-in `prover` class (host/prover.cpp -> this library): its own `Prove Time`
     line on SHA256_64.pws (the class's proveTime(): host wall time inside prover methods, like prover.cpp:549-551).
-    (2) the same method-by-method API (one launch + a 48-byte copy + a host sync per round) on the benchmark circuit."""
+    (2) the same method-by-method API (one launch per round; the polynomial comes back through mapped pinned memory the host spins on)
+    on the benchmark circuit."""
     import re
     import tempfile
     out = {}

@@ -890,7 +890,41 @@ struct Engine {
         ev_used = 0;
     }
 
+    // Interactive fast path (vp_round, one GPU): 64 bytes of pinned host memory mapped into the device -- the round kernel
+    // leaves {a, b, c} and a sequence number there (RoundArgs::host_poly / host_seq) and the host spins on the number.
+    struct RoundSlot { F poly[3]; unsigned int seq; unsigned int pad[3]; };
+    RoundSlot* h_round = nullptr;    // host address
+    RoundSlot* d_round = nullptr;    // the same memory as the device sees it
+    unsigned int round_seq = 0;
+    const vp_F* fast_prev = nullptr; // set around do_round by vp_round: previous challenge by value
+    bool fast_out = false;           // set around do_round by vp_round: also write the polynomial to h_round
+    void round_slot_alloc() {
+        if (h_round) return;
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(RoundSlot), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }   // (falls back to the copy path)
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+        memset(h, 0, sizeof(RoundSlot));
+        h_round = static_cast<RoundSlot*>(h);
+        d_round = static_cast<RoundSlot*>(d);
+    }
+    // waits for sequence number `want` in the slot; polls the stream now and then so that a failed launch cannot hang the host
+    void round_slot_wait(unsigned int want) {
+        volatile unsigned int* seq = &h_round->seq;
+        for (unsigned long it = 1;; ++it) {
+            if (*seq == want) break;
+            if ((it & 0xfffu) == 0) {
+                const cudaError_t q = cudaStreamQuery(stream);
+                if (q == cudaErrorNotReady) continue;
+                CK(q);
+                if (*seq != want) throw CudaError{"vp_round: the round kernel finished without delivering its polynomial"};
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+
     ~Engine() {
+        if (h_round) cudaFreeHost(h_round);
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -1005,6 +1039,12 @@ struct Engine {
         if (h_chal.size() < idx + cnt) h_chal.resize(idx + cnt, f_zero());
         memcpy(h_chal.data() + idx, v, cnt * sizeof(F));
     }
+    // the host copy only (vp_round's fast path hands the value to the round kernel, which files it in d_chal)
+    void set_chal_host(uint32_t idx, const vp_F* v) {
+        if (v->re >= P || v->im >= P) throw std::invalid_argument("challenge " + std::to_string(idx) + " is not canonical (components must be < p)");
+        if (h_chal.size() < (size_t)idx + 1) h_chal.resize((size_t)idx + 1, f_zero());
+        memcpy(h_chal.data() + idx, v, sizeof(F));
+    }
     void get_tr(uint32_t idx, vp_F* out, size_t cnt = 1) {
         CK(cudaMemcpyAsync(out, d_tr.p + idx, cnt * sizeof(F), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1052,6 +1092,7 @@ void Engine::build(const Circuit& circ, int dev, int world_, int rank_, const ui
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (world_ == 1 && !getenv("VP_ROUND_COPY")) round_slot_alloc();   // VP_ROUND_COPY=1: the copy + synchronise path (A/B timing)
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     n_sm = prop.multiProcessorCount;
@@ -1916,7 +1957,17 @@ void Engine::do_init_liu(int i, bool write_a) {
 // scaled by (1 - previous challenge) although no fold is pending. poly_out: where the polynomial goes (default: transcript).
 void Engine::do_round(const SumcheckPlan& P, int j, uint32_t ci_prev, uint32_t tr_out, const F* at_init, bool continues, F* poly_out) {
     const RoundPlan& R = P.r[j - 1];
-    RoundArgs a;
+    RoundArgs a{};
+    if (fast_prev) {
+        a.prev_by_value = 1;
+        a.prev_val = F{fast_prev->re, fast_prev->im};
+        a.prev_w = d_chal.p + ci_prev;
+    }
+    if (fast_out) {
+        a.host_poly = d_round->poly;
+        a.host_seq = &d_round->seq;
+        a.seq = ++round_seq;
+    }
     const int ib = R.in_buf, ob = ib ^ 1;
     a.inV = bufV[ib].p; a.inM = bufM[ib].p; a.inA = bufA[ib].p;
     a.outV = bufV[ob].p; a.outM = bufM[ob].p; a.outA = bufA[ob].p;
@@ -3121,13 +3172,25 @@ extern "C" int vp_round(vp_ctx* ctx, int phase, const vp_F* previous_random, vp_
     const PhasePlan& PP = phase_plan(e, phase);
     if (e.round >= PP.rounds) return fail(VP_ERR_ARG, "vp_round: all %d rounds already done", PP.rounds);
     const uint32_t ci = phase_ci(e, phase);
-    if (e.round >= 1) e.set_chal(ci + (uint32_t)(e.round - 1), previous_random);  // r_arr.at(round-1) = prev (prover.cpp:441)
+    const bool fast = !PP.sharded && e.h_round != nullptr;
+    if (e.round >= 1) {   // r_arr.at(round-1) = prev (prover.cpp:441)
+        if (fast) e.set_chal_host(ci + (uint32_t)(e.round - 1), previous_random);   // the kernel files it on the device
+        else e.set_chal(ci + (uint32_t)(e.round - 1), previous_random);
+    }
     ++e.round;
     const uint32_t tr = (phase == 1 ? D.tr_p1 : phase == 2 ? D.tr_p2 : D.tr_liu) + 3u * (uint32_t)(e.round - 1);
     const F* at_init = phase == 2 ? e.scal(Engine::SC_UNARY) : nullptr;
     if (PP.sharded) e.sharded_round(PP, phase, e.round, ci, tr, at_init);
-    else e.do_round(PP.planB, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, at_init);
-    e.get_tr(tr, out_abc, 3);
+    else if (fast) {
+        struct Reset { Engine& e; ~Reset() { e.fast_prev = nullptr; e.fast_out = false; } } reset{e};
+        e.fast_prev = e.round >= 2 ? previous_random : nullptr;
+        e.fast_out = true;
+        e.do_round(PP.planB, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, at_init);
+        CK(cudaGetLastError());
+        e.round_slot_wait(e.round_seq);
+        memcpy(out_abc, e.h_round->poly, 3 * sizeof(F));
+    } else e.do_round(PP.planB, e.round, ci + (uint32_t)std::max(0, e.round - 2), tr, at_init);
+    if (!fast) e.get_tr(tr, out_abc, 3);
     e.proof_size += 3 * sizeof(F);
     return VP_OK;
     API_END
@@ -3774,7 +3837,7 @@ extern "C" int vp_sumcheck_run(vp_sumcheck* s, const vp_F* r, vp_F* out, float* 
     CK(cudaEventRecord(s->ev[0], st));
     for (int j = 1; j <= n; ++j) {
         const RoundPlan& R = s->plan.r[j - 1];
-        RoundArgs a;
+        RoundArgs a{};
         const int ib = R.in_buf, ob = ib ^ 1;
         a.inV = s->bufV[ib].p; a.inM = s->bufM[ib].p; a.inA = s->bufA[ib].p;
         a.outV = s->bufV[ob].p; a.outM = s->bufM[ob].p; a.outA = s->bufA[ob].p;

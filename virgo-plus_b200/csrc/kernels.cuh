@@ -886,6 +886,16 @@ struct RoundArgs {
     uint32_t first_round;     // 1: add_term is not scaled by (1 - prev) (prev == 0)
     uint32_t reset_add_term;  // 1: start from add_term = *at_init (or 0)
     const F* at_init;         // initial add_term of the phase (phase 2: the unary-gate sum), may be null
+    // Interactive fast path (vp_round on one GPU): the previous challenge comes BY VALUE (prev_by_value != 0; the last
+    // block also files it at prev_w for the kernels that read the challenge array later) and the round polynomial is also
+    // written to host_poly -- pinned host memory mapped into the device -- followed by the sequence number host_seq the
+    // host spins on: no copy call, no stream synchronisation per round.
+    F prev_val;
+    F* prev_w;
+    uint32_t prev_by_value;
+    F* host_poly;
+    unsigned int* host_seq;
+    unsigned int seq;
 };
 
 VP_D F ld_bound(const F* base, uint32_t idx, uint32_t live) { return idx < live ? ld_f(base + idx) : f_zero(); }
@@ -1025,7 +1035,7 @@ __global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
     for (uint32_t i = threadIdx.x; i < p.n_tabs; i += blockDim.x) s_wend[i] = p.tabs[i].work_end;
     __syncthreads();
     FoldK rk = make_foldk(f_zero());
-    if (FOLD) rk = make_foldk(*p.prev_r);
+    if (FOLD) rk = make_foldk(p.prev_by_value ? p.prev_val : *p.prev_r);
     RoundAcc acc;
     racc_init(acc);
     round_work<FOLD, true>(acc, p.tabs, p.n_tabs, s_wend, p.inV, p.inM, p.inA, p.outV, p.outM, p.outA, rk,
@@ -1035,12 +1045,21 @@ __global__ void __launch_bounds__(256, 2) k_round(RoundArgs p) {
     if (!grid_sum<3>(v, smem, p.partials, p.counter)) return;
     if (threadIdx.x != 0) return;
     F at = p.reset_add_term ? (p.at_init ? *p.at_init : f_zero()) : *p.add_term;
-    const F prev = p.first_round ? f_zero() : *p.prev_r;
+    const F prev = p.first_round ? f_zero() : (p.prev_by_value ? p.prev_val : *p.prev_r);
+    if (p.prev_by_value) st_f(p.prev_w, p.prev_val);
     at = collapse_update<true>(at, p.cols, p.n_cols, p.inV, p.inM, p.inA, FOLD, !p.first_round, prev, rk, p.claims);
     st_f(p.add_term, at);
+    const F b = f_sub(v[1], at), c = f_add(v[2], at);
     st_f(p.out_poly + 0, v[0]);
-    st_f(p.out_poly + 1, f_sub(v[1], at));
-    st_f(p.out_poly + 2, f_add(v[2], at));
+    st_f(p.out_poly + 1, b);
+    st_f(p.out_poly + 2, c);
+    if (p.host_poly) {
+        st_f(p.host_poly + 0, v[0]);
+        st_f(p.host_poly + 1, b);
+        st_f(p.host_poly + 2, c);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.host_seq), "r"(p.seq) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------ K7: finalize

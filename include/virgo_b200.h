@@ -211,6 +211,10 @@ float vp_last_commit_ms(const vp_ctx* ctx);   /* device time of the last vp_comm
  * Not reproduced: bitLength(0) == 7 (the reference's 4-point inverse FFT, see above). */
 int vp_commit_public(vp_ctx* ctx, const vp_F* pub, size_t n, const vp_F* mask, size_t n_mask, uint8_t root_h[32], vp_F all_sum[65]);
 int vp_commit_public_export(vp_ctx* ctx, vp_F* h_eval, vp_F* vow, uint8_t* leaf_hash, uint8_t* tree);
+/* The 64 codewords of commitment `which` (0: after vp_commit_private, 1: after vp_commit_public) in the layout of
+ * fri::witness_rs_codeword_interleaved[which] (fri.cpp:69-96): out[(j << 7) | (slice << 1) | h] = codeword[slice][j + h *
+ * slice_size / 2], 64 * slice_size elements; transposed on the device. Before the first vp_fri_commit_steps call. */
+int vp_commit_export_interleaved(vp_ctx* ctx, int which, vp_F* out);
 /* The same on a host array of n canonical field elements, zero-padded to 2^log_len (6 <= log_len <= 30). */
 int vp_pc_commit(int device, const vp_F* array, size_t n, int log_len, uint8_t root[32], vp_F* l_eval, uint8_t* leaf_hash,
                  uint8_t* tree, float* device_ms);

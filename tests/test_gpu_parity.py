@@ -769,8 +769,15 @@ def test_pc_fri_on_context_stepwise_and_restart(B, O, sha_circuit):
     p.commit_private()
     with pytest.raises(B.VpError):
         p.fri_commit_steps(_rand_fe(B, rng, 1))              # no virtual oracle yet
+    def interleaved(ev, N):   # fri.cpp:69-96: [(j << 7) | (slice << 1) | h] = codeword[slice][j + h N/2]
+        return np.ascontiguousarray(ev[:64 * N].reshape(64, 2, N // 2).transpose(2, 0, 1)).reshape(-1)
+    N = 1 << (b - 1)
+    _assert_same(p.commit_export_interleaved(0), interleaved(p.commit_export()["l_eval"], N), "interleaved codewords of the first commitment")
     q = O.beta_table(_rand_fe(B, rng, b))
     root_h, _ = p.commit_public(q)
+    a_in = np.zeros(c.num_inputs, B.F_DTYPE)
+    a_in["re"] = c.inputs()
+    _assert_same(p.commit_export_interleaved(1), interleaved(O.pc_commit_public(a_in, q, b)["h_eval"], N), "interleaved codewords of the second commitment")
     r = _rand_fe(B, rng, b - 6)
     assert p.fri_steps == b - 6
     one_by_one = [p.fri_commit_steps(r[k:k + 1])[0] for k in range(len(r))]

@@ -115,6 +115,7 @@ def _declare(L):
     L.vp_pc_commit_public.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.vp_commit_public.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp]
     L.vp_commit_public_export.argtypes = [vp, vp, vp, vp, vp]
+    L.vp_commit_export_interleaved.argtypes = [vp, C.c_int, vp]
     L.vp_fri_commit_steps.argtypes = [vp, vp, C.c_int, vp]
     L.vp_fri_steps.argtypes = [vp]
     L.vp_fri_restart.argtypes = [vp]
@@ -645,6 +646,11 @@ class Prover:
         code, tree = np.zeros(64 * m, F_DTYPE), np.zeros(32 * m, np.uint8)
         _ck(lib().vp_fri_export_level(self.h, lvl, _ptr(code), _ptr(tree)))
         return code, tree.tobytes()
+
+    def commit_export_interleaved(self, which):
+        out = np.zeros(64 * int(lib().vp_commit_slice_size(self.h)), F_DTYPE)
+        _ck(lib().vp_commit_export_interleaved(self.h, which, _ptr(out)))
+        return out
 
     def commit_export(self):
         ss = int(lib().vp_commit_slice_size(self.h))

@@ -3411,6 +3411,15 @@ extern "C" int vp_commit_public_export(vp_ctx* ctx, vp_F* h_eval, vp_F* vow, uin
     return VP_OK;
     API_END
 }
+extern "C" int vp_commit_export_interleaved(vp_ctx* ctx, int which, vp_F* out) {
+    if (!ctx || !out || (which != 0 && which != 1)) return fail(VP_ERR_ARG, "bad argument");
+    API_BEGIN
+    Engine& e = ctx->e;
+    if (!e.pc) return fail(VP_ERR_ARG, "vp_commit_export_interleaved before vp_commit_private");
+    pc_export_interleaved(e.pc, e.stream, which, reinterpret_cast<F*>(out));
+    return VP_OK;
+    API_END
+}
 extern "C" uint64_t vp_commit_slice_size(const vp_ctx* ctx) { return (ctx && ctx->e.pc) ? pc_slice_size(ctx->e.pc) : 0; }
 extern "C" float vp_last_commit_ms(const vp_ctx* ctx) { return ctx ? ctx->e.last_commit_ms : 0.f; }
 // Stand-alone form on a host array (any field elements, e.g. test vectors): array[0..n) zero-padded to 2^log_len.

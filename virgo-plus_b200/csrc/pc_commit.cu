@@ -249,6 +249,20 @@ __global__ void __launch_bounds__(256) k_pc_vow(const F* __restrict__ l_eval, co
     for (uint32_t i = threadIdx.x; i < (2 * PC_SLICES) << PC_VOW_LEAVES_LOG; i += blockDim.x) pc_st(o + i, sh[i]);
 }
 
+// fri.cpp:69-96: the 64 codewords of a commitment interleaved as pairs of opposite points, out[(j << 7) | (s << 1) | h] =
+// eval[s][j + h N/2] -- what witness_rs_codeword_interleaved holds. Same tiling as k_pc_vow: 16 leaves (32 KB) per block.
+__global__ void __launch_bounds__(256) k_pc_interleave(const F* __restrict__ eval, uint32_t log_N, F* __restrict__ out) {
+    __shared__ __align__(16) F sh[(2 * PC_SLICES) << PC_VOW_LEAVES_LOG];
+    const uint32_t half = 1u << (log_N - 1), leaves = 1u << PC_VOW_LEAVES_LOG, j0 = blockIdx.x << PC_VOW_LEAVES_LOG;
+    for (uint32_t i = threadIdx.x; i < (2 * PC_SLICES) << PC_VOW_LEAVES_LOG; i += blockDim.x) {
+        const uint32_t jj = i & (leaves - 1), hf = (i >> PC_VOW_LEAVES_LOG) & 1u, sl = i >> (PC_VOW_LEAVES_LOG + 1);
+        sh[(jj << (PC_LOG_SLICES + 1)) | (sl << 1) | hf] = pc_ld(eval + ((size_t)sl << log_N) + j0 + jj + hf * half);
+    }
+    __syncthreads();
+    F* o = out + ((size_t)j0 << (PC_LOG_SLICES + 1));
+    for (uint32_t i = threadIdx.x; i < (2 * PC_SLICES) << PC_VOW_LEAVES_LOG; i += blockDim.x) pc_st(o + i, sh[i]);
+}
+
 // ---- SHA3-256 of a 64-byte block (my_hhash.h:27-33 -> XKCP SHA3_256; FIPS 202): one Keccak-f[1600] permutation
 __constant__ uint64_t PC_KECCAK_RC[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
@@ -743,6 +757,24 @@ void pc_fri_export(PcCommit* p, cudaStream_t st, int lvl, F* code, uint8_t* tree
     const size_t m = p->N >> (lvl + 1);
     if (code) PCK(cudaMemcpyAsync(code, p->fri_code + PC_SLICES * pc_fri_offset(p, lvl), PC_SLICES * m * sizeof(F), cudaMemcpyDeviceToHost, st));
     if (tree) PCK(cudaMemcpyAsync(tree, p->fri_tree + pc_fri_offset(p, lvl) * 4, m * 32, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+}
+
+// which = 0: l_eval (after pc_commit), 1: h_eval_arr (after pc_commit_public) -> out[64 N] in the layout of
+// fri::witness_rs_codeword_interleaved[which]. Staged in the FRI level buffer (free at both points of the protocol: the FRI
+// steps come after the exports).
+void pc_export_interleaved(PcCommit* p, cudaStream_t st, int which, F* out) {
+    PCK(cudaSetDevice(p->device));
+    if (which == 1 && !p->q_eval) throw std::runtime_error("polynomial commitment: export before commit_public");
+    if (p->fri_step > 0) throw std::runtime_error("polynomial commitment: interleaved export after the FRI commit phase began");
+    if (!p->fri_code) {
+        PCK(cudaMalloc(&p->fri_code, (size_t)PC_SLICES * p->N * sizeof(F)));
+        PCK(cudaMalloc(&p->fri_tree, p->N * 32));
+    }
+    k_pc_interleave<<<(unsigned)((p->N / 2) >> PC_VOW_LEAVES_LOG), 256, 0, st>>>(which ? p->h_eval : p->l_eval, (uint32_t)p->log_N, p->fri_code);
+    ++p->launches;
+    PCK(cudaGetLastError());
+    PCK(cudaMemcpyAsync(out, p->fri_code, (size_t)PC_SLICES * p->N * sizeof(F), cudaMemcpyDeviceToHost, st));
     PCK(cudaStreamSynchronize(st));
 }
 

@@ -43,6 +43,9 @@ int pc_fri_steps_done(const PcCommit* p);
 void pc_fri_restart(PcCommit* p);
 float pc_fri_steps_run(PcCommit* p, const F* r, int n, cudaStream_t stream, uint8_t* roots);   // n steps, roots[n * 32]
 void pc_fri_export(PcCommit* p, cudaStream_t stream, int lvl, F* code, uint8_t* tree);
+// the codewords of commitment `which` (0: l_eval, 1: h_eval_arr) in the layout of fri::witness_rs_codeword_interleaved
+// (fri.cpp:69-96): out[(j << 7) | (slice << 1) | h] = eval[slice][j + h * slice_size / 2], 64 * slice_size elements
+void pc_export_interleaved(PcCommit* p, cudaStream_t stream, int which, F* out);
 uint64_t pc_launches(const PcCommit* p);
 
 }  // namespace vp

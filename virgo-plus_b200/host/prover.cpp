@@ -205,7 +205,15 @@ virgo::__hhash_digest prover::commit_private() {
     gpu_commit = true;
     const auto t0 = std::chrono::high_resolution_clock::now();
     __hhash_digest root;
+    double lap_ms[4] = {0, 0, 0, 0};
+    auto t_lap = t0;
+    auto lap = [&](int k) {
+        const auto now = std::chrono::high_resolution_clock::now();
+        lap_ms[k] = std::chrono::duration<double>(now - t_lap).count() * 1e3;
+        t_lap = now;
+    };
     ck(vp_commit_private(ctx, cf(mask.data()), mask.size(), reinterpret_cast<uint8_t *>(&root)), "vp_commit_private");
+    lap(0);
     // ---- poly_commit.h:45-67: slicing parameters, the (padded) mask
     poly_commit::pre_prepare_executed = true;
     poly_commit::slice_count = (1 << log_slice_number) + 1;
@@ -218,6 +226,7 @@ virgo::__hhash_digest prover::commit_private() {
     poly_commit::all_pri_msk_arr = new fieldElement[1];
     poly_commit::all_pri_msk_arr[0] = mask[0];
     init_scratch_pad(poly_commit::slice_size);                         // poly_commit.h:74: FFT scratch of the opening phase
+    lap(1);
     const int slice_size = poly_commit::slice_size, half = slice_size / 2;
     // ---- fri.cpp:36-139 (request_init_commit, oracle 0): bookkeeping + arrays
     const int lw = bl + rs_code_rate - log_slice_number;               // log_current_witness_size_per_slice
@@ -237,27 +246,28 @@ virgo::__hhash_digest prover::commit_private() {
     ck(vp_commit_export(ctx, mf(poly_commit::l_eval), reinterpret_cast<uint8_t *>(fri::leaf_hash[0]),
                         reinterpret_cast<uint8_t *>(fri::witness_merkle[0])),
        "vp_commit_export");
+    lap(2);
     fri::witness_rs_codeword_interleaved[0] = new fieldElement[1 << (bl + rs_code_rate)];
     const int log_leaf_size = log_slice_number + 1;
+    ck(vp_commit_export_interleaved(ctx, 0, mf(fri::witness_rs_codeword_interleaved[0])), "vp_commit_export_interleaved");   // (transposed on the device)
     for (int i = 0; i < slice_number; ++i) {                           // fri.cpp:69-96
         fri::witness_rs_codeword_before_arrange[0][i] = &poly_commit::l_eval[i * slice_size];
         fri::witness_rs_mapping[0][i] = new int[1 << lw];
-        const fieldElement *src = fri::witness_rs_codeword_before_arrange[0][i];
         for (int j = 0; j < half; ++j) {
             const int at = (j << log_leaf_size) | (i << 1);
             fri::witness_rs_mapping[0][i][j] = at;
             fri::witness_rs_mapping[0][i][j + half] = at;
-            fri::witness_rs_codeword_interleaved[0][at] = src[j];
-            fri::witness_rs_codeword_interleaved[0][at | 1] = src[j + half];
         }
     }
     witness_merkle_size[0] = half;
     fri::visited_init[0] = new bool[1 << lw]();
     fri::visited_witness[0] = new bool[1 << (bl + rs_code_rate)]();
+    lap(3);
     poly_prover.total_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     if (getenv("VP_TIMING"))
-        fprintf(stderr, "virgo_b200 prover: commit_private %.3f ms (device commit %.3f ms, the rest: copies + the reference's bookkeeping arrays)\n",
-                poly_prover.total_time * 1e3, (double)vp_last_commit_ms(ctx));
+        fprintf(stderr, "virgo_b200 prover: commit_private %.3f ms (device commit %.3f ms; vp_commit_private call %.3f, scratch pad %.3f, L_group + export %.3f, "
+                        "interleaving + flags %.3f)\n",
+                poly_prover.total_time * 1e3, (double)vp_last_commit_ms(ctx), lap_ms[0], lap_ms[1], lap_ms[2], lap_ms[3]);
     return root;
 }
 
@@ -320,16 +330,14 @@ virgo::__hhash_digest prover::commit_public(vector<F> &pub, F &inner_product_sum
     fri::witness_bit_length_per_slice = bl - log_slice_number;
     merkle_tree::size_after_padding = half;
     fri::witness_rs_codeword_interleaved[1] = new fieldElement[1 << (bl + rs_code_rate)];
+    ck(vp_commit_export_interleaved(ctx, 1, mf(fri::witness_rs_codeword_interleaved[1])), "vp_commit_export_interleaved");
     for (int i = 0; i < slice_number; ++i) {
         fri::witness_rs_codeword_before_arrange[1][i] = &poly_commit::h_eval_arr[i * slice_size];
         fri::witness_rs_mapping[1][i] = new int[1 << lw];
-        const fieldElement *src = fri::witness_rs_codeword_before_arrange[1][i];
         for (int j = 0; j < half; ++j) {
             const int at = (j << log_leaf_size) | (i << 1);
             fri::witness_rs_mapping[1][i][j] = at;
             fri::witness_rs_mapping[1][i][j + half] = at;
-            fri::witness_rs_codeword_interleaved[1][at] = src[j];
-            fri::witness_rs_codeword_interleaved[1][at | 1] = src[j + half];
         }
     }
     witness_merkle_size[1] = half;

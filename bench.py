@@ -566,6 +566,7 @@ def run_fft_gkr(B):
                      "verifier_ms": r["verifier_seconds"] * 1e3, "ok": r["ok"], "proof_size": r["proof_size"],
                      "claims_and_proof_size_equal_reference": claims == g["claims"] and r["proof_size"] == g["proof_size"],
                      "reference_cpu_seconds": g["reference_prover_seconds"]}
+    B.fft_gkr_release()
     out["what"] = ("eq table, lg inverse-FFT butterfly layers, 64 x 2^lg products and their sums evaluated on the device; 2 + 2 lg sumchecks "
                    "(one pass-kernel launch each) without a host round trip; the verifier's closed forms on the host (vp_fft_gkr). "
                    "first_call_wall_ms includes creating the two cached sumcheck objects")

@@ -254,6 +254,9 @@ int vp_pc_fri(int device, const vp_F* array, size_t n, const vp_F* pub, size_t n
  * optional (NULL to skip): layers = E, F_{lg-1}..F_0, S (2^lg each), P (64 * 2^lg), O (64); polys = 3 elements per round in
  * protocol order (vp_fft_gkr_poly_count(lg) rounds); claims = the running claim a_0, after the addition / mult /
  * intermediate layer, after every butterfly layer, then the final alpha, beta (4 + lg + 2 elements). 1 <= lg_size <= 24. */
+/* The two sumcheck objects of a size (lg_size and lg_size + 6 variables: device tables of 3 x 2 x 16 bytes per entry) are kept
+ * per (device, lg_size) for the next call; vp_fft_gkr_release() frees them. Calls are serialised by an internal lock. */
+void vp_fft_gkr_release(void);
 size_t vp_fft_gkr_rnd_count(int lg_size);
 size_t vp_fft_gkr_poly_count(int lg_size);
 int vp_fft_gkr(int device, int lg_size, const vp_F* rnd, size_t n_rnd, vp_F* layers, vp_F* polys, size_t polys_cap, vp_F* claims,

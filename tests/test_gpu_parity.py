@@ -860,3 +860,5 @@ def test_fft_gkr_argument_checks(B, O):
         B.fft_gkr(4, bad)                            # not canonical
     with pytest.raises(B.VpError):
         B.fft_gkr(0, rnd)
+    B.fft_gkr_release()                              # frees the cached sumcheck objects; the next call recreates them
+    assert B.fft_gkr(4, rnd)["ok"]

@@ -440,6 +440,10 @@ def draw_field(n, seed=3396):
     return out
 
 
+def fft_gkr_release():
+    lib().vp_fft_gkr_release()
+
+
 def fft_gkr_rnd_count(lg):
     return int(lib().vp_fft_gkr_rnd_count(lg))
 

@@ -3971,6 +3971,7 @@ extern "C" void vp_sumcheck_destroy(vp_sumcheck* s) {
 #include "fft_gkr.cuh"
 extern "C" size_t vp_fft_gkr_rnd_count(int lg_size) { return (lg_size < 1 || lg_size > 24) ? 0 : fg::rnd_count(lg_size); }
 extern "C" size_t vp_fft_gkr_poly_count(int lg_size) { return (lg_size < 1 || lg_size > 24) ? 0 : fg::poly_count(lg_size); }
+extern "C" void vp_fft_gkr_release(void) { fg::release_cache(); }
 // fft_circuit_gkr::fft_gkr (lib/virgo/src/fft_circuit_GKR.cpp:833-849) with the randomness handed in
 extern "C" int vp_fft_gkr(int device, int lg_size, const vp_F* rnd, size_t n_rnd, vp_F* layers, vp_F* polys, size_t polys_cap, vp_F* claims,
                           int* proof_size, int* ok, double* verifier_seconds, double* prover_seconds, float* device_ms) {

@@ -183,6 +183,18 @@ static void keep_result(vp_sumcheck* s, F* d_tr, size_t& at) {
     at += cnt;
 }
 
+using Cache = std::map<std::pair<int, int>, std::pair<vp_sumcheck*, vp_sumcheck*>>;
+static std::mutex& cache_mu() { static std::mutex m; return m; }
+static Cache& cache() { static Cache c; return c; }
+static void release_cache() {
+    std::lock_guard<std::mutex> lock(cache_mu());
+    for (auto& kv : cache()) {
+        if (kv.second.first) vp_sumcheck_destroy(kv.second.first);
+        if (kv.second.second) vp_sumcheck_destroy(kv.second.second);
+    }
+    cache().clear();
+}
+
 struct Result {
     int proof_size = 0, ok = 0;
     double verifier_seconds = 0, prover_seconds = 0;
@@ -198,10 +210,9 @@ static Result run(int device, int lg, const F* rnd, F* layers_out, F* polys_out,
     CK(cudaSetDevice(device));
     const uint32_t n = 1u << lg;
     // the two sumcheck objects (lg and lg + 6 variables) and their plans are kept for the next call of the same size
-    static std::mutex cache_mu;
-    static std::map<std::pair<int, int>, std::pair<vp_sumcheck*, vp_sumcheck*>> cache;
-    std::lock_guard<std::mutex> lock(cache_mu);   // (also serialises concurrent callers: the objects hold the working tables)
-    auto& slot = cache[{device, lg}];
+    // (release_cache() frees them)
+    std::lock_guard<std::mutex> lock(cache_mu());   // (also serialises concurrent callers: the objects hold the working tables)
+    auto& slot = cache()[{device, lg}];
     if (!slot.first && sumcheck_create_impl(lg, device, &slot.first, false) != VP_OK) throw CudaError{std::string("fft_gkr: ") + vp_last_error()};
     if (!slot.second && sumcheck_create_impl(lg + 6, device, &slot.second, false) != VP_OK) throw CudaError{std::string("fft_gkr: ") + vp_last_error()};
     vp_sumcheck *s_small = slot.first, *s_big = slot.second;

@@ -1,12 +1,13 @@
-/* TEST INFRASTRUCTURE ONLY -- CPU oracle for the commit phase of Virgo's polynomial commitment:
- * poly_commit_prover::commit_private_array. Plain-C restatement; every function cites the reference lines it follows
+/* TEST INFRASTRUCTURE ONLY -- CPU oracle for the prover side of Virgo's polynomial commitment:
+ * poly_commit_prover::commit_private_array, commit_public_array and the FRI commit phase (fri::commit_phase_step).
+ * Plain-C restatement; every function cites the reference lines it follows
  * (paths under /root/reference/lib/virgo/src). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * load this; the product never does.
  *
  * Parity status: PINNED -- tests/test_oracle.py compares it with the UNMODIFIED reference (oracle/_ref/ref_pc_commit,
  * the reference's own poly_commit_prover linked with its prebuilt XKCP SHA3) through the golden files
- * tests/golden/pc_*.json written by tests/golden/make_golden_pc.py: Merkle root, SHA-256 of the codeword array l_eval,
- * of the leaf hashes and of the Merkle tree array.
+ * tests/golden/pc_*.json written by tests/golden/make_golden_pc*.py: Merkle roots, SHA-256 of the codeword arrays, of the
+ * leaf hashes and Merkle trees, all_sum, the virtual oracle, every FRI level's root / codewords / tree.
  *
  * Third-party code on this path that is NOT in source form under /root/reference: SHA3-256 from the Keccak team's
  * XKCP (prebuilt libXKCP.a, version unrecorded; header lib/libXKCP.a.headers/SimpleFIPS202.h), called only through

@@ -248,29 +248,96 @@ def run_ours(args):
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),
                                   "launches_per_step": v["launches"] // args.steps} for k, v in prof.items() if v["launches"]}
 
-    # ---------------- correctness evidence for what was just timed (every N)
-    line["parity"] = env.parity(prover, circ, tr_e2e, all_inputs, ch, "sha256_64_x%d" % (inst * world),
-                                single_gpu_check=(world > 1 and not args.no_extras))
-    line["verifier"] = line["parity"]["verifier"]
-    prover.close()
-    del prover
-    if not args.no_extras:
-        if world == 1:
-            line["pc_commit"] = run_pc_commit(B, tmpl)
-            line["fft_gkr"] = run_fft_gkr(B)
-            line["sumcheck_c2"] = run_c2(B, peak)
-            line["single_proof_c1"] = run_c1(B, tmpl)
-            line["dropin"] = run_dropin(B, tmpl, circ, inst)
-            line["c4_single_gpu"] = run_c4(env, B, args)
-            line["cpu_baseline"] = cpu_baseline_sample(args)
-        else:
-            line["strong_c4"] = run_c4(env, B, args)
-            if world == 8:
-                line["c5"] = run_c5(env, B, tmpl, args)
-    if world > 1:
-        dist.destroy_process_group()
-    if rank == 0:
-        emit(line)
+    # From here on nothing may cost the headline: rank 0 prints the line even if an optional leg throws, hangs in a
+    # collective because another rank failed, or torchrun tears the job down (see LineGuard).
+    guard = LineGuard(line, armed=(rank == 0), deadline_s=args.extras_deadline)
+    try:
+        # ---------------- correctness evidence for what was just timed (every N)
+        line["parity"] = env.parity(prover, circ, tr_e2e, all_inputs, ch, "sha256_64_x%d" % (inst * world),
+                                    single_gpu_check=(world > 1 and not args.no_extras))
+        line["verifier"] = line["parity"]["verifier"]
+        prover.close()
+        del prover
+        if not args.no_extras:
+            if world == 1:
+                guard.leg("pc_commit", run_pc_commit, B, tmpl)
+                guard.leg("fft_gkr", run_fft_gkr, B)
+                guard.leg("sumcheck_c2", run_c2, B, peak)
+                guard.leg("single_proof_c1", run_c1, B, tmpl)
+                guard.leg("dropin", run_dropin, B, tmpl, circ, inst)
+                guard.leg("c4_single_gpu", run_c4, env, B, args)
+                guard.leg("cpu_baseline", cpu_baseline_sample, args)
+            else:
+                # collective legs: an exception on one rank would leave the others waiting, so it ends the run (the
+                # guard still prints what rank 0 has)
+                line["strong_c4"] = run_c4(env, B, args)
+                if world == 8:
+                    line["c5"] = run_c5(env, B, tmpl, args)
+        if world > 1:
+            dist.destroy_process_group()
+    except BaseException as e:
+        line["extras_error"] = f"{type(e).__name__}: {e}"[:400]
+        raise
+    finally:
+        guard.finish()
+
+
+class LineGuard:
+    """Makes sure the ONE JSON line is printed exactly once by rank 0, whatever happens after the timed regions.
+
+    The timed numbers are complete before the correctness legs and the side measurements start. Those legs can fail
+    in ways a try/except around them cannot catch: a rank blocked inside a C call (an NCCL collective whose peer
+    died) never returns to the interpreter, and torchrun answers a dead rank with SIGTERM to the others. So a
+    daemon thread waits on a pipe that (a) the signal wake-up fd writes to when SIGTERM / SIGINT arrive and (b)
+    times out after `deadline_s`; in both cases it prints the line with an `extras_error` note and ends the process.
+    finish() is the normal path: it prints the line from the main thread."""
+
+    def __init__(self, line, armed, deadline_s):
+        import threading
+        self.line, self.armed, self.deadline_s = line, armed, deadline_s
+        self.lock = threading.Lock()
+        self.done = False
+        if not armed:
+            return
+        import signal
+        self.rfd, self.wfd = os.pipe()
+        os.set_blocking(self.wfd, False)
+        try:
+            for sig in (signal.SIGTERM, signal.SIGINT):
+                signal.signal(sig, lambda *_: None)      # a Python-level handler, so the C-level one feeds the wake-up fd
+            signal.set_wakeup_fd(self.wfd, warn_on_full_buffer=False)
+        except ValueError:                                # not the main thread: time-out only
+            pass
+        threading.Thread(target=self._watch, daemon=True).start()
+
+    def leg(self, name, fn, *a):
+        """an optional single-process leg: its failure is recorded in its own slot"""
+        try:
+            self.line[name] = fn(*a)
+        except Exception as e:
+            self.line[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    def _emit_once(self, note=None):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if note:
+                self.line.setdefault("extras_error", note)
+            emit(self.line)
+
+    def _watch(self):
+        import select
+        r, _, _ = select.select([self.rfd], [], [], self.deadline_s)
+        if self.done:
+            return
+        self._emit_once("terminated by a signal after the timed regions (another rank failed?)" if r else
+                        f"the legs after the timed regions did not finish within {self.deadline_s} s")
+        os._exit(0 if not r else 1)
+
+    def finish(self):
+        if self.armed:
+            self._emit_once()
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
@@ -787,6 +854,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=1024, help="SHA256_64 instances per GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2 side measurements and the CPU sample")
+    ap.add_argument("--extras-deadline", type=float, default=900.0,
+                    help="seconds the legs after the timed regions may take before rank 0 prints the line without them")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -32,3 +32,49 @@ def test_our_arm_needs_a_gpu():
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]   # no number without a GPU
+
+
+_GUARD_SCRIPT = r'''
+import ctypes, os, sys
+sys.argv = ["bench.py"]
+sys.path.insert(0, %r)
+import bench
+line = {"metric": "m", "value": 1}
+g = bench.LineGuard(line, armed=True, deadline_s=float(os.environ["DL"]))
+g.leg("failing_leg", lambda: 1 / 0)
+g.leg("fine_leg", lambda: {"x": 2})
+sys.stderr.write("READY\n"); sys.stderr.flush()
+if os.environ["MODE"] == "ok":
+    g.finish(); g.finish()           # the line is printed once
+else:
+    libc = ctypes.CDLL(None)
+    while True:                      # a main thread stuck inside a C call (a collective whose peer died)
+        libc.sleep(30)
+'''
+
+
+def _run_guard(mode, deadline, send_term=False):
+    import signal
+    import time
+    p = subprocess.Popen([sys.executable, "-c", _GUARD_SCRIPT % ROOT], env=dict(os.environ, MODE=mode, DL=str(deadline)),
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if send_term:
+        assert p.stderr.readline().strip() == "READY"   # the guard is installed
+        time.sleep(1)                                    # main thread inside libc.sleep
+        p.send_signal(signal.SIGTERM)
+    out, err = p.communicate(timeout=120)
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, (out, err[-2000:])
+    return p.returncode, json.loads(lines[0])
+
+
+def test_bench_line_survives_failing_hanging_and_terminated_legs():
+    """bench.py's LineGuard: a side measurement that throws fills its own slot; a hang after the timed regions or a
+    SIGTERM from the launcher still yields the ONE JSON line (with a note), printed exactly once."""
+    rc, d = _run_guard("ok", 60)
+    assert rc == 0 and d["value"] == 1 and "ZeroDivisionError" in d["failing_leg"]["error"] and d["fine_leg"] == {"x": 2}
+    assert "extras_error" not in d
+    rc, d = _run_guard("hang", 2)
+    assert rc == 0 and d["value"] == 1 and "did not finish" in d["extras_error"]
+    rc, d = _run_guard("hang", 120, send_term=True)
+    assert rc != 0 and d["value"] == 1 and "signal" in d["extras_error"]

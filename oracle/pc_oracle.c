@@ -188,7 +188,7 @@ long opc_commit_private(const ofe* array, int log_len, const ofe* mask, int n_ma
     }
     /* fri.cpp:84-126: leaf i = chain over the 64 slices of H(eval_s[i] || eval_s[i + half] || previous), then the mask slice */
     const int half = slice_size / 2;
-    unsigned char* leaf = (unsigned char*)malloc((size_t)half * 32);
+    unsigned char* leaf = (unsigned char*)calloc((size_t)half, 32);
     for (int i = 0; i < half; ++i) {
         unsigned char h[32], data[64];
         memset(h, 0, 32);

@@ -862,3 +862,18 @@ def test_fft_gkr_argument_checks(B, O):
         B.fft_gkr(0, rnd)
     B.fft_gkr_release()                              # frees the cached sumcheck objects; the next call recreates them
     assert B.fft_gkr(4, rnd)["ok"]
+
+
+def test_random_pws_campaign_sample():
+    """A slice of tools/gpu_diff_campaign.py (seeded random .pws circuits x K instances: whole proof, method by method, lane
+    settings, verifier verdicts -- all against the oracle); profiles/r2f_gpu_diff_campaign.txt is the 1896-circuit run."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_diff_campaign.py"), "50001", "8"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    last = r.stdout.strip().splitlines()[-1]
+    assert last.startswith("gpu_diff_campaign:") and last.endswith(": 0 mismatches"), r.stdout[-2000:]
+    assert int(last.split()[1]) >= 10, last

@@ -174,6 +174,19 @@ def test_sharded_proof_matches_oracle_on_2_gpus():
 
 
 @pytest.mark.gpu
+def test_sharded_random_campaign_on_2_gpus():
+    """a slice of tests/dist_gpu_campaign.py: seeded random circuits x K instances on a context sharded over 2 GPUs
+    (whole proof, witness slices, method-by-method API, sharded verifier) against the oracle"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29657", os.path.join(ROOT, "tests", "dist_gpu_campaign.py"), "90001", "20"],
+                       capture_output=True, text=True, timeout=900)
+    assert "DIST_CAMPAIGN PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
 def test_dropin_program_on_2_gpus(tmp_path, sha_pws_text):
     """the reference's UNMODIFIED main + verifier, two copies of the program (VP_WORLD=2, one per GPU) sharing one sharded
     prover through the drop-in class: both must print `Verification pass` and the reference's proof size"""

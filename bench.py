@@ -247,6 +247,9 @@ def run_ours(args):
         add_step_int_frac(line["roofline"], inst, world, ms_resident, clocks)
     line["kernel_classes"] = {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None),
                                   "launches_per_step": v["launches"] // args.steps} for k, v in prof.items() if v["launches"]}
+    line["kernel_classes"]["note"] = ("per-class device time of the instrumented ONE-LANE pass; it overstates init_liu by one field "
+                                      "product per table entry (the pre-scaled beta_u table only exists on the second lane set of "
+                                      "the multi-lane runs that `value` times)")
 
     # From here on nothing may cost the headline: rank 0 prints the line even if an optional leg throws, hangs in a
     # collective because another rank failed, or torchrun tears the job down (see LineGuard).

@@ -493,3 +493,68 @@ def test_loader_and_oracle_match_live_reference_on_random_pws(B, O, seed, n_in, 
     assert H.circuit_dump(circ) == want_cb
     tr, ch, _ = O.OracleCircuit(circ.flat()).prove()
     assert H.transcript_text(circ, tr, ch) == want_tr
+
+
+# ------------------------------------------------------------------ Fiat-Shamir challenge source == the reference's own class
+def test_fiat_shamir_challenge_source_is_the_reference_transcript_cache(B, O, sha_circuit):
+    """The reference ships `transcriptCache` (lib/virgo/src/transcriptCache.hpp:14-50) but never calls it. Where the reference
+    is built (oracle/_ref/ref_tcache: the UNMODIFIED class behind a script reader), replay the store / draw sequence of
+    Fiat-Shamir mode (virgo-plus_b200/host/fiat_shamir.h) for an FS transcript through the reference's class: every draw must
+    be the challenge the oracle used and the product's host-side vp_fs_challenges recomputes. What stays this repo's own
+    design is only WHEN messages are stored and challenges drawn."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_tcache")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_tcache not built (needs /root/reference)")
+    seed = bytes((7 * i + 3) & 0xff for i in range(32))
+    for circ in (B.Circuit.random(5, 4, 21), B.Circuit.random(3, 1, 5), sha_circuit):
+        oc = O.OracleCircuit(circ.flat())
+        tr, ch = oc.prove_fs(seed)
+        n = circ.n_layers
+        max_bl = max(circ.bit_length(i) for i in range(n))
+        script, slots = ["S " + seed.hex()], []          # slots: the challenge index every draw fills, in draw order
+        fe = lambda x: script.append(f"F {int(x['re'])} {int(x['im'])}")
+
+        def draw(ci):
+            script.append("R")
+            slots.append(ci)
+
+        ti = ci = 0
+        for j in range(circ.bit_length(n - 1)):
+            draw(ci + j)
+        ci += circ.bit_length(n - 1)
+        fe(tr[ti]); ti += 1                                # Vres
+
+        def rounds(count, base):
+            nonlocal ti
+            for j in range(count):
+                fe(tr[ti]); fe(tr[ti + 1]); fe(tr[ti + 2]); ti += 3
+                draw(base + j)
+
+        for i in range(n - 1, 0, -1):
+            pb, m = circ.bit_length(i - 1), circ.max_dad_bit_length(i)
+            ci_ru, ci_assert = ci, ci + max_bl
+            ci_rv = ci_assert + 1
+            ci_sig = ci_rv + (m if m != -1 else 0)
+            ci_rliu = ci_sig + n
+            draw(ci_assert)
+            rounds(pb, ci_ru)
+            fe(tr[ti]); ti += 1                            # claim_u
+            if m != -1:
+                rounds(m, ci_rv)
+                for _ in range(i):
+                    fe(tr[ti]); ti += 1                    # claims_v
+            for k in range(n):
+                draw(ci_sig + k)
+            rounds(pb, ci_rliu)
+            fe(tr[ti]); ti += 1                            # claim_liu
+            ci = ci_rliu + max_bl
+        assert ti == len(tr) - 1 and ci == len(ch)         # the input MLE is stored last, no draw follows
+        r = subprocess.run([exe], input="\n".join(script) + "\n", capture_output=True, text=True, check=True)
+        draws = [tuple(int(x) for x in l.split()) for l in r.stdout.split("\n") if l.strip()]
+        assert len(draws) == len(slots)
+        want = np.zeros(len(ch), O.F_DTYPE)                # unused slots stay zero
+        for (re_, im_), k in zip(draws, slots):
+            want[k]["re"], want[k]["im"] = re_, im_
+        assert (want["re"] == ch["re"]).all() and (want["im"] == ch["im"]).all()
+        ch3 = circ.fs_challenges(seed, tr)                 # the product's host-side recomputation
+        assert (ch3["re"] == want["re"]).all() and (ch3["im"] == want["im"]).all()

@@ -558,3 +558,58 @@ def test_fiat_shamir_challenge_source_is_the_reference_transcript_cache(B, O, sh
         assert (want["re"] == ch["re"]).all() and (want["im"] == ch["im"]).all()
         ch3 = circ.fs_challenges(seed, tr)                 # the product's host-side recomputation
         assert (ch3["re"] == want["re"]).all() and (ch3["im"] == want["im"]).all()
+
+
+def test_gkrproof_bytes_are_read_and_rewritten_by_the_reference_container(B, O, sha_circuit, tmp_path):
+    """Where the reference is built: its own (dead) GKRProof::read (src/GKRProof.hpp:101-140) parses the byte stream
+    vp_transcript_to_gkrproof produces -- every member holds the transcript slice the layout says -- and its own
+    GKRProof::write (:23-58) reproduces those bytes. (oracle/ref_harness/ref_gkrproof.cpp: NetIO / PolyProof are empty
+    stand-ins; the product's two-element trailer sits where the reference's poly_proof would.)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gkrproof")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_gkrproof not built (needs /root/reference)")
+    for circ in (sha_circuit, B.Circuit.random(5, 4, 21)):
+        tr, _, _ = O.OracleCircuit(circ.flat()).prove()
+        blob = bytes(circ.to_gkrproof(tr))
+        path = tmp_path / "proof.bin"
+        path.write_bytes(blob)
+        out = subprocess.run([exe, str(path)], capture_output=True, text=True, check=True).stdout.split("\n")
+        assert out[-2] == f"consumed {len(blob) - 8 - 32} of {len(blob)} bytes; write() reproduces them: yes", out[-2]
+        # parse the members the reference found
+        it = iter(out[:-2])
+        fe = lambda: tuple(int(x) for x in next(it).split())
+        n = circ.n_layers
+
+        def flat_member(name):
+            head = next(it).split()
+            assert head[0] == name and int(head[1]) == n, head
+            return [fe() for _ in range(n)]
+
+        def nested_member(name, per):
+            head = next(it).split()
+            assert head[0] == name and int(head[1]) == n, head
+            rows = []
+            for _ in range(n):
+                cnt = int(next(it).split()[1])
+                rows.append([fe() for _ in range(cnt * per)])
+            return rows
+
+        cu, cl = flat_member("final_claims_u"), flat_member("final_claims")
+        cv = nested_member("final_claims_v", 1)
+        pu, pv, pl = nested_member("polys_u", 3), nested_member("polys_v", 3), nested_member("polys", 3)
+        # the same walk over the flat transcript as the reference's verifier makes (verifier.cpp:134-337)
+        t = lambda k: (int(tr[k]["re"]), int(tr[k]["im"]))
+        ti = 1
+        for i in range(n - 1, 0, -1):
+            pb, m = circ.bit_length(i - 1), circ.max_dad_bit_length(i)
+            assert pu[i] == [t(ti + k) for k in range(3 * pb)]; ti += 3 * pb
+            assert cu[i] == t(ti); ti += 1
+            if m != -1:
+                assert pv[i] == [t(ti + k) for k in range(3 * m)]; ti += 3 * m
+                assert cv[i] == [t(ti + k) for k in range(i)]; ti += i
+            else:
+                assert pv[i] == [] and cv[i] == []
+            assert pl[i] == [t(ti + k) for k in range(3 * pb)]; ti += 3 * pb
+            assert cl[i] == t(ti); ti += 1
+        assert ti == len(tr) - 1
+        assert cu[0] == (0, 0) and cl[0] == (0, 0) and pu[0] == [] and pv[0] == [] and pl[0] == [] and cv[0] == []

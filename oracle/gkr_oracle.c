@@ -865,10 +865,10 @@ int ogkr_verify(const ogkr_circuit* c, unsigned seed, const ofe* tr, int* fail_c
             for (int k = 0; k < n; ++k) sig[k] = verifier_draw();
             for (int k = 0; k < mbl; ++k) r_liu[k] = verifier_draw();
             previousSum = ofe_mul(sig[0], claim_u);
+            /* verifier.cpp:281-284: `~dadBitLength` is also true for an EMPTY subset (INT_MIN, circuit.cpp:73), so its claim
+             * (0 from an honest prover) is part of the sum: a tampered one fails the first Liu round of this layer */
             for (int j = i; j < n; ++j)
-                if (dad_bl(c, j, pre) >= 0)
-                    previousSum = ofe_add(previousSum, ofe_mul(sig[j - pre], claims_v[j][pre]));
-            /* ref also adds sig*claim for INT_MIN (empty) subsets; those claims are 0 */
+                previousSum = ofe_add(previousSum, ofe_mul(sig[j - pre], claims_v[j][pre]));
             for (int j = 0; j < pb; ++j) {
                 quad q = {tr[ti], tr[ti + 1], tr[ti + 2]};
                 ti += 3;

@@ -16,6 +16,9 @@
 #undef prover
 
 void ref_log(const char *tag, const F &x);
+// REF_TAMPER=<k> (ref_dump): the k-th prover->verifier message (transcript order: VRES, PA, PB, PC, CLAIM_*, ..., INPUT_MLE;
+// challenges are not counted) reaches the UNMODIFIED verifier with 1 added to it, and is logged as the verifier saw it.
+F ref_tamper(const F &x);
 
 class prover {
 public:
@@ -28,8 +31,11 @@ public:
     void sumcheckInitPhase2() { ref.sumcheckInitPhase2(); }
     void sumcheckInitLiu(vector<F>::const_iterator s) { ref.sumcheckInitLiu(s); }
 
-    quadratic_poly log_poly(const F &prev, const quadratic_poly &p) {
+    quadratic_poly log_poly(const F &prev, quadratic_poly p) {
         ref_log("CH", prev);
+        p.a = ref_tamper(p.a);
+        p.b = ref_tamper(p.b);
+        p.c = ref_tamper(p.c);
         ref_log("PA", p.a);
         ref_log("PB", p.b);
         ref_log("PC", p.c);
@@ -41,6 +47,7 @@ public:
 
     void sumcheckFinalize1(const F &prev, F &claim) {
         ref.sumcheckFinalize1(prev, claim);
+        claim = ref_tamper(claim);
         ref_log("CH", prev);
         ref_log("CLAIM_U", claim);
     }
@@ -49,15 +56,16 @@ public:
         ++n_fin2;
         // the verifier hands final_claims_v[layer].begin(), which has exactly `layer` entries; the
         // layer id counts down from size-1 on every sumcheckInit (prover.cpp:166,179)
-        for (int i = 0; i < cur_layer; ++i) ref_log("CLAIM_V", claims[i]);
+        for (int i = 0; i < cur_layer; ++i) { claims[i] = ref_tamper(claims[i]); ref_log("CLAIM_V", claims[i]); }
     }
     void sumcheckLiuFinalize(const F &prev, F &claim) {
         ref.sumcheckLiuFinalize(prev, claim);
+        claim = ref_tamper(claim);
         ref_log("CH", prev);
         ref_log("CLAIM_LIU", claim);
     }
     F Vres(const vector<F>::const_iterator &r_0, int r_0_size) {
-        F x = ref.Vres(r_0, r_0_size);
+        F x = ref_tamper(ref.Vres(r_0, r_0_size));
         ref_log("VRES", x);
         return x;
     }
@@ -68,6 +76,7 @@ public:
     F inner_prod(const vector<F> &a, const vector<F> &b, u64 l) { return ref.inner_prod(a, b, l); }
     virgo::__hhash_digest commit_public(vector<F> &pub, F &sum, std::vector<F> &mask, vector<F> &all_sum) {
         auto d = ref.commit_public(pub, sum, mask, all_sum);
+        sum = ref_tamper(sum);
         ref_log("INPUT_MLE", sum);
         return d;
     }

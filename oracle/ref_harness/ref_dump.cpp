@@ -7,6 +7,7 @@
 //   stdout                  : the reference's own statistics lines + "VERIFY 0|1"
 // usage: ref_dump <circuit.pws> <out_prefix>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <string>
 #include <vector>
@@ -19,6 +20,8 @@ void DAG_to_layered();
 
 static std::vector<std::pair<std::string, F>> g_log;
 void ref_log(const char *tag, const F &x) { g_log.emplace_back(tag, x); }
+static long g_msg = 0, g_tamper = -1;   // REF_TAMPER: see proxy_prover.h
+F ref_tamper(const F &x) { return g_msg++ == g_tamper ? x + F_ONE : x; }
 
 template <class T>
 static void put(FILE *f, const T &x) { fwrite(&x, sizeof(T), 1, f); }
@@ -55,6 +58,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "usage: %s <circuit.pws> <out_prefix>\n", argv[0]);
         return 2;
     }
+    if (getenv("REF_TAMPER")) g_tamper = atol(getenv("REF_TAMPER"));
     std::ifstream in(argv[1]);
     if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
     parse(in);

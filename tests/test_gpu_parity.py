@@ -877,3 +877,21 @@ def test_random_pws_campaign_sample():
     last = r.stdout.strip().splitlines()[-1]
     assert last.startswith("gpu_diff_campaign:") and last.endswith(": 0 mismatches"), r.stdout[-2000:]
     assert int(last.split()[1]) >= 10, last
+
+
+def test_device_verifier_gives_the_reference_verifiers_verdict_on_tampered_messages(B, O):
+    """vp_verify against what the UNMODIFIED reference verifier answered (tests/golden/verifier_verdicts.json, recorded by
+    tools/diff_reference_verifier.py): every third message of the six golden small circuits altered one at a time -- same
+    accept / failing check / layer, incl. non-zero claims for empty dad subsets (rejected at the Liu phase of the source layer)."""
+    import test_oracle as T
+    n = 0
+    for name, circ, oc, tr, cases in T.verifier_verdict_cases(B, O, stride=3):
+        p = B.Prover(circ, device=0)
+        got = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+        _assert_same(got, tr, name)
+        assert p.verify(tr) == (True, 0, 0)
+        for k, want in cases:
+            assert tuple(p.verify(T.tampered(B, tr, k))) == want, (name, k)
+            n += 1
+        p.close()
+    assert n > 700

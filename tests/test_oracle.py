@@ -613,3 +613,38 @@ def test_gkrproof_bytes_are_read_and_rewritten_by_the_reference_container(B, O, 
             assert cl[i] == t(ti); ti += 1
         assert ti == len(tr) - 1
         assert cu[0] == (0, 0) and cl[0] == (0, 0) and pu[0] == [] and pv[0] == [] and pl[0] == [] and cv[0] == []
+
+
+# ------------------------------------------------------------------ verifier (N2): verdicts of the UNMODIFIED reference verifier
+def verifier_verdict_cases(B, O, stride=1):
+    """(circuit, oracle circuit, honest transcript, [(message index, reference verdict)]) from tests/golden/verifier_verdicts.json:
+    what the stock verifier.cpp answered when message k reached it with 1 added (tools/diff_reference_verifier.py)."""
+    import json
+    with open(os.path.join(H.GOLDEN, "verifier_verdicts.json")) as f:
+        gold = json.load(f)
+    for name in SMALL:
+        circ = B.Circuit.from_pws_text(H.golden_bytes(name + ".pws.xz"))
+        oc = O.OracleCircuit(circ.flat())
+        tr, _, _ = oc.prove()
+        assert len(gold[name]) == len(tr)
+        yield name, circ, oc, tr, [(k, (bool(v[0]), v[1], v[2])) for k, v in sorted((int(k), v) for k, v in gold[name].items())][::stride]
+
+
+def tampered(B, tr, k):
+    t = tr.copy()
+    t[k]["re"] = (int(t[k]["re"]) + 1) % B.P
+    return t
+
+
+def test_oracle_verifier_gives_the_reference_verifiers_verdict_on_every_tampered_message(B, O):
+    """2117 cases: every message of the six golden small circuits, altered one at a time. Includes the claims a prover sends for
+    EMPTY dad subsets: the reference counts them in verifyLiu's claim (`~dadBitLength` is true for INT_MIN, verifier.cpp:281-284)
+    and rejects a non-zero one at the first Liu round of the source layer."""
+    n = 0
+    for name, circ, oc, tr, cases in verifier_verdict_cases(B, O):
+        assert oc.verify(tr) == (True, 0, 0)
+        for k, want in cases:
+            assert tuple(oc.verify(tampered(B, tr, k))) == want, (name, k)
+            n += 1
+        assert any(not w[0] for _, w in cases)
+    assert n == 2117

@@ -2440,8 +2440,9 @@ int Engine::verify(const F* tr, int* fail_code, int* fail_layer) {
         const F* sig = h_chal.data() + D.ci_sig;
         const F* r_liu = h_chal.data() + D.ci_rliu;
         previousSum = f_mul(sig[0], claim_u);
-        for (int j = i; j < n; ++j)
-            if (C.layers[j].dadSize[pre] > 0) previousSum = f_add(previousSum, f_mul(sig[j - pre], claims_v[j][pre]));
+        // verifier.cpp:281-284 tests `~dadBitLength`, which is also true for an EMPTY subset (dadBitLength == INT_MIN there,
+        // circuit.cpp:73): the claim the prover sent for it (0 if honest) counts, so a non-zero one is caught here
+        for (int j = i; j < n; ++j) previousSum = f_add(previousSum, f_mul(sig[j - pre], claims_v[j][pre]));
         for (int j = 0; j < pb; ++j, ti += 3) {
             if (!ok_sum(tr + ti, previousSum)) VP_FAIL(4, i);
             previousSum = ev(tr + ti, r_liu[j]);

@@ -209,8 +209,13 @@ def ref_prove(flat):
     oc = OracleCircuit(flat)
     tr = np.zeros(oc.transcript_len, F_DTYPE)
     ps, es = C.c_double(), C.c_double()
-    n = _ref.ref_gkr_prove(f["n_layers"], _p(f["layer_size"]), _p(f["ty"]), _p(f["l"]), _p(f["u"]), _p(f["v"]),
-                           _p(f["inputs"]), 3396, _p(tr), C.byref(ps), C.byref(es))
+    if np.any(f["c"]["re"] | f["c"]["im"]) or np.any(f["is_assert"]):   # gate constants / assert flags: the extended entry point
+        _ref.ref_gkr_prove2.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        n = _ref.ref_gkr_prove2(f["n_layers"], _p(f["layer_size"]), _p(f["ty"]), _p(f["l"]), _p(f["u"]), _p(f["v"]),
+                                _p(f["inputs"]), _p(f["c"]), _p(f["is_assert"]), _p(tr), C.byref(ps), C.byref(es))
+    else:
+        n = _ref.ref_gkr_prove(f["n_layers"], _p(f["layer_size"]), _p(f["ty"]), _p(f["l"]), _p(f["u"]), _p(f["v"]),
+                               _p(f["inputs"]), 3396, _p(tr), C.byref(ps), C.byref(es))
     assert n == len(tr), (n, len(tr))
     return tr, ps.value, es.value
 

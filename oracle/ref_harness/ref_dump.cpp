@@ -6,6 +6,11 @@
 //   <prefix>.circuit.bin    : the reference's layeredCircuit after subsetInit, flat (see dump_circuit)
 //   stdout                  : the reference's own statistics lines + "VERIFY 0|1"
 // usage: ref_dump <circuit.pws> <out_prefix>
+//        ref_dump <circuit.mem> <out_prefix>   a layered circuit handed over directly (gate types, constants and assert flags
+//                                              the .pws parser never produces): i32 n_layers; per layer u64 size; per gate
+//                                              u8 ty, i32 l, u64 u, u64 v, u64 c.real, u64 c.img, u8 is_assert (layer 0: u = input)
+//        REF_TAMPER=<k> in the environment: see proxy_prover.h
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -59,10 +64,41 @@ int main(int argc, char **argv) {
         return 2;
     }
     if (getenv("REF_TAMPER")) g_tamper = atol(getenv("REF_TAMPER"));
-    std::ifstream in(argv[1]);
-    if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
-    parse(in);
-    DAG_to_layered();
+    const std::string path = argv[1];
+    if (path.size() > 4 && path.substr(path.size() - 4) == ".mem") {
+        FILE *m = fopen(argv[1], "rb");
+        if (!m) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
+        auto get = [&](void *dst, size_t n) { if (fread(dst, 1, n, m) != n) { fprintf(stderr, "short circuit file\n"); exit(2); } };
+        int32_t n;
+        get(&n, 4);
+        c.size = n;
+        c.circuit.resize(n);
+        for (int i = 0; i < n; ++i) {
+            layer &L = c.circuit[i];
+            uint64_t sz;
+            get(&sz, 8);
+            L.size = sz;
+            L.gates.resize(sz);
+            for (u64 g = 0; g < sz; ++g) {
+                uint8_t ty, as;
+                int32_t l;
+                uint64_t u, v, cr, ci;
+                get(&ty, 1); get(&l, 4); get(&u, 8); get(&v, 8); get(&cr, 8); get(&ci, 8); get(&as, 1);
+                F cc = F_ZERO;
+                cc.real = cr;
+                cc.img = ci;
+                L.gates[g] = i == 0 ? gate(gateType::Input, -1, u, 0, F_ZERO, false) : gate((gateType)ty, l, u, v, cc, as != 0);
+            }
+            L.bitLength = (int)log2(L.size);   // main.cpp:133-136
+            if ((1ULL << L.bitLength) < L.size) ++L.bitLength;
+        }
+        fclose(m);
+    } else {
+        std::ifstream in(argv[1]);
+        if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
+        parse(in);
+        DAG_to_layered();
+    }
     F::init();
     c.subsetInit();
     dump_circuit((std::string(argv[2]) + ".circuit.bin").c_str());

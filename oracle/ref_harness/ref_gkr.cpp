@@ -22,10 +22,20 @@
 struct ofe { uint64_t re, im; };
 static inline ofe to_ofe(const F &x) { return ofe{x.real, x.img}; }
 
+// cst / is_assert (per gate, layer 0 included; may be null): gate constants of Addc / Mulc gates (any F, also complex) and
+// assert flags -- gate types and fields the .pws parser never produces but prover.cpp handles (prover.cpp:60-83,211,229-272).
+extern "C" int ref_gkr_prove2(int n_layers, const uint64_t *layer_size, const uint8_t *ty, const int32_t *l,
+                              const uint32_t *u, const uint32_t *v, const uint64_t *inputs, const ofe *cst,
+                              const uint8_t *is_assert, ofe *tr, double *prove_seconds, double *eval_seconds);
 extern "C" int ref_gkr_prove(int n_layers, const uint64_t *layer_size, const uint8_t *ty, const int32_t *l,
                              const uint32_t *u, const uint32_t *v, const uint64_t *inputs, unsigned seed,
                              ofe *tr, double *prove_seconds, double *eval_seconds) {
     (void)seed;  // F::init() seeds 3396 (fieldElement.cpp:108)
+    return ref_gkr_prove2(n_layers, layer_size, ty, l, u, v, inputs, nullptr, nullptr, tr, prove_seconds, eval_seconds);
+}
+extern "C" int ref_gkr_prove2(int n_layers, const uint64_t *layer_size, const uint8_t *ty, const int32_t *l,
+                              const uint32_t *u, const uint32_t *v, const uint64_t *inputs, const ofe *cst,
+                              const uint8_t *is_assert, ofe *tr, double *prove_seconds, double *eval_seconds) {
     layeredCircuit c;
     c.size = n_layers;
     c.circuit.resize(n_layers);
@@ -36,7 +46,11 @@ extern "C" int ref_gkr_prove(int n_layers, const uint64_t *layer_size, const uin
         L.gates.resize(L.size);
         for (u64 g = 0; g < L.size; ++g) {
             if (i == 0) L.gates[g] = gate(gateType::Input, -1, inputs[g], 0, F_ZERO, false);
-            else L.gates[g] = gate((gateType)ty[off + g], l[off + g], u[off + g], v[off + g], F_ZERO, false);
+            else {
+                F cc = F_ZERO;
+                if (cst) { cc.real = cst[off + g].re; cc.img = cst[off + g].im; }
+                L.gates[g] = gate((gateType)ty[off + g], l[off + g], u[off + g], v[off + g], cc, is_assert && is_assert[off + g]);
+            }
         }
         L.bitLength = (int)log2(L.size);  // main.cpp:133-136
         if ((1ULL << L.bitLength) < L.size) ++L.bitLength;

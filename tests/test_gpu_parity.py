@@ -895,3 +895,25 @@ def test_device_verifier_gives_the_reference_verifiers_verdict_on_tampered_messa
             n += 1
         p.close()
     assert n > 700
+
+
+def test_device_prover_and_verifier_equal_the_reference_on_all_gate_types(B, O):
+    """The circuits of tests/golden/verifier_verdicts_alltypes.json.xz (all gate types, real / complex constants, assert gates)
+    on the device: transcript == what the UNMODIFIED reference verifier accepted (hash recorded from that run), and vp_verify
+    gives the stock verifier's verdict on every sixth message altered."""
+    import hashlib
+    import test_oracle as T
+    n = 0
+    for seed, circ, oc, tr, cases in T.alltypes_verdict_cases(B, O, stride=3):
+        p = B.Prover(circ, device=0)
+        got = p.prove(inputs=circ.inputs(), challenges=circ.draw_challenges())
+        _assert_same(got, tr, f"all-types circuit {seed}")
+        assert p.verify(got) == (True, 0, 0)
+        for k, want in cases:
+            assert tuple(p.verify(T.tampered(B, tr, k))) == want, (seed, k)
+            n += 1
+        p.close()
+        p = B.Prover(circ, device=0)
+        _assert_same(B.prove_interactive(p, circ), tr, f"all-types circuit {seed}, method by method")
+        p.close()
+    assert n > 450

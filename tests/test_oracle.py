@@ -648,3 +648,37 @@ def test_oracle_verifier_gives_the_reference_verifiers_verdict_on_every_tampered
             n += 1
         assert any(not w[0] for _, w in cases)
     assert n == 2117
+
+
+def alltypes_verdict_cases(B, O, stride=1):
+    """tests/golden/verifier_verdicts_alltypes.json.xz (tools/diff_reference_alltypes.py): layered circuits over ALL gate types --
+    Addc / Mulc with real and complex constants, Copy, Not, assert gates: what the .pws parser never emits -- for which the
+    UNMODIFIED reference (stock prover + stock verifier incl. the commitment, in-memory mode of ref_dump) accepted the honest
+    run with exactly the oracle's transcript, and its verdict for every second message altered.
+    -> (seed, circuit, oracle circuit, honest transcript, [(message index, reference verdict)])"""
+    import json
+    gold = json.loads(H.golden_bytes("verifier_verdicts_alltypes.json.xz"))
+    for seed, g in sorted(gold.items(), key=lambda kv: int(kv[0])):
+        a = g["arrays"]
+        cst = np.zeros(len(a["c"]), B.F_DTYPE)
+        cst["re"] = [x[0] for x in a["c"]]
+        cst["im"] = [x[1] for x in a["c"]]
+        circ = B.Circuit.from_arrays(a["sizes"], a["ty"], a["l"], a["u"], a["v"], c=cst,
+                                     is_assert=a["is_assert"] if any(a["is_assert"]) else None)
+        oc = O.OracleCircuit(circ.flat())
+        tr, _, _ = oc.prove()
+        assert len(tr) == g["transcript_len"]
+        assert hashlib.sha256(np.ascontiguousarray(tr).tobytes()).hexdigest() == g["transcript_sha256"]   # what the stock verifier saw
+        yield seed, circ, oc, tr, [(k, (bool(v[0]), v[1], v[2])) for k, v in sorted((int(k), v) for k, v in g["verdicts"].items())][::stride]
+
+
+def test_oracle_equals_the_reference_on_all_gate_types_prover_and_verifier(B, O):
+    """16 circuits x every second message: the oracle prover's transcript is what the stock verifier accepted, and the oracle
+    verifier gives the stock verifier's verdict (failing check, layer) on each tampered message"""
+    n = 0
+    for seed, circ, oc, tr, cases in alltypes_verdict_cases(B, O):
+        assert oc.verify(tr) == (True, 0, 0)
+        for k, want in cases:
+            assert tuple(oc.verify(tampered(B, tr, k))) == want, (seed, k)
+            n += 1
+    assert n > 1500

@@ -917,3 +917,20 @@ def test_device_prover_and_verifier_equal_the_reference_on_all_gate_types(B, O):
         _assert_same(B.prove_interactive(p, circ), tr, f"all-types circuit {seed}, method by method")
         p.close()
     assert n > 450
+
+
+@pytest.mark.parametrize("name", ["small_allops", "small_chain", "small_notquirk", "small_random_a", "small_random_b", "small_random_c",
+                                  "sha256_64_x2"])
+def test_proof_size_equals_the_reference_statistics_line(B, O, sha_pws_text, name):
+    """prover::proofSize() (prover.cpp:553-555, printed by main.cpp as `proof size = ... kb`) through the method-by-method API:
+    the value the UNMODIFIED reference printed for the golden circuits (tests/golden/*.stats.txt), incl. the 16 bytes it counts for
+    every EMPTY dad subset (the INT_MIN quirk)."""
+    import re
+    import helpers as H
+    import test_oracle as T
+    circ = T._case_circuit(B, name, sha_pws_text)
+    want = float(re.search(r"proof size = ([0-9.]+) kb", H.golden_text(name + ".stats.txt")).group(1))
+    p = B.Prover(circ)
+    B.prove_interactive(p, circ)
+    assert abs(p.proofSize() - want) < 1e-9, (p.proofSize(), want)
+    p.close()

@@ -682,3 +682,28 @@ def test_oracle_equals_the_reference_on_all_gate_types_prover_and_verifier(B, O)
             assert tuple(oc.verify(tampered(B, tr, k))) == want, (seed, k)
             n += 1
     assert n > 1500
+
+
+def test_loader_statement_grammar_follows_the_reference_regexes(B):
+    """main.cpp:160-204: a line is a statement only if the WHOLE line matches one of the regexes (single spaces, `[0-9]+` ids with
+    any number of digits); everything else is skipped -- whatever numbers it holds. Found by tools/diff_reference_pws_format.py:
+    a malformed line with an overlong id used to make the loader reject the file."""
+    base = b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 * V1 E\nP V3 = V2 + V0 E\nP O4 = V3 E\n"
+    want = H.circuit_dump(B.Circuit.from_pws_text(base))
+    skipped = [b"P V1 = V0 +  V0 E", b"P V1 = V0 + V0 E ", b" P V1 = V0 + V0 E", b"P V1 = V0 + V0 E\r", b"P V1 = V0 xor V0 E",
+               b"P V1 = V0 + V0", b"V1 = V0 + V0 E", b"P V1 = V0 + I0 E", b"P V-1 = V0 + V0 E", b"P V1 = V0\t+ V0 E", b"P V1 = V0 + V0 E E",
+               b"p V1 = V0 + V0 E", b"P V1.0 = V0 + V0 E", b"P V1 = V0 MINUS V0 E", b"P V = I0 E", b"P V1 = V0 +V0 E", b"\x00",
+               b"P V99999999999999999999999 = I0 E x", b"P V99999999999999999999999 = V0 + V0", b"P V5 = V99999999999999999999999 NOTT V0 E"]
+    for junk in skipped:
+        assert H.circuit_dump(B.Circuit.from_pws_text(base + junk + b"\n")) == want, junk
+        assert H.circuit_dump(B.Circuit.from_pws_text(junk + b"\n" + base)) == want, junk
+    # match-preserving spellings: leading zeros; numbers the reference never uses (input index, NOT's second operand)
+    assert H.circuit_dump(B.Circuit.from_pws_text(b"P V0 = I0 E\nP V01 = I1 E\nP V002 = V000 * V1 E\nP V3 = V2 + V0 E\n")) == want
+    assert H.circuit_dump(B.Circuit.from_pws_text(base.replace(b"I0", b"I99999999999999999999999999"))) == want
+    a = B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 * V1 E\nP V3 = V1 NOT V99999999999999999999999 E\n")
+    b = B.Circuit.from_pws_text(b"P V0 = I0 E\nP V1 = I1 E\nP V2 = V0 * V1 E\nP V3 = V1 NOT V1 E\n")
+    assert H.circuit_dump(a) == H.circuit_dump(b)
+    # a WELL-FORMED statement with an impossible id is still an error (the reference's sscanf overflows: undefined there)
+    for bad in (b"P V99999999999999999999999 = I0 E", b"P V4 = V99999999999999999999999 + V0 E", b"P V4 = V0 + V99999999999999999999999 E"):
+        with pytest.raises(B.VpError):
+            B.Circuit.from_pws_text(base + bad + b"\n")

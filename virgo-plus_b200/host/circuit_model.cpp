@@ -215,12 +215,16 @@ struct DagGate {
 // as in the reference's Release build (assert(false) compiled out, main.cpp:204).
 static thread_local uint64_t dag_id_cap = 0;        // number of lines of the file: dense ids cannot exceed it
 static thread_local bool dag_overflow = false;      // a number too large to be an id / index was seen
-bool read_uint(const char*& p, const char* e, uint64_t& out) {
+// [0-9]+ like the reference's regexes (any number of digits, leading zeros allowed). A value too large to be an id sets
+// `big` and keeps consuming digits: whether that matters is decided once the WHOLE line is known to be a statement (the
+// reference skips a malformed line whatever numbers it holds, main.cpp:176-204).
+bool read_uint(const char*& p, const char* e, uint64_t& out, bool& big) {
     if (p >= e || *p < '0' || *p > '9') return false;
     uint64_t x = 0;
     while (p < e && *p >= '0' && *p <= '9') {
-        if (x > (1ULL << 40)) { dag_overflow = true; return false; }   // no silent wrap-around: the file is rejected
-        x = x * 10 + (uint64_t)(*p++ - '0');
+        if (x > (1ULL << 40)) big = true;   // no silent wrap-around
+        else x = x * 10 + (uint64_t)(*p - '0');
+        ++p;
     }
     out = x;
     return true;
@@ -235,21 +239,22 @@ bool eat(const char*& p, const char* e, const char* lit) {
 void parse_line(const char* p, const char* e, std::vector<DagGate>& dag, uint64_t& n_inputs_seen,
                 std::vector<uint64_t>& input_order) {
     uint64_t tgt, a, b;
+    bool big = false, big_ignored = false;
     if (!eat(p, e, "P ")) return;
     if (eat(p, e, "O")) {  // output line: parsed and dropped
         return;
     }
-    if (!eat(p, e, "V") || !read_uint(p, e, tgt) || !eat(p, e, " = ")) return;
+    if (!eat(p, e, "V") || !read_uint(p, e, tgt, big) || !eat(p, e, " = ")) return;
     DagGate g;
     if (eat(p, e, "I")) {
-        if (!read_uint(p, e, a) || !eat(p, e, " E") || p != e) return;
+        if (!read_uint(p, e, a, big_ignored) || !eat(p, e, " E") || p != e) return;   // the input index is never used (main.cpp:184-185)
         g.ty = Input;
         g.k0 = 'S';
         g.k1 = 'N';
         ++n_inputs_seen;
         input_order.push_back(tgt);
     } else {
-        if (!eat(p, e, "V") || !read_uint(p, e, a) || !eat(p, e, " ")) return;
+        if (!eat(p, e, "V") || !read_uint(p, e, a, big) || !eat(p, e, " ")) return;
         uint8_t ty;
         if (eat(p, e, "+ ")) ty = Add;
         else if (eat(p, e, "* ")) ty = Mul;
@@ -258,7 +263,7 @@ void parse_line(const char* p, const char* e, std::vector<DagGate>& dag, uint64_
         else if (eat(p, e, "minus ")) ty = Sub;
         else if (eat(p, e, "NOT ")) ty = Not;
         else return;
-        if (!eat(p, e, "V") || !read_uint(p, e, b) || !eat(p, e, " E") || p != e) return;
+        if (!eat(p, e, "V") || !read_uint(p, e, b, ty == Not ? big_ignored : big) || !eat(p, e, " E") || p != e) return;   // NOT: second operand unused
         g.ty = ty;
         g.k0 = 'V';
         g.in0 = a;
@@ -272,7 +277,7 @@ void parse_line(const char* p, const char* e, std::vector<DagGate>& dag, uint64_
     }
     // ids must be dense (dag_to_layered rejects holes), so an id far beyond the lines seen so far can never become
     // valid: refuse it here instead of allocating tgt + 1 entries for a hostile file
-    if (tgt > dag_id_cap) { dag_overflow = true; return; }
+    if (big || tgt > dag_id_cap) { dag_overflow = true; return; }   // a well-formed statement with an impossible id: the file is rejected
     if (tgt >= dag.size()) dag.resize(tgt + 1);
     dag[tgt] = g;
 }

@@ -707,3 +707,17 @@ def test_loader_statement_grammar_follows_the_reference_regexes(B):
     for bad in (b"P V99999999999999999999999 = I0 E", b"P V4 = V99999999999999999999999 + V0 E", b"P V4 = V0 + V99999999999999999999999 E"):
         with pytest.raises(B.VpError):
             B.Circuit.from_pws_text(base + bad + b"\n")
+
+
+@pytest.mark.parametrize("seed,K,complex_consts,with_assert", [(1, 1, False, False), (2, 1, True, True), (3, 3, True, False), (4, 5, False, True)])
+def test_oracle_matches_compiled_reference_on_all_gate_types(B, O, seed, K, complex_consts, with_assert):
+    """Addc / Mulc (real and complex constants), Copy, Not, assert gates, plain and replicated: the oracle prover's transcript ==
+    the unmodified reference prover's (libref_gkr.so, ref_gkr_prove2; tools/diff_reference_alltypes_prover.py ran 300 circuits)."""
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/libref_gkr.so not built (needs /root/reference)")
+    import test_gpu_parity as G
+    circ = G._all_types_circuit(B, 500 + seed, complex_consts=complex_consts, with_assert=with_assert)
+    flat = (circ.replicate(K).expand() if K > 1 else circ).flat()
+    want, _, _ = O.ref_prove(flat)
+    got, _, _ = O.OracleCircuit(flat).prove()
+    assert (got["re"] == want["re"]).all() and (got["im"] == want["im"]).all()
